@@ -1,0 +1,290 @@
+"""ORACLE (test infrastructure): plain-PyTorch fp32 restatement of the reference hot path.
+
+Follows (reference file:line, relative to /root/reference):
+  * ``mlp``                      nn/net_blocks.py:43-47     Linear -> ReLU -> BatchNorm1d per layer (BN last!)
+  * ``OracleEdgeConvFeatures``   nn/net_blocks.py:93-191    2 x DynamicEdgeConv (+skip xyz) (+global pool + lin)
+  * ``init_state``               nn/net_blocks.py:302-315   h0/c0 drawn with kaiming_normal_ on the CPU every call
+  * ``OracleLSTMDecoder``        nn/net_blocks.py:363-402   repeat encoding out_len x -> nn.LSTM -> Linear
+  * ``OracleFullPattern3D``      nn/nets.py:41-184          baseline model (pattern LSTM -> panel LSTM -> placement)
+  * ``OracleSegmentPattern3D``   nn/nets.py:187-299         attention model (per-point sparsemax -> 23 pooled encodings)
+  * ``panel_loop_loss``          nn/metrics/losses.py:19-51
+  * ``main_losses``              nn/metrics/composed_loss.py:294-321 (the 4 components active in att.yaml:124)
+The module tree / parameter names reproduce the reference state_dict so the shipped checkpoints load
+with strict=True.  ``tests/test_oracle_vs_reference.py`` checks this file against the unmodified reference code
+executed through ``oracle.ref_stubs`` (bit-exact on CPU); the committed fixtures in tests/golden/ come from that run.
+
+Differences from the reference that are deliberate and documented: ``init_state`` can be overridden by passing
+``lstm_state=(h0, c0)`` (the reference's states are fresh random draws on every forward -- SURVEY.md F3 -- so parity
+needs identical draws); the per-panel pooling loop is written as one batched contraction when ``fast=True`` (default
+False = the reference's 23-iteration loop order of operations).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import thirdparty as tp
+
+ATT_NN_CONFIG = {      # models/att/att.yaml:89-120 (NN section) -- values, not code
+    'model': 'GarmentSegmentPattern3D', 'feature_extractor': 'EdgeConvFeatures', 'conv_depth': 2,
+    'k_neighbors': 5, 'EConv_hidden': 200, 'EConv_hidden_depth': 2, 'EConv_feature': 150, 'EConv_aggr': 'max',
+    'global_pool': 'mean', 'skip_connections': True, 'graph_pooling': False, 'pool_ratio': 0.1,
+    'local_attention': True, 'panel_decoder': 'LSTMDecoderModule', 'panel_encoding_size': 250,
+    'panel_hidden_size': 250, 'panel_n_layers': 3, 'lstm_init': 'kaiming_normal_',
+    'pattern_decoder': 'LSTMDecoderModule', 'pattern_encoding_size': 250, 'pattern_hidden_size': 250,
+    'pattern_n_layers': 2, 'stitch_tag_dim': 3,
+}
+ATT_DATA_CONFIG = {    # models/att/att.yaml:44-51 (+ 23 panel classes => max_pattern_len 23)
+    'max_pattern_len': 23, 'max_panel_len': 14, 'element_size': 4, 'rotation_size': 4, 'translation_size': 3,
+}
+
+
+def mlp(widths):
+    return nn.Sequential(*[nn.Sequential(nn.Linear(a, b), nn.ReLU(), nn.BatchNorm1d(b))
+                           for a, b in zip(widths[:-1], widths[1:])])
+
+
+_POOLS = {'mean': tp.global_mean_pool, 'max': tp.global_max_pool, 'add': tp.global_add_pool}
+
+
+class OracleEdgeConvFeatures(nn.Module):
+    def __init__(self, out_size, config=None):
+        super().__init__()
+        cfg = {'conv_depth': 2, 'k_neighbors': 5, 'EConv_hidden': 200, 'EConv_hidden_depth': 2,
+               'EConv_feature': 112, 'EConv_aggr': 'max', 'global_pool': 'mean', 'skip_connections': False,
+               'graph_pooling': False, 'pool_ratio': 0.1}
+        cfg.update(config or {})
+        if cfg['graph_pooling']:
+            raise NotImplementedError('graph_pooling is out of scope (SURVEY.md section 2 row 4)')
+        if cfg['global_pool'] not in _POOLS:
+            raise ValueError('{} pooling is not supported'.format(cfg['global_pool']))
+        self.config = cfg
+        feat, hid, depth = cfg['EConv_feature'], cfg['EConv_hidden'], cfg['EConv_hidden_depth']
+        self.conv_layers = nn.ModuleList()
+        c_in = 3
+        for _ in range(cfg['conv_depth']):
+            self.conv_layers.append(tp.DynamicEdgeConv(mlp([2 * c_in] + [hid] * depth + [feat]),
+                                                       k=cfg['k_neighbors'], aggr=cfg['EConv_aggr']))
+            c_in = feat
+        self.global_pool = _POOLS[cfg['global_pool']]
+        self.lin = nn.Linear(feat + 3 if cfg['skip_connections'] else feat, out_size)
+
+    def forward(self, positions, global_pool=True):
+        B, N = positions.shape[:2]
+        pos = positions.reshape(B * N, positions.shape[-1])
+        batch = torch.arange(B, device=positions.device).repeat_interleave(N)
+        h = pos
+        for conv in self.conv_layers:
+            h = conv(h, batch)
+        if self.config['skip_connections']:
+            h = torch.cat([h, pos], dim=-1)
+        if not global_pool:
+            return None, h, batch
+        return self.lin(self.global_pool(h, batch, B)), h, batch
+
+
+def init_state(n_layers, batch, hidden, init_type='kaiming_normal_', device='cpu'):
+    """nn/net_blocks.py:302-315 -- drawn from the global CPU RNG, then moved."""
+    if not init_type:
+        return torch.zeros(n_layers, batch, hidden).to(device)
+    if 'kaiming_normal' in init_type:
+        t = torch.empty(n_layers, batch, hidden)
+        nn.init.kaiming_normal_(t)
+        return t.to(device)
+    raise NotImplementedError('{} tenzor initialization is not implemented'.format(init_type))
+
+
+class OracleLSTMDecoder(nn.Module):
+    def __init__(self, encoding_size, hidden_size, out_elem_size, n_layers, dropout=0,
+                 custom_init='kaiming_normal', **kwargs):
+        super().__init__()
+        self.custom_init, self.n_layers, self.hidden_size = custom_init, n_layers, hidden_size
+        self.lstm = nn.LSTM(encoding_size, hidden_size, n_layers, dropout=dropout, batch_first=True)
+        self.lin = nn.Linear(hidden_size, out_elem_size)
+        if custom_init:                       # nn/net_blocks.py:318-333: 2-D weights re-drawn, biases left alone
+            for name, p in self.lstm.named_parameters():
+                if 'weight' in name and p.dim() > 1:
+                    nn.init.kaiming_normal_(p)
+
+    def forward(self, enc, out_len, lstm_state=None):
+        rows = enc.shape[0]
+        seq = enc.unsqueeze(1).repeat(1, out_len, 1)
+        if lstm_state is None:
+            h0 = init_state(self.n_layers, rows, self.hidden_size, self.custom_init, enc.device)
+            c0 = init_state(self.n_layers, rows, self.hidden_size, self.custom_init, enc.device)
+        else:
+            h0, c0 = lstm_state
+        out, _ = self.lstm(seq, (h0, c0))
+        return self.lin(out.reshape(-1, self.hidden_size)).view(rows, out_len, -1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# losses (the four components active in the shipped att config)
+# ---------------------------------------------------------------------------------------------------
+def panel_loop_loss(outlines, num_edges, pad_xy=(0.0, 0.0), fast=False):
+    """nn/metrics/losses.py:19-51.  outlines [..., L, >=2]; num_edges flat [P] (None = no padding).
+    Panels with fewer than 3 edges contribute 0 but stay in the denominator."""
+    panels = outlines.reshape(-1, outlines.shape[-2], outlines.shape[-1])
+    P, L = panels.shape[:2]
+    pad = torch.as_tensor(pad_xy, dtype=panels.dtype, device=panels.device)
+    if fast:
+        ne = (torch.full((P,), L, device=panels.device) if num_edges is None else num_edges.to(panels.device))
+        live = (torch.arange(L, device=panels.device)[None, :] < ne[:, None]) & (ne[:, None] >= 3)
+        sums = ((panels[..., :2] - pad) * live[..., None].to(panels.dtype)).sum(dim=1)
+    else:
+        sums = torch.zeros(P, 2, device=panels.device)
+        for p in range(P):
+            n = int(num_edges[p]) if num_edges is not None else L
+            if n < 3:
+                continue
+            sums[p] = (panels[p][:n, :2] - pad).sum(dim=0)
+    sq = sums ** 2
+    return sq.sum() / (sq.shape[0] * sq.shape[1])
+
+
+def main_losses(preds, gt, loop_weight=1.0, pad_xy=(0.0, 0.0), fast=False):
+    """nn/metrics/composed_loss.py:301-321 with loss_components [shape, loop, rotation, translation]."""
+    dev = preds['outlines'].device
+    ne = gt['num_edges'].to(dev).int().view(-1)
+    parts = {
+        'pattern_loss': F.mse_loss(preds['outlines'], gt['outlines'].to(dev)),
+        'loop_loss': panel_loop_loss(preds['outlines'], ne, pad_xy, fast=fast),
+        'rotation_loss': F.mse_loss(preds['rotations'], gt['rotations'].to(dev)),
+        'translation_loss': F.mse_loss(preds['translations'], gt['translations'].to(dev)),
+    }
+    total = 0.
+    total = total + parts['pattern_loss']
+    total = total + loop_weight * parts['loop_loss']
+    total = total + parts['rotation_loss']
+    total = total + parts['translation_loss']
+    return total, parts
+
+
+class _OracleLoss:
+    """Callable with the reference's (loss, loss_dict, structure_update) return shape (composed_loss.py:284)."""
+
+    def __init__(self, loop_weight=1.0, pad_xy=(0.0, 0.0)):
+        self.loop_weight, self.pad_xy = loop_weight, pad_xy
+        self.config = {'loss_components': ['shape', 'loop', 'rotation', 'translation'],
+                       'quality_components': [], 'loop_loss_weight': loop_weight}
+        self.with_quality_eval = False
+        self.training = False
+
+    def __call__(self, preds, ground_truth, names=None, epoch=1000):
+        total, parts = main_losses(preds, ground_truth, self.loop_weight, self.pad_xy)
+        return total, parts, False
+
+    def train(self, mode=True):
+        self.training = mode
+
+    def eval(self):
+        self.training = False
+
+
+# ---------------------------------------------------------------------------------------------------
+# models
+# ---------------------------------------------------------------------------------------------------
+class OracleFullPattern3D(nn.Module):
+    """nn/nets.py:41-184 (baseline; also the parent that owns the panel decoder + placement head)."""
+
+    def __init__(self, data_config=None, config=None, in_loss_config=None, with_pattern_decoder=True):
+        super().__init__()
+        dc = dict(ATT_DATA_CONFIG)
+        dc.update({k: v for k, v in (data_config or {}).items() if k in ATT_DATA_CONFIG})
+        self.elem, self.panel_len, self.n_panels = dc['element_size'], dc['max_panel_len'], dc['max_pattern_len']
+        self.rot, self.tr = dc['rotation_size'], dc['translation_size']
+        cfg = {'panel_encoding_size': 250, 'panel_hidden_size': 250, 'panel_n_layers': 3,
+               'pattern_encoding_size': 250, 'pattern_hidden_size': 250, 'pattern_n_layers': 2, 'dropout': 0,
+               'lstm_init': 'kaiming_normal_', 'stitch_tag_dim': 3}
+        config = dict(config or {})
+        config.setdefault('panel_hidden_size', config.get('panel_encoding_size', 250))
+        config.setdefault('pattern_hidden_size', config.get('pattern_encoding_size', 250))
+        cfg.update(config)
+        self.config = cfg
+        pad = (0.0, 0.0)
+        st = (data_config or {}).get('standardize')
+        if st:                                # nn/metrics/eval_utils.py:80-87: pad = -shift/scale
+            pad = tuple(-s / c for s, c in zip(st['gt_shift']['outlines'][:2], st['gt_scale']['outlines'][:2]))
+        self.loss = _OracleLoss((in_loss_config or {}).get('loop_loss_weight', 1.0), pad)
+        self.feature_extractor = OracleEdgeConvFeatures(cfg['pattern_encoding_size'], cfg)
+        self.config.update(self.feature_extractor.config)
+        self.panel_decoder = OracleLSTMDecoder(cfg['panel_encoding_size'], cfg['panel_hidden_size'],
+                                               self.elem + cfg['stitch_tag_dim'] + 1, cfg['panel_n_layers'],
+                                               dropout=cfg['dropout'], custom_init=cfg['lstm_init'])
+        if with_pattern_decoder:
+            self.pattern_decoder = OracleLSTMDecoder(cfg['pattern_encoding_size'], cfg['pattern_hidden_size'],
+                                                     cfg['panel_encoding_size'], cfg['pattern_n_layers'],
+                                                     dropout=cfg['dropout'], custom_init=cfg['lstm_init'])
+        self.placement_decoder = nn.Linear(cfg['panel_encoding_size'], self.rot + self.tr)
+
+    def forward_panel_decode(self, flat_enc, batch_size, lstm_state=None):
+        seq = self.panel_decoder(flat_enc, self.panel_len, lstm_state=lstm_state)
+        place = self.placement_decoder(flat_enc)
+        seq = seq.reshape(batch_size, self.n_panels, self.panel_len, -1)
+        return {'outlines': seq[..., :self.elem],
+                'rotations': place[:, :self.rot].reshape(batch_size, self.n_panels, -1),
+                'translations': place[:, self.rot:].reshape(batch_size, self.n_panels, -1),
+                'stitch_tags': seq[..., self.elem:-1],
+                'free_edges_mask': seq[..., -1]}
+
+    def forward(self, positions, lstm_state=None, pattern_lstm_state=None, **kwargs):
+        enc = self.feature_extractor(positions)[0]
+        panels = self.pattern_decoder(enc, self.n_panels, lstm_state=pattern_lstm_state)
+        return self.forward_panel_decode(panels.reshape(-1, panels.shape[-1]), enc.shape[0], lstm_state)
+
+
+class OracleSegmentPattern3D(OracleFullPattern3D):
+    """nn/nets.py:187-299."""
+
+    def __init__(self, data_config=None, config=None, in_loss_config=None):
+        super().__init__(data_config, config, in_loss_config)
+        del self.pattern_decoder       # nn/nets.py:236 (built first so the RNG stream matches the reference's init)
+        self.save_att_weights = False
+        self.config.setdefault('local_attention', False)
+        feat = self.feature_extractor.config['EConv_feature']
+        skip = 3 if self.config['skip_connections'] else 0
+        att_in = feat + skip + (0 if self.config['local_attention'] else self.config['pattern_encoding_size'])
+        self.point_segment_mlp = nn.Sequential(mlp([att_in, att_in, att_in, self.n_panels]), tp.Sparsemax(dim=1))
+        self.panel_dec_lin = nn.Linear(feat + skip, self.feature_extractor.config['panel_encoding_size'])
+
+    def forward_panel_enc_from_3d(self, positions, fast=False):
+        B = positions.shape[0]
+        glob, feats, batch = self.feature_extractor(positions, not self.config['local_attention'])
+        n_pts = feats.shape[0] // B
+        if self.config['local_attention']:
+            w = self.point_segment_mlp(feats)
+        else:
+            rep = glob.unsqueeze(1).repeat(1, n_pts, 1).view(-1, glob.shape[-1])
+            w = self.point_segment_mlp(torch.cat([rep, feats], dim=-1))
+        if fast and self.config['global_pool'] == 'mean':
+            pooled = torch.einsum('bnp,bnf->bpf', w.view(B, n_pts, -1), feats.view(B, n_pts, -1)) / n_pts
+            enc = self.panel_dec_lin(pooled)
+        else:
+            per_panel = []
+            for p in range(w.shape[-1]):
+                pooled = self.feature_extractor.global_pool(w[:, p].unsqueeze(-1) * feats, batch, B)
+                per_panel.append(self.panel_dec_lin(pooled).view(B, -1, self.panel_dec_lin.out_features))
+            enc = torch.cat(per_panel, dim=1)
+        att = w.view(B, -1, w.shape[-1]) if self.save_att_weights else []
+        return enc, att
+
+    def forward(self, positions, lstm_state=None, fast=False, **kwargs):
+        B = positions.shape[0]
+        enc, att = self.forward_panel_enc_from_3d(positions, fast=fast)
+        out = self.forward_panel_decode(enc.reshape(-1, enc.shape[-1]), B, lstm_state)
+        if len(att) > 0:
+            out['att_weights'] = att
+        return out
+
+
+def synthetic_ground_truth(B, seed=11, n_panels=23, panel_len=14, device='cpu'):
+    """Synthetic GT of SURVEY.md section 8d / A.4: N(0,1) targets, num_edges in {0, 3..14}, zero rows past num_edges."""
+    g = torch.Generator().manual_seed(seed)
+    ne = torch.randint(2, panel_len + 1, (B, n_panels), generator=g)
+    ne = torch.where(ne < 3, torch.zeros_like(ne), ne)
+    outl = torch.randn(B, n_panels, panel_len, 4, generator=g)
+    live = torch.arange(panel_len)[None, None, :] < ne[..., None]
+    outl = outl * live[..., None]
+    gt = {'outlines': outl, 'rotations': torch.randn(B, n_panels, 4, generator=g),
+          'translations': torch.randn(B, n_panels, 3, generator=g), 'num_edges': ne,
+          'num_panels': (ne > 0).sum(-1)}
+    return {k: v.to(device) for k, v in gt.items()}
