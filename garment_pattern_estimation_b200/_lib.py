@@ -1,0 +1,112 @@
+"""ctypes binding of libnt_b200.so (C ABI declared in include/nt_b200.h).
+
+There is NO fallback: if the library is missing and cannot be built, or a call returns non-zero, a RuntimeError is
+raised (error convention of the reference: RuntimeError, nn/trainer.py:60).
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+
+NT_PROD_PLAIN, NT_PROD_EDGE = 0, 1
+NT_EPI_BIAS, NT_EPI_RELU_STATS, NT_EPI_RELU_MAXMIN, NT_EPI_BNRELU_BWD = 0, 1, 2, 3
+
+
+class GemmArgs(ctypes.Structure):
+    """Mirror of `struct nt_gemm_args`."""
+    _fields_ = [
+        ('rows', c_int64), ('K', c_int), ('n_out', c_int), ('producer', c_int), ('epilogue', c_int),
+        ('a', c_void_p), ('lda', c_int),
+        ('pq', c_void_p), ('ldpq', c_int), ('qoff', c_int),
+        ('idx', c_void_p), ('k', c_int), ('n_per_cloud', c_int),
+        ('w', c_void_p), ('ldw', c_int), ('bias', c_void_p),
+        ('out', c_void_p), ('ldo', c_int),
+        ('stats', c_void_p),
+        ('vmax', c_void_p), ('vmin', c_void_p), ('imax', c_void_p), ('imin', c_void_p),
+        ('aux', c_void_p), ('ldaux', c_int), ('aux_edge', c_int),
+        ('k0', c_void_p), ('k1', c_void_p), ('mu', c_void_p),
+        ('colsum', c_void_p),
+    ]
+
+
+_SIGNATURES = {
+    'nt_last_error': (ctypes.c_char_p, []),
+    'nt_version': (c_int, []),
+    'nt_built_arch': (c_int, []),
+    'nt_launch_count': (c_int64, []),
+    'nt_knn': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'nt_gemm_nt': (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
+    'nt_gemm_tn': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64,
+                           c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    'nt_gemm_tn_centered': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64,
+                                    c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
+                                    c_void_p]),
+    'nt_bn_fold': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'nt_edge_stats': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    'nt_maxmin_finish': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                 c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'nt_bn_apply': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
+    'nt_bn_bwd_reduce': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int,
+                                 c_void_p, c_void_p]),
+    'nt_bn_relu_bwd_last': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p,
+                                    c_void_p]),
+    'nt_linear_bn_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'nt_edge_scatter': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_int,
+                                c_void_p]),
+    'nt_sparsemax_fwd': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    'nt_sparsemax_bwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    'nt_attn_pool_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                 c_void_p]),
+    'nt_attn_pool_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                 c_void_p, c_void_p, c_int, c_int, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
+_lib = None
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the .so is absent and nvcc is available).  Raises RuntimeError otherwise."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001 -- turn every build problem into the documented error type
+            raise RuntimeError('libnt_b200.so is missing and could not be built ({}); the B200 hot path has no '
+                               'CPU or library fallback'.format(e))
+    try:
+        lib = ctypes.CDLL(path)
+    except OSError as e:
+        raise RuntimeError('cannot load {}: {}'.format(path, e))
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise RuntimeError('{} does not export {} (stale build? run garment_pattern_estimation_b200/build.py '
+                               '--force)'.format(path, name))
+        fn.restype, fn.argtypes = restype, argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = load().nt_last_error()
+        raise RuntimeError('libnt_b200 {}: {}'.format(what, msg.decode() if msg else 'status %d' % rc))
+
+
+def launch_count():
+    return int(load().nt_launch_count())

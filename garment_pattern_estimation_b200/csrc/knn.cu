@@ -1,0 +1,162 @@
+// Brute-force kNN graph build (distance + top-k fused), sm_100a.
+//
+// Replaces torch_cluster.knn as reached from DynamicEdgeConv.forward (reference nn/net_blocks.py:127-135,174).
+// Bit-exactness contract (oracle/knn_oracle.c): squared distance = sequential fp32 chain
+//     acc = fma(c_d - q_d, c_d - q_d, acc),  d = 0..D-1
+// and the result is the k lexicographically smallest (distance, index) pairs, ascending.
+//
+// Mapping: one thread owns one query and its private sorted top-K list in registers; a CTA of 256 queries of one
+// cloud sweeps the cloud's candidates in tiles of TC rows staged in shared memory.  Every lane reads the SAME
+// candidate word (shared-memory broadcast), so the kernel is bound by the FP32 pipe: 2 instructions (FADD + FFMA)
+// per pair-dimension, the minimum the bit-exact direct form allows.  TC independent chains per thread give the ILP.
+// Zero padding (candidate and query padded to a multiple of 4 dims with 0) is exact: fma(0,0,acc) == acc.
+#include "common.cuh"
+
+namespace nt {
+
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_TC = 32;   // candidates per tile (independent fma chains per thread)
+constexpr int KNN_DC = 16;   // dims per query-register chunk
+
+template <int K>
+__device__ __forceinline__ void topk_insert(float (&ld)[K], int (&li)[K], float d, int c) {
+    // caller guarantees d < ld[K-1]; insert before the first entry that is strictly greater (stable for ties)
+#pragma unroll
+    for (int e = K - 1; e >= 0; --e) {
+        bool prev_gt = (e > 0) ? (ld[e > 0 ? e - 1 : 0] > d) : false;
+        bool cur_gt = ld[e] > d;
+        float nd = prev_gt ? ld[e > 0 ? e - 1 : 0] : (cur_gt ? d : ld[e]);
+        int ni = prev_gt ? li[e > 0 ? e - 1 : 0] : (cur_gt ? c : li[e]);
+        ld[e] = nd;
+        li[e] = ni;
+    }
+}
+
+// NG = number of float4 groups of this chunk (1..4)
+template <int NG>
+__device__ __forceinline__ void chain_chunk(float (&acc)[KNN_TC], const float *__restrict__ tile, int Dp, int d0,
+                                            const float (&qv)[KNN_DC]) {
+#pragma unroll
+    for (int c = 0; c < KNN_TC; ++c) {
+        const float4 *row = reinterpret_cast<const float4 *>(tile + c * Dp + d0);
+        float a = acc[c];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            float4 cv = row[g];
+            float d;
+            d = __fsub_rn(cv.x, qv[4 * g + 0]); a = __fmaf_rn(d, d, a);
+            d = __fsub_rn(cv.y, qv[4 * g + 1]); a = __fmaf_rn(d, d, a);
+            d = __fsub_rn(cv.z, qv[4 * g + 2]); a = __fmaf_rn(d, d, a);
+            d = __fsub_rn(cv.w, qv[4 * g + 3]); a = __fmaf_rn(d, d, a);
+        }
+        acc[c] = a;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(KNN_THREADS, (K <= 16) ? 2 : 1)
+knn_kernel(const float *__restrict__ x, int N, int D, int ldx, int k, int32_t *__restrict__ idx) {
+    extern __shared__ __align__(16) float tile[];   // [KNN_TC][Dp]
+    const int Dp = (D + 3) & ~3;
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * KNN_THREADS + threadIdx.x;
+    const bool q_ok = q < N;
+    const float *cloud = x + (size_t)b * N * ldx;
+    const float *xq = cloud + (size_t)(q_ok ? q : 0) * ldx;
+    const bool qvec = ((ldx & 3) == 0) && aligned16(x);
+
+    float ld[K];
+    int li[K];
+#pragma unroll
+    for (int e = 0; e < K; ++e) { ld[e] = 1e10f; li[e] = -1; }
+
+    const int full_chunks = Dp / KNN_DC;
+    const int tail_groups = (Dp - full_chunks * KNN_DC) >> 2;
+
+    for (int c0 = 0; c0 < N; c0 += KNN_TC) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < KNN_TC * Dp; i += KNN_THREADS) {
+            int c = i / Dp, d = i - c * Dp;
+            float v = 0.f;
+            if (c0 + c < N && d < D) v = __ldg(cloud + (size_t)(c0 + c) * ldx + d);
+            tile[i] = v;
+        }
+        __syncthreads();
+
+        float acc[KNN_TC];
+#pragma unroll
+        for (int c = 0; c < KNN_TC; ++c) acc[c] = 0.f;
+
+        for (int ch = 0; ch <= full_chunks; ++ch) {
+            const int d0 = ch * KNN_DC;
+            const int groups = (ch < full_chunks) ? (KNN_DC / 4) : tail_groups;
+            if (groups == 0) break;
+            float qv[KNN_DC];
+#pragma unroll
+            for (int g = 0; g < KNN_DC / 4; ++g) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g < groups && q_ok) {
+                    const int d = d0 + 4 * g;
+                    if (qvec && d + 3 < D) {
+                        v = __ldg(reinterpret_cast<const float4 *>(xq + d));
+                    } else {
+                        if (d + 0 < D) v.x = __ldg(xq + d + 0);
+                        if (d + 1 < D) v.y = __ldg(xq + d + 1);
+                        if (d + 2 < D) v.z = __ldg(xq + d + 2);
+                        if (d + 3 < D) v.w = __ldg(xq + d + 3);
+                    }
+                }
+                qv[4 * g + 0] = v.x; qv[4 * g + 1] = v.y; qv[4 * g + 2] = v.z; qv[4 * g + 3] = v.w;
+            }
+            switch (groups) {
+                case 4: chain_chunk<4>(acc, tile, Dp, d0, qv); break;
+                case 3: chain_chunk<3>(acc, tile, Dp, d0, qv); break;
+                case 2: chain_chunk<2>(acc, tile, Dp, d0, qv); break;
+                default: chain_chunk<1>(acc, tile, Dp, d0, qv); break;
+            }
+        }
+
+#pragma unroll
+        for (int c = 0; c < KNN_TC; ++c) {
+            if (c0 + c < N && acc[c] < ld[K - 1]) topk_insert<K>(ld, li, acc[c], c0 + c);
+        }
+    }
+
+    if (q_ok) {
+        int32_t *o = idx + ((size_t)b * N + q) * k;
+#pragma unroll
+        for (int e = 0; e < K; ++e)
+            if (e < k) o[e] = li[e];
+    }
+}
+
+template <int K>
+static int launch_knn(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
+    const int Dp = (D + 3) & ~3;
+    size_t smem = (size_t)KNN_TC * Dp * sizeof(float);
+    if (smem > 200 * 1024) return fail("nt_knn: feature dimension %s too large for the staging tile (D=%ld)", "", D);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(knn_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail("nt_knn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    dim3 grid((N + KNN_THREADS - 1) / KNN_THREADS, B);
+    knn_kernel<K><<<grid, KNN_THREADS, smem, st>>>(x, N, D, ldx, k, idx);
+    return check_launch("nt_knn");
+}
+
+}  // namespace nt
+
+extern "C" int nt_knn(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *stream) {
+    using namespace nt;
+    NT_REQUIRE(x && idx, "nt_knn: null pointer");
+    NT_REQUIRE(B >= 0 && N >= 0 && D >= 1 && ldx >= D, "nt_knn: bad shape");
+    NT_REQUIRE(k >= 1 && k <= 32, "nt_knn: k must be in [1, 32]");
+    NT_REQUIRE(k <= N || N == 0, "nt_knn: k must not exceed the number of points per cloud");
+    NT_REQUIRE(B <= 65535, "nt_knn: at most 65535 clouds per call");
+    if (B == 0 || N == 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (k <= 5) return launch_knn<5>(x, B, N, D, ldx, k, idx, st);
+    if (k <= 8) return launch_knn<8>(x, B, N, D, ldx, k, idx, st);
+    if (k <= 16) return launch_knn<16>(x, B, N, D, ldx, k, idx, st);
+    return launch_knn<32>(x, B, N, D, ldx, k, idx, st);
+}

@@ -1,0 +1,346 @@
+// BatchNorm bookkeeping, aggregation finish, and the element-wise / column-reduction pieces of the MLP() backward
+// (reference nn/net_blocks.py:43-47: Linear -> ReLU -> BatchNorm1d, BN after ReLU and also on the last layer).
+// All of these are bandwidth-trivial next to the GEMMs; they exist so that no [rows, C] tensor makes an extra trip
+// through HBM for BN normalisation (the affine is folded into the next Linear's weights instead).
+#include "common.cuh"
+
+namespace nt {
+
+// ---------------------------------------------------------------------------------------------------------
+// bn_fold: statistics -> (mean, rstd, s, t), running-buffer update, fold into the next Linear.
+// grid = n_next + 1 blocks; block b < n_next folds output row b, the last block writes the per-channel vectors.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bn_channel(const double *stats, int64_t count, int C, int c, const float *gamma,
+                                           const float *beta, const float *rmean, const float *rvar, float eps,
+                                           int training, float &mean, float &var_b, float &rstd, float &s, float &t) {
+    if (training) {
+        double m = stats[c] / (double)count;
+        double v = stats[C + c] / (double)count - m * m;
+        if (v < 0.0) v = 0.0;
+        mean = (float)m; var_b = (float)v;
+        rstd = (float)(1.0 / sqrt(v + (double)eps));
+    } else {
+        mean = rmean[c]; var_b = rvar[c];
+        rstd = 1.0f / sqrtf(var_b + eps);
+    }
+    s = gamma[c] * rstd;
+    t = beta[c] - mean * s;
+}
+
+__global__ void bn_fold_kernel(const double *stats, int64_t count, int C, const float *gamma, const float *beta,
+                               float *rmean, float *rvar, int64_t *nbt, float momentum, float eps, int training,
+                               float *mean_o, float *rstd_o, float *s_o, float *t_o,
+                               const float *w_next, const float *b_next, int n_next,
+                               float *w_f, float *w_ft, float *b_f) {
+    __shared__ float red[32];
+    const int o = blockIdx.x;
+    if (o < n_next) {
+        float part = 0.f;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float mean, var_b, rstd, s, t;
+            bn_channel(stats, count, C, c, gamma, beta, rmean, rvar, eps, training, mean, var_b, rstd, s, t);
+            float w = w_next[(int64_t)o * C + c];
+            float wf = w * s;
+            w_f[(int64_t)o * C + c] = wf;
+            if (w_ft) w_ft[(int64_t)c * n_next + o] = wf;
+            part = fmaf(w, t, part);
+        }
+        part = warp_sum(part);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.f;
+            for (int i = 0; i < (blockDim.x + 31) / 32; ++i) tot += red[i];
+            b_f[o] = (b_next ? b_next[o] : 0.f) + tot;
+        }
+    } else {
+        // NOTE: this block READS the running buffers before updating them; the fold blocks above only read them in
+        // eval mode, where they are not written.
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float mean, var_b, rstd, s, t;
+            bn_channel(stats, count, C, c, gamma, beta, rmean, rvar, eps, training, mean, var_b, rstd, s, t);
+            mean_o[c] = mean; rstd_o[c] = rstd; s_o[c] = s; t_o[c] = t;
+            if (training && rmean && rvar) {
+                float unbiased = count > 1 ? var_b * ((float)count / (float)(count - 1)) : var_b;
+                rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+                rvar[c] = (1.f - momentum) * rvar[c] + momentum * unbiased;
+            }
+        }
+        if (training && nbt && threadIdx.x == 0) *nbt += 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void maxmin_finish_kernel(const float *vmax, const float *vmin, const uint8_t *imax, const uint8_t *imin,
+                                     const float *s, const float *t, int64_t M, int C, float *out, int ldo,
+                                     uint8_t *sel, float *vsel, const float *tail_src, int tail_ld, int tail) {
+    const int W = C + tail;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * W) return;
+    int64_t m = i / W;
+    int c = (int)(i - m * W);
+    if (c < C) {
+        float sc = s[c];
+        bool up = sc >= 0.f;
+        int64_t o = m * C + c;
+        float v = up ? vmax[o] : vmin[o];
+        out[m * ldo + c] = fmaf(v, sc, t[c]);
+        if (sel) sel[o] = up ? imax[o] : imin[o];
+        if (vsel) vsel[o] = v;
+    } else {
+        out[m * ldo + c] = tail_src[m * tail_ld + (c - C)];
+    }
+}
+
+__global__ void bn_apply_kernel(const float *a, int lda, const float *s, const float *t, int64_t rows, int C,
+                                float *out, int ldo) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * C) return;
+    int64_t r = i / C;
+    int c = (int)(i - r * C);
+    out[r * ldo + c] = fmaf(a[r * lda + c], s[c], t[c]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// column reductions: block (32, 8); blockIdx.y selects a 32-column slab, blockIdx.x a row chunk
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CR_ROWS = 512;   // rows per block
+
+__global__ void bn_bwd_reduce_kernel(const float *g, int ldg, const float *v, int ldv, const float *mu,
+                                     const float *rstd, int64_t rows, int C, double *sums) {
+    __shared__ float r0[8][33], r1[8][33];
+    const int c = blockIdx.y * 32 + threadIdx.x;
+    const int64_t rbeg = (int64_t)blockIdx.x * CR_ROWS;
+    const int64_t rend = min(rows, rbeg + CR_ROWS);
+    float a0 = 0.f, a1 = 0.f;
+    if (c < C) {
+        const float m = v ? mu[c] : 0.f, rs = v ? rstd[c] : 0.f;
+        for (int64_t r = rbeg + threadIdx.y; r < rend; r += 8) {
+            float gv = g[r * ldg + c];
+            a0 += gv;
+            if (v) a1 = fmaf(gv, (v[r * ldv + c] - m) * rs, a1);
+        }
+    }
+    r0[threadIdx.y][threadIdx.x] = a0; r1[threadIdx.y][threadIdx.x] = a1;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s0 += r0[i][threadIdx.x]; s1 += r1[i][threadIdx.x]; }
+        atomicAdd(sums + c, (double)s0);
+        if (v) atomicAdd(sums + C + c, (double)s1);
+    }
+}
+
+// statistics of the FIRST activation a1 = relu(P[centre] + Q[neighbour]) (no GEMM in front of it at edge level)
+__global__ void edge_stats_kernel(const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
+                                  int64_t rows, int H, double *stats) {
+    __shared__ float r0[8][33], r1[8][33];
+    const int c = blockIdx.y * 32 + threadIdx.x;
+    const int64_t rbeg = (int64_t)blockIdx.x * CR_ROWS;
+    const int64_t rend = min(rows, rbeg + CR_ROWS);
+    float a0 = 0.f, a1 = 0.f;
+    if (c < H) {
+        for (int64_t r = rbeg + threadIdx.y; r < rend; r += 8) {
+            float v;
+            if (idx) {
+                const int64_t centre = r / k;
+                const int64_t j = (centre / n_per_cloud) * (int64_t)n_per_cloud + idx[r];
+                v = pq[centre * ldpq + c] + pq[j * ldpq + qoff + c];
+            } else {
+                v = pq[r * ldpq + c];
+            }
+            v = fmaxf(v, 0.f);
+            a0 += v;
+            a1 = fmaf(v, v, a1);
+        }
+    }
+    r0[threadIdx.y][threadIdx.x] = a0; r1[threadIdx.y][threadIdx.x] = a1;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < H) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s0 += r0[i][threadIdx.x]; s1 += r1[i][threadIdx.x]; }
+        atomicAdd(stats + c, (double)s0);
+        atomicAdd(stats + H + c, (double)s1);
+    }
+}
+
+__global__ void bn_relu_bwd_last_kernel(const float *a, int lda, const float *g, int ldg, const uint8_t *sel, int k,
+                                        const float *s, const float *mu, const float *rstd, const double *sums,
+                                        int64_t count, int64_t rows, int C, float *dz, int lddz, double *colsum) {
+    __shared__ float r0[8][33];
+    const int c = blockIdx.y * 32 + threadIdx.x;
+    const int64_t rbeg = (int64_t)blockIdx.x * CR_ROWS;
+    const int64_t rend = min(rows, rbeg + CR_ROWS);
+    float acc = 0.f;
+    if (c < C) {
+        const float inv = 1.0f / (float)count;
+        const float sc = s[c], m = mu[c], rs = rstd[c];
+        const float dbeta = (float)sums[c] * inv, dgamma = (float)sums[C + c] * inv;
+        for (int64_t r = rbeg + threadIdx.y; r < rend; r += 8) {
+            const float av = a[r * lda + c];
+            float out = 0.f;
+            if (av > 0.f) {
+                const int64_t node = r / k;
+                float gs = 0.f;
+                if (!sel || sel[node * C + c] == (uint8_t)(r - node * k)) gs = g[node * ldg + c];
+                out = sc * (gs - dbeta - (av - m) * rs * dgamma);
+            }
+            dz[r * lddz + c] = out;
+            acc += out;
+        }
+    }
+    r0[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C && colsum) {
+        float s0 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s0 += r0[i][threadIdx.x];
+        atomicAdd(colsum + c, (double)s0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void linear_bn_bwd_kernel(const double *rawc, const double *csum, int n_out, int C, const float *w,
+                                     const float *s, const float *beta, const float *rstd, int64_t count,
+                                     float *dW, float *db, float *dgamma, float *dbeta, float *k0, float *k1) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0) {
+        for (int o = threadIdx.x; o < n_out; o += blockDim.x) db[o] = (float)csum[o];
+    }
+    if (c >= C) return;
+    const double sc = s[c], bc = beta[c];
+    double db_acc = 0.0, dg_acc = 0.0;
+    for (int o = 0; o < n_out; ++o) {
+        const double cs = csum[o];
+        const double rw = rawc[(int64_t)o * C + c];
+        const double wv = w[(int64_t)o * C + c];
+        // y_prev = a*s + t with a = (a - mean) + mean  =>  dW = s * rawc + csum * (s*mean + t) = s * rawc + csum * beta
+        dW[(int64_t)o * C + c] = (float)(rw * sc + cs * bc);
+        db_acc += wv * cs;
+        dg_acc += wv * rw;
+    }
+    dg_acc *= (double)rstd[c];
+    dbeta[c] = (float)db_acc; dgamma[c] = (float)dg_acc;
+    const double inv = 1.0 / (double)count;
+    k0[c] = (float)(sc * db_acc * inv);
+    k1[c] = (float)(sc * (double)rstd[c] * dg_acc * inv);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void edge_scatter_kernel(const float *dz, int lddz, const int32_t *idx, int k, int n_per_cloud,
+                                    int64_t M, int H, float *dpq, int lddpq) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * H) return;
+    int64_t m = i / H;
+    int h = (int)(i - m * H);
+    const int64_t base = (m / n_per_cloud) * (int64_t)n_per_cloud;
+    float sum = 0.f;
+    for (int sl = 0; sl < k; ++sl) {
+        const int64_t e = m * k + sl;
+        const float v = dz[e * lddz + h];
+        sum += v;
+        if (v != 0.f) atomicAdd(dpq + (base + idx[e]) * lddpq + H + h, v);
+    }
+    dpq[m * lddpq + h] = sum;
+}
+
+static inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace nt
+
+using namespace nt;
+
+extern "C" int nt_bn_fold(const double *stats, int64_t count, int C, const float *gamma, const float *beta,
+                          float *running_mean, float *running_var, int64_t *num_batches_tracked, float momentum,
+                          float eps, int training, float *mean, float *rstd, float *s, float *t,
+                          const float *w_next, const float *b_next, int n_next, float *w_f, float *w_ft, float *b_f,
+                          void *stream) {
+    NT_REQUIRE(C >= 1 && gamma && beta && mean && rstd && s && t, "nt_bn_fold: bad arguments");
+    NT_REQUIRE(training ? (stats != nullptr && count >= 1) : (running_mean && running_var),
+               "nt_bn_fold: statistics missing");
+    if (!w_next) n_next = 0;
+    NT_REQUIRE(n_next == 0 || (w_f && b_f), "nt_bn_fold: fold outputs missing");
+    bn_fold_kernel<<<n_next + 1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        stats, count, C, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, training, mean,
+        rstd, s, t, w_next, b_next, n_next, w_f, w_ft, b_f);
+    return check_launch("nt_bn_fold");
+}
+
+extern "C" int nt_maxmin_finish(const float *vmax, const float *vmin, const uint8_t *imax, const uint8_t *imin,
+                                const float *s, const float *t, int64_t M, int C, float *out, int ldo, uint8_t *sel,
+                                float *vsel, const float *tail_src, int tail_ld, int tail, void *stream) {
+    NT_REQUIRE(vmax && vmin && imax && imin && s && t && out && M >= 0 && C >= 1, "nt_maxmin_finish: bad arguments");
+    NT_REQUIRE(tail >= 0 && ldo >= C + tail && (tail == 0 || tail_src), "nt_maxmin_finish: bad tail/ldo");
+    if (M == 0) return 0;
+    const int64_t n = M * (C + tail);
+    maxmin_finish_kernel<<<blocks_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        vmax, vmin, imax, imin, s, t, M, C, out, ldo, sel, vsel, tail_src, tail_ld, tail);
+    return check_launch("nt_maxmin_finish");
+}
+
+extern "C" int nt_bn_apply(const float *a, int lda, const float *s, const float *t, int64_t rows, int C, float *out,
+                           int ldo, void *stream) {
+    NT_REQUIRE(a && s && t && out && rows >= 0 && C >= 1 && lda >= C && ldo >= C, "nt_bn_apply: bad arguments");
+    if (rows == 0) return 0;
+    bn_apply_kernel<<<blocks_for(rows * C, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, lda, s, t, rows,
+                                                                                                   C, out, ldo);
+    return check_launch("nt_bn_apply");
+}
+
+extern "C" int nt_bn_bwd_reduce(const float *g, int ldg, const float *v, int ldv, const float *mu, const float *rstd,
+                                int64_t rows, int C, double *sums, void *stream) {
+    NT_REQUIRE(g && sums && rows >= 0 && C >= 1 && ldg >= C, "nt_bn_bwd_reduce: bad arguments");
+    NT_REQUIRE(!v || (mu && rstd && ldv >= C), "nt_bn_bwd_reduce: bad BN operands");
+    if (rows == 0) return 0;
+    dim3 grid(blocks_for(rows, CR_ROWS), (C + 31) / 32), block(32, 8);
+    bn_bwd_reduce_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, ldg, v, ldv, mu, rstd, rows, C,
+                                                                                   sums);
+    return check_launch("nt_bn_bwd_reduce");
+}
+
+extern "C" int nt_edge_stats(const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
+                             int64_t rows, int H, double *stats, void *stream) {
+    NT_REQUIRE(pq && stats && rows >= 0 && H >= 1 && ldpq >= H, "nt_edge_stats: bad arguments");
+    NT_REQUIRE(!idx || (k >= 1 && n_per_cloud >= 1), "nt_edge_stats: edge operand needs k and n_per_cloud");
+    if (rows == 0) return 0;
+    dim3 grid(blocks_for(rows, CR_ROWS), (H + 31) / 32), block(32, 8);
+    edge_stats_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pq, ldpq, qoff, idx, k, n_per_cloud,
+                                                                                rows, H, stats);
+    return check_launch("nt_edge_stats");
+}
+
+extern "C" int nt_bn_relu_bwd_last(const float *a, int lda, const float *g, int ldg, const uint8_t *sel, int k,
+                                   const float *s, const float *mu, const float *rstd, const double *sums,
+                                   int64_t count, int64_t rows, int C, float *dz, int lddz, double *colsum,
+                                   void *stream) {
+    NT_REQUIRE(a && g && s && mu && rstd && sums && dz && k >= 1 && count >= 1 && C >= 1, "nt_bn_relu_bwd_last: bad arguments");
+    NT_REQUIRE(lda >= C && ldg >= C && lddz >= C && rows % k == 0, "nt_bn_relu_bwd_last: bad strides");
+    if (rows == 0) return 0;
+    dim3 grid(blocks_for(rows, CR_ROWS), (C + 31) / 32), block(32, 8);
+    bn_relu_bwd_last_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        a, lda, g, ldg, sel, k, s, mu, rstd, sums, count, rows, C, dz, lddz, colsum);
+    return check_launch("nt_bn_relu_bwd_last");
+}
+
+extern "C" int nt_linear_bn_bwd(const double *rawc, const double *csum, int n_out, int C, const float *w,
+                                const float *s, const float *beta, const float *rstd, int64_t count,
+                                float *dW, float *db, float *dgamma, float *dbeta, float *k0, float *k1, void *stream) {
+    NT_REQUIRE(rawc && csum && dW && db && n_out >= 1 && C >= 1, "nt_linear_bn_bwd: bad arguments");
+    NT_REQUIRE(w && s && beta && rstd && dgamma && dbeta && k0 && k1 && count >= 1,
+               "nt_linear_bn_bwd: BN operands missing");
+    linear_bn_bwd_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        rawc, csum, n_out, C, w, s, beta, rstd, count, dW, db, dgamma, dbeta, k0, k1);
+    return check_launch("nt_linear_bn_bwd");
+}
+
+extern "C" int nt_edge_scatter(const float *dz, int lddz, const int32_t *idx, int k, int n_per_cloud, int64_t M, int H,
+                               float *dpq, int lddpq, void *stream) {
+    NT_REQUIRE(dz && idx && dpq && k >= 1 && n_per_cloud >= 1 && M >= 0 && H >= 1 && lddz >= H && lddpq >= 2 * H,
+               "nt_edge_scatter: bad arguments");
+    if (M == 0) return 0;
+    edge_scatter_kernel<<<blocks_for(M * H, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        dz, lddz, idx, k, n_per_cloud, M, H, dpq, lddpq);
+    return check_launch("nt_edge_scatter");
+}

@@ -1,0 +1,200 @@
+"""Drop-in building blocks: same names, constructor arguments, ``.config`` dicts, forward signatures and state_dict keys
+as the reference's ``nn/net_blocks.py`` -- with the arithmetic running in libnt_b200.so (sm_100a).
+
+The reference resolves these classes BY NAME (``getattr(blocks, config['feature_extractor'])`` nn/nets.py:100-101,
+``getattr(blocks, config['panel_decoder'])`` nn/nets.py:106-115, ``blocks.MLP(...)`` nn/nets.py:224), so installing this
+module as ``net_blocks`` swaps the hot path under the unmodified ``nets.py`` / ``trainer.py``.
+
+In scope: ``MLP``, ``EdgeConvFeatures`` (+ ``DynamicEdgeConv``), ``LSTMDecoderModule``.
+Out of scope and therefore absent: PointNet++ blocks, graph-pooling variants, GRU / MLP / double-reverse decoders.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+# ----------------------------------------------------------------------------------------------------------
+# MLP  (reference nn/net_blocks.py:43-47)
+# ----------------------------------------------------------------------------------------------------------
+class FusedMLP(nn.Sequential):
+    """``Sequential[Sequential(Linear, ReLU, BatchNorm1d)]*`` as parameter container (state_dict keys ``L.0.*`` /
+    ``L.2.*`` are the reference's), evaluated by the fused GEMM kernels: BN after ReLU, training-mode statistics over
+    all rows, the BN affine folded into the next Linear."""
+
+    def layer_pairs(self):
+        return [(blk[0], blk[2]) for blk in self]
+
+    def forward(self, x):
+        return ops.fused_mlp(x, self.layer_pairs(), self.training, mode='plain')
+
+
+def MLP(channels, batch_norm=True):
+    if not batch_norm:
+        raise NotImplementedError('the reference ignores batch_norm=False as well (nn/net_blocks.py:43-47)')
+    if len(channels) < 3:
+        raise NotImplementedError('MLP needs at least two Linear layers on the B200 path')
+    return FusedMLP(*[nn.Sequential(nn.Linear(channels[i - 1], channels[i]), nn.ReLU(), nn.BatchNorm1d(channels[i]))
+                      for i in range(1, len(channels))])
+
+
+# ----------------------------------------------------------------------------------------------------------
+# DynamicEdgeConv  (torch_geometric.nn.DynamicEdgeConv as used at nn/net_blocks.py:127-135)
+# ----------------------------------------------------------------------------------------------------------
+class DynamicEdgeConv(nn.Module):
+    """out_i = max_{j in kNN(i)} nn([x_i, x_j - x_i]) with the kNN graph rebuilt from the current features.
+
+    The attribute name ``nn`` is part of the state_dict contract (``conv_layers.N.nn.L.{0,2}.*``).  Clouds are the
+    dense equal-size layout the reference always produces (nn/net_blocks.py:164-167): pass (B, N)."""
+
+    def __init__(self, nn, k, aggr='max', **kwargs):
+        super().__init__()
+        if aggr != 'max':
+            raise NotImplementedError("only aggr='max' (every shipped config) runs on the B200 path")
+        self.nn = nn
+        self.k = k
+        self.aggr = aggr
+        self.last_index = None      # kNN indices of the last forward (int32 [M, k], local) -- for parity tests
+
+    def forward(self, x, batch=None, cloud_shape=None, tail_src=None):
+        if cloud_shape is None:
+            if batch is None:
+                cloud_shape = (1, x.shape[0])
+            else:                      # PyG signature: derive (B, N) from the batch vector (costs a host sync)
+                B = int(batch.max().item()) + 1
+                cloud_shape = (B, x.shape[0] // B)
+        B, N = cloud_shape
+        idx = ops.knn_graph(x.detach(), B, N, self.k)
+        self.last_index = idx
+        return ops.fused_mlp(x, self.nn.layer_pairs(), self.nn.training, mode='edge', idx=idx, k=self.k,
+                             n_per_cloud=N, tail_src=tail_src)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# global pools (torch_geometric.nn.global_*_pool; nn/net_blocks.py:145-150) on the dense equal-size layout
+# ----------------------------------------------------------------------------------------------------------
+def _dense(x, batch, size):
+    B = int(size) if size is not None else int(batch.max().item()) + 1
+    return x.view(B, x.shape[0] // B, x.shape[-1])
+
+
+def global_mean_pool(x, batch, size=None):
+    return _dense(x, batch, size).mean(dim=1)
+
+
+def global_max_pool(x, batch, size=None):
+    return _dense(x, batch, size).max(dim=1).values
+
+
+def global_add_pool(x, batch, size=None):
+    return _dense(x, batch, size).sum(dim=1)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# EdgeConvFeatures  (reference nn/net_blocks.py:93-191)
+# ----------------------------------------------------------------------------------------------------------
+class EdgeConvFeatures(nn.Module):
+    """Point-cloud encoder: conv_depth x DynamicEdgeConv (+ skip-concat of xyz) (+ global pool + Linear)."""
+
+    def __init__(self, out_size, config={}):
+        super().__init__()
+        self.config = {
+            'conv_depth': 2, 'k_neighbors': 5, 'EConv_hidden': 200, 'EConv_hidden_depth': 2, 'EConv_feature': 112,
+            'EConv_aggr': 'max', 'global_pool': 'mean', 'skip_connections': False, 'graph_pooling': False,
+            'pool_ratio': 0.1,
+        }
+        self.config.update(config)
+        cfg = self.config
+        if cfg['graph_pooling']:
+            raise NotImplementedError('graph_pooling (ASAPooling) is outside the B200 hot path (SURVEY.md section 2)')
+        feat, hid, depth = cfg['EConv_feature'], cfg['EConv_hidden'], cfg['EConv_hidden_depth']
+        self.conv_layers = nn.ModuleList()
+        c_in = 3
+        for _ in range(cfg['conv_depth']):
+            self.conv_layers.append(DynamicEdgeConv(MLP([2 * c_in] + [hid] * depth + [feat]),
+                                                    k=cfg['k_neighbors'], aggr=cfg['EConv_aggr']))
+            c_in = feat
+        pools = {'max': global_max_pool, 'mean': global_mean_pool, 'add': global_add_pool}
+        if cfg['global_pool'] not in pools:
+            raise ValueError('{} pooling is not supported'.format(cfg['global_pool']))
+        self.global_pool = pools[cfg['global_pool']]
+        self.lin = nn.Linear(feat + 3 if cfg['skip_connections'] else feat, out_size)
+        self._batch_cache = {}
+
+    def _batch_vector(self, B, N, device):
+        key = (B, N, str(device))
+        if key not in self._batch_cache:
+            self._batch_cache = {key: torch.arange(B, device=device).repeat_interleave(N)}
+        return self._batch_cache[key]
+
+    def forward(self, positions, global_pool=True):
+        B, N = positions.shape[0], positions.shape[1]
+        pos_flat = positions.reshape(B * N, positions.shape[-1])
+        batch = self._batch_vector(B, N, positions.device)
+        out = pos_flat
+        last = len(self.conv_layers) - 1
+        for i, conv in enumerate(self.conv_layers):
+            # the skip connection (cat[out, pos], nn/net_blocks.py:178-180) is written by the last layer's epilogue
+            tail = pos_flat if (i == last and self.config['skip_connections']) else None
+            out = conv(out, cloud_shape=(B, N), tail_src=tail)
+        if global_pool:
+            pooled = self.global_pool(out, batch, B)
+            return ops.linear(pooled, self.lin.weight, self.lin.bias), out, batch
+        return None, out, batch
+
+
+# ----------------------------------------------------------------------------------------------------------
+# LSTM decoder  (reference nn/net_blocks.py:302-333, 363-402)
+# ----------------------------------------------------------------------------------------------------------
+def _init_weights(module, init_type=''):
+    if not init_type:
+        return
+    if 'kaiming_normal' not in init_type:
+        raise NotImplementedError('{} weight initialization is not implemented'.format(init_type))
+    for name, param in module.named_parameters():
+        if 'weight' in name and param.dim() > 1:
+            nn.init.kaiming_normal_(param)
+
+
+def initial_state(n_layers, rows, hidden, device, init_type='', generator=None):
+    """h0 / c0 of the decoders.  The reference draws them with kaiming_normal_ on the CPU on EVERY forward and copies
+    them over (nn/net_blocks.py:302-315); here the same distribution -- N(0, 2 / (rows * hidden)) -- is
+    drawn directly on the device.  Zeros when init_type is empty, as in the reference."""
+    if not init_type:
+        return torch.zeros(n_layers, rows, hidden, device=device)
+    if 'kaiming_normal' not in init_type:
+        raise NotImplementedError('{} tenzor initialization is not implemented'.format(init_type))
+    std = math.sqrt(2.0 / float(rows * hidden))
+    return torch.randn(n_layers, rows, hidden, device=device, generator=generator) * std
+
+
+class LSTMDecoderModule(nn.Module):
+    """Encoding -> repeated out_len times -> nn.LSTM (cuDNN) -> Linear.  ``lstm_state=(h0, c0)`` or the
+    ``state_provider`` attribute inject the initial states (needed for parity: the reference's are random)."""
+
+    def __init__(self, encoding_size, hidden_size, out_elem_size, n_layers, dropout=0, custom_init='kaiming_normal',
+                 **kwargs):
+        super().__init__()
+        self.custom_init = custom_init
+        self.n_layers = n_layers
+        self.encoding_size = encoding_size
+        self.hidden_size = hidden_size
+        self.out_elem_size = out_elem_size
+        self.lstm = nn.LSTM(encoding_size, hidden_size, n_layers, dropout=dropout, batch_first=True)
+        self.lin = nn.Linear(hidden_size, out_elem_size)
+        _init_weights(self.lstm, init_type=custom_init)
+        self.state_provider = None      # callable(n_layers, rows, hidden, device) -> (h0, c0)
+
+    def forward(self, batch_enc, out_len, lstm_state=None):
+        rows = batch_enc.size(0)
+        dec_input = batch_enc.unsqueeze(1).expand(rows, out_len, batch_enc.shape[-1]).contiguous()
+        if lstm_state is None and self.state_provider is not None:
+            lstm_state = self.state_provider(self.n_layers, rows, self.hidden_size, batch_enc.device)
+        if lstm_state is None:
+            lstm_state = (initial_state(self.n_layers, rows, self.hidden_size, batch_enc.device, self.custom_init),
+                          initial_state(self.n_layers, rows, self.hidden_size, batch_enc.device, self.custom_init))
+        out, _ = self.lstm(dec_input, lstm_state)
+        out = ops.linear(out.reshape(-1, self.hidden_size), self.lin.weight, self.lin.bias)
+        return out.view(rows, out_len, -1)

@@ -1,0 +1,476 @@
+"""Host-side operator layer: torch tensors in, libnt_b200.so kernels out.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every FLOP of the operators below runs in the
+hand-written sm_100a kernels behind the C ABI of include/nt_b200.h.  Nothing in this file has a CPU or library
+fallback: tensors must live on a CUDA device and the extension must load.
+
+Operators (reference call sites in parentheses, relative to /root/reference):
+  * ``knn_graph``        kNN indices of every point inside its cloud (torch_cluster.knn via nn/net_blocks.py:174)
+  * ``fused_mlp``        MLP() = [Linear -> ReLU -> BatchNorm1d] x L  (nn/net_blocks.py:43-47), in two row modes:
+                         'edge'  -- DynamicEdgeConv: message MLP on [x_i, x_j - x_i] + max aggregation over k
+                                    (nn/net_blocks.py:127-135,174), optional skip-concat of the positions (:178-180)
+                         'plain' -- per-point MLP (point_segment_mlp, nn/nets.py:223-226)
+  * ``sparsemax``        sparsemax.Sparsemax(dim=1) on [rows, P<=32] (nn/nets.py:225)
+  * ``attention_pool``   the per-panel weighted global_mean_pool loop as one contraction (nn/nets.py:263-276)
+  * ``linear``           nn.Linear on rows (panel_dec_lin nn/nets.py:232, placement_decoder nn/nets.py:128)
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (GemmArgs, NT_EPI_BIAS, NT_EPI_BNRELU_BWD, NT_EPI_RELU_MAXMIN, NT_EPI_RELU_STATS, NT_PROD_EDGE,
+                   NT_PROD_PLAIN)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# plumbing
+# ----------------------------------------------------------------------------------------------------------
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('garment_pattern_estimation_b200: tensors must be on a CUDA device '
+                               '(the B200 hot path has no CPU fallback)')
+
+
+def _rows2d(t):
+    """(tensor, row stride) for a 2-D fp32 tensor whose last dim is dense."""
+    assert t.dim() == 2 and t.dtype == torch.float32
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t, (t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0)))
+
+
+class EdgeSrc:
+    """Operand description of NT_PROD_EDGE: relu(pq[centre, :H] + pq[nbr, qoff:qoff+H])."""
+
+    def __init__(self, pq, H, idx=None, k=1, n_per_cloud=1):
+        self.pq, self.H, self.idx, self.k, self.n_per_cloud = pq, H, idx, k, n_per_cloud
+        self.ldpq = pq.stride(0)
+        self.qoff = H if idx is not None else 0
+
+
+def gemm_nt(rows, K, n_out, w, ldw, epilogue, a=None, lda=0, edge=None, bias=None, out=None, ldo=0, stats=None,
+            agg=None, k_agg=0, aux=None, ldaux=0, aux_edge=False, k0=None, k1=None, mu=None, colsum=None):
+    g = GemmArgs()
+    g.rows, g.K, g.n_out = int(rows), int(K), int(n_out)
+    g.producer = NT_PROD_PLAIN if edge is None or a is not None else NT_PROD_EDGE
+    g.epilogue = epilogue
+    g.a, g.lda = _p(a), int(lda)
+    if edge is not None:
+        g.pq, g.ldpq, g.qoff = _p(edge.pq), int(edge.ldpq), int(edge.qoff)
+        g.idx, g.k, g.n_per_cloud = _p(edge.idx), int(edge.k), int(edge.n_per_cloud)
+    if k_agg:
+        g.k = int(k_agg)
+    g.w, g.ldw, g.bias = _p(w), int(ldw), _p(bias)
+    g.out, g.ldo = _p(out), int(ldo)
+    g.stats = _p(stats)
+    if agg is not None:
+        g.vmax, g.vmin, g.imax, g.imin = (_p(t) for t in agg)
+    g.aux, g.ldaux, g.aux_edge = _p(aux), int(ldaux), int(bool(aux_edge))
+    g.k0, g.k1, g.mu, g.colsum = _p(k0), _p(k1), _p(mu), _p(colsum)
+    _lib.check(_lib.load().nt_gemm_nt(ctypes.byref(g), _stream()), 'nt_gemm_nt')
+
+
+def gemm_tn(a, lda, m, rows, out, b=None, ldb=0, n=0, edge=None, mu=None):
+    """out[m, n] += sum_r a[r, m] * Bop[r, n].  With `mu` the B operand is centred and `out` must be float64."""
+    lib = _lib.load()
+    if mu is not None:
+        assert out.dtype == torch.float64
+        if edge is not None:
+            rc = lib.nt_gemm_tn_centered(_p(a), lda, m, None, 0, n, rows, _p(edge.pq), edge.ldpq, edge.qoff,
+                                         _p(edge.idx), edge.k, edge.n_per_cloud, _p(mu), _p(out), out.stride(0),
+                                         _stream())
+        else:
+            rc = lib.nt_gemm_tn_centered(_p(a), lda, m, _p(b), ldb, n, rows, None, 0, 0, None, 1, 1, _p(mu), _p(out),
+                                         out.stride(0), _stream())
+        _lib.check(rc, 'nt_gemm_tn_centered')
+        return
+    if edge is not None:
+        rc = lib.nt_gemm_tn(_p(a), lda, m, None, 0, n, rows, _p(edge.pq), edge.ldpq, edge.qoff, _p(edge.idx),
+                            edge.k, edge.n_per_cloud, _p(out), out.stride(0), _stream())
+    else:
+        rc = lib.nt_gemm_tn(_p(a), lda, m, _p(b), ldb, n, rows, None, 0, 0, None, 1, 1, _p(out), out.stride(0),
+                            _stream())
+    _lib.check(rc, 'nt_gemm_tn')
+
+
+# ----------------------------------------------------------------------------------------------------------
+# kNN
+# ----------------------------------------------------------------------------------------------------------
+def knn_graph(x, B, N, k):
+    """x: [B*N, D] fp32 (row stride free).  Returns idx [B*N, k] int32, LOCAL to each cloud, ascending by
+    (squared distance, index), self included.  Bit-exact with oracle/knn_oracle.c."""
+    _require_cuda(x)
+    x, ldx = _rows2d(x)
+    if x.shape[0] != B * N:
+        raise RuntimeError('knn_graph: expected {} rows, got {}'.format(B * N, x.shape[0]))
+    idx = torch.empty(B * N, k, dtype=torch.int32, device=x.device)
+    _lib.check(_lib.load().nt_knn(_p(x), B, N, x.shape[1], ldx, k, _p(idx), _stream()), 'nt_knn')
+    return idx
+
+
+def edge_index_from_knn(idx, B, N):
+    """PyG-style edge_index [2, E] int64 (row 0 = source/neighbour j, row 1 = target/centre i), the layout
+    DynamicEdgeConv builds from torch_cluster.knn(...).flip([0])."""
+    M, k = idx.shape
+    base = (torch.arange(M, device=idx.device) // N * N).unsqueeze(1)
+    src = (idx.long() + base).reshape(-1)
+    dst = torch.arange(M, device=idx.device).repeat_interleave(k)
+    return torch.stack([src, dst], dim=0)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# fused MLP  (Linear -> ReLU -> BN) x L, edge or plain rows
+# ----------------------------------------------------------------------------------------------------------
+class _BNBuffers:
+    """Non-differentiable BatchNorm state handed to the autograd function (updated in place like nn.BatchNorm1d)."""
+
+    def __init__(self, running_mean, running_var, num_batches_tracked, momentum, eps):
+        self.running_mean, self.running_var, self.nbt = running_mean, running_var, num_batches_tracked
+        self.momentum = 0.1 if momentum is None else float(momentum)
+        self.eps = float(eps)
+
+
+class _FusedMLPFunction(torch.autograd.Function):
+    """params = (W_0, b_0, gamma_1, beta_1, W_1, b_1, gamma_2, beta_2, ...): 4 tensors per layer."""
+
+    @staticmethod
+    def forward(ctx, x, idx, tail_src, meta, *params):
+        lib = _lib.load()
+        mode, training, bn_bufs = meta['mode'], meta['training'], meta['bn']
+        L = len(params) // 4
+        if L < 2:
+            raise NotImplementedError('fused_mlp needs at least two Linear layers (EConv_hidden_depth >= 1)')
+        Ws = [params[4 * l] for l in range(L)]
+        bs = [params[4 * l + 1] for l in range(L)]
+        gammas = [params[4 * l + 2] for l in range(L)]
+        betas = [params[4 * l + 3] for l in range(L)]
+        _require_cuda(x, *params)
+        dev = x.device
+        x, ldx = _rows2d(x)
+        M, C = x.shape
+        widths = [W.shape[0] for W in Ws]           # H_1 .. H_L
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        # ---- first Linear, evaluated per POINT (edge mode: split W_0 = [W_a | W_b] on [x_i, x_j - x_i])
+        H1 = widths[0]
+        if mode == 'edge':
+            k, N = meta['k'], meta['n_per_cloud']
+            W0 = Ws[0]
+            if W0.shape[1] != 2 * C:
+                raise RuntimeError('edge MLP expects first Linear with {} inputs, got {}'.format(2 * C, W0.shape[1]))
+            Wc = torch.cat([W0[:, :C] - W0[:, C:], W0[:, C:]], dim=0).contiguous()      # [2*H1, C]
+            bc = torch.cat([bs[0], torch.zeros_like(bs[0])])
+            pq = torch.empty(M, 2 * H1, **f32)
+            gemm_nt(M, C, 2 * H1, Wc, C, NT_EPI_BIAS, a=x, lda=ldx, bias=bc, out=pq, ldo=2 * H1)
+            R = M * k
+            src = EdgeSrc(pq, H1, idx, k, N)
+        else:
+            k, N = 1, 1
+            Wc = Ws[0].contiguous()
+            pq = torch.empty(M, H1, **f32)
+            gemm_nt(M, C, H1, Wc, C, NT_EPI_BIAS, a=x, lda=ldx, bias=bs[0].contiguous(), out=pq, ldo=H1)
+            R = M
+            src = EdgeSrc(pq, H1)
+
+        def fold(layer, stats, next_layer):
+            """BN `layer` (0-based, follows Linear `layer`): stats -> affine; fold into Linear `next_layer`."""
+            Cn = widths[layer]
+            vec = torch.empty(4, Cn, **f32)           # mean, rstd, s, t
+            buf = bn_bufs[layer]
+            if next_layer is not None:
+                n_next = widths[next_layer]
+                w_f = torch.empty(n_next, Cn, **f32)
+                w_ft = torch.empty(Cn, n_next, **f32)
+                b_f = torch.empty(n_next, **f32)
+                wn, bn_ = Ws[next_layer].contiguous(), bs[next_layer].contiguous()
+            else:
+                n_next, w_f, w_ft, b_f, wn, bn_ = 0, None, None, None, None, None
+            _lib.check(lib.nt_bn_fold(_p(stats), R, Cn, _p(gammas[layer].contiguous()), _p(betas[layer].contiguous()),
+                                      _p(buf.running_mean), _p(buf.running_var), _p(buf.nbt), buf.momentum, buf.eps,
+                                      int(training), _p(vec[0]), _p(vec[1]), _p(vec[2]), _p(vec[3]),
+                                      _p(wn), _p(bn_), n_next, _p(w_f), _p(w_ft), _p(b_f), _stream()), 'nt_bn_fold')
+            return vec, w_f, w_ft, b_f
+
+        # ---- BN_1 statistics of a_1 = relu(P + Q) (no GEMM at row level)
+        stats = torch.zeros(2 * H1, dtype=torch.float64, device=dev) if training else None
+        if training:
+            _lib.check(lib.nt_edge_stats(_p(pq), src.ldpq, src.qoff, _p(src.idx), src.k, src.n_per_cloud, R, H1,
+                                         _p(stats), _stream()), 'nt_edge_stats')
+        bn_vec = [None] * L
+        w_fts = [None] * L            # w_fts[l] = (W_l . diag(s_l))^T, l >= 1
+        bn_vec[0], w_f, w_fts[1], b_f = fold(0, stats, 1)
+
+        # ---- middle layers: a_{l+1} = relu(a_l . W_l'^T + b_l'), statistics in the epilogue
+        acts = [None] * (L + 1)       # acts[l] = a_l for l >= 2 (a_1 is recomputed from pq)
+        for l in range(1, L - 1):
+            Hn = widths[l]
+            stats = torch.zeros(2 * Hn, dtype=torch.float64, device=dev) if training else None
+            out = torch.empty(R, Hn, **f32)
+            if l == 1:
+                gemm_nt(R, widths[0], Hn, w_f, widths[0], NT_EPI_RELU_STATS, edge=src, bias=b_f, out=out, ldo=Hn,
+                        stats=stats)
+            else:
+                gemm_nt(R, widths[l - 1], Hn, w_f, widths[l - 1], NT_EPI_RELU_STATS, a=acts[l], lda=widths[l - 1],
+                        bias=b_f, out=out, ldo=Hn, stats=stats)
+            acts[l + 1] = out
+            bn_vec[l], w_f, w_fts[l + 1], b_f = fold(l, stats, l + 1)
+
+        # ---- last layer
+        HL, Kin = widths[L - 1], widths[L - 2]
+        stats = torch.zeros(2 * HL, dtype=torch.float64, device=dev) if training else None
+        last_in = dict(edge=src) if L == 2 else dict(a=acts[L - 1], lda=Kin)
+        need_bwd = training and any(ctx.needs_input_grad)
+        if mode == 'edge':
+            tail = 0 if tail_src is None else tail_src.shape[1]
+            a_last = torch.empty(R, HL, **f32) if need_bwd else None
+            agg = (torch.empty(M, HL, **f32), torch.empty(M, HL, **f32),
+                   torch.empty(M, HL, dtype=torch.uint8, device=dev), torch.empty(M, HL, dtype=torch.uint8, device=dev))
+            gemm_nt(R, Kin, HL, w_f, Kin, NT_EPI_RELU_MAXMIN, bias=b_f, out=a_last, ldo=HL, stats=stats, agg=agg,
+                    k_agg=k, **last_in)
+            bn_vec[L - 1], _, _, _ = fold(L - 1, stats, None)
+            out = torch.empty(M, HL + tail, **f32)
+            sel = torch.empty(M, HL, dtype=torch.uint8, device=dev) if need_bwd else None
+            vsel = torch.empty(M, HL, **f32) if need_bwd else None
+            ts, tld = (None, 0)
+            if tail:
+                ts, tld = _rows2d(tail_src)
+            _lib.check(lib.nt_maxmin_finish(_p(agg[0]), _p(agg[1]), _p(agg[2]), _p(agg[3]), _p(bn_vec[L - 1][2]),
+                                            _p(bn_vec[L - 1][3]), M, HL, _p(out), HL + tail, _p(sel), _p(vsel),
+                                            _p(ts), tld, tail, _stream()), 'nt_maxmin_finish')
+        else:
+            a_last = torch.empty(R, HL, **f32)
+            gemm_nt(R, Kin, HL, w_f, Kin, NT_EPI_RELU_STATS, bias=b_f, out=a_last, ldo=HL, stats=stats, **last_in)
+            bn_vec[L - 1], _, _, _ = fold(L - 1, stats, None)
+            out = torch.empty(M, HL, **f32)
+            _lib.check(lib.nt_bn_apply(_p(a_last), HL, _p(bn_vec[L - 1][2]), _p(bn_vec[L - 1][3]), R, HL, _p(out), HL,
+                                       _stream()), 'nt_bn_apply')
+            sel = vsel = None
+            tail = 0
+        acts[L] = a_last
+
+        ctx.meta = None
+        if need_bwd:
+            ctx.meta = dict(mode=mode, k=k, N=N, L=L, widths=widths, M=M, C=C, R=R, tail=tail, ldx=ldx)
+            ctx.save_for_backward(x, idx, pq, Wc, sel, vsel, *Ws, *[a for a in acts[2:]], *bn_vec, *w_fts[1:], *betas)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        m = ctx.meta
+        if m is None:
+            raise RuntimeError('fused_mlp: backward through an eval-mode (running-statistics) forward is not supported')
+        mode, k, N, L, widths, M, C, R, tail = (m[key] for key in ('mode', 'k', 'N', 'L', 'widths', 'M', 'C', 'R', 'tail'))
+        sv = ctx.saved_tensors
+        x, idx, pq, Wc, sel, vsel = sv[:6]
+        Ws = list(sv[6:6 + L])
+        acts = [None, None] + list(sv[6 + L:6 + L + (L - 1)])             # acts[2..L]
+        bn_vec = list(sv[6 + 2 * L - 1:6 + 3 * L - 1])
+        w_fts = [None] + list(sv[6 + 3 * L - 1:6 + 4 * L - 2])            # w_fts[1..L-1]
+        betas = list(sv[6 + 4 * L - 2:6 + 5 * L - 2])
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        H1, HL = widths[0], widths[L - 1]
+        src = EdgeSrc(pq, H1, idx, k, N) if mode == 'edge' else EdgeSrc(pq, H1)
+        gout, ldg = _rows2d(gout)
+
+        grads_W, grads_b, grads_g, grads_beta = [None] * L, [None] * L, [None] * L, [None] * L
+
+        # ---- trailing BN (after the aggregation in edge mode): column sums, then dz_L for every row
+        mean, rstd, s, t = bn_vec[L - 1]
+        sums = torch.zeros(2 * HL, **f64)
+        v_ref = vsel if mode == 'edge' else acts[L]
+        _lib.check(lib.nt_bn_bwd_reduce(_p(gout), ldg, _p(v_ref), HL, _p(mean), _p(rstd), M, HL, _p(sums), _stream()),
+                   'nt_bn_bwd_reduce')
+        grads_beta[L - 1] = sums[:HL].float()
+        grads_g[L - 1] = sums[HL:].float()
+        dz = torch.empty(R, HL, **f32)
+        csum = torch.zeros(HL, **f64)
+        _lib.check(lib.nt_bn_relu_bwd_last(_p(acts[L]), HL, _p(gout), ldg, _p(sel), k, _p(s), _p(mean), _p(rstd),
+                                           _p(sums), R, R, HL, _p(dz), HL, _p(csum), _stream()), 'nt_bn_relu_bwd_last')
+
+        # ---- walk down the Linear layers L-1 .. 1
+        for l in range(L - 1, 0, -1):
+            Hout, Hin = widths[l], widths[l - 1]
+            pmean, prstd, ps, pt = bn_vec[l - 1]
+            raw = torch.zeros(Hout, Hin, **f64)            # dz^T . (a_l - mean_l), accumulated in double
+            if l == 1:
+                gemm_tn(dz, Hout, Hout, R, raw, n=Hin, edge=src, mu=pmean)
+            else:
+                gemm_tn(dz, Hout, Hout, R, raw, b=acts[l], ldb=Hin, n=Hin, mu=pmean)
+            dW = torch.empty(Hout, Hin, **f32)
+            db = torch.empty(Hout, **f32)
+            vecs = torch.empty(4, Hin, **f32)          # dgamma, dbeta, k0, k1
+            _lib.check(lib.nt_linear_bn_bwd(_p(raw), _p(csum), Hout, Hin, _p(Ws[l].contiguous()), _p(ps),
+                                            _p(betas[l - 1].contiguous()), _p(prstd), R, _p(dW), _p(db), _p(vecs[0]),
+                                            _p(vecs[1]), _p(vecs[2]), _p(vecs[3]), _stream()), 'nt_linear_bn_bwd')
+            grads_W[l], grads_b[l] = dW, db
+            grads_g[l - 1], grads_beta[l - 1] = vecs[0], vecs[1]
+            csum_prev = torch.zeros(Hin, **f64)
+            if l == 1:
+                dz_prev = torch.empty(R, Hin, **f32)
+                gemm_nt(R, Hout, Hin, w_fts[l], Hout, NT_EPI_BNRELU_BWD, a=dz, lda=Hout, edge=src, out=dz_prev,
+                        ldo=Hin, aux_edge=True, k0=vecs[2], k1=vecs[3], mu=pmean, colsum=csum_prev)
+            else:
+                dz_prev = torch.empty(R, Hin, **f32)   # saved activations stay intact (retain_graph-safe)
+                gemm_nt(R, Hout, Hin, w_fts[l], Hout, NT_EPI_BNRELU_BWD, a=dz, lda=Hout, out=dz_prev, ldo=Hin,
+                        aux=acts[l], ldaux=Hin, k0=vecs[2], k1=vecs[3], mu=pmean, colsum=csum_prev)
+            dz, csum = dz_prev, csum_prev
+
+        # ---- first Linear (per point)
+        grads_b[0] = csum.float()
+        gx = None
+        if mode == 'edge':
+            dpq = torch.zeros(M, 2 * H1, **f32)
+            _lib.check(lib.nt_edge_scatter(_p(dz), H1, _p(idx), k, N, M, H1, _p(dpq), 2 * H1, _stream()),
+                       'nt_edge_scatter')
+            dWc = torch.zeros(2 * H1, C, **f32)
+            gemm_tn(dpq, 2 * H1, 2 * H1, M, dWc, b=x, ldb=m['ldx'], n=C)
+            grads_W[0] = torch.cat([dWc[:H1], dWc[H1:] - dWc[:H1]], dim=1)
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty(M, C, **f32)
+                WcT = Wc.t().contiguous()              # [C, 2*H1]
+                gemm_nt(M, 2 * H1, C, WcT, 2 * H1, NT_EPI_BIAS, a=dpq, lda=2 * H1, out=gx, ldo=C)
+        else:
+            dW0 = torch.zeros(H1, C, **f32)
+            gemm_tn(dz, H1, H1, M, dW0, b=x, ldb=m['ldx'], n=C)
+            grads_W[0] = dW0
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty(M, C, **f32)
+                WT = Wc.t().contiguous()               # [C, H1]
+                gemm_nt(M, H1, C, WT, H1, NT_EPI_BIAS, a=dz, lda=H1, out=gx, ldo=C)
+
+        g_tail = None
+        if tail and ctx.needs_input_grad[2]:
+            g_tail = gout[:, HL:HL + tail].contiguous()
+        flat = []
+        for l in range(L):
+            flat += [grads_W[l], grads_b[l], grads_g[l], grads_beta[l]]
+        return (gx, None, g_tail, None, *flat)
+
+
+def fused_mlp(x, layers, training, mode='plain', idx=None, k=1, n_per_cloud=1, tail_src=None):
+    """layers: list of (nn.Linear, nn.BatchNorm1d) pairs (the reference's Sequential(Linear, ReLU, BatchNorm1d))."""
+    params, bufs = [], []
+    for lin, bn in layers:
+        params += [lin.weight, lin.bias, bn.weight, bn.bias]
+        bufs.append(_BNBuffers(bn.running_mean, bn.running_var, bn.num_batches_tracked, bn.momentum, bn.eps))
+    meta = dict(mode=mode, training=bool(training), bn=bufs, k=int(k), n_per_cloud=int(n_per_cloud))
+    return _FusedMLPFunction.apply(x, idx, tail_src, meta, *params)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# sparsemax / attention pooling / linear
+# ----------------------------------------------------------------------------------------------------------
+class _SparsemaxFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z):
+        _require_cuda(z)
+        z = z.contiguous()
+        rows, P = z.shape
+        out = torch.empty_like(z)
+        _lib.check(_lib.load().nt_sparsemax_fwd(_p(z), rows, P, _p(out), _stream()), 'nt_sparsemax_fwd')
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out, = ctx.saved_tensors
+        g = g.contiguous()
+        gz = torch.empty_like(out)
+        _lib.check(_lib.load().nt_sparsemax_bwd(_p(out), _p(g), out.shape[0], out.shape[1], _p(gz), _stream()),
+                   'nt_sparsemax_bwd')
+        return gz
+
+
+def sparsemax(z):
+    """Sparsemax over dim 1 of a [rows, P] tensor, P <= 32."""
+    if z.dim() != 2:
+        raise RuntimeError('sparsemax expects [rows, P]')
+    return _SparsemaxFunction.apply(z)
+
+
+class _AttnPoolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w, feat, B, N, scale):
+        _require_cuda(w, feat)
+        w = w.contiguous()
+        feat, ldf = _rows2d(feat)
+        P, F = w.shape[1], feat.shape[1]
+        enc = torch.zeros(B, P, F, dtype=torch.float32, device=w.device)
+        _lib.check(_lib.load().nt_attn_pool_fwd(_p(w), _p(feat), ldf, B, N, P, F, scale, _p(enc), _stream()),
+                   'nt_attn_pool_fwd')
+        ctx.save_for_backward(w, feat)
+        ctx.dims = (B, N, P, F, scale, ldf)
+        return enc
+
+    @staticmethod
+    def backward(ctx, genc):
+        w, feat = ctx.saved_tensors
+        B, N, P, F, scale, ldf = ctx.dims
+        genc = genc.contiguous()
+        gw = torch.empty_like(w) if ctx.needs_input_grad[0] else None
+        gfeat = torch.empty(B * N, F, dtype=torch.float32, device=w.device) if ctx.needs_input_grad[1] else None
+        _lib.check(_lib.load().nt_attn_pool_bwd(_p(genc), _p(w), _p(feat), ldf, B, N, P, F, scale, _p(gw), _p(gfeat), F,
+                                                0, _stream()), 'nt_attn_pool_bwd')
+        return gw, gfeat, None, None, None
+
+
+def attention_pool(weights, feats, B, N, scale):
+    """enc[b, p, :] = scale * sum_n weights[b*N+n, p] * feats[b*N+n, :]  ->  [B, P, F]."""
+    return _AttnPoolFunction.apply(weights, feats, B, N, float(scale))
+
+
+class _LinearFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _require_cuda(x, weight)
+        x, ldx = _rows2d(x)
+        rows, K = x.shape
+        n_out = weight.shape[0]
+        w = weight.contiguous()
+        out = torch.empty(rows, n_out, dtype=torch.float32, device=x.device)
+        gemm_nt(rows, K, n_out, w, K, NT_EPI_BIAS, a=x, lda=ldx, bias=None if bias is None else bias.contiguous(),
+                out=out, ldo=n_out)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g, ldg = _rows2d(g)
+        rows, K = x.shape
+        n_out = w.shape[0]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty(rows, K, dtype=torch.float32, device=x.device)
+            wt = w.t().contiguous()
+            gemm_nt(rows, n_out, K, wt, n_out, NT_EPI_BIAS, a=g, lda=ldg, out=gx, ldo=K)
+        if ctx.needs_input_grad[1]:
+            gw = torch.zeros(n_out, K, dtype=torch.float32, device=x.device)
+            gemm_tn(g, ldg, n_out, rows, gw, b=x, ldb=x.stride(0) if rows > 1 else K, n=K)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            sums = torch.zeros(n_out, dtype=torch.float64, device=x.device)
+            _lib.check(_lib.load().nt_bn_bwd_reduce(_p(g), ldg, None, 0, None, None, rows, n_out, _p(sums), _stream()),
+                       'nt_bn_bwd_reduce')
+            gb = sums.float()
+        return gx, gw, gb
+
+
+def linear(x, weight, bias=None):
+    """nn.Linear on a [rows, K] tensor through the library's GEMM."""
+    lead = x.shape[:-1]
+    out = _LinearFunction.apply(x.reshape(-1, x.shape[-1]), weight, bias)
+    return out.view(*lead, weight.shape[0])

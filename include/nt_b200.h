@@ -1,0 +1,170 @@
+/*
+ * nt_b200.h -- C ABI of the B200-native NeuralTailor hot path (libnt_b200.so, sm_100a).
+ *
+ * The reference (maria-korosteleva/Garment-Pattern-Estimation) owns no native code: its hot path reaches
+ * third-party CUDA/ATen kernels through Python.  Every entry point below replaces one of those borrowed
+ * operators; the comment above each names the reference call site (file:line under /root/reference) it serves.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated; fp32 row-major;
+ *     `ld*` arguments are row strides in elements.
+ *   - the caller owns every buffer (PyTorch tensors in the shipped host code); the library never allocates or
+ *     frees user-visible memory and keeps no global mutable state.
+ *   - every function only ENQUEUES work on `stream` (a cudaStream_t passed as void*); no hidden synchronisation.
+ *   - return value: 0 = ok, non-zero = error (message via nt_last_error(), thread-local).  No exceptions cross
+ *     the ABI.  The Python host maps non-zero to RuntimeError (reference convention: nn/trainer.py:60).
+ *   - "rows" are points (M = B*N) or edges (E = M*k); edge row e belongs to centre point e / k, slot e % k,
+ *     and its neighbour is  (e / k / N) * N + idx[e]   (idx holds indices LOCAL to the cloud).
+ */
+#ifndef NT_B200_H
+#define NT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+const char *nt_last_error(void);
+int nt_version(void);                          /* ABI version, bumped on incompatible change */
+int nt_built_arch(void);                       /* 100 for sm_100a */
+/* number of kernels launched by this library in the calling process since load (bench.py's gpu_launches) */
+int64_t nt_launch_count(void);
+
+/* ---- kNN graph: torch_cluster.knn via DynamicEdgeConv.forward (nn/net_blocks.py:127-135,174) ------------
+ * For every point of every cloud: the k nearest points of the SAME cloud by squared L2 over D features, self
+ * included, ascending by (distance, index); distance = sequential fp32 fma chain over d = 0..D-1 (bit-exact with
+ * oracle/knn_oracle.c).  x: [B*N, >=D] with row stride ldx.  idx: [B*N, k] int32, local to the cloud.
+ * Requires 1 <= k <= 32 and k <= N. */
+int nt_knn(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *stream);
+
+/* ---- generic fused row GEMM:  out = epilogue( producer(A) . W^T )   (W: [n_out, K] like nn.Linear.weight) --
+ * Serves the Linear layers of MLP() (nn/net_blocks.py:43-47) inside DynamicEdgeConv.message (edge rows) and
+ * point_segment_mlp / panel_dec_lin / placement_decoder (nn/nets.py:223-233,254-276; point rows).
+ *
+ * producer (what a row of A is):
+ *   NT_PROD_PLAIN : A[r, :] = a[r*lda + :]
+ *   NT_PROD_EDGE  : A[r, :] = relu( pq[c*ldpq + :] + pq[j*ldpq + qoff + :] ),  c = r / k, j = neighbour of edge r
+ *                   (idx == NULL: A[r, :] = relu(pq[r*ldpq + :]) -- the first activation of a per-point MLP)
+ * epilogue:
+ *   NT_EPI_BIAS        : out = acc + bias
+ *   NT_EPI_RELU_STATS  : v = relu(acc + bias); out = v (if out != NULL); stats[0:n_out] += sum_r v,
+ *                        stats[n_out:2n_out] += sum_r v*v (double; training-mode BatchNorm1d statistics)
+ *   NT_EPI_RELU_MAXMIN : RELU_STATS plus, per centre point, max and min of v over its k edge rows with the
+ *                        first slot attaining them (EdgeConv max aggregation commuted past the trailing BN)
+ *   NT_EPI_BNRELU_BWD  : g = acc; a = aux row (plain or EDGE producer); dz = a > 0 ? g - k0 - (a - mu)*k1 : 0;
+ *                        out = dz; colsum[0:n_out] += sum_r dz   (backward of Linear<-BN<-ReLU in one pass)
+ */
+enum { NT_PROD_PLAIN = 0, NT_PROD_EDGE = 1 };
+enum { NT_EPI_BIAS = 0, NT_EPI_RELU_STATS = 1, NT_EPI_RELU_MAXMIN = 2, NT_EPI_BNRELU_BWD = 3 };
+
+typedef struct nt_gemm_args {
+    /* problem */
+    int64_t rows;            /* rows of A / out */
+    int K;                   /* inner dimension */
+    int n_out;               /* output columns */
+    int producer, epilogue;
+    /* NT_PROD_PLAIN */
+    const float *a; int lda;
+    /* NT_PROD_EDGE (also used by the aux operand of NT_EPI_BNRELU_BWD when aux_edge != 0) */
+    const float *pq; int ldpq; int qoff;
+    const int32_t *idx; int k; int n_per_cloud;
+    /* weights */
+    const float *w; int ldw; const float *bias;
+    /* outputs */
+    float *out; int ldo;
+    double *stats;                                   /* [2*n_out] */
+    float *vmax, *vmin; uint8_t *imax, *imin;        /* [rows/k, n_out] */
+    /* NT_EPI_BNRELU_BWD */
+    const float *aux; int ldaux; int aux_edge;
+    const float *k0, *k1, *mu;                       /* [n_out] each */
+    double *colsum;                                  /* [n_out] */
+} nt_gemm_args;
+
+int nt_gemm_nt(const nt_gemm_args *args, void *stream);
+
+/* Weight-gradient GEMM: out[m, n] += sum_r A[r, m] * Bop[r, n]  (out must be zeroed by the caller; fp32 atomics).
+ * Bop is a plain matrix (b, ldb) or, when pq != NULL, the EDGE producer above.  Backward of nn.Linear. */
+int nt_gemm_tn(const float *a, int lda, int m, const float *b, int ldb, int n, int64_t rows,
+               const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
+               float *out, int ldo, void *stream);
+
+/* Same contraction with the B operand centred per column (Bop[r, n] - mu[n]) and accumulated in DOUBLE across CTAs
+ * (each CTA sums at most 1024 rows in fp32): the moments the BatchNorm backward needs. */
+int nt_gemm_tn_centered(const float *a, int lda, int m, const float *b, int ldb, int n, int64_t rows,
+                        const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
+                        const float *mu, double *out, int ldo, void *stream);
+
+/* ---- BatchNorm1d bookkeeping (nn/net_blocks.py:46; BN placed AFTER ReLU, statistics over all rows) ---------
+ * Turns accumulated statistics (or running statistics when training == 0) into the affine y = a*s + t, updates
+ * the running buffers (momentum, unbiased variance) in training mode, and folds the affine into the NEXT Linear:
+ *   w_f = w_next * diag(s)  [n_next, C],  w_ft = w_f^T  [C, n_next],  b_f = b_next + w_next . t.
+ * w_next may be NULL (last layer).  Outputs mean/rstd/s/t are [C]. */
+int nt_bn_fold(const double *stats, int64_t count, int C, const float *gamma, const float *beta,
+               float *running_mean, float *running_var, int64_t *num_batches_tracked,
+               float momentum, float eps, int training,
+               float *mean, float *rstd, float *s, float *t,
+               const float *w_next, const float *b_next, int n_next, float *w_f, float *w_ft, float *b_f,
+               void *stream);
+
+/* Statistics of the first activation of an MLP, a1 = NT_PROD_EDGE row (see above): stats[0:H] += sum a1,
+ * stats[H:2H] += sum a1^2 over `rows` rows (double). */
+int nt_edge_stats(const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
+                  int64_t rows, int H, double *stats, void *stream);
+
+/* EdgeConv aggregation finish (DynamicEdgeConv aggr='max', nn/net_blocks.py:127-135): out[m, c] =
+ * s[c] >= 0 ? s*vmax + t : s*vmin + t; sel = slot that produced it, vsel = the pre-BN value it had (both optional,
+ * [M, C], kept for the backward).  Optionally appends `tail` columns copied from tail_src (the skip connection,
+ * nn/net_blocks.py:178-180).  out row stride ldo. */
+int nt_maxmin_finish(const float *vmax, const float *vmin, const uint8_t *imax, const uint8_t *imin,
+                     const float *s, const float *t, int64_t M, int C, float *out, int ldo, uint8_t *sel,
+                     float *vsel, const float *tail_src, int tail_ld, int tail, void *stream);
+
+/* y = a*s + t on [rows, C] (trailing BN of a per-point MLP). */
+int nt_bn_apply(const float *a, int lda, const float *s, const float *t, int64_t rows, int C,
+                float *out, int ldo, void *stream);
+
+/* Column reductions for the trailing BN's backward.  g: [rows_g, C] upstream gradient; v: the BN input the gradient
+ * refers to (same shape): sums[0:C] += sum g, sums[C:2C] += sum g * (v - mu) * rstd  (double accumulators).
+ * v == NULL: plain column sum only (bias gradient of a Linear). */
+int nt_bn_bwd_reduce(const float *g, int ldg, const float *v, int ldv, const float *mu, const float *rstd,
+                     int64_t rows, int C, double *sums, void *stream);
+
+/* Backward through the trailing BN + ReLU for every row: dz[r, c] = a > 0 ? s*(gsel - dbeta/cnt - xhat*dgamma/cnt) : 0
+ * where gsel = g[r / k, c] if sel == NULL or sel[r / k, c] == r % k, else 0.  a, dz: [rows, C]; colsum += sum dz. */
+int nt_bn_relu_bwd_last(const float *a, int lda, const float *g, int ldg, const uint8_t *sel, int k,
+                        const float *s, const float *mu, const float *rstd, const double *sums, int64_t count,
+                        int64_t rows, int C, float *dz, int lddz, double *colsum, void *stream);
+
+/* Backward bookkeeping of one folded Linear (Linear_l fed by BN_{l} output y = a*s + t):
+ * from rawc = dz^T . (a_prev - mean) [n_out, C] (nt_gemm_tn_centered, double), csum = sum_r dz [n_out] (double) and the
+ * previous BN's (s, beta, rstd):  dW = s*rawc + csum (x) beta,  db = csum,  dbeta = W^T csum,
+ * dgamma[c] = rstd[c] * sum_o W[o,c]*rawc[o,c], and the vectors of the next NT_EPI_BNRELU_BWD epilogue:
+ * k0 = s*dbeta/cnt, k1 = s*rstd*dgamma/cnt.  (Centring removes the mean^2/var cancellation of the raw moment.) */
+int nt_linear_bn_bwd(const double *rawc, const double *csum, int n_out, int C, const float *w,
+                     const float *s, const float *beta, const float *rstd, int64_t count,
+                     float *dW, float *db, float *dgamma, float *dbeta, float *k0, float *k1, void *stream);
+
+/* EdgeConv first-layer scatter: dz: [E, H] gradient of the pre-activation P[c] + Q[j];
+ * dpq[c, 0:H] = sum over the k slots, dpq[j, H:2H] += dz (atomic).  dpq must be zeroed by the caller. */
+int nt_edge_scatter(const float *dz, int lddz, const int32_t *idx, int k, int n_per_cloud, int64_t M, int H,
+                    float *dpq, int lddpq, void *stream);
+
+/* ---- attention head ----------------------------------------------------------------------------------------
+ * Sparsemax over the last dimension (sparsemax.Sparsemax(dim=1), nn/nets.py:225,255): P <= 32 columns. */
+int nt_sparsemax_fwd(const float *z, int64_t rows, int P, float *out, void *stream);
+int nt_sparsemax_bwd(const float *out, const float *g, int64_t rows, int P, float *gz, void *stream);
+
+/* The 23-iteration weighted pooling loop of nn/nets.py:263-276 as one contraction:
+ * enc[b, p, f] = scale * sum_n w[b, n, p] * feat[b, n, f]   (scale = 1/N for global_mean_pool).  enc zeroed by caller. */
+int nt_attn_pool_fwd(const float *w, const float *feat, int ldf, int B, int N, int P, int F, float scale,
+                     float *enc, void *stream);
+/* gw[b,n,p] = scale * sum_f genc[b,p,f]*feat[b,n,f];  gfeat[b,n,f] (+)= scale * sum_p w[b,n,p]*genc[b,p,f] */
+int nt_attn_pool_bwd(const float *genc, const float *w, const float *feat, int ldf, int B, int N, int P, int F,
+                     float scale, float *gw, float *gfeat, int ldgf, int accumulate_gfeat, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NT_B200_H */

@@ -1,0 +1,245 @@
+"""GPU parity tests of the individual operators (call through the C ABI via ops.py).
+
+kNN: bit-exact against the oracle C restatement and the committed known-answer fixtures.
+Float operators: within 1e-3 relative (tests/helpers.py REL_TOL) of a plain-PyTorch fp32 reference of the same op.
+"""
+import os
+
+import pytest
+import torch
+
+from helpers import REL_TOL, assert_close, global_index, ref_edgeconv, rel_err, torch_mlp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops(cuda_device):
+    from garment_pattern_estimation_b200 import ops as _ops
+    return _ops
+
+
+# ------------------------------------------------------------------------------------------------------------
+# kNN
+# ------------------------------------------------------------------------------------------------------------
+def _knn_gpu(ops, x, k, dev):
+    B, N, D = x.shape
+    return ops.knn_graph(x.to(dev).reshape(B * N, D), B, N, k).view(B, N, k).cpu()
+
+
+def test_knn_known_answers(ops, cuda_device, golden_dir):
+    cases = torch.load(os.path.join(golden_dir, 'knn_kat.pt'))
+    for name, c in cases.items():
+        got = _knn_gpu(ops, c['x'], c['k'], cuda_device)
+        assert torch.equal(got, c['idx']), 'kNN indices differ from the golden vector: ' + name
+
+
+@pytest.mark.parametrize('B,N,D,k', [(1, 5, 3, 5), (2, 33, 3, 4), (3, 1000, 3, 5), (2, 777, 150, 5), (2, 1024, 150, 16),
+                                      (1, 300, 64, 32), (2, 257, 153, 8), (4, 50, 1, 3)])
+def test_knn_bit_exact_vs_oracle(ops, cuda_device, B, N, D, k):
+    from oracle import knn as oknn
+    x = torch.randn(B, N, D, generator=torch.Generator().manual_seed(B * 1000 + N + D))
+    got = _knn_gpu(ops, x, k, cuda_device)
+    want = oknn.knn_indices(x, k, nthreads=8)
+    assert torch.equal(got, want)
+
+
+def test_knn_quantised_ties(ops, cuda_device):
+    """coordinates on a coarse grid -> many exactly equal distances; order must be (distance, index)."""
+    from oracle import knn as oknn
+    x = torch.randint(0, 4, (2, 400, 3), generator=torch.Generator().manual_seed(5)).float()
+    assert torch.equal(_knn_gpu(ops, x, 8, cuda_device), oknn.knn_indices(x, 8))
+
+
+def test_knn_strided_input(ops, cuda_device):
+    """feature matrix embedded in a wider buffer (row stride > D)."""
+    from oracle import knn as oknn
+    B, N, D = 2, 200, 150
+    wide = torch.randn(B * N, 160, generator=torch.Generator().manual_seed(3)).to(cuda_device)
+    got = ops.knn_graph(wide[:, :D], B, N, 5).view(B, N, 5).cpu()
+    want = oknn.knn_indices(wide[:, :D].cpu().reshape(B, N, D), 5)
+    assert torch.equal(got, want)
+
+
+def test_knn_full_size_properties(ops, cuda_device):
+    """BASELINE C2 shape (N=2048, 150-d): bit-exact on 2 clouds, plus size-independent properties on 8."""
+    from oracle import knn as oknn
+    B, N, D, k = 8, 2048, 150, 5
+    x = torch.randn(B, N, D, generator=torch.Generator().manual_seed(77))
+    got = _knn_gpu(ops, x, k, cuda_device)
+    assert torch.equal(got[:2], oknn.knn_indices(x[:2], k, nthreads=8))
+    assert torch.equal(got[:, :, 0], torch.arange(N).expand(B, N).int())          # self is the nearest (distance 0)
+    assert int(got.min()) >= 0 and int(got.max()) < N
+    srt = got.sort(dim=-1).values
+    assert bool((srt[..., 1:] != srt[..., :-1]).all())                            # no neighbour listed twice
+    d = (x.unsqueeze(2) - torch.gather(x.unsqueeze(1).expand(B, N, N, D), 2,
+                                        got.long().unsqueeze(-1).expand(B, N, k, D))).pow(2).sum(-1)
+    assert bool((d[..., 1:] >= d[..., :-1] - 1e-3).all())                         # ascending distances
+
+
+def test_knn_rejects_bad_k(ops, cuda_device):
+    x = torch.randn(40, 3, device=cuda_device)
+    with pytest.raises(RuntimeError):
+        ops.knn_graph(x, 1, 40, 33)
+    with pytest.raises(RuntimeError):
+        ops.knn_graph(x, 4, 10, 11)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fused MLP: edge rows (DynamicEdgeConv) and plain rows
+# ------------------------------------------------------------------------------------------------------------
+def _copy_mlp(dst_mlp, src_mlp):
+    dst_mlp.load_state_dict(src_mlp.state_dict())
+
+
+@pytest.mark.parametrize('C,widths,k,B,N,tail', [
+    (3, [200, 200, 150], 5, 2, 300, 0),
+    (150, [200, 200, 150], 5, 2, 257, 3),
+    (6, [32, 24], 4, 3, 64, 0),            # two Linear layers (EConv_hidden_depth = 1)
+    (5, [16, 48, 40, 20], 16, 1, 130, 0),  # four Linear layers, k = 16
+])
+@pytest.mark.parametrize('training', [True, False])
+def test_edgeconv_matches_torch(ops, cuda_device, C, widths, k, B, N, tail, training):
+    from garment_pattern_estimation_b200 import net_blocks as nb
+    dev = cuda_device
+    torch.manual_seed(11)
+    ref_mlp = torch_mlp([2 * C] + widths).to(dev)
+    with torch.no_grad():       # non-trivial BN affine incl. negative gammas (the shipped ckpt has 5.5 % negative)
+        for blk in ref_mlp:
+            blk[2].weight.copy_(torch.randn_like(blk[2].weight))
+            blk[2].bias.copy_(torch.randn_like(blk[2].bias) * 0.3)
+            blk[2].running_mean.copy_(torch.rand_like(blk[2].running_mean))
+            blk[2].running_var.copy_(torch.rand_like(blk[2].running_var) + 0.5)
+    mine = nb.DynamicEdgeConv(nb.MLP([2 * C] + widths), k=k).to(dev)
+    _copy_mlp(mine.nn, ref_mlp)
+    ref_mlp.train(training)
+    mine.train(training)
+
+    x = torch.randn(B * N, C, device=dev)
+    pos = torch.randn(B * N, 3, device=dev) if tail else None
+    x1 = x.clone().requires_grad_(training)
+    x2 = x.clone().requires_grad_(training)
+    out = mine(x1, cloud_shape=(B, N), tail_src=pos)
+    idx = global_index(mine.last_index, N)
+    want = ref_edgeconv(x2, idx, ref_mlp)
+    if tail:
+        want = torch.cat([want, pos], dim=-1)
+    assert out.shape == want.shape
+    assert_close(out, want, what='edgeconv forward')
+    if not training:
+        return
+    g = torch.randn_like(want)
+    out.backward(g)
+    want.backward(g)
+    assert_close(x1.grad, x2.grad, what='grad wrt input features')
+    for (n1, p1), (n2, p2) in zip(mine.nn.named_parameters(), ref_mlp.named_parameters()):
+        assert n1 == n2
+        assert_close(p1.grad, p2.grad, what='grad ' + n1)
+    for (n1, b1), (n2, b2) in zip(mine.nn.named_buffers(), ref_mlp.named_buffers()):
+        if b1.dtype.is_floating_point:
+            assert_close(b1, b2, what='BN buffer ' + n1)
+        else:
+            assert torch.equal(b1, b2), n1
+
+
+@pytest.mark.parametrize('widths,rows', [([153, 153, 153, 23], 1000), ([16, 200, 200, 200, 1], 333), ([7, 9, 5], 64)])
+@pytest.mark.parametrize('training', [True, False])
+def test_plain_mlp_matches_torch(ops, cuda_device, widths, rows, training):
+    from garment_pattern_estimation_b200 import net_blocks as nb
+    dev = cuda_device
+    torch.manual_seed(3)
+    ref_mlp = torch_mlp(widths).to(dev)
+    with torch.no_grad():
+        for blk in ref_mlp:
+            blk[2].weight.copy_(torch.randn_like(blk[2].weight))
+            blk[2].bias.copy_(torch.randn_like(blk[2].bias) * 0.3)
+    mine = nb.MLP(widths).to(dev)
+    _copy_mlp(mine, ref_mlp)
+    ref_mlp.train(training)
+    mine.train(training)
+    x = torch.randn(rows, widths[0], device=dev)
+    x1 = x.clone().requires_grad_(training)
+    x2 = x.clone().requires_grad_(training)
+    out, want = mine(x1), ref_mlp(x2)
+    assert_close(out, want, what='mlp forward')
+    if not training:
+        return
+    g = torch.randn_like(want)
+    out.backward(g)
+    want.backward(g)
+    assert_close(x1.grad, x2.grad, what='grad wrt input')
+    for (n1, p1), (n2, p2) in zip(mine.named_parameters(), ref_mlp.named_parameters()):
+        assert_close(p1.grad, p2.grad, what='grad ' + n1)
+    for (n1, b1), (n2, b2) in zip(mine.named_buffers(), ref_mlp.named_buffers()):
+        if b1.dtype.is_floating_point:
+            assert_close(b1, b2, what='BN buffer ' + n1)
+
+
+def test_eval_mode_backward_is_refused(ops, cuda_device):
+    from garment_pattern_estimation_b200 import net_blocks as nb
+    mlp = nb.MLP([4, 8, 3]).to(cuda_device).eval()
+    x = torch.randn(10, 4, device=cuda_device, requires_grad=True)
+    with pytest.raises(RuntimeError):
+        mlp(x).sum().backward()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# sparsemax / attention pooling / linear
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('rows,P', [(1000, 23), (17, 1), (64, 32), (5, 2)])
+def test_sparsemax_matches_published_algorithm(ops, cuda_device, rows, P):
+    from oracle.thirdparty import Sparsemax
+    z = (torch.randn(rows, P, generator=torch.Generator().manual_seed(rows)) * 2).to(cuda_device)
+    z[0] = 0.5                                        # full tie row
+    z1, z2 = z.clone().requires_grad_(True), z.clone().requires_grad_(True)
+    out, want = ops.sparsemax(z1), Sparsemax(dim=1)(z2)
+    assert_close(out, want, tol=1e-5, what='sparsemax forward')
+    assert torch.allclose(out.sum(-1), torch.ones(rows, device=cuda_device), atol=1e-5)
+    assert bool(((out == 0) == (want == 0)).all()), 'support set differs'
+    g = torch.randn_like(out)
+    out.backward(g)
+    want.backward(g)
+    assert_close(z1.grad, z2.grad, tol=1e-5, what='sparsemax backward')
+
+
+@pytest.mark.parametrize('B,N,P,F', [(3, 300, 23, 153), (1, 64, 4, 300), (2, 129, 32, 7)])
+def test_attention_pool_matches_reference_loop(ops, cuda_device, B, N, P, F):
+    dev = cuda_device
+    w = torch.rand(B * N, P, device=dev)
+    f = torch.randn(B * N, F, device=dev)
+    w1, f1 = w.clone().requires_grad_(True), f.clone().requires_grad_(True)
+    w2, f2 = w.clone().requires_grad_(True), f.clone().requires_grad_(True)
+    enc = ops.attention_pool(w1, f1, B, N, 1.0 / N)
+    # reference order of operations: per panel, weights * features, mean over the cloud (nn/nets.py:263-276)
+    want = torch.stack([(w2[:, p:p + 1] * f2).view(B, N, F).mean(dim=1) for p in range(P)], dim=1)
+    assert_close(enc, want, what='attention pool forward')
+    g = torch.randn_like(want)
+    enc.backward(g)
+    want.backward(g)
+    assert_close(w1.grad, w2.grad, what='attention pool grad weights')
+    assert_close(f1.grad, f2.grad, what='attention pool grad features')
+
+
+@pytest.mark.parametrize('rows,K,n_out', [(46, 153, 250), (736, 250, 7), (1, 5, 3), (10304, 250, 8)])
+def test_linear_matches_torch(ops, cuda_device, rows, K, n_out):
+    dev = cuda_device
+    lin = torch.nn.Linear(K, n_out).to(dev)
+    x = torch.randn(rows, K, device=dev)
+    x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    w1, b1 = lin.weight.detach().clone().requires_grad_(True), lin.bias.detach().clone().requires_grad_(True)
+    out = ops.linear(x1, w1, b1)
+    want = lin(x2)
+    assert_close(out, want, what='linear forward')
+    g = torch.randn_like(want)
+    out.backward(g)
+    want.backward(g)
+    assert_close(x1.grad, x2.grad, what='linear grad x')
+    assert_close(w1.grad, lin.weight.grad, what='linear grad w')
+    assert_close(b1.grad, lin.bias.grad, what='linear grad b')
+
+
+def test_cpu_tensors_are_refused(ops):
+    with pytest.raises(RuntimeError):
+        ops.knn_graph(torch.randn(10, 3), 1, 10, 3)
+    with pytest.raises(RuntimeError):
+        ops.sparsemax(torch.randn(4, 5))
