@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Headline benchmark: point-clouds/sec of one full TRAINING STEP (H2D -> forward -> 4-term loss -> backward ->
+gradient all-reduce -> Adam) of the attention model on synthetic clouds (BASELINE.json configs[1] = C2:
+models/att architecture, N = 2048 points, batch 32 per GPU, k = 5), plus the roofline of the dominant kernel and the
+oracle's CPU timing on the same box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  `value` = clouds/s with the inputs already resident in HBM, device-timed with CUDA events,
+max over ranks; `e2e` = the same step through the public module API with inputs in pinned HOST memory (H2D every step, loss
+read back every step).  Weak scaling: every rank keeps 32 clouds.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(points=2048, batch_per_gpu=32, k=5)           # BASELINE.json configs[1] (C2)
+CPU_SAMPLE_CLOUDS = 4                                          # bounded CPU sample (cpu_baseline / --impl reference)
+SEED_INIT = 916143406                                          # models/att/att.yaml:147
+FP32_LANES_PER_SM, SMS = 128, 148
+
+
+def att_configs(k):
+    from oracle import model as om       # config VALUES only (att.yaml); the oracle code is not on the measured path
+    nc = dict(om.ATT_NN_CONFIG)
+    nc['k_neighbors'] = k
+    lc = {'loss_components': ['shape', 'loop', 'rotation', 'translation'], 'quality_components': [],
+          'loop_loss_weight': 1., 'panel_origin_invariant_loss': False, 'panel_order_inariant_loss': False}
+    return dict(om.ATT_DATA_CONFIG), nc, lc
+
+
+def synthetic_batch(B, N, seed):
+    """Positions ~ N(0,1) (the reference standardises its inputs, nn/data/transforms.py:35-49) + GT of SURVEY 8d."""
+    from oracle import model as om
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, N, 3, generator=g), om.synthetic_ground_truth(B, seed=seed + 1)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (pure-PyTorch restatement of the reference path; the reference itself cannot be imported on the
+# GPU box -- torch_geometric / torch_cluster / sparsemax are not installable and /root/reference is absent there)
+# ------------------------------------------------------------------------------------------------------------
+def cpu_train_steps(steps, warmup, k):
+    from oracle import model as om
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dc, nc, lc = att_configs(k)
+    torch.manual_seed(SEED_INIT)
+    model = om.OracleSegmentPattern3D(dc, nc, lc).train()
+    opt = torch.optim.Adam(model.parameters(), lr=2e-3)
+    x, gt = synthetic_batch(CPU_SAMPLE_CLOUDS, WORKLOAD['points'], seed=1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = model(x, fast=True)
+        loss, _ = om.main_losses(out, gt, fast=True)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return CPU_SAMPLE_CLOUDS / sec, sec, cores
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    cps, sec, cores = cpu_train_steps(steps, warmup, WORKLOAD['k'])
+    sample = '{} clouds x {} pts per step, {} timed steps (oracle port of nn/nets.py + nn/net_blocks.py, torch CPU ' \
+             'fp32, {} threads)'.format(CPU_SAMPLE_CLOUDS, WORKLOAD['points'], steps, cores)
+    line = {
+        'impl': 'reference', 'metric': 'point-clouds/sec (fwd+bwd+optimizer, training step)', 'value': cps,
+        'unit': 'clouds/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args.gpus),
+        'cpu_baseline': {'value': cps, 'unit': 'clouds/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': cps, 'unit': 'clouds/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {'workload': 'C2: attention model (models/att NN config) training step, N=2048 pts/cloud, k=5, '
+                        'batch 32 clouds per GPU, Adam lr 2e-3, random init seed 916143406',
+            'global_batch': WORKLOAD['batch_per_gpu'] * n_gpus, 'points': WORKLOAD['points'],
+            'parallelism': 'dp{}'.format(n_gpus),
+            'l2': 'per-step activations (~1.9 GB) exceed the 126 MB L2 and 4 distinct input batches rotate; no flush'}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference_arm(args, rank)
+        return
+
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the B200 hot path has no CPU fallback '
+                           '(use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    import garment_pattern_estimation_b200 as g
+    from garment_pattern_estimation_b200 import _lib, ops
+    from garment_pattern_estimation_b200.parallel import FlatDataParallel
+
+    B, N, k = WORKLOAD['batch_per_gpu'], WORKLOAD['points'], WORKLOAD['k']
+    dc, nc, lc = att_configs(k)
+    torch.manual_seed(SEED_INIT)
+    model = g.GarmentSegmentPattern3D(dc, nc, lc).to(dev).train()
+    wrapper = FlatDataParallel(model, device_ids=[dev], auto_reduce=False)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-3)
+
+    # 4 distinct synthetic batches per rank, in pinned host memory (e2e) and resident copies (value)
+    host, resident = [], []
+    for i in range(4):
+        x, gt = synthetic_batch(B, N, seed=1234 + 100 * rank + i)
+        hx = x.pin_memory()
+        hgt = {kk: v.pin_memory() for kk, v in gt.items()}
+        host.append((hx, hgt))
+        resident.append((hx.to(dev), {kk: v.to(dev) for kk, v in hgt.items()}))
+    h2d_bytes = host[0][0].numel() * 4 + sum(v.numel() * v.element_size() for v in host[0][1].values())
+
+    def train_step(x, gt):
+        out = wrapper(x)
+        loss, _, _ = model.loss(out, gt)
+        loss.backward()
+        wrapper.reduce_gradients()
+        opt.step()
+        wrapper.zero_grad()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        start.record()
+        for i in range(steps):
+            fn(i)
+        end.record()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - l0
+        ms = torch.tensor([start.elapsed_time(end)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item()), launches
+
+    # ---- warm-up
+    for i in range(args.warmup):
+        train_step(*resident[i % 4])
+
+    # ---- value: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = timed(lambda i: train_step(*resident[i % 4]), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers, H2D of inputs and D2H of the loss every step
+    def e2e_step(i):
+        hx, hgt = host[i % 4]
+        x = hx.to(dev, non_blocking=True)
+        gt = {kk: v.to(dev, non_blocking=True) for kk, v in hgt.items()}
+        loss = train_step(x, gt)
+        return float(loss.item())                    # device -> host read of the step's result
+
+    for i in range(2):
+        e2e_step(i)
+    e2e_ms, _ = timed(e2e_step, args.steps)
+    e2e_value = world * B / (e2e_ms / args.steps * 1e-3)
+
+    # ---- per-kernel-group device times (CUDA events on the launching stream) for the roofline of the dominant kernel
+    ops.EVENT_SINK = {}
+    for i in range(3):
+        train_step(*resident[i % 4])
+    torch.cuda.synchronize()
+    groups = {name: sum(s.elapsed_time(e) for s, e in evs) / 3.0 for name, evs in ops.EVENT_SINK.items()}
+    counts = {name: len(evs) / 3.0 for name, evs in ops.EVENT_SINK.items()}
+    ops.EVENT_SINK = None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+
+    knn_name = 'nt_knn[D=150]'
+    knn_ms = groups.get(knn_name, 0.0) / max(counts.get(knn_name, 1.0), 1.0)      # average launch duration
+    feat = 150
+    alg_bytes = B * (4 * feat * N + 4 * N * k)            # read the [N,150] fp32 features once + write int32 indices
+    pair_dims = B * N * N * feat
+    flops = B * N * N * (3 * feat - 1)                    # (3C-1) N^2 per cloud
+    sm_clock = (clocks or {}).get('sm_mhz') or peaks.get('sm_max_mhz', 1965.0)
+    fp32_peak = SMS * FP32_LANES_PER_SM * 2 * sm_clock * 1e6 / 1e12
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'knn_traffic.json')) as f:
+            traffic = json.load(f).get('dram_bytes_per_launch')
+    except (OSError, ValueError):
+        pass
+    roofline = {
+        'kernel': 'nt::knn_kernel<5> on the 150-d EdgeConv features (kNN-L2), {} clouds x {} pts per launch'.format(B, N),
+        'bound': 'hbm', 'achieved': alg_bytes / (knn_ms * 1e-3) / 1e9 if knn_ms else None, 'peak': hbm_peak,
+        'unit': 'GB/s', 'frac': (alg_bytes / (knn_ms * 1e-3) / 1e9 / hbm_peak) if knn_ms else None,
+        'traffic': traffic, 'peak_source': peak_src, 'launch_ms': knn_ms,
+        'share_of_step': groups.get(knn_name, 0.0) / ms_per_step if ms_per_step else None,
+        'note': 'the bit-exact direct-form distance is FP32-ALU bound (SURVEY.md F9: 718+ flop/B), so the HBM fraction '
+                'is small by construction; the binding roofline is `compute`',
+        'compute': {'bound': 'fp32_alu', 'achieved': flops / (knn_ms * 1e-3) / 1e12 if knn_ms else None,
+                    'peak': fp32_peak, 'unit': 'TFLOP/s',
+                    'frac': (flops / (knn_ms * 1e-3) / 1e12 / fp32_peak) if knn_ms else None,
+                    'pair_dims_per_s': pair_dims / (knn_ms * 1e-3) if knn_ms else None,
+                    'peak_source': 'nominal 148 SM x 128 lanes x 2 x {:.0f} MHz (median SM clock during the run)'
+                    .format(sm_clock)},
+    }
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        cps, sec, cores = cpu_train_steps(steps=2, warmup=1, k=k)
+        cpu_baseline = {'value': cps, 'unit': 'clouds/s', 'cores': cores, 'kind': 'port',
+                        'sample': '{} clouds x {} pts per step, 2 timed steps after 1 warm-up ({:.1f} s/step); oracle '
+                                  'port of the reference path, torch CPU fp32'.format(CPU_SAMPLE_CLOUDS, N, sec)}
+
+    line = {
+        'metric': 'point-clouds/sec (fwd+bwd+optimizer, training step)', 'value': value, 'unit': 'clouds/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(world),
+        'e2e': {'value': e2e_value, 'unit': 'clouds/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
+                'ms_per_step': e2e_ms / args.steps},
+        'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps,
+        'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+        'kernel_ms_per_step': {kk: round(v, 4) for kk, v in sorted(groups.items(), key=lambda kv: -kv[1])},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

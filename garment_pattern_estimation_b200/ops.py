@@ -34,6 +34,22 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+EVENT_SINK = None     # set to a dict to collect (start, end) CUDA-event pairs per kernel group (bench.py roofline)
+
+
+def _call(name, fn, *args, group=None):
+    """Invoke one C-ABI entry point, raise RuntimeError on a non-zero status, and -- when EVENT_SINK is a dict --
+    bracket the launch with CUDA events on the launching stream."""
+    if EVENT_SINK is None:
+        _lib.check(fn(*args), name)
+        return
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    _lib.check(fn(*args), name)
+    end.record()
+    EVENT_SINK.setdefault(group or name, []).append((start, end))
+
+
 def _require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -47,6 +63,10 @@ def _rows2d(t):
     if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
         t = t.contiguous()
     return t, (t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0)))
+
+
+_EPI_NAMES = {NT_EPI_BIAS: 'bias', NT_EPI_RELU_STATS: 'relu_stats', NT_EPI_RELU_MAXMIN: 'relu_maxmin',
+              NT_EPI_BNRELU_BWD: 'bnrelu_bwd'}
 
 
 class EdgeSrc:
@@ -77,30 +97,23 @@ def gemm_nt(rows, K, n_out, w, ldw, epilogue, a=None, lda=0, edge=None, bias=Non
         g.vmax, g.vmin, g.imax, g.imin = (_p(t) for t in agg)
     g.aux, g.ldaux, g.aux_edge = _p(aux), int(ldaux), int(bool(aux_edge))
     g.k0, g.k1, g.mu, g.colsum = _p(k0), _p(k1), _p(mu), _p(colsum)
-    _lib.check(_lib.load().nt_gemm_nt(ctypes.byref(g), _stream()), 'nt_gemm_nt')
+    _call('nt_gemm_nt', _lib.load().nt_gemm_nt, ctypes.byref(g), _stream(),
+          group='nt_gemm_nt[%s,%s]' % (_EPI_NAMES[epilogue], 'edge' if g.producer == NT_PROD_EDGE else 'plain'))
 
 
 def gemm_tn(a, lda, m, rows, out, b=None, ldb=0, n=0, edge=None, mu=None):
     """out[m, n] += sum_r a[r, m] * Bop[r, n].  With `mu` the B operand is centred and `out` must be float64."""
     lib = _lib.load()
+    if edge is not None:
+        bop = (None, 0, n, rows, _p(edge.pq), edge.ldpq, edge.qoff, _p(edge.idx), edge.k, edge.n_per_cloud)
+    else:
+        bop = (_p(b), ldb, n, rows, None, 0, 0, None, 1, 1)
     if mu is not None:
         assert out.dtype == torch.float64
-        if edge is not None:
-            rc = lib.nt_gemm_tn_centered(_p(a), lda, m, None, 0, n, rows, _p(edge.pq), edge.ldpq, edge.qoff,
-                                         _p(edge.idx), edge.k, edge.n_per_cloud, _p(mu), _p(out), out.stride(0),
-                                         _stream())
-        else:
-            rc = lib.nt_gemm_tn_centered(_p(a), lda, m, _p(b), ldb, n, rows, None, 0, 0, None, 1, 1, _p(mu), _p(out),
-                                         out.stride(0), _stream())
-        _lib.check(rc, 'nt_gemm_tn_centered')
-        return
-    if edge is not None:
-        rc = lib.nt_gemm_tn(_p(a), lda, m, None, 0, n, rows, _p(edge.pq), edge.ldpq, edge.qoff, _p(edge.idx),
-                            edge.k, edge.n_per_cloud, _p(out), out.stride(0), _stream())
+        _call('nt_gemm_tn_centered', lib.nt_gemm_tn_centered, _p(a), lda, m, *bop, _p(mu), _p(out), out.stride(0),
+              _stream())
     else:
-        rc = lib.nt_gemm_tn(_p(a), lda, m, _p(b), ldb, n, rows, None, 0, 0, None, 1, 1, _p(out), out.stride(0),
-                            _stream())
-    _lib.check(rc, 'nt_gemm_tn')
+        _call('nt_gemm_tn', lib.nt_gemm_tn, _p(a), lda, m, *bop, _p(out), out.stride(0), _stream())
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -114,7 +127,8 @@ def knn_graph(x, B, N, k):
     if x.shape[0] != B * N:
         raise RuntimeError('knn_graph: expected {} rows, got {}'.format(B * N, x.shape[0]))
     idx = torch.empty(B * N, k, dtype=torch.int32, device=x.device)
-    _lib.check(_lib.load().nt_knn(_p(x), B, N, x.shape[1], ldx, k, _p(idx), _stream()), 'nt_knn')
+    _call('nt_knn', _lib.load().nt_knn, _p(x), B, N, x.shape[1], ldx, k, _p(idx), _stream(),
+          group='nt_knn[D=%d]' % x.shape[1])
     return idx
 
 
@@ -195,17 +209,17 @@ class _FusedMLPFunction(torch.autograd.Function):
                 wn, bn_ = Ws[next_layer].contiguous(), bs[next_layer].contiguous()
             else:
                 n_next, w_f, w_ft, b_f, wn, bn_ = 0, None, None, None, None, None
-            _lib.check(lib.nt_bn_fold(_p(stats), R, Cn, _p(gammas[layer].contiguous()), _p(betas[layer].contiguous()),
+            _call('nt_bn_fold', _lib.load().nt_bn_fold, _p(stats), R, Cn, _p(gammas[layer].contiguous()), _p(betas[layer].contiguous()),
                                       _p(buf.running_mean), _p(buf.running_var), _p(buf.nbt), buf.momentum, buf.eps,
                                       int(training), _p(vec[0]), _p(vec[1]), _p(vec[2]), _p(vec[3]),
-                                      _p(wn), _p(bn_), n_next, _p(w_f), _p(w_ft), _p(b_f), _stream()), 'nt_bn_fold')
+                                      _p(wn), _p(bn_), n_next, _p(w_f), _p(w_ft), _p(b_f), _stream())
             return vec, w_f, w_ft, b_f
 
         # ---- BN_1 statistics of a_1 = relu(P + Q) (no GEMM at row level)
         stats = torch.zeros(2 * H1, dtype=torch.float64, device=dev) if training else None
         if training:
-            _lib.check(lib.nt_edge_stats(_p(pq), src.ldpq, src.qoff, _p(src.idx), src.k, src.n_per_cloud, R, H1,
-                                         _p(stats), _stream()), 'nt_edge_stats')
+            _call('nt_edge_stats', _lib.load().nt_edge_stats, _p(pq), src.ldpq, src.qoff, _p(src.idx), src.k, src.n_per_cloud, R, H1,
+                                         _p(stats), _stream())
         bn_vec = [None] * L
         w_fts = [None] * L            # w_fts[l] = (W_l . diag(s_l))^T, l >= 1
         bn_vec[0], w_f, w_fts[1], b_f = fold(0, stats, 1)
@@ -244,16 +258,16 @@ class _FusedMLPFunction(torch.autograd.Function):
             ts, tld = (None, 0)
             if tail:
                 ts, tld = _rows2d(tail_src)
-            _lib.check(lib.nt_maxmin_finish(_p(agg[0]), _p(agg[1]), _p(agg[2]), _p(agg[3]), _p(bn_vec[L - 1][2]),
+            _call('nt_maxmin_finish', _lib.load().nt_maxmin_finish, _p(agg[0]), _p(agg[1]), _p(agg[2]), _p(agg[3]), _p(bn_vec[L - 1][2]),
                                             _p(bn_vec[L - 1][3]), M, HL, _p(out), HL + tail, _p(sel), _p(vsel),
-                                            _p(ts), tld, tail, _stream()), 'nt_maxmin_finish')
+                                            _p(ts), tld, tail, _stream())
         else:
             a_last = torch.empty(R, HL, **f32)
             gemm_nt(R, Kin, HL, w_f, Kin, NT_EPI_RELU_STATS, bias=b_f, out=a_last, ldo=HL, stats=stats, **last_in)
             bn_vec[L - 1], _, _, _ = fold(L - 1, stats, None)
             out = torch.empty(M, HL, **f32)
-            _lib.check(lib.nt_bn_apply(_p(a_last), HL, _p(bn_vec[L - 1][2]), _p(bn_vec[L - 1][3]), R, HL, _p(out), HL,
-                                       _stream()), 'nt_bn_apply')
+            _call('nt_bn_apply', _lib.load().nt_bn_apply, _p(a_last), HL, _p(bn_vec[L - 1][2]), _p(bn_vec[L - 1][3]), R, HL, _p(out), HL,
+                                       _stream())
             sel = vsel = None
             tail = 0
         acts[L] = a_last
@@ -291,14 +305,13 @@ class _FusedMLPFunction(torch.autograd.Function):
         mean, rstd, s, t = bn_vec[L - 1]
         sums = torch.zeros(2 * HL, **f64)
         v_ref = vsel if mode == 'edge' else acts[L]
-        _lib.check(lib.nt_bn_bwd_reduce(_p(gout), ldg, _p(v_ref), HL, _p(mean), _p(rstd), M, HL, _p(sums), _stream()),
-                   'nt_bn_bwd_reduce')
+        _call('nt_bn_bwd_reduce', _lib.load().nt_bn_bwd_reduce, _p(gout), ldg, _p(v_ref), HL, _p(mean), _p(rstd), M, HL, _p(sums), _stream())
         grads_beta[L - 1] = sums[:HL].float()
         grads_g[L - 1] = sums[HL:].float()
         dz = torch.empty(R, HL, **f32)
         csum = torch.zeros(HL, **f64)
-        _lib.check(lib.nt_bn_relu_bwd_last(_p(acts[L]), HL, _p(gout), ldg, _p(sel), k, _p(s), _p(mean), _p(rstd),
-                                           _p(sums), R, R, HL, _p(dz), HL, _p(csum), _stream()), 'nt_bn_relu_bwd_last')
+        _call('nt_bn_relu_bwd_last', _lib.load().nt_bn_relu_bwd_last, _p(acts[L]), HL, _p(gout), ldg, _p(sel), k, _p(s), _p(mean), _p(rstd),
+                                           _p(sums), R, R, HL, _p(dz), HL, _p(csum), _stream())
 
         # ---- walk down the Linear layers L-1 .. 1
         for l in range(L - 1, 0, -1):
@@ -312,9 +325,9 @@ class _FusedMLPFunction(torch.autograd.Function):
             dW = torch.empty(Hout, Hin, **f32)
             db = torch.empty(Hout, **f32)
             vecs = torch.empty(4, Hin, **f32)          # dgamma, dbeta, k0, k1
-            _lib.check(lib.nt_linear_bn_bwd(_p(raw), _p(csum), Hout, Hin, _p(Ws[l].contiguous()), _p(ps),
+            _call('nt_linear_bn_bwd', _lib.load().nt_linear_bn_bwd, _p(raw), _p(csum), Hout, Hin, _p(Ws[l].contiguous()), _p(ps),
                                             _p(betas[l - 1].contiguous()), _p(prstd), R, _p(dW), _p(db), _p(vecs[0]),
-                                            _p(vecs[1]), _p(vecs[2]), _p(vecs[3]), _stream()), 'nt_linear_bn_bwd')
+                                            _p(vecs[1]), _p(vecs[2]), _p(vecs[3]), _stream())
             grads_W[l], grads_b[l] = dW, db
             grads_g[l - 1], grads_beta[l - 1] = vecs[0], vecs[1]
             csum_prev = torch.zeros(Hin, **f64)
@@ -333,8 +346,7 @@ class _FusedMLPFunction(torch.autograd.Function):
         gx = None
         if mode == 'edge':
             dpq = torch.zeros(M, 2 * H1, **f32)
-            _lib.check(lib.nt_edge_scatter(_p(dz), H1, _p(idx), k, N, M, H1, _p(dpq), 2 * H1, _stream()),
-                       'nt_edge_scatter')
+            _call('nt_edge_scatter', _lib.load().nt_edge_scatter, _p(dz), H1, _p(idx), k, N, M, H1, _p(dpq), 2 * H1, _stream())
             dWc = torch.zeros(2 * H1, C, **f32)
             gemm_tn(dpq, 2 * H1, 2 * H1, M, dWc, b=x, ldb=m['ldx'], n=C)
             grads_W[0] = torch.cat([dWc[:H1], dWc[H1:] - dWc[:H1]], dim=1)
@@ -380,7 +392,7 @@ class _SparsemaxFunction(torch.autograd.Function):
         z = z.contiguous()
         rows, P = z.shape
         out = torch.empty_like(z)
-        _lib.check(_lib.load().nt_sparsemax_fwd(_p(z), rows, P, _p(out), _stream()), 'nt_sparsemax_fwd')
+        _call('nt_sparsemax_fwd', _lib.load().nt_sparsemax_fwd, _p(z), rows, P, _p(out), _stream())
         ctx.save_for_backward(out)
         return out
 
@@ -389,8 +401,7 @@ class _SparsemaxFunction(torch.autograd.Function):
         out, = ctx.saved_tensors
         g = g.contiguous()
         gz = torch.empty_like(out)
-        _lib.check(_lib.load().nt_sparsemax_bwd(_p(out), _p(g), out.shape[0], out.shape[1], _p(gz), _stream()),
-                   'nt_sparsemax_bwd')
+        _call('nt_sparsemax_bwd', _lib.load().nt_sparsemax_bwd, _p(out), _p(g), out.shape[0], out.shape[1], _p(gz), _stream())
         return gz
 
 
@@ -409,8 +420,7 @@ class _AttnPoolFunction(torch.autograd.Function):
         feat, ldf = _rows2d(feat)
         P, F = w.shape[1], feat.shape[1]
         enc = torch.zeros(B, P, F, dtype=torch.float32, device=w.device)
-        _lib.check(_lib.load().nt_attn_pool_fwd(_p(w), _p(feat), ldf, B, N, P, F, scale, _p(enc), _stream()),
-                   'nt_attn_pool_fwd')
+        _call('nt_attn_pool_fwd', _lib.load().nt_attn_pool_fwd, _p(w), _p(feat), ldf, B, N, P, F, scale, _p(enc), _stream())
         ctx.save_for_backward(w, feat)
         ctx.dims = (B, N, P, F, scale, ldf)
         return enc
@@ -422,8 +432,8 @@ class _AttnPoolFunction(torch.autograd.Function):
         genc = genc.contiguous()
         gw = torch.empty_like(w) if ctx.needs_input_grad[0] else None
         gfeat = torch.empty(B * N, F, dtype=torch.float32, device=w.device) if ctx.needs_input_grad[1] else None
-        _lib.check(_lib.load().nt_attn_pool_bwd(_p(genc), _p(w), _p(feat), ldf, B, N, P, F, scale, _p(gw), _p(gfeat), F,
-                                                0, _stream()), 'nt_attn_pool_bwd')
+        _call('nt_attn_pool_bwd', _lib.load().nt_attn_pool_bwd, _p(genc), _p(w), _p(feat), ldf, B, N, P, F, scale, _p(gw), _p(gfeat), F,
+                                                0, _stream())
         return gw, gfeat, None, None, None
 
 
@@ -463,8 +473,7 @@ class _LinearFunction(torch.autograd.Function):
             gemm_tn(g, ldg, n_out, rows, gw, b=x, ldb=x.stride(0) if rows > 1 else K, n=K)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             sums = torch.zeros(n_out, dtype=torch.float64, device=x.device)
-            _lib.check(_lib.load().nt_bn_bwd_reduce(_p(g), ldg, None, 0, None, None, rows, n_out, _p(sums), _stream()),
-                       'nt_bn_bwd_reduce')
+            _call('nt_bn_bwd_reduce', _lib.load().nt_bn_bwd_reduce, _p(g), ldg, None, 0, None, None, rows, n_out, _p(sums), _stream())
             gb = sums.float()
         return gx, gw, gb
 

@@ -9,7 +9,11 @@ reference call site it serves.  Parity against the real binaries is UNPINNED (se
 import torch
 import torch.nn as nn
 
+import os
+
 from . import knn as _knn
+
+KNN_THREADS = os.cpu_count() or 1     # host threads for the brute-force search (queries are independent)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -40,7 +44,7 @@ def knn_graph(x, batch, k):
     B, N = _equal_cloud_layout(x, batch)
     if N < k:
         raise NotImplementedError("oracle knn_graph: clouds with fewer than k points are outside the hot path")
-    idx_local = _knn.knn_indices(x.detach().float().cpu().reshape(B, N, -1), k)        # [B, N, k] int32
+    idx_local = _knn.knn_indices(x.detach().float().cpu().reshape(B, N, -1), k, nthreads=KNN_THREADS)   # [B,N,k]
     offs = (torch.arange(B, dtype=torch.int64) * N).view(B, 1, 1)
     return (idx_local.long() + offs).reshape(B * N, k).to(x.device)
 

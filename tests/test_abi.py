@@ -1,0 +1,62 @@
+"""The C-ABI shared library: builds for sm_100a, loads without a GPU, exports every symbol include/nt_b200.h declares,
+and the Python binding table covers exactly that set.  No compute calls here (CPU box)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'nt_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(nt_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_header_declares_the_hot_path_entry_points():
+    syms = _declared_symbols()
+    for must in ('nt_knn', 'nt_gemm_nt', 'nt_gemm_tn', 'nt_bn_fold', 'nt_maxmin_finish', 'nt_sparsemax_fwd',
+                 'nt_sparsemax_bwd', 'nt_attn_pool_fwd', 'nt_attn_pool_bwd', 'nt_last_error'):
+        assert must in syms
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from garment_pattern_estimation_b200 import _lib, build
+    path = build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    for sym in _declared_symbols():
+        assert hasattr(lib, sym), 'libnt_b200.so does not export ' + sym
+    assert sorted(_lib.EXPORTED_SYMBOLS) == _declared_symbols(), 'ctypes table and header disagree'
+    loaded = _lib.load()
+    assert loaded.nt_version() >= 1 and loaded.nt_built_arch() == 100
+    assert loaded.nt_launch_count() >= 0
+
+
+def test_library_contains_sm_100a_code_only():
+    from garment_pattern_estimation_b200 import build
+    path = build.build()
+    try:
+        out = subprocess.run(['cuobjdump', '-lelf', path], capture_output=True, text=True, timeout=60).stdout
+    except (OSError, subprocess.TimeoutExpired):
+        pytest.skip('cuobjdump unavailable')
+    archs = set(re.findall(r'sm_(\d+a?)', out))
+    assert archs == {'100a'}, archs
+
+
+def test_bad_arguments_return_error_codes_not_crashes():
+    """argument validation happens before any CUDA call, so it can be exercised on a CPU box"""
+    from garment_pattern_estimation_b200 import _lib
+    lib = _lib.load()
+    assert lib.nt_knn(None, 1, 10, 3, 3, 5, None, None) != 0
+    assert b'null' in lib.nt_last_error()
+    buf = (ctypes.c_float * 64)()
+    ibuf = (ctypes.c_int32 * 64)()
+    assert lib.nt_knn(ctypes.cast(buf, ctypes.c_void_p), 1, 4, 3, 3, 64, ctypes.cast(ibuf, ctypes.c_void_p), None) != 0
+    assert b'k must be' in lib.nt_last_error()
+    assert lib.nt_sparsemax_fwd(ctypes.cast(buf, ctypes.c_void_p), 2, 33, ctypes.cast(buf, ctypes.c_void_p), None) != 0
+    with pytest.raises(RuntimeError):
+        _lib.check(1, 'nt_sparsemax_fwd')

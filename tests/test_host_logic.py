@@ -1,0 +1,232 @@
+"""CPU tests of the host side: the reference-facing module surface (names, config merging, state_dict contract, error
+behaviour), the vectorised loss against the reference's loop form, and the data-parallel wrapper over gloo (world size 2)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _att():
+    from oracle import model as om
+    return dict(om.ATT_DATA_CONFIG), dict(om.ATT_NN_CONFIG), {
+        'loss_components': ['shape', 'loop', 'rotation', 'translation'], 'quality_components': [],
+        'panel_origin_invariant_loss': False, 'panel_order_inariant_loss': False}
+
+
+def test_state_dict_contract_matches_survey_a2():
+    import garment_pattern_estimation_b200 as g
+    dc, nc, lc = _att()
+    model = g.GarmentSegmentPattern3D(dc, nc, lc)
+    sd = model.state_dict()
+    shapes = {k: tuple(v.shape) for k, v in sd.items()}
+    assert shapes['feature_extractor.conv_layers.0.nn.0.0.weight'] == (200, 6)
+    assert shapes['feature_extractor.conv_layers.1.nn.0.0.weight'] == (200, 300)
+    assert shapes['feature_extractor.conv_layers.1.nn.2.0.weight'] == (150, 200)
+    assert shapes['feature_extractor.conv_layers.0.nn.1.2.running_var'] == (200,)
+    assert sd['feature_extractor.conv_layers.0.nn.1.2.num_batches_tracked'].dtype == torch.int64
+    assert shapes['feature_extractor.lin.weight'] == (250, 153)
+    assert shapes['panel_decoder.lstm.weight_ih_l2'] == (1000, 250) and shapes['panel_decoder.lin.weight'] == (8, 250)
+    assert shapes['placement_decoder.weight'] == (7, 250)
+    assert shapes['point_segment_mlp.0.2.0.weight'] == (23, 153) and shapes['panel_dec_lin.weight'] == (250, 153)
+    assert not any(k.startswith('pattern_decoder') for k in sd)
+    assert sum(p.numel() for p in model.parameters()) == 1842589
+    # wrapped checkpoints carry the 'module.' prefix (nn/trainer.py:275-291)
+    from garment_pattern_estimation_b200.parallel import FlatDataParallel
+    wrapped = FlatDataParallel(model)
+    assert all(k.startswith('module.') for k in wrapped.state_dict())
+    assert wrapped.module is model and len(wrapped.device_ids) == 1
+
+
+def test_same_seed_gives_same_init_as_oracle_and_baseline_model_builds():
+    import garment_pattern_estimation_b200 as g
+    from oracle import model as om
+    dc, nc, lc = _att()
+    torch.manual_seed(123)
+    a = g.GarmentSegmentPattern3D(dict(dc), dict(nc), dict(lc)).state_dict()
+    torch.manual_seed(123)
+    b = om.OracleSegmentPattern3D(dict(dc), dict(nc), dict(lc)).state_dict()
+    assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+    nc2 = dict(nc)
+    nc2.update(model='GarmentFullPattern3D', skip_connections=False)
+    base = g.GarmentFullPattern3D(dict(dc), nc2, dict(lc))
+    keys = base.state_dict().keys()
+    assert 'pattern_decoder.lstm.weight_ih_l1' in keys and 'feature_extractor.lin.weight' in keys
+    assert base.state_dict()['feature_extractor.lin.weight'].shape == (250, 150)
+
+
+def test_config_merging_follows_the_reference():
+    import garment_pattern_estimation_b200 as g
+    from garment_pattern_estimation_b200 import net_blocks as nb
+    dc, nc, lc = _att()
+    model = g.GarmentSegmentPattern3D(dc, nc, lc)
+    # block defaults .update()-ed with the whole NN config, then merged back (nn/net_blocks.py:98-110, nn/nets.py:102-103)
+    assert model.feature_extractor.config['panel_encoding_size'] == 250
+    assert model.config['EConv_feature'] == 150 and model.config['k_neighbors'] == 5
+    assert model.config['loss']['loss_components'] == ['shape', 'loop', 'rotation', 'translation']
+    enc = nb.EdgeConvFeatures(10)
+    assert enc.config['EConv_feature'] == 112 and enc.config['skip_connections'] is False
+    assert enc.lin.in_features == 112
+    assert callable(enc.global_pool)
+
+
+def test_error_behaviour_matches_reference_conventions():
+    from garment_pattern_estimation_b200 import net_blocks as nb
+    with pytest.raises(ValueError):                                   # nn/net_blocks.py:152
+        nb.EdgeConvFeatures(10, {'global_pool': 'median'})
+    with pytest.raises(NotImplementedError):                          # nn/net_blocks.py:313
+        nb.initial_state(3, 4, 5, 'cpu', init_type='xavier')
+    with pytest.raises(NotImplementedError):                          # nn/net_blocks.py:332
+        nb.LSTMDecoderModule(8, 8, 4, 1, custom_init='xavier')
+    with pytest.raises(NotImplementedError):
+        nb.EdgeConvFeatures(10, {'graph_pooling': True})
+    enc = nb.EdgeConvFeatures(10)
+    with pytest.raises(RuntimeError):                                 # no CPU fallback
+        enc(torch.randn(2, 16, 3))
+
+
+def test_global_pools_on_dense_layout():
+    from garment_pattern_estimation_b200 import net_blocks as nb
+    x = torch.randn(3 * 7, 5)
+    batch = torch.arange(3).repeat_interleave(7)
+    assert torch.allclose(nb.global_mean_pool(x, batch, 3), x.view(3, 7, 5).mean(1))
+    assert torch.allclose(nb.global_max_pool(x, batch), x.view(3, 7, 5).max(1).values)
+    assert torch.allclose(nb.global_add_pool(x, batch, 3), x.view(3, 7, 5).sum(1))
+
+
+def test_initial_state_distribution_matches_reference_draw():
+    from garment_pattern_estimation_b200 import net_blocks as nb
+    from oracle import model as om
+    torch.manual_seed(0)
+    mine = nb.initial_state(3, 736, 250, 'cpu', 'kaiming_normal_')
+    ref = om.init_state(3, 736, 250)
+    assert mine.shape == ref.shape
+    assert abs(float(mine.std()) / float(ref.std()) - 1) < 0.02 and abs(float(mine.mean())) < 1e-4
+    assert float(nb.initial_state(2, 3, 4, 'cpu', '').abs().sum()) == 0
+
+
+def test_vectorised_loss_equals_reference_loop_form():
+    from garment_pattern_estimation_b200.losses import ComposedPatternLoss, panel_loop_loss
+    from oracle import model as om
+    dc, _, lc = _att()
+    B = 5
+    gt = om.synthetic_ground_truth(B, seed=3)
+    gt['num_edges'][0, :3] = torch.tensor([0, 2, 14])                 # < 3 edges contribute 0 but count in the mean
+    preds = {'outlines': torch.randn(B, 23, 14, 4, requires_grad=True), 'rotations': torch.randn(B, 23, 4),
+             'translations': torch.randn(B, 23, 3)}
+    loop_ref = om.panel_loop_loss(preds['outlines'], gt['num_edges'].view(-1), fast=False)
+    loop_new = panel_loop_loss(preds['outlines'], gt['num_edges'].view(-1))
+    assert torch.allclose(loop_ref, loop_new, rtol=1e-6, atol=1e-8)
+    loss_obj = ComposedPatternLoss(dc, lc)
+    total, parts, flag = loss_obj(preds, gt, epoch=3)
+    want, want_parts = om.main_losses(preds, gt)
+    assert flag is False and set(parts) == set(want_parts)
+    assert torch.allclose(total, want, rtol=1e-6)
+    g1, = torch.autograd.grad(total, preds['outlines'], retain_graph=True)
+    g2, = torch.autograd.grad(want, preds['outlines'])
+    assert torch.allclose(g1, g2, rtol=1e-5, atol=1e-8)
+    assert panel_loop_loss(torch.randn(4, 14, 4)).dim() == 0          # no num_edges => no padding assumed
+    with pytest.raises(NotImplementedError):
+        ComposedPatternLoss(dc, {'loss_components': ['shape', 'stitch'], 'panel_origin_invariant_loss': False,
+                                 'panel_order_inariant_loss': False})
+    loss_obj.train(True)
+    assert loss_obj.training is True
+    loss_obj.eval()
+    assert loss_obj.training is False
+
+
+# ------------------------------------------------------------------------------------------------------------
+# data-parallel wrapper over gloo, world size 2 (the N>1 path of SURVEY.md section 8e on CPU)
+# ------------------------------------------------------------------------------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _dp_worker(rank, world, port, results):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from garment_pattern_estimation_b200.parallel import FlatDataParallel
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)                      # different init per rank: the wrapper must broadcast rank 0's
+        net = nn.Sequential(nn.Linear(6, 8), nn.BatchNorm1d(8), nn.ReLU(), nn.Linear(8, 3))
+        unused = nn.Linear(4, 4)                           # never used in forward: gradient stays zero
+        net.add_module('unused', unused)
+        fwd = lambda m, x: m[3](m[2](m[1](m[0](x))))       # noqa: E731
+        dp = FlatDataParallel(net, auto_reduce=True)
+        torch.manual_seed(7)
+        X, Y = torch.randn(8, 6), torch.randn(8, 3)        # the same global batch on both ranks
+        xs, ys = dp.shard(X), dp.shard(Y)
+        opt = torch.optim.SGD(net.parameters(), lr=0.1)
+        for it in range(2):
+            loss = ((fwd(dp.module, xs) - ys) ** 2).mean()
+            loss.backward()                                # auto all-reduce at the end of backward
+            opt.step()
+            opt.zero_grad(set_to_none=(it == 0))           # the reference Trainer's default drops the flat views once
+        dp.sync_buffers()
+        flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+        results[rank] = (flat.clone(), net[1].running_mean.clone(), float(unused.weight.grad.abs().sum())
+                         if unused.weight.grad is not None else 0.0)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_data_parallel_gloo_world2_matches_single_process():
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_dp_worker, args=(world, port, results), nprocs=world, join=True)
+    p0, rm0, unused0 = results[0]
+    p1, rm1, unused1 = results[1]
+    assert torch.equal(p0, p1), 'replicas diverged'
+    assert torch.equal(rm0, rm1), 'BN buffers must follow rank 0'
+    assert unused0 == 0.0 and unused1 == 0.0
+    # single-process replay: per-rank BN statistics, averaged gradients (DataParallel semantics)
+    torch.manual_seed(100)
+    net = nn.Sequential(nn.Linear(6, 8), nn.BatchNorm1d(8), nn.ReLU(), nn.Linear(8, 3))
+    net.add_module('unused', nn.Linear(4, 4))
+    replicas = [net, None]
+    import copy
+    replicas[1] = copy.deepcopy(net)
+    torch.manual_seed(7)
+    X, Y = torch.randn(8, 6), torch.randn(8, 3)
+    for it in range(2):
+        grads = []
+        for r, m in enumerate(replicas):
+            for p in m.parameters():
+                p.grad = None
+            xs, ys = X[r * 4:(r + 1) * 4], Y[r * 4:(r + 1) * 4]
+            loss = ((m[3](m[2](m[1](m[0](xs)))) - ys) ** 2).mean()
+            loss.backward()
+            grads.append([p.grad if p.grad is not None else torch.zeros_like(p) for p in m.parameters()])
+        for m in replicas:
+            with torch.no_grad():
+                for p, g0, g1 in zip(m.parameters(), grads[0], grads[1]):
+                    p -= 0.1 * (g0 + g1) / 2
+    want = torch.cat([p.detach().reshape(-1) for p in replicas[0].parameters()])
+    assert torch.allclose(p0, want, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rm0, replicas[0][1].running_mean, rtol=1e-5, atol=1e-7)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` prints one JSON line with the agreed keys (tiny run: it times the CPU oracle)."""
+    import json
+    import subprocess
+    env = dict(os.environ, OMP_NUM_THREADS='4')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                          '--warmup', '1'], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'clouds/s' and line['value'] > 0
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['higher_is_better'] is True

@@ -1,0 +1,151 @@
+"""CPU tests of the ORACLE: it must reproduce the committed golden vectors (generated from the unmodified reference code,
+tests/golden/make_golden.py) and, where the reference tree is present, the reference itself bit-for-bit."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close
+
+
+def test_knn_oracle_reproduces_known_answers(golden_dir):
+    from oracle import knn as oknn
+    cases = torch.load(os.path.join(golden_dir, 'knn_kat.pt'))
+    assert 'reference_smoke_collinear_k5' in cases
+    for name, c in cases.items():
+        idx, dist = oknn.knn_indices(c['x'], c['k'], return_dist=True)
+        assert torch.equal(idx, c['idx']), name
+        assert torch.equal(dist, c['dist']), name          # same fmaf chain -> bit-identical distances
+        idx_mt = oknn.knn_indices(c['x'], c['k'], nthreads=4)
+        assert torch.equal(idx_mt, c['idx']), name + ' (threaded)'
+
+
+def test_knn_oracle_collinear_tie_rule():
+    """the reference's own smoke input (nn/net_blocks.py:505-506): equispaced collinear points => exact distance ties;
+    the lower index must come first and the query itself is its own nearest neighbour."""
+    from oracle import knn as oknn
+    x = torch.arange(1, 601, dtype=torch.float32).view(2, -1, 3)
+    idx = oknn.knn_indices(x, 5)
+    assert idx.shape == (2, 100, 5)
+    assert idx[0, 50].tolist() == [50, 49, 51, 48, 52]
+    assert idx[0, 0].tolist() == [0, 1, 2, 3, 4] and idx[1, 99].tolist() == [99, 98, 97, 96, 95]
+
+
+def test_knn_oracle_matches_float64_brute_force():
+    """independent check of the neighbour SETS with float64 distances on inputs without near-ties."""
+    from oracle import knn as oknn
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 120, 6)).astype(np.float32)
+    idx = oknn.knn_indices(x, 7).numpy()
+    d = ((x[:, :, None, :].astype(np.float64) - x[:, None, :, :].astype(np.float64)) ** 2).sum(-1)
+    want = np.argsort(d, axis=-1, kind='stable')[:, :, :7]
+    assert (np.sort(idx, -1) == np.sort(want, -1)).all()
+
+
+def test_knn_oracle_argument_errors():
+    from oracle import knn as oknn
+    with pytest.raises(RuntimeError):
+        oknn.knn_indices(torch.randn(1, 10, 3), 0)
+
+
+def test_sparsemax_oracle_properties():
+    from oracle.thirdparty import Sparsemax
+    z = torch.randn(64, 23, dtype=torch.float64, requires_grad=True)
+    p = Sparsemax(dim=1)(z)
+    assert torch.allclose(p.sum(-1), torch.ones(64, dtype=torch.float64))
+    assert bool((p >= 0).all()) and bool((p == 0).any())
+    # projection property: adding a constant to a row does not change the output
+    assert torch.allclose(Sparsemax(dim=1)(z + 3.0), p)
+    assert torch.autograd.gradcheck(lambda t: Sparsemax(dim=1)(t), (z[:4],), atol=1e-6)
+
+
+def _golden_model(gold):
+    from oracle import model as om
+    dc = dict(om.ATT_DATA_CONFIG)
+    torch.manual_seed(gold['seed_init'])
+    return om.OracleSegmentPattern3D(dc, dict(om.ATT_NN_CONFIG), {})
+
+
+def test_oracle_reproduces_reference_golden_random_init(golden_dir):
+    from oracle import model as om
+    gold = torch.load(os.path.join(golden_dir, 'att_random_init.pt'))
+    model = _golden_model(gold)
+    chk = float(sum(v.double().abs().sum() for v in model.state_dict().values() if v.dtype.is_floating_point))
+    assert abs(chk - gold['state_checksum']) <= 1e-9 * gold['state_checksum']
+    model.train()
+    out = model(gold['x'], lstm_state=(gold['h0'], gold['c0']))
+    for key, want in gold['out_train'].items():
+        assert_close(out[key], want, tol=1e-5, what='oracle train ' + key)
+    loss, parts = om.main_losses(out, gold['gt'])
+    assert abs(float(loss) - float(gold['loss'])) <= 1e-5 * abs(float(gold['loss']))
+    loss.backward()
+    named = dict(model.named_parameters())
+    for name, dig in gold['grads'].items():
+        g = named[name].grad.reshape(-1)
+        assert abs(float(g.double().norm()) - dig['norm']) <= 1e-4 * max(dig['norm'], 1e-12), name
+    assert named['feature_extractor.lin.weight'].grad is None
+    # the vectorised loss and pooling variants used by the CPU baseline agree with the loop forms
+    loss_fast, _ = om.main_losses(out, gold['gt'], fast=True)
+    assert abs(float(loss_fast) - float(loss)) <= 1e-6 * abs(float(loss))
+
+
+def test_oracle_eval_and_knn_golden(golden_dir):
+    from oracle import knn as oknn
+    gold = torch.load(os.path.join(golden_dir, 'att_random_init.pt'))
+    model = _golden_model(gold).eval()
+    with torch.no_grad():
+        out = model(gold['x'], lstm_state=(gold['h0'], gold['c0']))
+        fast = model(gold['x'], lstm_state=(gold['h0'], gold['c0']), fast=True)
+    for key, want in gold['out_eval'].items():
+        assert_close(out[key], want, tol=1e-5, what='oracle eval ' + key)
+        assert_close(fast[key], want, tol=1e-5, what='oracle eval (batched pooling) ' + key)
+    assert torch.equal(oknn.knn_indices(gold['x'], 5), gold['knn_idx_eval'][0])
+
+
+def test_oracle_loads_shipped_checkpoint_if_present(golden_dir):
+    ck = os.path.join(golden_dir, '_ckpt', 'att_state.pt')
+    if not os.path.exists(ck):
+        pytest.skip('extracted checkpoint fixture absent')
+    from oracle import model as om
+    gold = torch.load(os.path.join(golden_dir, 'att_shipped_ckpt.pt'))
+    model = om.OracleSegmentPattern3D(dict(om.ATT_DATA_CONFIG), dict(om.ATT_NN_CONFIG), {})
+    model.load_state_dict(torch.load(ck), strict=True)
+    model.eval()
+    model.save_att_weights = True
+    with torch.no_grad():
+        out = model(gold['x'], lstm_state=(gold['h0'], gold['c0']))
+    for key, want in gold['out_eval'].items():
+        assert_close(out[key], want, tol=1e-5, what='oracle shipped ' + key)
+
+
+def test_oracle_equals_unmodified_reference_when_available():
+    """Runs only where /root/reference exists (the build container): the reference's own nets.py, executed through
+    oracle.ref_stubs, must agree with the oracle restatement bit-for-bit on CPU."""
+    from oracle import ref_stubs
+    if not ref_stubs.reference_available():
+        pytest.skip('reference tree not present on this machine')
+    from oracle import model as om
+    nets, _ = ref_stubs.import_reference()
+    dc, nc, lc = ref_stubs.att_configs()
+    torch.manual_seed(5)
+    ref = nets.GarmentSegmentPattern3D(dict(dc), dict(nc), dict(lc))
+    torch.manual_seed(5)
+    mine = om.OracleSegmentPattern3D(dict(dc), dict(nc), dict(lc))
+    sr, sm = ref.state_dict(), mine.state_dict()
+    assert list(sr.keys()) == list(sm.keys()) and all(torch.equal(sr[k], sm[k]) for k in sr)
+    x = torch.randn(2, 150, 3, generator=torch.Generator().manual_seed(1))
+    gt = om.synthetic_ground_truth(2)
+    ref.loss.with_quality_eval = False
+    for mode in (True, False):
+        ref.train(mode)
+        mine.train(mode)
+        torch.manual_seed(7)
+        o1 = ref(x)
+        torch.manual_seed(7)
+        o2 = mine(x)
+        assert all(torch.equal(o1[k], o2[k]) for k in o1)
+        l1, d1, _ = ref.loss(o1, dict(gt), epoch=0)
+        l2, d2, _ = mine.loss(o2, dict(gt))
+        assert float(l1) == float(l2)
+    mine.load_state_dict(ref_stubs.att_checkpoint_state(), strict=True)

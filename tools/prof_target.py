@@ -1,0 +1,25 @@
+"""Developer tool for ncu captures: runs a few launches of one hot kernel at the C2 shape (B=32, N=2048)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from garment_pattern_estimation_b200 import ops  # noqa: E402
+from garment_pattern_estimation_b200 import net_blocks as nb  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else 'knn'
+B, N, k = 32, 2048, 5
+dev = torch.device('cuda:0')
+torch.manual_seed(0)
+if what == 'knn':
+    x = torch.randn(B * N, 150, device=dev)
+    for _ in range(3):
+        ops.knn_graph(x, B, N, k)
+elif what == 'edgeconv':
+    conv = nb.DynamicEdgeConv(nb.MLP([300, 200, 200, 150]), k=k).to(dev).train()
+    x = torch.randn(B * N, 150, device=dev, requires_grad=True)
+    for _ in range(2):
+        out = conv(x, cloud_shape=(B, N))
+        out.sum().backward()
+torch.cuda.synchronize()
