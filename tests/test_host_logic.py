@@ -230,3 +230,38 @@ def test_bench_reference_arm_contract():
     assert line['impl'] == 'reference' and line['unit'] == 'clouds/s' and line['value'] > 0
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['higher_is_better'] is True
+
+
+def test_blocks_drop_into_unmodified_reference_nets_when_available():
+    """INTEGRATION.md swap A: the reference's own nn/nets.py, with this package installed as `net_blocks`, builds the
+    attention model, loads the shipped checkpoint strict=True and routes forward() into the B200 blocks (which refuse CPU
+    tensors).  Needs /root/reference (build container only); runs in a subprocess to keep sys.modules clean."""
+    import subprocess
+    from oracle import ref_stubs
+    if not ref_stubs.reference_available():
+        pytest.skip('reference tree not present on this machine')
+    code = r'''
+import sys, types, torch
+sys.path.insert(0, %r)
+from oracle import ref_stubs
+ref_stubs.install()                                   # stubs for entmax / data / torch_geometric (unused below)
+import garment_pattern_estimation_b200.net_blocks as b200_blocks
+import garment_pattern_estimation_b200.nets as b200_nets
+sys.modules['net_blocks'] = b200_blocks
+sys.modules['sparsemax'] = types.SimpleNamespace(Sparsemax=b200_nets.Sparsemax)
+import nets                                           # the UNMODIFIED reference module
+assert nets.blocks is b200_blocks
+dc, nc, lc = ref_stubs.att_configs()
+model = nets.GarmentSegmentPattern3D(dc, nc, lc)
+assert type(model.feature_extractor).__module__ == 'garment_pattern_estimation_b200.net_blocks'
+print(model.load_state_dict(ref_stubs.att_checkpoint_state(), strict=True))
+model.eval()
+try:
+    model(torch.randn(2, 32, 3))
+except RuntimeError as e:
+    assert 'CUDA device' in str(e), e
+    print('forward reached the B200 blocks')
+''' % ROOT
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert 'All keys matched' in out.stdout and 'forward reached the B200 blocks' in out.stdout
