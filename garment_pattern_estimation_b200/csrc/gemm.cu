@@ -9,6 +9,7 @@
 // POINT, and no [E, 2C] edge tensor is ever materialised).  Epilogues fuse bias, ReLU, BatchNorm statistics,
 // the max/min aggregation over the k neighbours, and the BN+ReLU backward.
 #include "common.cuh"
+#include "gemm_params.cuh"
 
 namespace nt {
 
@@ -16,36 +17,6 @@ constexpr int G_THREADS = 256;
 constexpr int G_TM = 128;   // rows per CTA tile
 constexpr int G_TN = 64;    // output columns per CTA tile
 constexpr int G_TK = 16;    // inner step
-
-struct EdgeSrc {
-    const float *pq; int ldpq; int qoff; const int32_t *idx; int k; int n_per_cloud;
-};
-
-// value of the EDGE producer at (row r, column c)
-__device__ __forceinline__ void edge_row_ptrs(const EdgeSrc &s, int64_t r, const float *&p, const float *&q) {
-    if (s.idx) {
-        int64_t centre = r / s.k;
-        int64_t base = (centre / s.n_per_cloud) * (int64_t)s.n_per_cloud;
-        int64_t j = base + s.idx[r];
-        p = s.pq + centre * s.ldpq;
-        q = s.pq + j * s.ldpq + s.qoff;
-    } else {
-        p = s.pq + r * s.ldpq;
-        q = nullptr;
-    }
-}
-
-struct NTParams {
-    int64_t rows; int K; int n_out; int rows_per_tile;
-    const float *a; int lda;
-    EdgeSrc e;
-    const float *w; int ldw; const float *bias;
-    float *out; int ldo;
-    double *stats;
-    float *vmax, *vmin; uint8_t *imax, *imin; int k_agg;
-    const float *aux; int ldaux; int aux_edge; EdgeSrc ae;
-    const float *k0, *k1, *mu; double *colsum;
-};
 
 template <int PROD, int EPI>
 __global__ void __launch_bounds__(G_THREADS) gemm_nt_kernel(NTParams p) {
@@ -339,13 +310,16 @@ extern "C" int nt_gemm_nt(const nt_gemm_args *g, void *stream) {
         if (g->idx) NT_REQUIRE(g->k >= 1 && g->n_per_cloud >= 1, "nt_gemm_nt: edge operand needs k and n_per_cloud");
     } else return fail("nt_gemm_nt: unknown producer %s%ld", "", g->producer);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool tc = g->w_split != nullptr;
     switch (g->epilogue) {
         case NT_EPI_BIAS:
             NT_REQUIRE(g->out && g->ldo >= g->n_out, "nt_gemm_nt: bad output");
             NT_REQUIRE(g->producer == NT_PROD_PLAIN, "nt_gemm_nt: NT_EPI_BIAS needs the plain producer");
+            if (tc) return launch_nt_tc(p, g->producer, g->epilogue, g->w_split, st);
             return launch_nt<NT_PROD_PLAIN, NT_EPI_BIAS>(p, st);
         case NT_EPI_RELU_STATS:
             NT_REQUIRE(g->out == nullptr || g->ldo >= g->n_out, "nt_gemm_nt: bad output");
+            if (tc) return launch_nt_tc(p, g->producer, g->epilogue, g->w_split, st);
             return g->producer == NT_PROD_PLAIN ? launch_nt<NT_PROD_PLAIN, NT_EPI_RELU_STATS>(p, st)
                                                 : launch_nt<NT_PROD_EDGE, NT_EPI_RELU_STATS>(p, st);
         case NT_EPI_RELU_MAXMIN:
@@ -353,12 +327,14 @@ extern "C" int nt_gemm_nt(const nt_gemm_args *g, void *stream) {
             NT_REQUIRE(g->rows % g->k == 0, "nt_gemm_nt: rows must be a multiple of k");
             NT_REQUIRE(g->vmax && g->vmin && g->imax && g->imin, "nt_gemm_nt: aggregation outputs missing");
             p.rows_per_tile = (G_TM / g->k) * g->k;
+            if (tc) return launch_nt_tc(p, g->producer, g->epilogue, g->w_split, st);
             return g->producer == NT_PROD_PLAIN ? launch_nt<NT_PROD_PLAIN, NT_EPI_RELU_MAXMIN>(p, st)
                                                 : launch_nt<NT_PROD_EDGE, NT_EPI_RELU_MAXMIN>(p, st);
         case NT_EPI_BNRELU_BWD:
             NT_REQUIRE(g->out && g->ldo >= g->n_out && g->k0 && g->k1 && g->mu, "nt_gemm_nt: bwd operands missing");
             NT_REQUIRE(g->aux_edge ? (g->pq != nullptr) : (g->aux != nullptr), "nt_gemm_nt: aux operand missing");
             NT_REQUIRE(g->producer == NT_PROD_PLAIN, "nt_gemm_nt: NT_EPI_BNRELU_BWD needs the plain producer");
+            if (tc) return launch_nt_tc(p, g->producer, g->epilogue, g->w_split, st);
             return launch_nt<NT_PROD_PLAIN, NT_EPI_BNRELU_BWD>(p, st);
         default: return fail("nt_gemm_nt: unknown epilogue %s%ld", "", g->epilogue);
     }

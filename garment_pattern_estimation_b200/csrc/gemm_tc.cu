@@ -1,0 +1,363 @@
+// Tensor-core engine for the fused row GEMMs (sm_100a): tcgen05.mma with the accumulator in TMEM.
+//
+//   out = epilogue( producer(A) . W^T )       A: [rows, K] produced on the fly, W: [n_out, K]  (same contract as gemm.cu)
+//
+// Precision: the reference computes these Linear layers in fp32 (cuBLAS SGEMM, TF32 off).  To stay inside the 1e-3
+// activation tolerance AND keep the second EdgeConv layer's kNN graph stable, every fp32 operand is split into two bf16
+// terms (x = hi + lo, |x - hi - lo| <= 2^-17 |x|) and each K-step issues three MMAs  hi.hi + hi.lo + lo.hi  into the
+// same fp32 TMEM accumulator (error-compensated "bf16x3", ~1e-5 relative).
+//
+// CTA = one tile of up to 128 rows x N_tile (<= 256) columns; 2 CTAs per SM (85 KB smem, 256 TMEM columns each) so one
+// CTA's epilogue overlaps the other's main loop.
+//   warps 0-3 : A-operand producers during the main loop (thread = row: gather / ReLU / split / st.shared in the UMMA
+//               no-swizzle K-major core-matrix layout), then the epilogue (tcgen05.ld, thread = row).
+//   warp 4    : barrier init + single-thread MMA issue (tcgen05.mma / tcgen05.commit).
+//   warp 5    : TMEM alloc / dealloc.
+//   W tiles   : pre-split bf16 in the same core-matrix layout (nt_gemm_prepare_weights), one cp.async.bulk per stage.
+#include "gemm_params.cuh"
+#include "tc_common.cuh"
+
+namespace nt {
+using namespace tc;
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_M = 128;          // UMMA M
+constexpr int TC_KB = 32;          // K elements per stage (4 chunks of 8 bf16 = 16 B)
+constexpr int TC_STAGES = 2;
+constexpr int TC_A_BYTES = 4 * TC_M * 16;          // one of hi / lo: [4 chunks][128 rows][16 B]
+
+struct TCGeom {
+    int n_tile;          // columns per CTA (multiple of 16, <= 256)
+    int n_tiles;         // column tiles
+    int num_kb;          // K blocks
+    int tmem_cols;       // pow2 >= 32 allocation
+};
+
+__host__ __device__ inline TCGeom tc_geometry(int n_out, int K) {
+    TCGeom g;
+    g.n_tiles = (n_out + 255) / 256;
+    int per = (n_out + g.n_tiles - 1) / g.n_tiles;
+    g.n_tile = ((per + 15) / 16) * 16;
+    g.num_kb = (K + TC_KB - 1) / TC_KB;
+    int c = 32;
+    while (c < g.n_tile) c <<= 1;
+    g.tmem_cols = c;
+    return g;
+}
+__host__ __device__ inline size_t tc_stage_bytes(int n_tile) { return 2 * TC_A_BYTES + (size_t)n_tile * 128; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// weight pre-split: W [n_out, K] fp32 -> per (column tile, K block): [hi|lo][chunk 0..3][n 0..n_tile)[8 bf16]
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void tc_prepare_weights_kernel(const float *__restrict__ w, int ldw, int n_out, int K, TCGeom g,
+                                          uint4 *__restrict__ out) {
+    // one thread per 16-byte chunk of the hi plane (and the matching lo chunk)
+    const int64_t per_block = (int64_t)4 * g.n_tile;                     // chunks per plane per (tile, kb)
+    const int64_t total = (int64_t)g.n_tiles * g.num_kb * per_block;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t blk = i / per_block;
+    const int within = (int)(i - blk * per_block);
+    const int j = within / g.n_tile, n = within - j * g.n_tile;
+    const int tile = (int)(blk / g.num_kb), kb = (int)(blk - (int64_t)tile * g.num_kb);
+    const int col = tile * g.n_tile + n;
+    const int k0 = kb * TC_KB + j * 8;
+    __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        float v = (col < n_out && k0 + e < K) ? w[(int64_t)col * ldw + k0 + e] : 0.f;
+        split_bf16(v, hi[e], lo[e]);
+    }
+    uint4 *base = out + blk * (2 * per_block);
+    base[within] = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
+    base[per_block + within] = make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load8(const float *src, int k, int K, bool vec, float (&v)[8]) {
+    if (vec && k + 7 < K) {
+        float4 a = __ldg(reinterpret_cast<const float4 *>(src + k));
+        float4 b = __ldg(reinterpret_cast<const float4 *>(src + k + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (k + e < K) ? __ldg(src + k + e) : 0.f;
+    }
+}
+
+template <int PROD, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, const uint8_t *__restrict__ w_split, TCGeom g) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const size_t stage_bytes = tc_stage_bytes(g.n_tile);
+    uint8_t *stage_base[TC_STAGES] = {smem, smem + stage_bytes};
+    uint8_t *tail = smem + TC_STAGES * stage_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(tail);              // [2]
+    uint64_t *empty = full + TC_STAGES;                               // [2]
+    uint64_t *tmem_full = empty + TC_STAGES;                          // [1]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    float *red = reinterpret_cast<float *>(tail + 64);                // [2][256]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * p.rows_per_tile;
+    const int rows_here = (int)min((int64_t)p.rows_per_tile, p.rows - row0);
+    const int tile_n = blockIdx.y;
+    const int col0 = tile_n * g.n_tile;
+
+    if (tid < 128) {
+        for (int i = tid; i < 512; i += 128) red[i] = 0.f;
+    }
+    if (warp == 4 && lane == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 128 + 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)g.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // =========================== A-operand producers (thread = row) ===========================
+        const int r = tid;
+        const bool r_ok = r < rows_here;
+        const float *ap = nullptr, *aq = nullptr;
+        bool vec = false;
+        if (r_ok) {
+            if (PROD == NT_PROD_PLAIN) {
+                ap = p.a + (row0 + r) * (int64_t)p.lda;
+                vec = ((p.lda & 3) == 0) && aligned16(p.a);
+            } else {
+                edge_row_ptrs(p.e, row0 + r, ap, aq);
+                vec = ((p.e.ldpq & 3) == 0) && ((p.e.qoff & 3) == 0) && aligned16(p.e.pq);
+            }
+        }
+        const uint8_t *wsrc = w_split + (size_t)tile_n * g.num_kb * ((size_t)g.n_tile * 128);
+        for (int kb = 0; kb < g.num_kb; ++kb) {
+            const int s = kb & 1, use = kb >> 1;
+            mbar_wait(&empty[s], (use & 1) ^ 1);
+            uint8_t *a_hi = stage_base[s], *a_lo = a_hi + TC_A_BYTES, *b_all = a_lo + TC_A_BYTES;
+            if (tid == 0) {
+                const uint32_t bytes = (uint32_t)g.n_tile * 128u;
+                mbar_arrive_expect_tx(&full[s], bytes);
+                bulk_g2s(b_all, wsrc + (size_t)kb * bytes, bytes, &full[s]);
+            }
+            float v[4][8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = kb * TC_KB + j * 8;
+                if (!r_ok || k >= p.K) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
+                } else if (PROD == NT_PROD_PLAIN) {
+                    load8(ap, k, p.K, vec, v[j]);
+                } else {
+                    load8(ap, k, p.K, vec, v[j]);
+                    if (aq) {
+                        float q[8];
+                        load8(aq, k, p.K, vec, q);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[j][e] += q[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[j][e] = fmaxf(v[j][e], 0.f);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split_bf16(v[j][e], hi[e], lo[e]);
+                *reinterpret_cast<uint4 *>(a_hi + j * (TC_M * 16) + r * 16) =
+                    make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
+                *reinterpret_cast<uint4 *>(a_lo + j * (TC_M * 16) + r * 16) =
+                    make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
+            }
+            fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&full[s]);
+        }
+
+        // =========================== epilogue (thread = row, TMEM lane = row) ===========================
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        float *vt = reinterpret_cast<float *>(smem);                    // [128][33] staging (aliases stage 0)
+        const bool valid = r_ok;
+        const int64_t grow = row0 + r;
+        const float *aux_p = nullptr, *aux_q = nullptr;
+        if (EPI == NT_EPI_BNRELU_BWD && valid) {
+            if (p.aux_edge) edge_row_ptrs(p.ae, grow, aux_p, aux_q);
+            else aux_p = p.aux + grow * (int64_t)p.ldaux;
+        }
+        const int n_chunks = (g.n_tile + 31) / 32;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const int c0 = ch * 32;
+            float acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+            float s1[32], s2[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int c = col0 + c0 + i;
+                const bool c_ok = (c0 + i) < g.n_tile && c < p.n_out;
+                float o = 0.f, q1 = 0.f, q2 = 0.f;
+                if (EPI == NT_EPI_BIAS) {
+                    o = acc[i] + ((c_ok && p.bias) ? __ldg(p.bias + c) : 0.f);
+                } else if (EPI == NT_EPI_RELU_STATS || EPI == NT_EPI_RELU_MAXMIN) {
+                    o = fmaxf(acc[i] + ((c_ok && p.bias) ? __ldg(p.bias + c) : 0.f), 0.f);
+                    if (valid && c_ok) { q1 = o; q2 = o * o; }
+                } else {   // NT_EPI_BNRELU_BWD
+                    if (valid && c_ok) {
+                        float a = aux_p[c];
+                        if (p.aux_edge) {
+                            if (aux_q) a += __ldg(aux_q + c);
+                            a = fmaxf(a, 0.f);
+                        }
+                        o = (a > 0.f) ? (acc[i] - __ldg(p.k0 + c) - (a - __ldg(p.mu + c)) * __ldg(p.k1 + c)) : 0.f;
+                        q1 = o;
+                    }
+                }
+                acc[i] = o; s1[i] = q1; s2[i] = q2;
+            }
+            // ---- stores: each thread owns 32 consecutive columns of its row
+            if (valid && p.out) {
+                float *dst = p.out + grow * (int64_t)p.ldo + col0 + c0;
+                const bool full_chunk = (c0 + 32 <= g.n_tile) && (col0 + c0 + 32 <= p.n_out);
+                if (full_chunk && ((p.ldo & 3) == 0) && (((col0 + c0) & 3) == 0) && aligned16(p.out)) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4 *>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if ((c0 + i) < g.n_tile && col0 + c0 + i < p.n_out) dst[i] = acc[i];
+                }
+            }
+            // ---- per-column statistics of this warp's 32 rows -> smem accumulators
+            if (EPI != NT_EPI_BIAS) {
+                const bool want = (EPI == NT_EPI_BNRELU_BWD) ? (p.colsum != nullptr) : (p.stats != nullptr);
+                if (want) {
+                    float t1 = warp_column_sums(s1, lane);
+                    atomicAdd(&red[c0 + lane], t1);
+                    if (EPI != NT_EPI_BNRELU_BWD) {
+                        float t2 = warp_column_sums(s2, lane);
+                        atomicAdd(&red[256 + c0 + lane], t2);
+                    }
+                }
+            }
+            // ---- max / min over the k edge rows of every centre point
+            if (EPI == NT_EPI_RELU_MAXMIN) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) vt[r * 33 + i] = acc[i];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int kk = p.k_agg;
+                const int nodes_here = rows_here / kk;
+                const int64_t node0 = row0 / kk;
+                for (int t = tid; t < nodes_here * 32; t += 128) {
+                    const int nd = t >> 5, cc = t & 31;
+                    const int c = col0 + c0 + cc;
+                    if ((c0 + cc) >= g.n_tile || c >= p.n_out) continue;
+                    float mx = vt[(nd * kk) * 33 + cc], mn = mx;
+                    int ix = 0, in = 0;
+                    for (int sl = 1; sl < kk; ++sl) {
+                        float x = vt[(nd * kk + sl) * 33 + cc];
+                        if (x > mx) { mx = x; ix = sl; }
+                        if (x < mn) { mn = x; in = sl; }
+                    }
+                    const int64_t o = (node0 + nd) * (int64_t)p.n_out + c;
+                    p.vmax[o] = mx; p.vmin[o] = mn; p.imax[o] = (uint8_t)ix; p.imin[o] = (uint8_t)in;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+        if (EPI != NT_EPI_BIAS) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int c = tid; c < g.n_tile; c += 128) {
+                const int col = col0 + c;
+                if (col >= p.n_out) continue;
+                if (EPI == NT_EPI_BNRELU_BWD) {
+                    if (p.colsum) atomicAdd(p.colsum + col, (double)red[c]);
+                } else if (p.stats) {
+                    atomicAdd(p.stats + col, (double)red[c]);
+                    atomicAdd(p.stats + p.n_out + col, (double)red[256 + c]);
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // =========================== MMA issuer (one thread) ===========================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(TC_M, (uint32_t)g.n_tile, 0, 0);
+            const uint32_t lbo_a = TC_M * 16, lbo_b = (uint32_t)g.n_tile * 16, sbo = 128;
+            for (int kb = 0; kb < g.num_kb; ++kb) {
+                const int s = kb & 1, use = kb >> 1;
+                mbar_wait(&full[s], use & 1);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(stage_base[s]), a_lo = a_hi + TC_A_BYTES;
+                const uint32_t b_hi = a_lo + TC_A_BYTES, b_lo = b_hi + 4 * lbo_b;
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const uint64_t dah = make_smem_desc(a_hi + kk * 2 * lbo_a, lbo_a, sbo);
+                    const uint64_t dal = make_smem_desc(a_lo + kk * 2 * lbo_a, lbo_a, sbo);
+                    const uint64_t dbh = make_smem_desc(b_hi + kk * 2 * lbo_b, lbo_b, sbo);
+                    const uint64_t dbl = make_smem_desc(b_lo + kk * 2 * lbo_b, lbo_b, sbo);
+                    umma_bf16(tmem_base, dah, dbh, idesc, (kb | kk) ? 1u : 0u);
+                    umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+                    umma_bf16(tmem_base, dal, dbh, idesc, 1u);
+                }
+                umma_commit(&empty[s]);            // stage reusable once these MMAs have read it
+            }
+            umma_commit(tmem_full);                // accumulator complete -> epilogue
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+}
+
+template <int PROD, int EPI>
+static int launch_tc(const NTParams &p, const void *w_split, cudaStream_t st) {
+    const TCGeom g = tc_geometry(p.n_out, p.K);
+    const size_t smem = TC_STAGES * tc_stage_bytes(g.n_tile) + 64 + 2 * 256 * sizeof(float);
+    static bool configured = false;     // per instantiation; the attribute is idempotent, races are harmless
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel<PROD, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(TC_STAGES * tc_stage_bytes(256) + 64 + 2 * 256 * sizeof(float)));
+        if (e != cudaSuccess) return fail("nt_gemm_nt(tc): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid((unsigned)((p.rows + p.rows_per_tile - 1) / p.rows_per_tile), g.n_tiles);
+    gemm_nt_tc_kernel<PROD, EPI><<<grid, TC_THREADS, smem, st>>>(p, reinterpret_cast<const uint8_t *>(w_split), g);
+    return check_launch("nt_gemm_nt(tc)");
+}
+
+int launch_nt_tc(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st) {
+    const bool edge = producer == NT_PROD_EDGE;
+    switch (epilogue) {
+        case NT_EPI_BIAS: return launch_tc<NT_PROD_PLAIN, NT_EPI_BIAS>(p, w_split, st);
+        case NT_EPI_RELU_STATS:
+            return edge ? launch_tc<NT_PROD_EDGE, NT_EPI_RELU_STATS>(p, w_split, st)
+                        : launch_tc<NT_PROD_PLAIN, NT_EPI_RELU_STATS>(p, w_split, st);
+        case NT_EPI_RELU_MAXMIN:
+            return edge ? launch_tc<NT_PROD_EDGE, NT_EPI_RELU_MAXMIN>(p, w_split, st)
+                        : launch_tc<NT_PROD_PLAIN, NT_EPI_RELU_MAXMIN>(p, w_split, st);
+        default: return launch_tc<NT_PROD_PLAIN, NT_EPI_BNRELU_BWD>(p, w_split, st);
+    }
+}
+
+}  // namespace nt
+
+using namespace nt;
+
+extern "C" int64_t nt_gemm_weights_bytes(int n_out, int K) {
+    if (n_out < 1 || K < 1) return 0;
+    const TCGeom g = tc_geometry(n_out, K);
+    return (int64_t)g.n_tiles * g.num_kb * g.n_tile * 128;
+}
+
+extern "C" int nt_gemm_prepare_weights(const float *w, int ldw, int n_out, int K, void *w_split, void *stream) {
+    NT_REQUIRE(w && w_split && n_out >= 1 && K >= 1 && ldw >= K, "nt_gemm_prepare_weights: bad arguments");
+    NT_REQUIRE((reinterpret_cast<uintptr_t>(w_split) & 15u) == 0, "nt_gemm_prepare_weights: w_split must be 16-byte aligned");
+    const TCGeom g = tc_geometry(n_out, K);
+    const int64_t total = (int64_t)g.n_tiles * g.num_kb * 4 * g.n_tile;
+    tc_prepare_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        w, ldw, n_out, K, g, reinterpret_cast<uint4 *>(w_split));
+    return check_launch("nt_gemm_prepare_weights");
+}

@@ -78,9 +78,23 @@ class EdgeSrc:
         self.qoff = H if idx is not None else 0
 
 
+GEMM_ENGINE = 'tc'    # 'tc' = tcgen05 tensor-core engine (product path); 'simt' = fp32 CUDA-core engine (validation only)
+
+
+def prepare_weights(w, ldw, n_out, K):
+    """bf16 hi/lo split of W in UMMA core-matrix layout for the tensor-core engine (a few hundred KB)."""
+    lib = _lib.load()
+    nbytes = int(lib.nt_gemm_weights_bytes(n_out, K))
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    _call('nt_gemm_prepare_weights', lib.nt_gemm_prepare_weights, _p(w), ldw, n_out, K, _p(buf), _stream())
+    return buf
+
+
 def gemm_nt(rows, K, n_out, w, ldw, epilogue, a=None, lda=0, edge=None, bias=None, out=None, ldo=0, stats=None,
             agg=None, k_agg=0, aux=None, ldaux=0, aux_edge=False, k0=None, k1=None, mu=None, colsum=None):
+    w_split = prepare_weights(w, ldw, n_out, K) if GEMM_ENGINE == 'tc' else None
     g = GemmArgs()
+    g.w_split = _p(w_split)
     g.rows, g.K, g.n_out = int(rows), int(K), int(n_out)
     g.producer = NT_PROD_PLAIN if edge is None or a is not None else NT_PROD_EDGE
     g.epilogue = epilogue

@@ -70,8 +70,9 @@ typedef struct nt_gemm_args {
     /* NT_PROD_EDGE (also used by the aux operand of NT_EPI_BNRELU_BWD when aux_edge != 0) */
     const float *pq; int ldpq; int qoff;
     const int32_t *idx; int k; int n_per_cloud;
-    /* weights */
-    const float *w; int ldw; const float *bias;
+    /* weights: w is always required; w_split (from nt_gemm_prepare_weights) selects the tcgen05 tensor-core engine,
+     * w_split == NULL runs the fp32 CUDA-core engine (kept for validation, not used by the shipped host code) */
+    const float *w; int ldw; const float *bias; const void *w_split;
     /* outputs */
     float *out; int ldo;
     double *stats;                                   /* [2*n_out] */
@@ -83,6 +84,11 @@ typedef struct nt_gemm_args {
 } nt_gemm_args;
 
 int nt_gemm_nt(const nt_gemm_args *args, void *stream);
+
+/* Tensor-core operand preparation: splits W [n_out, K] (fp32) into bf16 hi/lo planes laid out as UMMA core matrices per
+ * (column tile, 32-wide K block).  w_split must hold nt_gemm_weights_bytes(n_out, K) bytes, 16-byte aligned. */
+int64_t nt_gemm_weights_bytes(int n_out, int K);
+int nt_gemm_prepare_weights(const float *w, int ldw, int n_out, int K, void *w_split, void *stream);
 
 /* Weight-gradient GEMM: out[m, n] += sum_r A[r, m] * Bop[r, n]  (out must be zeroed by the caller; fp32 atomics).
  * Bop is a plain matrix (b, ldb) or, when pq != NULL, the EDGE producer above.  Backward of nn.Linear. */

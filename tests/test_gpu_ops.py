@@ -243,3 +243,26 @@ def test_cpu_tensors_are_refused(ops):
         ops.knn_graph(torch.randn(10, 3), 1, 10, 3)
     with pytest.raises(RuntimeError):
         ops.sparsemax(torch.randn(4, 5))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) engine vs the fp32 CUDA-core engine on identical operands
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('rows,K,n_out', [(1000, 200, 200), (257, 150, 400), (5000, 153, 23), (129, 3, 400),
+                                          (640, 300, 200), (128, 32, 16), (77, 250, 7)])
+def test_tc_engine_linear_matches_cuda_core_engine(ops, cuda_device, rows, K, n_out):
+    dev = cuda_device
+    g = torch.Generator(device='cpu').manual_seed(rows + K)
+    x = torch.randn(rows, K, generator=g).to(dev)
+    w = (torch.randn(n_out, K, generator=g) / K ** 0.5).to(dev)
+    b = torch.randn(n_out, generator=g).to(dev)
+    want = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    outs = {}
+    for engine in ('tc', 'simt'):
+        ops.GEMM_ENGINE = engine
+        try:
+            outs[engine] = ops.linear(x, w, b)
+        finally:
+            ops.GEMM_ENGINE = 'tc'
+    assert rel_err(outs['simt'], want) < 1e-5
+    assert rel_err(outs['tc'], want) < 5e-5, 'bf16x3 error-compensated product should be ~1e-5'
