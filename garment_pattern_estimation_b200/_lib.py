@@ -12,6 +12,7 @@ c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int6
 
 NT_PROD_PLAIN, NT_PROD_EDGE = 0, 1
 NT_EPI_BIAS, NT_EPI_RELU_STATS, NT_EPI_RELU_MAXMIN, NT_EPI_BNRELU_BWD = 0, 1, 2, 3
+NT_PREC_BF16X3, NT_PREC_TF32X3 = 0, 1
 
 
 class GemmArgs(ctypes.Structure):
@@ -21,7 +22,7 @@ class GemmArgs(ctypes.Structure):
         ('a', c_void_p), ('lda', c_int),
         ('pq', c_void_p), ('ldpq', c_int), ('qoff', c_int),
         ('idx', c_void_p), ('k', c_int), ('n_per_cloud', c_int),
-        ('w', c_void_p), ('ldw', c_int), ('bias', c_void_p), ('w_split', c_void_p),
+        ('w', c_void_p), ('ldw', c_int), ('bias', c_void_p), ('w_split', c_void_p), ('precision', c_int),
         ('out', c_void_p), ('ldo', c_int),
         ('stats', c_void_p),
         ('vmax', c_void_p), ('vmin', c_void_p), ('imax', c_void_p), ('imin', c_void_p),
@@ -38,8 +39,8 @@ _SIGNATURES = {
     'nt_launch_count': (c_int64, []),
     'nt_knn': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'nt_gemm_nt': (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
-    'nt_gemm_weights_bytes': (c_int64, [c_int, c_int]),
-    'nt_gemm_prepare_weights': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'nt_gemm_weights_bytes': (c_int64, [c_int, c_int, c_int]),
+    'nt_gemm_prepare_weights': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'nt_gemm_tn': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64,
                            c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     'nt_gemm_tn_centered': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64,

@@ -315,11 +315,11 @@ extern "C" int nt_gemm_nt(const nt_gemm_args *g, void *stream) {
         case NT_EPI_BIAS:
             NT_REQUIRE(g->out && g->ldo >= g->n_out, "nt_gemm_nt: bad output");
             NT_REQUIRE(g->producer == NT_PROD_PLAIN, "nt_gemm_nt: NT_EPI_BIAS needs the plain producer");
-            if (tc) return launch_nt_tc(p, g->producer, g->epilogue, g->w_split, st);
+            if (tc) return launch_nt_tc(p, g->producer, g->epilogue, g->precision, g->w_split, st);
             return launch_nt<NT_PROD_PLAIN, NT_EPI_BIAS>(p, st);
         case NT_EPI_RELU_STATS:
             NT_REQUIRE(g->out == nullptr || g->ldo >= g->n_out, "nt_gemm_nt: bad output");
-            if (tc) return launch_nt_tc(p, g->producer, g->epilogue, g->w_split, st);
+            if (tc) return launch_nt_tc(p, g->producer, g->epilogue, g->precision, g->w_split, st);
             return g->producer == NT_PROD_PLAIN ? launch_nt<NT_PROD_PLAIN, NT_EPI_RELU_STATS>(p, st)
                                                 : launch_nt<NT_PROD_EDGE, NT_EPI_RELU_STATS>(p, st);
         case NT_EPI_RELU_MAXMIN:
@@ -327,14 +327,14 @@ extern "C" int nt_gemm_nt(const nt_gemm_args *g, void *stream) {
             NT_REQUIRE(g->rows % g->k == 0, "nt_gemm_nt: rows must be a multiple of k");
             NT_REQUIRE(g->vmax && g->vmin && g->imax && g->imin, "nt_gemm_nt: aggregation outputs missing");
             p.rows_per_tile = (G_TM / g->k) * g->k;
-            if (tc) return launch_nt_tc(p, g->producer, g->epilogue, g->w_split, st);
+            if (tc) return launch_nt_tc(p, g->producer, g->epilogue, g->precision, g->w_split, st);
             return g->producer == NT_PROD_PLAIN ? launch_nt<NT_PROD_PLAIN, NT_EPI_RELU_MAXMIN>(p, st)
                                                 : launch_nt<NT_PROD_EDGE, NT_EPI_RELU_MAXMIN>(p, st);
         case NT_EPI_BNRELU_BWD:
             NT_REQUIRE(g->out && g->ldo >= g->n_out && g->k0 && g->k1 && g->mu, "nt_gemm_nt: bwd operands missing");
             NT_REQUIRE(g->aux_edge ? (g->pq != nullptr) : (g->aux != nullptr), "nt_gemm_nt: aux operand missing");
             NT_REQUIRE(g->producer == NT_PROD_PLAIN, "nt_gemm_nt: NT_EPI_BNRELU_BWD needs the plain producer");
-            if (tc) return launch_nt_tc(p, g->producer, g->epilogue, g->w_split, st);
+            if (tc) return launch_nt_tc(p, g->producer, g->epilogue, g->precision, g->w_split, st);
             return launch_nt<NT_PROD_PLAIN, NT_EPI_BNRELU_BWD>(p, st);
         default: return fail("nt_gemm_nt: unknown epilogue %s%ld", "", g->epilogue);
     }

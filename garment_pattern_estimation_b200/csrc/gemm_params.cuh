@@ -36,6 +36,6 @@ struct NTParams {
 
 
 // tensor-core engine entry (gemm_tc.cu); w_split = weights pre-split by nt_gemm_prepare_weights
-int launch_nt_tc(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st);
+int launch_nt_tc(const NTParams &p, int producer, int epilogue, int precision, const void *w_split, cudaStream_t st);
 
 }  // namespace nt

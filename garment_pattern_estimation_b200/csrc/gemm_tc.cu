@@ -22,29 +22,48 @@ using namespace tc;
 
 constexpr int TC_THREADS = 192;
 constexpr int TC_M = 128;          // UMMA M
-constexpr int TC_KB = 32;          // K elements per stage (4 chunks of 8 bf16 = 16 B)
+// a stage holds 4 chunks of 16 B along K: 32 bf16 elements (NT_PREC_BF16X3) or 16 tf32 elements (NT_PREC_TF32X3)
 constexpr int TC_STAGES = 2;
 constexpr int TC_A_BYTES = 4 * TC_M * 16;          // one of hi / lo: [4 chunks][128 rows][16 B]
 
 struct TCGeom {
+    int epc;             // elements per 16-byte chunk: 8 (bf16) or 4 (tf32)
     int n_tile;          // columns per CTA (multiple of 16, <= 256)
     int n_tiles;         // column tiles
     int num_kb;          // K blocks
     int tmem_cols;       // pow2 >= 32 allocation
 };
 
-__host__ __device__ inline TCGeom tc_geometry(int n_out, int K) {
+__host__ __device__ inline TCGeom tc_geometry(int n_out, int K, int precision) {
     TCGeom g;
+    g.epc = precision == NT_PREC_TF32X3 ? 4 : 8;
     g.n_tiles = (n_out + 255) / 256;
     int per = (n_out + g.n_tiles - 1) / g.n_tiles;
     g.n_tile = ((per + 15) / 16) * 16;
-    g.num_kb = (K + TC_KB - 1) / TC_KB;
+    g.num_kb = (K + 4 * g.epc - 1) / (4 * g.epc);
     int c = 32;
     while (c < g.n_tile) c <<= 1;
     g.tmem_cols = c;
     return g;
 }
 __host__ __device__ inline size_t tc_stage_bytes(int n_tile) { return 2 * TC_A_BYTES + (size_t)n_tile * 128; }
+
+// one 16-byte chunk (8 bf16 or 4 tf32 values) of the hi and lo planes
+__device__ __forceinline__ void pack_chunk(const float (&v)[8], bool tf32, uint4 &h, uint4 &l) {
+    if (tf32) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_tf32(v[e], hi[e], lo[e]);
+        h = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        l = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    } else {
+        __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_bf16(v[e], hi[e], lo[e]);
+        h = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
+        l = make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
+    }
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // weight pre-split: W [n_out, K] fp32 -> per (column tile, K block): [hi|lo][chunk 0..3][n 0..n_tile)[8 bf16]
@@ -61,31 +80,34 @@ __global__ void tc_prepare_weights_kernel(const float *__restrict__ w, int ldw, 
     const int j = within / g.n_tile, n = within - j * g.n_tile;
     const int tile = (int)(blk / g.num_kb), kb = (int)(blk - (int64_t)tile * g.num_kb);
     const int col = tile * g.n_tile + n;
-    const int k0 = kb * TC_KB + j * 8;
-    __nv_bfloat16 hi[8], lo[8];
+    const int k0 = (kb * 4 + j) * g.epc;
+    float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        float v = (col < n_out && k0 + e < K) ? w[(int64_t)col * ldw + k0 + e] : 0.f;
-        split_bf16(v, hi[e], lo[e]);
-    }
+    for (int e = 0; e < 8; ++e) v[e] = (e < g.epc && col < n_out && k0 + e < K) ? w[(int64_t)col * ldw + k0 + e] : 0.f;
     uint4 *base = out + blk * (2 * per_block);
-    base[within] = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
-    base[per_block + within] = make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
+    uint4 h, l;
+    pack_chunk(v, g.epc == 4, h, l);
+    base[within] = h;
+    base[per_block + within] = l;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load8(const float *src, int k, int K, bool vec, float (&v)[8]) {
-    if (vec && k + 7 < K) {
+template <int EPC>
+__device__ __forceinline__ void load_chunk(const float *src, int k, int K, bool vec, float (&v)[8]) {
+    if (vec && k + EPC - 1 < K) {
         float4 a = __ldg(reinterpret_cast<const float4 *>(src + k));
-        float4 b = __ldg(reinterpret_cast<const float4 *>(src + k + 4));
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        if (EPC == 8) {
+            float4 b = __ldg(reinterpret_cast<const float4 *>(src + k + 4));
+            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
     } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (k + e < K) ? __ldg(src + k + e) : 0.f;
+        for (int e = 0; e < EPC; ++e) v[e] = (k + e < K) ? __ldg(src + k + e) : 0.f;
     }
 }
 
-template <int PROD, int EPI>
+template <int PROD, int EPI, bool TF32>
 __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, const uint8_t *__restrict__ w_split, TCGeom g) {
     extern __shared__ __align__(128) uint8_t smem[];
     const size_t stage_bytes = tc_stage_bytes(g.n_tile);
@@ -97,6 +119,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
     float *red = reinterpret_cast<float *>(tail + 64);                // [2][256]
 
+    constexpr int EPC = TF32 ? 4 : 8;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t row0 = (int64_t)blockIdx.x * p.rows_per_tile;
     const int rows_here = (int)min((int64_t)p.rows_per_tile, p.rows - row0);
@@ -145,33 +168,29 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
             float v[4][8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int k = kb * TC_KB + j * 8;
-                if (!r_ok || k >= p.K) {
+                const int k = (kb * 4 + j) * EPC;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
-                } else if (PROD == NT_PROD_PLAIN) {
-                    load8(ap, k, p.K, vec, v[j]);
-                } else {
-                    load8(ap, k, p.K, vec, v[j]);
-                    if (aq) {
-                        float q[8];
-                        load8(aq, k, p.K, vec, q);
+                for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
+                if (r_ok && k < p.K) {
+                    load_chunk<EPC>(ap, k, p.K, vec, v[j]);
+                    if (PROD == NT_PROD_EDGE) {
+                        if (aq) {
+                            float q[8];
+                            load_chunk<EPC>(aq, k, p.K, vec, q);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[j][e] += q[e];
+                            for (int e = 0; e < EPC; ++e) v[j][e] += q[e];
+                        }
+#pragma unroll
+                        for (int e = 0; e < EPC; ++e) v[j][e] = fmaxf(v[j][e], 0.f);
                     }
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[j][e] = fmaxf(v[j][e], 0.f);
                 }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) split_bf16(v[j][e], hi[e], lo[e]);
-                *reinterpret_cast<uint4 *>(a_hi + j * (TC_M * 16) + r * 16) =
-                    make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
-                *reinterpret_cast<uint4 *>(a_lo + j * (TC_M * 16) + r * 16) =
-                    make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
+                uint4 h, l;
+                pack_chunk(v[j], TF32, h, l);
+                *reinterpret_cast<uint4 *>(a_hi + j * (TC_M * 16) + r * 16) = h;
+                *reinterpret_cast<uint4 *>(a_lo + j * (TC_M * 16) + r * 16) = l;
             }
             fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&full[s]);
@@ -284,7 +303,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
     } else if (warp == 4) {
         // =========================== MMA issuer (one thread) ===========================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(TC_M, (uint32_t)g.n_tile, 0, 0);
+            const uint32_t idesc = TF32 ? make_idesc_tf32(TC_M, (uint32_t)g.n_tile, 0, 0)
+                                        : make_idesc_bf16(TC_M, (uint32_t)g.n_tile, 0, 0);
             const uint32_t lbo_a = TC_M * 16, lbo_b = (uint32_t)g.n_tile * 16, sbo = 128;
             for (int kb = 0; kb < g.num_kb; ++kb) {
                 const int s = kb & 1, use = kb >> 1;
@@ -298,9 +318,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
                     const uint64_t dal = make_smem_desc(a_lo + kk * 2 * lbo_a, lbo_a, sbo);
                     const uint64_t dbh = make_smem_desc(b_hi + kk * 2 * lbo_b, lbo_b, sbo);
                     const uint64_t dbl = make_smem_desc(b_lo + kk * 2 * lbo_b, lbo_b, sbo);
-                    umma_bf16(tmem_base, dah, dbh, idesc, (kb | kk) ? 1u : 0u);
-                    umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-                    umma_bf16(tmem_base, dal, dbh, idesc, 1u);
+                    if (TF32) {
+                        umma_tf32(tmem_base, dah, dbh, idesc, (kb | kk) ? 1u : 0u);
+                        umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                        umma_tf32(tmem_base, dal, dbh, idesc, 1u);
+                    } else {
+                        umma_bf16(tmem_base, dah, dbh, idesc, (kb | kk) ? 1u : 0u);
+                        umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+                        umma_bf16(tmem_base, dal, dbh, idesc, 1u);
+                    }
                 }
                 umma_commit(&empty[s]);            // stage reusable once these MMAs have read it
             }
@@ -312,50 +338,58 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
     if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
 }
 
-template <int PROD, int EPI>
+template <int PROD, int EPI, bool TF32>
 static int launch_tc(const NTParams &p, const void *w_split, cudaStream_t st) {
-    const TCGeom g = tc_geometry(p.n_out, p.K);
+    const TCGeom g = tc_geometry(p.n_out, p.K, TF32 ? NT_PREC_TF32X3 : NT_PREC_BF16X3);
     const size_t smem = TC_STAGES * tc_stage_bytes(g.n_tile) + 64 + 2 * 256 * sizeof(float);
     static bool configured = false;     // per instantiation; the attribute is idempotent, races are harmless
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel<PROD, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel<PROD, EPI, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(TC_STAGES * tc_stage_bytes(256) + 64 + 2 * 256 * sizeof(float)));
         if (e != cudaSuccess) return fail("nt_gemm_nt(tc): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     dim3 grid((unsigned)((p.rows + p.rows_per_tile - 1) / p.rows_per_tile), g.n_tiles);
-    gemm_nt_tc_kernel<PROD, EPI><<<grid, TC_THREADS, smem, st>>>(p, reinterpret_cast<const uint8_t *>(w_split), g);
+    gemm_nt_tc_kernel<PROD, EPI, TF32><<<grid, TC_THREADS, smem, st>>>(p, reinterpret_cast<const uint8_t *>(w_split), g);
     return check_launch("nt_gemm_nt(tc)");
 }
 
-int launch_nt_tc(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st) {
+template <bool TF32>
+static int dispatch_tc(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st) {
     const bool edge = producer == NT_PROD_EDGE;
     switch (epilogue) {
-        case NT_EPI_BIAS: return launch_tc<NT_PROD_PLAIN, NT_EPI_BIAS>(p, w_split, st);
+        case NT_EPI_BIAS: return launch_tc<NT_PROD_PLAIN, NT_EPI_BIAS, TF32>(p, w_split, st);
         case NT_EPI_RELU_STATS:
-            return edge ? launch_tc<NT_PROD_EDGE, NT_EPI_RELU_STATS>(p, w_split, st)
-                        : launch_tc<NT_PROD_PLAIN, NT_EPI_RELU_STATS>(p, w_split, st);
+            return edge ? launch_tc<NT_PROD_EDGE, NT_EPI_RELU_STATS, TF32>(p, w_split, st)
+                        : launch_tc<NT_PROD_PLAIN, NT_EPI_RELU_STATS, TF32>(p, w_split, st);
         case NT_EPI_RELU_MAXMIN:
-            return edge ? launch_tc<NT_PROD_EDGE, NT_EPI_RELU_MAXMIN>(p, w_split, st)
-                        : launch_tc<NT_PROD_PLAIN, NT_EPI_RELU_MAXMIN>(p, w_split, st);
-        default: return launch_tc<NT_PROD_PLAIN, NT_EPI_BNRELU_BWD>(p, w_split, st);
+            return edge ? launch_tc<NT_PROD_EDGE, NT_EPI_RELU_MAXMIN, TF32>(p, w_split, st)
+                        : launch_tc<NT_PROD_PLAIN, NT_EPI_RELU_MAXMIN, TF32>(p, w_split, st);
+        default: return launch_tc<NT_PROD_PLAIN, NT_EPI_BNRELU_BWD, TF32>(p, w_split, st);
     }
+}
+
+int launch_nt_tc(const NTParams &p, int producer, int epilogue, int precision, const void *w_split, cudaStream_t st) {
+    return precision == NT_PREC_TF32X3 ? dispatch_tc<true>(p, producer, epilogue, w_split, st)
+                                       : dispatch_tc<false>(p, producer, epilogue, w_split, st);
 }
 
 }  // namespace nt
 
 using namespace nt;
 
-extern "C" int64_t nt_gemm_weights_bytes(int n_out, int K) {
+extern "C" int64_t nt_gemm_weights_bytes(int n_out, int K, int precision) {
     if (n_out < 1 || K < 1) return 0;
-    const TCGeom g = tc_geometry(n_out, K);
+    const TCGeom g = tc_geometry(n_out, K, precision);
     return (int64_t)g.n_tiles * g.num_kb * g.n_tile * 128;
 }
 
-extern "C" int nt_gemm_prepare_weights(const float *w, int ldw, int n_out, int K, void *w_split, void *stream) {
+extern "C" int nt_gemm_prepare_weights(const float *w, int ldw, int n_out, int K, int precision, void *w_split,
+                                       void *stream) {
     NT_REQUIRE(w && w_split && n_out >= 1 && K >= 1 && ldw >= K, "nt_gemm_prepare_weights: bad arguments");
+    NT_REQUIRE(precision == NT_PREC_BF16X3 || precision == NT_PREC_TF32X3, "nt_gemm_prepare_weights: bad precision");
     NT_REQUIRE((reinterpret_cast<uintptr_t>(w_split) & 15u) == 0, "nt_gemm_prepare_weights: w_split must be 16-byte aligned");
-    const TCGeom g = tc_geometry(n_out, K);
+    const TCGeom g = tc_geometry(n_out, K, precision);
     const int64_t total = (int64_t)g.n_tiles * g.num_kb * 4 * g.n_tile;
     tc_prepare_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         w, ldw, n_out, K, g, reinterpret_cast<uint4 *>(w_split));

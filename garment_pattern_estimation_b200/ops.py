@@ -81,20 +81,22 @@ class EdgeSrc:
 GEMM_ENGINE = 'tc'    # 'tc' = tcgen05 tensor-core engine (product path); 'simt' = fp32 CUDA-core engine (validation only)
 
 
-def prepare_weights(w, ldw, n_out, K):
-    """bf16 hi/lo split of W in UMMA core-matrix layout for the tensor-core engine (a few hundred KB)."""
+def prepare_weights(w, ldw, n_out, K, precision):
+    """hi/lo split of W in UMMA core-matrix layout for the tensor-core engine (a few hundred KB)."""
     lib = _lib.load()
-    nbytes = int(lib.nt_gemm_weights_bytes(n_out, K))
+    nbytes = int(lib.nt_gemm_weights_bytes(n_out, K, precision))
     buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-    _call('nt_gemm_prepare_weights', lib.nt_gemm_prepare_weights, _p(w), ldw, n_out, K, _p(buf), _stream())
+    _call('nt_gemm_prepare_weights', lib.nt_gemm_prepare_weights, _p(w), ldw, n_out, K, precision, _p(buf), _stream())
     return buf
 
 
 def gemm_nt(rows, K, n_out, w, ldw, epilogue, a=None, lda=0, edge=None, bias=None, out=None, ldo=0, stats=None,
-            agg=None, k_agg=0, aux=None, ldaux=0, aux_edge=False, k0=None, k1=None, mu=None, colsum=None):
-    w_split = prepare_weights(w, ldw, n_out, K) if GEMM_ENGINE == 'tc' else None
+            agg=None, k_agg=0, aux=None, ldaux=0, aux_edge=False, k0=None, k1=None, mu=None, colsum=None, grad_gemm=False):
+    # forward-path GEMMs run TF32x3 (fp32-like), gradient GEMMs BF16x3 (see include/nt_b200.h)
+    precision = _lib.NT_PREC_BF16X3 if epilogue == NT_EPI_BNRELU_BWD or grad_gemm else _lib.NT_PREC_TF32X3
+    w_split = prepare_weights(w, ldw, n_out, K, precision) if GEMM_ENGINE == 'tc' else None
     g = GemmArgs()
-    g.w_split = _p(w_split)
+    g.w_split, g.precision = _p(w_split), precision
     g.rows, g.K, g.n_out = int(rows), int(K), int(n_out)
     g.producer = NT_PROD_PLAIN if edge is None or a is not None else NT_PROD_EDGE
     g.epilogue = epilogue
@@ -367,7 +369,7 @@ class _FusedMLPFunction(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 gx = torch.empty(M, C, **f32)
                 WcT = Wc.t().contiguous()              # [C, 2*H1]
-                gemm_nt(M, 2 * H1, C, WcT, 2 * H1, NT_EPI_BIAS, a=dpq, lda=2 * H1, out=gx, ldo=C)
+                gemm_nt(M, 2 * H1, C, WcT, 2 * H1, NT_EPI_BIAS, a=dpq, lda=2 * H1, out=gx, ldo=C, grad_gemm=True)
         else:
             dW0 = torch.zeros(H1, C, **f32)
             gemm_tn(dz, H1, H1, M, dW0, b=x, ldb=m['ldx'], n=C)
@@ -375,7 +377,7 @@ class _FusedMLPFunction(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 gx = torch.empty(M, C, **f32)
                 WT = Wc.t().contiguous()               # [C, H1]
-                gemm_nt(M, H1, C, WT, H1, NT_EPI_BIAS, a=dz, lda=H1, out=gx, ldo=C)
+                gemm_nt(M, H1, C, WT, H1, NT_EPI_BIAS, a=dz, lda=H1, out=gx, ldo=C, grad_gemm=True)
 
         g_tail = None
         if tail and ctx.needs_input_grad[2]:
@@ -481,7 +483,7 @@ class _LinearFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = torch.empty(rows, K, dtype=torch.float32, device=x.device)
             wt = w.t().contiguous()
-            gemm_nt(rows, n_out, K, wt, n_out, NT_EPI_BIAS, a=g, lda=ldg, out=gx, ldo=K)
+            gemm_nt(rows, n_out, K, wt, n_out, NT_EPI_BIAS, a=g, lda=ldg, out=gx, ldo=K, grad_gemm=True)
         if ctx.needs_input_grad[1]:
             gw = torch.zeros(n_out, K, dtype=torch.float32, device=x.device)
             gemm_tn(g, ldg, n_out, rows, gw, b=x, ldb=x.stride(0) if rows > 1 else K, n=K)

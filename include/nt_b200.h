@@ -58,6 +58,10 @@ int nt_knn(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, vo
  */
 enum { NT_PROD_PLAIN = 0, NT_PROD_EDGE = 1 };
 enum { NT_EPI_BIAS = 0, NT_EPI_RELU_STATS = 1, NT_EPI_RELU_MAXMIN = 2, NT_EPI_BNRELU_BWD = 3 };
+/* tensor-core operand precision: both split every fp32 operand into hi + lo and issue hi.hi + hi.lo + lo.hi into an fp32
+ * TMEM accumulator.  TF32X3 (~1e-6 relative, fp32-SGEMM-like; forward path, keeps the dynamic kNN graph and the ReLU
+ * masks aligned with the fp32 reference) costs twice the tensor-pipe time of BF16X3 (~1e-5; gradient GEMMs). */
+enum { NT_PREC_BF16X3 = 0, NT_PREC_TF32X3 = 1 };
 
 typedef struct nt_gemm_args {
     /* problem */
@@ -72,7 +76,7 @@ typedef struct nt_gemm_args {
     const int32_t *idx; int k; int n_per_cloud;
     /* weights: w is always required; w_split (from nt_gemm_prepare_weights) selects the tcgen05 tensor-core engine,
      * w_split == NULL runs the fp32 CUDA-core engine (kept for validation, not used by the shipped host code) */
-    const float *w; int ldw; const float *bias; const void *w_split;
+    const float *w; int ldw; const float *bias; const void *w_split; int precision;
     /* outputs */
     float *out; int ldo;
     double *stats;                                   /* [2*n_out] */
@@ -86,9 +90,9 @@ typedef struct nt_gemm_args {
 int nt_gemm_nt(const nt_gemm_args *args, void *stream);
 
 /* Tensor-core operand preparation: splits W [n_out, K] (fp32) into bf16 hi/lo planes laid out as UMMA core matrices per
- * (column tile, 32-wide K block).  w_split must hold nt_gemm_weights_bytes(n_out, K) bytes, 16-byte aligned. */
-int64_t nt_gemm_weights_bytes(int n_out, int K);
-int nt_gemm_prepare_weights(const float *w, int ldw, int n_out, int K, void *w_split, void *stream);
+ * (column tile, K block of 32 bf16 / 16 tf32 elements).  w_split must hold nt_gemm_weights_bytes(n_out, K) bytes, 16-byte aligned. */
+int64_t nt_gemm_weights_bytes(int n_out, int K, int precision);
+int nt_gemm_prepare_weights(const float *w, int ldw, int n_out, int K, int precision, void *w_split, void *stream);
 
 /* Weight-gradient GEMM: out[m, n] += sum_r A[r, m] * Bop[r, n]  (out must be zeroed by the caller; fp32 atomics).
  * Bop is a plain matrix (b, ldb) or, when pq != NULL, the EDGE producer above.  Backward of nn.Linear. */
