@@ -156,16 +156,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
             }
         }
         const uint8_t *wsrc = w_split + (size_t)tile_n * g.num_kb * ((size_t)g.n_tile * 128);
-        for (int kb = 0; kb < g.num_kb; ++kb) {
-            const int s = kb & 1, use = kb >> 1;
-            mbar_wait(&empty[s], (use & 1) ^ 1);
-            uint8_t *a_hi = stage_base[s], *a_lo = a_hi + TC_A_BYTES, *b_all = a_lo + TC_A_BYTES;
-            if (tid == 0) {
-                const uint32_t bytes = (uint32_t)g.n_tile * 128u;
-                mbar_arrive_expect_tx(&full[s], bytes);
-                bulk_g2s(b_all, wsrc + (size_t)kb * bytes, bytes, &full[s]);
-            }
-            float v[4][8];
+        // register double-buffering: the global loads of K block kb+1 are issued right after block kb has been handed
+        // to the tensor core, so their latency overlaps the wait for the stage to drain
+        float v[4][8];
+        auto fetch = [&](int kb) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int k = (kb * 4 + j) * EPC;
@@ -185,6 +179,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
                     }
                 }
             }
+        };
+        fetch(0);
+        for (int kb = 0; kb < g.num_kb; ++kb) {
+            const int s = kb & 1, use = kb >> 1;
+            mbar_wait(&empty[s], (use & 1) ^ 1);
+            uint8_t *a_hi = stage_base[s], *a_lo = a_hi + TC_A_BYTES, *b_all = a_lo + TC_A_BYTES;
+            if (tid == 0) {
+                const uint32_t bytes = (uint32_t)g.n_tile * 128u;
+                mbar_arrive_expect_tx(&full[s], bytes);
+                bulk_g2s(b_all, wsrc + (size_t)kb * bytes, bytes, &full[s]);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint4 h, l;
@@ -194,14 +199,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
             }
             fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&full[s]);
+            if (kb + 1 < g.num_kb) fetch(kb + 1);
         }
 
         // =========================== epilogue (thread = row, TMEM lane = row) ===========================
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         float *vt = reinterpret_cast<float *>(smem);                    // [128][33] staging (aliases stage 0)
+        float *tw = reinterpret_cast<float *>(stage_base[1]) + warp * (32 * 33);   // per-warp 32x33 transposition tile
         const bool valid = r_ok;
         const int64_t grow = row0 + r;
+        const int64_t wrow0 = row0 + warp * 32;                          // first row of this warp
+        const int wrows = max(0, min(32, rows_here - warp * 32));        // valid rows of this warp
         const float *aux_p = nullptr, *aux_q = nullptr;
         if (EPI == NT_EPI_BNRELU_BWD && valid) {
             if (p.aux_edge) edge_row_ptrs(p.ae, grow, aux_p, aux_q);
@@ -212,6 +221,29 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
             const int c0 = ch * 32;
             float acc[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+            const int cl = col0 + c0 + lane;                             // the column this lane owns in row-wise passes
+            const bool cl_ok = (c0 + lane) < g.n_tile && cl < p.n_out;
+            float auxv[32];
+            if (EPI == NT_EPI_BNRELU_BWD) {
+                // coalesced read of the aux rows (lane = column), transposed through smem so each thread gets its row
+                for (int rr = 0; rr < wrows; ++rr) {
+                    const float *pp = reinterpret_cast<const float *>(__shfl_sync(0xffffffffu, (unsigned long long)aux_p, rr));
+                    const float *qq = reinterpret_cast<const float *>(__shfl_sync(0xffffffffu, (unsigned long long)aux_q, rr));
+                    float a = 0.f;
+                    if (cl_ok) {
+                        a = pp[cl];
+                        if (p.aux_edge) {
+                            if (qq) a += __ldg(qq + cl);
+                            a = fmaxf(a, 0.f);
+                        }
+                    }
+                    tw[rr * 33 + lane] = a;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) auxv[i] = tw[lane * 33 + i];
+                __syncwarp();
+            }
             float s1[32], s2[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -225,30 +257,23 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
                     if (valid && c_ok) { q1 = o; q2 = o * o; }
                 } else {   // NT_EPI_BNRELU_BWD
                     if (valid && c_ok) {
-                        float a = aux_p[c];
-                        if (p.aux_edge) {
-                            if (aux_q) a += __ldg(aux_q + c);
-                            a = fmaxf(a, 0.f);
-                        }
+                        const float a = auxv[i];
                         o = (a > 0.f) ? (acc[i] - __ldg(p.k0 + c) - (a - __ldg(p.mu + c)) * __ldg(p.k1 + c)) : 0.f;
                         q1 = o;
                     }
                 }
                 acc[i] = o; s1[i] = q1; s2[i] = q2;
             }
-            // ---- stores: each thread owns 32 consecutive columns of its row
-            if (valid && p.out) {
-                float *dst = p.out + grow * (int64_t)p.ldo + col0 + c0;
-                const bool full_chunk = (c0 + 32 <= g.n_tile) && (col0 + c0 + 32 <= p.n_out);
-                if (full_chunk && ((p.ldo & 3) == 0) && (((col0 + c0) & 3) == 0) && aligned16(p.out)) {
+            // ---- stores: transpose through smem so every warp store writes 128 contiguous bytes of one row
+            if (p.out) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<float4 *>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if ((c0 + i) < g.n_tile && col0 + c0 + i < p.n_out) dst[i] = acc[i];
+                for (int i = 0; i < 32; ++i) tw[lane * 33 + i] = acc[i];
+                __syncwarp();
+                if (cl_ok) {
+                    float *dst = p.out + wrow0 * (int64_t)p.ldo + cl;
+                    for (int rr = 0; rr < wrows; ++rr) dst[(int64_t)rr * p.ldo] = tw[rr * 33 + lane];
                 }
+                __syncwarp();
             }
             // ---- per-column statistics of this warp's 32 rows -> smem accumulators
             if (EPI != NT_EPI_BIAS) {

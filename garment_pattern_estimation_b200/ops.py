@@ -57,6 +57,16 @@ def _require_cuda(*tensors):
                                '(the B200 hot path has no CPU fallback)')
 
 
+def _pad4(c):
+    return (c + 3) // 4 * 4
+
+
+def _rowbuf(rows, cols, device):
+    """[rows, cols] fp32 workspace whose row stride is padded to a multiple of 4 floats (16-byte aligned rows for the
+    vectorised producers / epilogues).  Only the first `cols` columns are ever read or written."""
+    return torch.empty(rows, _pad4(cols), dtype=torch.float32, device=device)
+
+
 def _rows2d(t):
     """(tensor, row stride) for a 2-D fp32 tensor whose last dim is dense."""
     assert t.dim() == 2 and t.dtype == torch.float32
@@ -200,15 +210,15 @@ class _FusedMLPFunction(torch.autograd.Function):
                 raise RuntimeError('edge MLP expects first Linear with {} inputs, got {}'.format(2 * C, W0.shape[1]))
             Wc = torch.cat([W0[:, :C] - W0[:, C:], W0[:, C:]], dim=0).contiguous()      # [2*H1, C]
             bc = torch.cat([bs[0], torch.zeros_like(bs[0])])
-            pq = torch.empty(M, 2 * H1, **f32)
-            gemm_nt(M, C, 2 * H1, Wc, C, NT_EPI_BIAS, a=x, lda=ldx, bias=bc, out=pq, ldo=2 * H1)
+            pq = _rowbuf(M, 2 * H1, dev)
+            gemm_nt(M, C, 2 * H1, Wc, C, NT_EPI_BIAS, a=x, lda=ldx, bias=bc, out=pq, ldo=pq.stride(0))
             R = M * k
             src = EdgeSrc(pq, H1, idx, k, N)
         else:
             k, N = 1, 1
             Wc = Ws[0].contiguous()
-            pq = torch.empty(M, H1, **f32)
-            gemm_nt(M, C, H1, Wc, C, NT_EPI_BIAS, a=x, lda=ldx, bias=bs[0].contiguous(), out=pq, ldo=H1)
+            pq = _rowbuf(M, H1, dev)
+            gemm_nt(M, C, H1, Wc, C, NT_EPI_BIAS, a=x, lda=ldx, bias=bs[0].contiguous(), out=pq, ldo=pq.stride(0))
             R = M
             src = EdgeSrc(pq, H1)
 
@@ -245,27 +255,28 @@ class _FusedMLPFunction(torch.autograd.Function):
         for l in range(1, L - 1):
             Hn = widths[l]
             stats = torch.zeros(2 * Hn, dtype=torch.float64, device=dev) if training else None
-            out = torch.empty(R, Hn, **f32)
+            out = _rowbuf(R, Hn, dev)
             if l == 1:
-                gemm_nt(R, widths[0], Hn, w_f, widths[0], NT_EPI_RELU_STATS, edge=src, bias=b_f, out=out, ldo=Hn,
-                        stats=stats)
+                gemm_nt(R, widths[0], Hn, w_f, widths[0], NT_EPI_RELU_STATS, edge=src, bias=b_f, out=out,
+                        ldo=out.stride(0), stats=stats)
             else:
-                gemm_nt(R, widths[l - 1], Hn, w_f, widths[l - 1], NT_EPI_RELU_STATS, a=acts[l], lda=widths[l - 1],
-                        bias=b_f, out=out, ldo=Hn, stats=stats)
+                gemm_nt(R, widths[l - 1], Hn, w_f, widths[l - 1], NT_EPI_RELU_STATS, a=acts[l], lda=acts[l].stride(0),
+                        bias=b_f, out=out, ldo=out.stride(0), stats=stats)
             acts[l + 1] = out
             bn_vec[l], w_f, w_fts[l + 1], b_f = fold(l, stats, l + 1)
 
         # ---- last layer
         HL, Kin = widths[L - 1], widths[L - 2]
         stats = torch.zeros(2 * HL, dtype=torch.float64, device=dev) if training else None
-        last_in = dict(edge=src) if L == 2 else dict(a=acts[L - 1], lda=Kin)
+        last_in = dict(edge=src) if L == 2 else dict(a=acts[L - 1], lda=acts[L - 1].stride(0))
         need_bwd = training and any(ctx.needs_input_grad)
         if mode == 'edge':
             tail = 0 if tail_src is None else tail_src.shape[1]
-            a_last = torch.empty(R, HL, **f32) if need_bwd else None
+            a_last = _rowbuf(R, HL, dev) if need_bwd else None
+            ld_last = a_last.stride(0) if need_bwd else 0
             agg = (torch.empty(M, HL, **f32), torch.empty(M, HL, **f32),
                    torch.empty(M, HL, dtype=torch.uint8, device=dev), torch.empty(M, HL, dtype=torch.uint8, device=dev))
-            gemm_nt(R, Kin, HL, w_f, Kin, NT_EPI_RELU_MAXMIN, bias=b_f, out=a_last, ldo=HL, stats=stats, agg=agg,
+            gemm_nt(R, Kin, HL, w_f, Kin, NT_EPI_RELU_MAXMIN, bias=b_f, out=a_last, ldo=ld_last, stats=stats, agg=agg,
                     k_agg=k, **last_in)
             bn_vec[L - 1], _, _, _ = fold(L - 1, stats, None)
             out = torch.empty(M, HL + tail, **f32)
@@ -278,11 +289,12 @@ class _FusedMLPFunction(torch.autograd.Function):
                                             _p(bn_vec[L - 1][3]), M, HL, _p(out), HL + tail, _p(sel), _p(vsel),
                                             _p(ts), tld, tail, _stream())
         else:
-            a_last = torch.empty(R, HL, **f32)
-            gemm_nt(R, Kin, HL, w_f, Kin, NT_EPI_RELU_STATS, bias=b_f, out=a_last, ldo=HL, stats=stats, **last_in)
+            a_last = _rowbuf(R, HL, dev)
+            gemm_nt(R, Kin, HL, w_f, Kin, NT_EPI_RELU_STATS, bias=b_f, out=a_last, ldo=a_last.stride(0), stats=stats,
+                    **last_in)
             bn_vec[L - 1], _, _, _ = fold(L - 1, stats, None)
             out = torch.empty(M, HL, **f32)
-            _call('nt_bn_apply', _lib.load().nt_bn_apply, _p(a_last), HL, _p(bn_vec[L - 1][2]), _p(bn_vec[L - 1][3]), R, HL, _p(out), HL,
+            _call('nt_bn_apply', _lib.load().nt_bn_apply, _p(a_last), a_last.stride(0), _p(bn_vec[L - 1][2]), _p(bn_vec[L - 1][3]), R, HL, _p(out), HL,
                                        _stream())
             sel = vsel = None
             tail = 0
@@ -321,13 +333,13 @@ class _FusedMLPFunction(torch.autograd.Function):
         mean, rstd, s, t = bn_vec[L - 1]
         sums = torch.zeros(2 * HL, **f64)
         v_ref = vsel if mode == 'edge' else acts[L]
-        _call('nt_bn_bwd_reduce', _lib.load().nt_bn_bwd_reduce, _p(gout), ldg, _p(v_ref), HL, _p(mean), _p(rstd), M, HL, _p(sums), _stream())
+        _call('nt_bn_bwd_reduce', _lib.load().nt_bn_bwd_reduce, _p(gout), ldg, _p(v_ref), v_ref.stride(0), _p(mean), _p(rstd), M, HL, _p(sums), _stream())
         grads_beta[L - 1] = sums[:HL].float()
         grads_g[L - 1] = sums[HL:].float()
-        dz = torch.empty(R, HL, **f32)
+        dz = _rowbuf(R, HL, dev)
         csum = torch.zeros(HL, **f64)
-        _call('nt_bn_relu_bwd_last', _lib.load().nt_bn_relu_bwd_last, _p(acts[L]), HL, _p(gout), ldg, _p(sel), k, _p(s), _p(mean), _p(rstd),
-                                           _p(sums), R, R, HL, _p(dz), HL, _p(csum), _stream())
+        _call('nt_bn_relu_bwd_last', _lib.load().nt_bn_relu_bwd_last, _p(acts[L]), acts[L].stride(0), _p(gout), ldg, _p(sel), k, _p(s), _p(mean), _p(rstd),
+                                           _p(sums), R, R, HL, _p(dz), dz.stride(0), _p(csum), _stream())
 
         # ---- walk down the Linear layers L-1 .. 1
         for l in range(L - 1, 0, -1):
@@ -335,9 +347,9 @@ class _FusedMLPFunction(torch.autograd.Function):
             pmean, prstd, ps, pt = bn_vec[l - 1]
             raw = torch.zeros(Hout, Hin, **f64)            # dz^T . (a_l - mean_l), accumulated in double
             if l == 1:
-                gemm_tn(dz, Hout, Hout, R, raw, n=Hin, edge=src, mu=pmean)
+                gemm_tn(dz, dz.stride(0), Hout, R, raw, n=Hin, edge=src, mu=pmean)
             else:
-                gemm_tn(dz, Hout, Hout, R, raw, b=acts[l], ldb=Hin, n=Hin, mu=pmean)
+                gemm_tn(dz, dz.stride(0), Hout, R, raw, b=acts[l], ldb=acts[l].stride(0), n=Hin, mu=pmean)
             dW = torch.empty(Hout, Hin, **f32)
             db = torch.empty(Hout, **f32)
             vecs = torch.empty(4, Hin, **f32)          # dgamma, dbeta, k0, k1
@@ -348,13 +360,13 @@ class _FusedMLPFunction(torch.autograd.Function):
             grads_g[l - 1], grads_beta[l - 1] = vecs[0], vecs[1]
             csum_prev = torch.zeros(Hin, **f64)
             if l == 1:
-                dz_prev = torch.empty(R, Hin, **f32)
-                gemm_nt(R, Hout, Hin, w_fts[l], Hout, NT_EPI_BNRELU_BWD, a=dz, lda=Hout, edge=src, out=dz_prev,
-                        ldo=Hin, aux_edge=True, k0=vecs[2], k1=vecs[3], mu=pmean, colsum=csum_prev)
+                dz_prev = _rowbuf(R, Hin, dev)
+                gemm_nt(R, Hout, Hin, w_fts[l], Hout, NT_EPI_BNRELU_BWD, a=dz, lda=dz.stride(0), edge=src, out=dz_prev,
+                        ldo=dz_prev.stride(0), aux_edge=True, k0=vecs[2], k1=vecs[3], mu=pmean, colsum=csum_prev)
             else:
-                dz_prev = torch.empty(R, Hin, **f32)   # saved activations stay intact (retain_graph-safe)
-                gemm_nt(R, Hout, Hin, w_fts[l], Hout, NT_EPI_BNRELU_BWD, a=dz, lda=Hout, out=dz_prev, ldo=Hin,
-                        aux=acts[l], ldaux=Hin, k0=vecs[2], k1=vecs[3], mu=pmean, colsum=csum_prev)
+                dz_prev = _rowbuf(R, Hin, dev)         # saved activations stay intact (retain_graph-safe)
+                gemm_nt(R, Hout, Hin, w_fts[l], Hout, NT_EPI_BNRELU_BWD, a=dz, lda=dz.stride(0), out=dz_prev,
+                        ldo=dz_prev.stride(0), aux=acts[l], ldaux=acts[l].stride(0), k0=vecs[2], k1=vecs[3], mu=pmean, colsum=csum_prev)
             dz, csum = dz_prev, csum_prev
 
         # ---- first Linear (per point)
@@ -362,7 +374,7 @@ class _FusedMLPFunction(torch.autograd.Function):
         gx = None
         if mode == 'edge':
             dpq = torch.zeros(M, 2 * H1, **f32)
-            _call('nt_edge_scatter', _lib.load().nt_edge_scatter, _p(dz), H1, _p(idx), k, N, M, H1, _p(dpq), 2 * H1, _stream())
+            _call('nt_edge_scatter', _lib.load().nt_edge_scatter, _p(dz), dz.stride(0), _p(idx), k, N, M, H1, _p(dpq), 2 * H1, _stream())
             dWc = torch.zeros(2 * H1, C, **f32)
             gemm_tn(dpq, 2 * H1, 2 * H1, M, dWc, b=x, ldb=m['ldx'], n=C)
             grads_W[0] = torch.cat([dWc[:H1], dWc[H1:] - dWc[:H1]], dim=1)
@@ -372,12 +384,12 @@ class _FusedMLPFunction(torch.autograd.Function):
                 gemm_nt(M, 2 * H1, C, WcT, 2 * H1, NT_EPI_BIAS, a=dpq, lda=2 * H1, out=gx, ldo=C, grad_gemm=True)
         else:
             dW0 = torch.zeros(H1, C, **f32)
-            gemm_tn(dz, H1, H1, M, dW0, b=x, ldb=m['ldx'], n=C)
+            gemm_tn(dz, dz.stride(0), H1, M, dW0, b=x, ldb=m['ldx'], n=C)
             grads_W[0] = dW0
             if ctx.needs_input_grad[0]:
                 gx = torch.empty(M, C, **f32)
                 WT = Wc.t().contiguous()               # [C, H1]
-                gemm_nt(M, H1, C, WT, H1, NT_EPI_BIAS, a=dz, lda=H1, out=gx, ldo=C, grad_gemm=True)
+                gemm_nt(M, H1, C, WT, H1, NT_EPI_BIAS, a=dz, lda=dz.stride(0), out=gx, ldo=C, grad_gemm=True)
 
         g_tail = None
         if tail and ctx.needs_input_grad[2]:
