@@ -41,11 +41,12 @@ _SIGNATURES = {
     'nt_gemm_nt': (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
     'nt_gemm_weights_bytes': (c_int64, [c_int, c_int, c_int]),
     'nt_gemm_prepare_weights': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'nt_gemm_tn_workspace_bytes': (c_int64, []),
     'nt_gemm_tn': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64,
-                           c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+                           c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'nt_gemm_tn_centered': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64,
                                     c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
-                                    c_void_p]),
+                                    c_void_p, c_void_p]),
     'nt_bn_fold': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -342,7 +342,7 @@ extern "C" int nt_gemm_nt(const nt_gemm_args *g, void *stream) {
 
 static int gemm_tn_impl(const float *a, int lda, int m, const float *b, int ldb, int n, int64_t rows,
                         const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
-                        const float *mu, void *out, int out_double, int ldo, void *stream) {
+                        const float *mu, void *out, int out_double, int ldo, void *workspace, void *stream) {
     using namespace nt;
     NT_REQUIRE(a && out && m >= 1 && n >= 1 && lda >= m && ldo >= n && rows >= 0, "nt_gemm_tn: bad arguments");
     NT_REQUIRE(pq ? (ldpq >= n) : (b != nullptr && ldb >= n), "nt_gemm_tn: bad B operand");
@@ -351,6 +351,9 @@ static int gemm_tn_impl(const float *a, int lda, int m, const float *b, int ldb,
     p.a = a; p.lda = lda; p.m = m; p.b = b; p.ldb = ldb; p.n = n; p.rows = rows;
     p.e = EdgeSrc{pq, ldpq, qoff, idx, k > 0 ? k : 1, n_per_cloud > 0 ? n_per_cloud : 1};
     p.b_edge = pq != nullptr; p.out = out; p.ldo = ldo; p.mu = mu;
+    if (workspace)      // tensor-core engine (the shipped host code always passes a workspace)
+        return gemm_tn_tc(a, lda, m, b, ldb, n, rows, p.e, p.b_edge, mu, out, out_double, ldo,
+                          reinterpret_cast<float *>(workspace), reinterpret_cast<cudaStream_t>(stream));
     const int tiles = ((m + T_TM - 1) / T_TM) * ((n + T_TN - 1) / T_TN);
     int64_t splits = (4 * 148 + tiles - 1) / tiles;                       // ~4 CTAs per SM in flight
     if (out_double) {                                                     // short fp32 partials for the statistics
@@ -372,13 +375,14 @@ static int gemm_tn_impl(const float *a, int lda, int m, const float *b, int ldb,
 
 extern "C" int nt_gemm_tn(const float *a, int lda, int m, const float *b, int ldb, int n, int64_t rows,
                           const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
-                          float *out, int ldo, void *stream) {
-    return gemm_tn_impl(a, lda, m, b, ldb, n, rows, pq, ldpq, qoff, idx, k, n_per_cloud, nullptr, out, 0, ldo, stream);
+                          float *out, int ldo, void *workspace, void *stream) {
+    return gemm_tn_impl(a, lda, m, b, ldb, n, rows, pq, ldpq, qoff, idx, k, n_per_cloud, nullptr, out, 0, ldo, workspace,
+                        stream);
 }
 
 extern "C" int nt_gemm_tn_centered(const float *a, int lda, int m, const float *b, int ldb, int n, int64_t rows,
                                    const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
-                                   const float *mu, double *out, int ldo, void *stream) {
+                                   const float *mu, double *out, int ldo, void *workspace, void *stream) {
     NT_REQUIRE(mu != nullptr, "nt_gemm_tn_centered: mu missing");
-    return gemm_tn_impl(a, lda, m, b, ldb, n, rows, pq, ldpq, qoff, idx, k, n_per_cloud, mu, out, 1, ldo, stream);
+    return gemm_tn_impl(a, lda, m, b, ldb, n, rows, pq, ldpq, qoff, idx, k, n_per_cloud, mu, out, 1, ldo, workspace, stream);
 }

@@ -38,4 +38,8 @@ struct NTParams {
 // tensor-core engine entry (gemm_tc.cu); w_split = weights pre-split by nt_gemm_prepare_weights
 int launch_nt_tc(const NTParams &p, int producer, int epilogue, int precision, const void *w_split, cudaStream_t st);
 
+// tensor-core weight-gradient engine (gemm_tn_tc.cu)
+int gemm_tn_tc(const float *a, int lda, int m, const float *b, int ldb, int n, int64_t rows, const EdgeSrc &e, int b_edge,
+               const float *mu, void *out, int out_double, int ldo, float *workspace, cudaStream_t st);
+
 }  // namespace nt

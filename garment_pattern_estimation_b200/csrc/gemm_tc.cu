@@ -211,10 +211,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
         const int64_t grow = row0 + r;
         const int64_t wrow0 = row0 + warp * 32;                          // first row of this warp
         const int wrows = max(0, min(32, rows_here - warp * 32));        // valid rows of this warp
-        const float *aux_p = nullptr, *aux_q = nullptr;
-        if (EPI == NT_EPI_BNRELU_BWD && valid) {
-            if (p.aux_edge) edge_row_ptrs(p.ae, grow, aux_p, aux_q);
-            else aux_p = p.aux + grow * (int64_t)p.ldaux;
+        // aux row pointers of all 128 rows, shared through smem (stage 0 is free; the aggregation tile is not used here)
+        const float **rowp = reinterpret_cast<const float **>(smem);
+        const float **rowq = rowp + 128;
+        if (EPI == NT_EPI_BNRELU_BWD) {
+            const float *aux_p = nullptr, *aux_q = nullptr;
+            if (valid) {
+                if (p.aux_edge) edge_row_ptrs(p.ae, grow, aux_p, aux_q);
+                else aux_p = p.aux + grow * (int64_t)p.ldaux;
+            }
+            rowp[r] = aux_p; rowq[r] = aux_q;
+            __syncwarp();                        // every warp only reads the 32 entries it wrote itself
         }
         const int n_chunks = (g.n_tile + 31) / 32;
         for (int ch = 0; ch < n_chunks; ++ch) {
@@ -226,13 +233,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
             float auxv[32];
             if (EPI == NT_EPI_BNRELU_BWD) {
                 // coalesced read of the aux rows (lane = column), transposed through smem so each thread gets its row
-                for (int rr = 0; rr < wrows; ++rr) {
-                    const float *pp = reinterpret_cast<const float *>(__shfl_sync(0xffffffffu, (unsigned long long)aux_p, rr));
-                    const float *qq = reinterpret_cast<const float *>(__shfl_sync(0xffffffffu, (unsigned long long)aux_q, rr));
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr) {
                     float a = 0.f;
-                    if (cl_ok) {
+                    if (rr < wrows && cl_ok) {
+                        const float *pp = rowp[warp * 32 + rr];
                         a = pp[cl];
                         if (p.aux_edge) {
+                            const float *qq = rowq[warp * 32 + rr];
                             if (qq) a += __ldg(qq + cl);
                             a = fmaxf(a, 0.f);
                         }

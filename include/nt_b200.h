@@ -94,17 +94,20 @@ int nt_gemm_nt(const nt_gemm_args *args, void *stream);
 int64_t nt_gemm_weights_bytes(int n_out, int K, int precision);
 int nt_gemm_prepare_weights(const float *w, int ldw, int n_out, int K, int precision, void *w_split, void *stream);
 
-/* Weight-gradient GEMM: out[m, n] += sum_r A[r, m] * Bop[r, n]  (out must be zeroed by the caller; fp32 atomics).
- * Bop is a plain matrix (b, ldb) or, when pq != NULL, the EDGE producer above.  Backward of nn.Linear. */
+/* Weight-gradient GEMM: out[m, n] += sum_r A[r, m] * Bop[r, n]  (out must be zeroed / initialised by the caller).
+ * Bop is a plain matrix (b, ldb) or, when pq != NULL, the EDGE producer above.  Backward of nn.Linear.
+ * workspace: nt_gemm_tn_workspace_bytes() bytes of device memory -> tcgen05 tensor-core engine (TF32x3, per-CTA partial
+ * products reduced deterministically in double); workspace == NULL -> fp32 CUDA-core engine with atomics (validation). */
+int64_t nt_gemm_tn_workspace_bytes(void);
 int nt_gemm_tn(const float *a, int lda, int m, const float *b, int ldb, int n, int64_t rows,
                const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
-               float *out, int ldo, void *stream);
+               float *out, int ldo, void *workspace, void *stream);
 
 /* Same contraction with the B operand centred per column (Bop[r, n] - mu[n]) and accumulated in DOUBLE across CTAs
  * (each CTA sums at most 1024 rows in fp32): the moments the BatchNorm backward needs. */
 int nt_gemm_tn_centered(const float *a, int lda, int m, const float *b, int ldb, int n, int64_t rows,
                         const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
-                        const float *mu, double *out, int ldo, void *stream);
+                        const float *mu, double *out, int ldo, void *workspace, void *stream);
 
 /* ---- BatchNorm1d bookkeeping (nn/net_blocks.py:46; BN placed AFTER ReLU, statistics over all rows) ---------
  * Turns accumulated statistics (or running statistics when training == 0) into the affine y = a*s + t, updates

@@ -266,3 +266,27 @@ def test_tc_engine_linear_matches_cuda_core_engine(ops, cuda_device, rows, K, n_
             ops.GEMM_ENGINE = 'tc'
     assert rel_err(outs['simt'], want) < 1e-5
     assert rel_err(outs['tc'], want) < 5e-5, 'bf16x3 error-compensated product should be ~1e-5'
+
+
+@pytest.mark.parametrize('rows,m,n', [(5000, 150, 200), (777, 200, 200), (300, 400, 3), (100000, 23, 153), (64, 8, 250),
+                                      (4096, 400, 150)])
+def test_tc_weight_gradient_gemm_matches_float64(ops, cuda_device, rows, m, n):
+    """out = A^T . B on the tensor cores (TF32x3, deterministic split reduction) vs a float64 reference, plain and centred."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(rows + m)
+    a = torch.randn(rows, m, generator=g).to(dev)
+    b = (torch.randn(rows, n, generator=g) + 0.5).to(dev)
+    mu = b.mean(0)
+    want = a.double().t() @ b.double()
+    want_c = a.double().t() @ (b.double() - mu.double())
+    for engine in ('tc', 'simt'):
+        ops.GEMM_ENGINE = engine
+        try:
+            out = torch.zeros(m, n, device=dev)
+            ops.gemm_tn(a, a.stride(0), m, rows, out, b=b, ldb=b.stride(0), n=n)
+            out_c = torch.zeros(m, n, dtype=torch.float64, device=dev)
+            ops.gemm_tn(a, a.stride(0), m, rows, out_c, b=b, ldb=b.stride(0), n=n, mu=mu)
+        finally:
+            ops.GEMM_ENGINE = 'tc'
+        assert rel_err(out, want) < 2e-5, engine
+        assert rel_err(out_c, want_c) < 2e-5, engine
