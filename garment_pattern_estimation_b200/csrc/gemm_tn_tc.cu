@@ -1,9 +1,12 @@
 // Tensor-core weight-gradient GEMM (sm_100a, tcgen05 + TMEM):   out[m, n] (+)= sum_r A[r, m] * Bop[r, n]
 //
-// The reduction runs over ROWS (points / edges, up to millions) and the output is small (<= 400 x 300), so both operands
-// are "MN-major" for the tensor core: a row r of A / Bop is contiguous along m / n.  Each CTA owns a contiguous slice of
-// rows, streams it through a 3-stage shared-memory ring in 16-row stages (TF32x3 error-compensated split, see gemm_tc.cu)
-// and accumulates a full [<=256 x <=256] partial product in TMEM (2 M-tiles of 128 lanes).  Partials go to a workspace
+// The reduction runs over ROWS (points / edges, up to millions) and the output is small (<= 400 x 300).  In memory a row r
+// of A / Bop is contiguous along m / n, i.e. the operands are MN-major for the tensor core; the producers TRANSPOSE them
+// on the way into shared memory (lane = m, four scalar loads from four consecutive rows -> one 16-byte K-chunk), so the
+// MMAs see the same K-major no-swizzle core-matrix layout as gemm_tc.cu.  (tcgen05 kind::tf32 with MN-major no-swizzle
+// descriptors returned all-zero accumulators on this hardware/toolchain; the transposing producer avoids that path.)
+// Each CTA owns a contiguous slice of rows, streams it through a 3-stage shared-memory ring in 16-row stages (TF32x3
+// error-compensated split) and accumulates a full [<=256 x <=256] partial product in TMEM (2 M-tiles of 128 lanes).  Partials go to a workspace
 // ([splits, m_pad, n_pad] fp32, coalesced) and a second kernel reduces them in double -- deterministic, no atomics.
 //
 // Bop = plain matrix, or the EdgeConv edge activation relu(P[centre] + Q[nbr]) gathered on the fly, optionally centred
@@ -17,7 +20,6 @@ using namespace tc;
 constexpr int TN_THREADS = 192;
 constexpr int TN_RB = 16;                       // rows (K of the MMA) per stage = 2 tf32 k-steps of 8
 constexpr int TN_STAGES = 3;
-constexpr int TN_SBO = TN_RB * 16 + 16;         // 272 B between 4-element m/n groups (+16 B pad: conflict-free STS)
 constexpr int TN_MAX_M = 256, TN_MAX_N = 256;
 
 struct TNTCParams {
@@ -31,19 +33,21 @@ struct TNTCParams {
     float *partial;                              // [splits, m_pad, n_pad]
 };
 
-__device__ __forceinline__ void tn_store_chunk(uint8_t *hi_plane, uint8_t *lo_plane, int group, int r, const float (&v)[4]) {
+// one 16-byte K-chunk (4 consecutive rows r of one output row m / n) of the hi and lo planes
+__device__ __forceinline__ void tn_store_chunk(uint8_t *hi_plane, uint8_t *lo_plane, int chunk, int rows_pad, int row,
+                                               const float (&v)[4]) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) split_tf32(v[e], h[e], l[e]);
-    const int off = group * TN_SBO + r * 16;
+    const int off = (chunk * rows_pad + row) * 16;
     *reinterpret_cast<uint4 *>(hi_plane + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4 *>(lo_plane + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int ga = p.m_pad / 4, gb = p.n_pad / 4;                 // 16-byte groups per row of A / B
-    const size_t a_plane = (size_t)ga * TN_SBO, b_plane = (size_t)gb * TN_SBO;
+    // plane = [4 K-chunks][rows_pad][16 B]  (K-major core matrices: LBO = rows_pad*16, SBO = 128)
+    const size_t a_plane = (size_t)4 * p.m_pad * 16, b_plane = (size_t)4 * p.n_pad * 16;
     const size_t stage_bytes = 2 * a_plane + 2 * b_plane;
     uint8_t *tail = smem + TN_STAGES * stage_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(tail);
@@ -72,63 +76,48 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p)
     const int n_stages = (int)((max((int64_t)0, r_end - r_begin) + TN_RB - 1) / TN_RB);
 
     if (warp < 4) {
-        // =========================== producers: 8 threads per row, groups strided by 8 ===========================
-        const int rl = tid >> 3;                 // row inside the stage, 0..15
-        const int g0 = tid & 7;
-        const bool veca = ((p.lda & 3) == 0) && aligned16(p.a) && ((p.m0 & 3) == 0);
-        const bool vecb = p.b_edge ? (((p.e.ldpq & 3) == 0) && ((p.e.qoff & 3) == 0) && aligned16(p.e.pq) && ((p.n0 & 3) == 0))
-                                   : (((p.ldb & 3) == 0) && aligned16(p.b) && ((p.n0 & 3) == 0));
-        constexpr int MAXA = TN_MAX_M / 4 / 8, MAXB = TN_MAX_N / 4 / 8;     // 8 groups per thread each
+        // =========================== producers: warp = K-chunk (4 rows), lane = output row (m or n) ===========================
+        const int j = warp;                                              // rows 4j .. 4j+3 of the 16-row stage
+        constexpr int MAXA = TN_MAX_M / 32, MAXB = TN_MAX_N / 32;          // output rows per lane
+        const int ia = p.m_pad / 32, ib = (p.n_pad + 31) / 32;
         float va[MAXA][4], vb[MAXB][4];
 
-        auto load4 = [&](const float *row, int col, int width, bool vec, float (&v)[4]) {
-            if (vec && col + 3 < width) {
-                float4 t = __ldg(reinterpret_cast<const float4 *>(row + col));
-                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = (col + e < width) ? __ldg(row + col + e) : 0.f;
-            }
-        };
         auto fetch = [&](int st) {
-            const int64_t r = r_begin + (int64_t)st * TN_RB + rl;
-            const bool ok = r < r_end;
-            const float *arow = ok ? p.a + r * p.lda : nullptr;
-            const float *bp = nullptr, *bq = nullptr;
-            if (ok) {
-                if (p.b_edge) edge_row_ptrs(p.e, r, bp, bq);
-                else bp = p.b + r * p.ldb;
+            const int64_t rbase = r_begin + (int64_t)st * TN_RB + 4 * j;
+            const float *arow[4], *bp[4], *bq[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t r = rbase + i;
+                arow[i] = bp[i] = bq[i] = nullptr;
+                if (r < r_end) {
+                    arow[i] = p.a + r * p.lda;
+                    if (p.b_edge) edge_row_ptrs(p.e, r, bp[i], bq[i]);
+                    else bp[i] = p.b + r * p.ldb;
+                }
             }
 #pragma unroll
-            for (int i = 0; i < MAXA; ++i) {
-                const int g = g0 + 8 * i;
+            for (int t = 0; t < MAXA; ++t) {
+                const int col = p.m0 + t * 32 + lane;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) va[i][e] = 0.f;
-                if (ok && g < ga) load4(arow, p.m0 + g * 4, p.m, veca, va[i]);
+                for (int i = 0; i < 4; ++i) va[t][i] = (t < ia && arow[i] && col < p.m) ? __ldg(arow[i] + col) : 0.f;
             }
 #pragma unroll
-            for (int i = 0; i < MAXB; ++i) {
-                const int g = g0 + 8 * i;
+            for (int t = 0; t < MAXB; ++t) {
+                const int col = p.n0 + t * 32 + lane;
+                const bool c_ok = t < ib && (t * 32 + lane) < p.n_pad && col < p.n;
+                const float mu = (c_ok && p.mu) ? __ldg(p.mu + col) : 0.f;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) vb[i][e] = 0.f;
-                if (ok && g < gb) {
-                    const int col = p.n0 + g * 4;
-                    load4(bp, col, p.n, vecb, vb[i]);
-                    if (p.b_edge) {
-                        if (bq) {
-                            float q[4];
-                            load4(bq, col, p.n, vecb, q);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) vb[i][e] += q[e];
+                for (int i = 0; i < 4; ++i) {
+                    float v = 0.f;
+                    if (c_ok && bp[i]) {
+                        v = __ldg(bp[i] + col);
+                        if (p.b_edge) {
+                            if (bq[i]) v += __ldg(bq[i] + col);
+                            v = fmaxf(v, 0.f);
                         }
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) vb[i][e] = fmaxf(vb[i][e], 0.f);
+                        v -= mu;
                     }
-                    if (p.mu) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (col + e < p.n) vb[i][e] -= __ldg(p.mu + col + e);
-                    }
+                    vb[t][i] = v;
                 }
             }
         };
@@ -139,15 +128,11 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p)
             mbar_wait(&empty[s], (use & 1) ^ 1);
             uint8_t *a_hi = smem + s * stage_bytes, *a_lo = a_hi + a_plane, *b_hi = a_lo + a_plane, *b_lo = b_hi + b_plane;
 #pragma unroll
-            for (int i = 0; i < MAXA; ++i) {
-                const int g = g0 + 8 * i;
-                if (g < ga) tn_store_chunk(a_hi, a_lo, g, rl, va[i]);
-            }
+            for (int t = 0; t < MAXA; ++t)
+                if (t < ia) tn_store_chunk(a_hi, a_lo, j, p.m_pad, t * 32 + lane, va[t]);
 #pragma unroll
-            for (int i = 0; i < MAXB; ++i) {
-                const int g = g0 + 8 * i;
-                if (g < gb) tn_store_chunk(b_hi, b_lo, g, rl, vb[i]);
-            }
+            for (int t = 0; t < MAXB; ++t)
+                if (t < ib && (t * 32 + lane) < p.n_pad) tn_store_chunk(b_hi, b_lo, j, p.n_pad, t * 32 + lane, vb[t]);
             fence_proxy_async();
             mbar_arrive(&full[s]);
             if (st + 1 < n_stages) fetch(st + 1);
@@ -183,7 +168,8 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p)
     } else if (warp == 4) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(128, (uint32_t)p.n_pad, 1, 1);        // both operands MN-major
+            const uint32_t idesc = make_idesc_tf32(128, (uint32_t)p.n_pad, 0, 0);        // K-major after the transposing producer
+            const uint32_t lbo_a = (uint32_t)p.m_pad * 16, lbo_b = (uint32_t)p.n_pad * 16;
             for (int st = 0; st < n_stages; ++st) {
                 const int s = st % TN_STAGES, use = st / TN_STAGES;
                 mbar_wait(&full[s], use & 1);
@@ -191,13 +177,13 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p)
                 const uint32_t a_hi = smem_u32(smem + s * stage_bytes), a_lo = a_hi + (uint32_t)a_plane;
                 const uint32_t b_hi = a_lo + (uint32_t)a_plane, b_lo = b_hi + (uint32_t)b_plane;
 #pragma unroll
-                for (int ks = 0; ks < TN_RB / 8; ++ks) {
-                    const uint64_t dbh = make_smem_desc(b_hi + ks * 128, 128, TN_SBO);
-                    const uint64_t dbl = make_smem_desc(b_lo + ks * 128, 128, TN_SBO);
+                for (int ks = 0; ks < TN_RB / 8; ++ks) {                                  // one MMA = K 8 = 2 chunks
+                    const uint64_t dbh = make_smem_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128);
+                    const uint64_t dbl = make_smem_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
                     for (int mt = 0; mt < m_tiles; ++mt) {
-                        const uint32_t moff = (uint32_t)mt * 32u * TN_SBO;               // 32 groups of 4 = 128 m-elements
-                        const uint64_t dah = make_smem_desc(a_hi + moff + ks * 128, 128, TN_SBO);
-                        const uint64_t dal = make_smem_desc(a_lo + moff + ks * 128, 128, TN_SBO);
+                        const uint32_t moff = (uint32_t)mt * 128u * 16u;                 // 128 output rows further down the plane
+                        const uint64_t dah = make_smem_desc(a_hi + moff + ks * 2 * lbo_a, lbo_a, 128);
+                        const uint64_t dal = make_smem_desc(a_lo + moff + ks * 2 * lbo_a, lbo_a, 128);
                         const uint32_t d = tmem_base + (uint32_t)(mt * p.n_pad);
                         umma_tf32(d, dah, dbh, idesc, (st | ks) ? 1u : 0u);
                         umma_tf32(d, dah, dbl, idesc, 1u);
@@ -248,7 +234,7 @@ int gemm_tn_tc(const float *a, int lda, int m, const float *b, int ldb, int n, i
             p.m_pad = (m - m0 > 128) ? 256 : 128;
             p.n_pad = ((min(n - n0, TN_MAX_N) + 15) / 16) * 16;
             p.partial = workspace;
-            const size_t stage_bytes = 2 * (size_t)(p.m_pad / 4) * TN_SBO + 2 * (size_t)(p.n_pad / 4) * TN_SBO;
+            const size_t stage_bytes = 2 * (size_t)4 * p.m_pad * 16 + 2 * (size_t)4 * p.n_pad * 16;
             const size_t smem = TN_STAGES * stage_bytes + 128;
             static bool configured = false;
             if (!configured) {
