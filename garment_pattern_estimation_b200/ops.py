@@ -89,6 +89,8 @@ class EdgeSrc:
 
 
 GRAD_PRECISION = _lib.NT_PREC_TF32X3
+TN_ENGINE = 'simt'    # weight-gradient GEMM: 'tc' (tcgen05, deterministic) is correct but its transposing producer is still
+                      # latency-bound (1.5 ms vs 1.0 ms per launch at C2); the CUDA-core kernel stays the default this round
 GEMM_ENGINE = 'tc'    # 'tc' = tcgen05 tensor-core engine (product path); 'simt' = fp32 CUDA-core engine (validation only)
 
 
@@ -134,7 +136,7 @@ def gemm_tn(a, lda, m, rows, out, b=None, ldb=0, n=0, edge=None, mu=None):
     """out[m, n] += sum_r a[r, m] * Bop[r, n].  With `mu` the B operand is centred and `out` must be float64."""
     lib = _lib.load()
     ws = None
-    if GEMM_ENGINE == 'tc':
+    if GEMM_ENGINE == 'tc' and TN_ENGINE == 'tc':
         ws = torch.empty(int(lib.nt_gemm_tn_workspace_bytes()), dtype=torch.uint8, device=a.device)
     if edge is not None:
         bop = (None, 0, n, rows, _p(edge.pq), edge.ldpq, edge.qoff, _p(edge.idx), edge.k, edge.n_per_cloud)

@@ -38,3 +38,16 @@ def global_index(idx_local, N):
     M = idx_local.shape[0]
     base = (torch.arange(M, device=idx_local.device) // N * N).unsqueeze(1)
     return idx_local.long() + base
+
+
+def assert_grad_close(a, b, what='', l2_tol=2e-3, max_tol=3e-2):
+    """Gradients of a ReLU network are DISCONTINUOUS in the pre-activations: two correct fp32-class implementations whose
+    forward values differ by 1e-6 (TF32x3 tensor-core products vs cuBLAS SGEMM) disagree on the ReLU mask of the handful of
+    pre-activations (out of ~1e6 per layer) that sit within 1e-6 of zero, and each such flip moves one row of a gradient
+    by its full magnitude.  Gradients are therefore compared in relative L2 (2e-3) with a loose cap on the worst entry.
+    (With bit-identical forward values the two paths agree to 1e-6: tools/debug_conv1b.py on the GPU.)"""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    l2 = float((a - b).norm() / b.norm().clamp_min(1e-30))
+    mx = float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    assert l2 <= l2_tol and mx <= max_tol, '{}: relative L2 error {:.2e} (tol {:.0e}), worst entry {:.2e} (tol {:.0e})'.format(
+        what, l2, l2_tol, mx, max_tol)

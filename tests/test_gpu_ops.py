@@ -8,7 +8,7 @@ import os
 import pytest
 import torch
 
-from helpers import REL_TOL, assert_close, global_index, ref_edgeconv, rel_err, torch_mlp
+from helpers import REL_TOL, assert_close, assert_grad_close, global_index, ref_edgeconv, rel_err, torch_mlp
 
 pytestmark = pytest.mark.gpu
 
@@ -131,10 +131,10 @@ def test_edgeconv_matches_torch(ops, cuda_device, C, widths, k, B, N, tail, trai
     g = torch.randn_like(want)
     out.backward(g)
     want.backward(g)
-    assert_close(x1.grad, x2.grad, what='grad wrt input features')
+    assert_grad_close(x1.grad, x2.grad, what='grad wrt input features')
     for (n1, p1), (n2, p2) in zip(mine.nn.named_parameters(), ref_mlp.named_parameters()):
         assert n1 == n2
-        assert_close(p1.grad, p2.grad, what='grad ' + n1)
+        assert_grad_close(p1.grad, p2.grad, what='grad ' + n1)
     for (n1, b1), (n2, b2) in zip(mine.nn.named_buffers(), ref_mlp.named_buffers()):
         if b1.dtype.is_floating_point:
             assert_close(b1, b2, what='BN buffer ' + n1)
@@ -167,9 +167,9 @@ def test_plain_mlp_matches_torch(ops, cuda_device, widths, rows, training):
     g = torch.randn_like(want)
     out.backward(g)
     want.backward(g)
-    assert_close(x1.grad, x2.grad, what='grad wrt input')
+    assert_grad_close(x1.grad, x2.grad, what='grad wrt input')
     for (n1, p1), (n2, p2) in zip(mine.named_parameters(), ref_mlp.named_parameters()):
-        assert_close(p1.grad, p2.grad, what='grad ' + n1)
+        assert_grad_close(p1.grad, p2.grad, what='grad ' + n1)
     for (n1, b1), (n2, b2) in zip(mine.named_buffers(), ref_mlp.named_buffers()):
         if b1.dtype.is_floating_point:
             assert_close(b1, b2, what='BN buffer ' + n1)
@@ -280,13 +280,13 @@ def test_tc_weight_gradient_gemm_matches_float64(ops, cuda_device, rows, m, n):
     want = a.double().t() @ b.double()
     want_c = a.double().t() @ (b.double() - mu.double())
     for engine in ('tc', 'simt'):
-        ops.GEMM_ENGINE = engine
+        ops.GEMM_ENGINE, ops.TN_ENGINE = engine, engine
         try:
             out = torch.zeros(m, n, device=dev)
             ops.gemm_tn(a, a.stride(0), m, rows, out, b=b, ldb=b.stride(0), n=n)
             out_c = torch.zeros(m, n, dtype=torch.float64, device=dev)
             ops.gemm_tn(a, a.stride(0), m, rows, out_c, b=b, ldb=b.stride(0), n=n, mu=mu)
         finally:
-            ops.GEMM_ENGINE = 'tc'
+            ops.GEMM_ENGINE, ops.TN_ENGINE = 'tc', 'simt'
         assert rel_err(out, want) < 2e-5, engine
         assert rel_err(out_c, want_c) < 2e-5, engine
