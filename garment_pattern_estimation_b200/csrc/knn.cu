@@ -5,7 +5,7 @@
 //     acc = fma(c_d - q_d, c_d - q_d, acc),  d = 0..D-1
 // and the result is the k lexicographically smallest (distance, index) pairs, ascending.
 //
-// Mapping: one thread owns one query and its private sorted top-K list in registers; a CTA of 256 queries of one
+// Mapping: one thread owns one query and its private sorted top-K list in registers; a CTA of 64 queries of one
 // cloud sweeps the cloud's candidates in tiles of TC rows staged in shared memory.  Every lane reads the SAME
 // candidate word (shared-memory broadcast), so the kernel is bound by the FP32 pipe: 2 instructions (FADD + FFMA)
 // per pair-dimension, the minimum the bit-exact direct form allows.  TC independent chains per thread give the ILP.
@@ -14,9 +14,10 @@
 
 namespace nt {
 
-constexpr int KNN_THREADS = 256;
-constexpr int KNN_TC = 32;   // candidates per tile (independent fma chains per thread)
-constexpr int KNN_DC = 16;   // dims per query-register chunk
+constexpr int KNN_THREADS = 64;   // 2 warps per CTA, 8 CTAs per SM: C2 gives 1024 CTAs on 1184 resident slots (7 vs 6.92 per SM)
+constexpr int KNN_TC = 32;        // candidates per tile (independent fma chains per thread)
+constexpr int KNN_DC = 16;        // dims per query-register chunk
+constexpr int KNN_PRUNE_EVERY = 2;  // re-evaluate the warp-level alive mask every 2 chunks (32 dims)
 
 template <int K>
 __device__ __forceinline__ void topk_insert(float (&ld)[K], int (&li)[K], float d, int c) {
@@ -32,29 +33,57 @@ __device__ __forceinline__ void topk_insert(float (&ld)[K], int (&li)[K], float 
     }
 }
 
-// NG = number of float4 groups of this chunk (1..4)
+// One dim-chunk (NG float4 groups) of the fma chains of the candidates whose bit is set in `alive` (warp-uniform).
+// Candidates are handled in pairs so two independent chains interleave inside every branch.
 template <int NG>
-__device__ __forceinline__ void chain_chunk(float (&acc)[KNN_TC], const float *__restrict__ tile, int Dp, int d0,
-                                            const float (&qv)[KNN_DC]) {
+__device__ __forceinline__ void chain_chunk(float (&acc)[KNN_TC], unsigned alive, const float *__restrict__ tile, int Dp,
+                                            int d0, const float (&qv)[KNN_DC]) {
 #pragma unroll
-    for (int c = 0; c < KNN_TC; ++c) {
-        const float4 *row = reinterpret_cast<const float4 *>(tile + c * Dp + d0);
-        float a = acc[c];
+    for (int c = 0; c < KNN_TC; c += 2) {
+        if ((alive >> c) & 3u) {
+            const float4 *r0 = reinterpret_cast<const float4 *>(tile + c * Dp + d0);
+            const float4 *r1 = reinterpret_cast<const float4 *>(tile + (c + 1) * Dp + d0);
+            float a0 = acc[c], a1 = acc[c + 1];
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            float4 cv = row[g];
-            float d;
-            d = __fsub_rn(cv.x, qv[4 * g + 0]); a = __fmaf_rn(d, d, a);
-            d = __fsub_rn(cv.y, qv[4 * g + 1]); a = __fmaf_rn(d, d, a);
-            d = __fsub_rn(cv.z, qv[4 * g + 2]); a = __fmaf_rn(d, d, a);
-            d = __fsub_rn(cv.w, qv[4 * g + 3]); a = __fmaf_rn(d, d, a);
+            for (int g = 0; g < NG; ++g) {
+                const float4 u = r0[g], w = r1[g];
+                float d, e;
+                d = __fsub_rn(u.x, qv[4 * g + 0]); e = __fsub_rn(w.x, qv[4 * g + 0]); a0 = __fmaf_rn(d, d, a0); a1 = __fmaf_rn(e, e, a1);
+                d = __fsub_rn(u.y, qv[4 * g + 1]); e = __fsub_rn(w.y, qv[4 * g + 1]); a0 = __fmaf_rn(d, d, a0); a1 = __fmaf_rn(e, e, a1);
+                d = __fsub_rn(u.z, qv[4 * g + 2]); e = __fsub_rn(w.z, qv[4 * g + 2]); a0 = __fmaf_rn(d, d, a0); a1 = __fmaf_rn(e, e, a1);
+                d = __fsub_rn(u.w, qv[4 * g + 3]); e = __fsub_rn(w.w, qv[4 * g + 3]); a0 = __fmaf_rn(d, d, a0); a1 = __fmaf_rn(e, e, a1);
+            }
+            acc[c] = a0; acc[c + 1] = a1;
         }
-        acc[c] = a;
     }
 }
 
+__device__ __forceinline__ void load_query_chunk(const float *__restrict__ xq, int d0, int groups, int D, bool q_ok, bool qvec,
+                                                 float (&qv)[KNN_DC]) {
+#pragma unroll
+    for (int g = 0; g < KNN_DC / 4; ++g) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < groups && q_ok) {
+            const int d = d0 + 4 * g;
+            if (qvec && d + 3 < D) {
+                v = __ldg(reinterpret_cast<const float4 *>(xq + d));
+            } else {
+                if (d + 0 < D) v.x = __ldg(xq + d + 0);
+                if (d + 1 < D) v.y = __ldg(xq + d + 1);
+                if (d + 2 < D) v.z = __ldg(xq + d + 2);
+                if (d + 3 < D) v.w = __ldg(xq + d + 3);
+            }
+        }
+        qv[4 * g + 0] = v.x; qv[4 * g + 1] = v.y; qv[4 * g + 2] = v.z; qv[4 * g + 3] = v.w;
+    }
+}
+
+// Exactness of the pruning: every term of the chain is >= 0 and fmaf rounding is monotone, so the partial sums never
+// decrease.  A candidate whose partial sum is already >= the current k-th best distance of EVERY lane of the warp can never
+// satisfy the strict insertion test `dist < kth` for any of them, so its remaining dimensions are skipped; the (partial)
+// value it keeps still fails that test.  Thresholds only tighten, so a stale alive bit is merely conservative.
 template <int K>
-__global__ void __launch_bounds__(KNN_THREADS, (K <= 16) ? 2 : 1)
+__global__ void __launch_bounds__(KNN_THREADS, (K <= 16) ? 8 : 4)
 knn_kernel(const float *__restrict__ x, int N, int D, int ldx, int k, int32_t *__restrict__ idx) {
     extern __shared__ __align__(16) float tile[];   // [KNN_TC][Dp]
     const int Dp = (D + 3) & ~3;
@@ -72,6 +101,10 @@ knn_kernel(const float *__restrict__ x, int N, int D, int ldx, int k, int32_t *_
 
     const int full_chunks = Dp / KNN_DC;
     const int tail_groups = (Dp - full_chunks * KNN_DC) >> 2;
+    const int n_chunks = full_chunks + (tail_groups ? 1 : 0);
+
+    float qv[KNN_DC], qn[KNN_DC];
+    load_query_chunk(xq, 0, (0 < full_chunks) ? KNN_DC / 4 : tail_groups, D, q_ok, qvec, qn);
 
     for (int c0 = 0; c0 < N; c0 += KNN_TC) {
         __syncthreads();
@@ -86,33 +119,30 @@ knn_kernel(const float *__restrict__ x, int N, int D, int ldx, int k, int32_t *_
         float acc[KNN_TC];
 #pragma unroll
         for (int c = 0; c < KNN_TC; ++c) acc[c] = 0.f;
+        unsigned alive = (c0 + KNN_TC <= N) ? 0xffffffffu : ((1u << (N - c0)) - 1u);
 
-        for (int ch = 0; ch <= full_chunks; ++ch) {
+        for (int ch = 0; ch < n_chunks; ++ch) {
             const int d0 = ch * KNN_DC;
             const int groups = (ch < full_chunks) ? (KNN_DC / 4) : tail_groups;
-            if (groups == 0) break;
-            float qv[KNN_DC];
 #pragma unroll
-            for (int g = 0; g < KNN_DC / 4; ++g) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g < groups && q_ok) {
-                    const int d = d0 + 4 * g;
-                    if (qvec && d + 3 < D) {
-                        v = __ldg(reinterpret_cast<const float4 *>(xq + d));
-                    } else {
-                        if (d + 0 < D) v.x = __ldg(xq + d + 0);
-                        if (d + 1 < D) v.y = __ldg(xq + d + 1);
-                        if (d + 2 < D) v.z = __ldg(xq + d + 2);
-                        if (d + 3 < D) v.w = __ldg(xq + d + 3);
-                    }
-                }
-                qv[4 * g + 0] = v.x; qv[4 * g + 1] = v.y; qv[4 * g + 2] = v.z; qv[4 * g + 3] = v.w;
+            for (int i = 0; i < KNN_DC; ++i) qv[i] = qn[i];
+            {   // prefetch the query values of the NEXT chunk (wrapping to chunk 0 for the next tile)
+                const int nch = (ch + 1 < n_chunks) ? ch + 1 : 0;
+                load_query_chunk(xq, nch * KNN_DC, (nch < full_chunks) ? KNN_DC / 4 : tail_groups, D, q_ok, qvec, qn);
             }
             switch (groups) {
-                case 4: chain_chunk<4>(acc, tile, Dp, d0, qv); break;
-                case 3: chain_chunk<3>(acc, tile, Dp, d0, qv); break;
-                case 2: chain_chunk<2>(acc, tile, Dp, d0, qv); break;
-                default: chain_chunk<1>(acc, tile, Dp, d0, qv); break;
+                case 4: chain_chunk<4>(acc, alive, tile, Dp, d0, qv); break;
+                case 3: chain_chunk<3>(acc, alive, tile, Dp, d0, qv); break;
+                case 2: chain_chunk<2>(acc, alive, tile, Dp, d0, qv); break;
+                default: chain_chunk<1>(acc, alive, tile, Dp, d0, qv); break;
+            }
+            if ((ch % KNN_PRUNE_EVERY) == KNN_PRUNE_EVERY - 1 && ch + 1 < n_chunks) {
+                const float thr = q_ok ? ld[K - 1] : -1.f;          // idle lanes never keep a candidate alive
+                unsigned keep = 0;
+#pragma unroll
+                for (int c = 0; c < KNN_TC; ++c)
+                    if (__any_sync(0xffffffffu, acc[c] < thr)) keep |= (1u << c);
+                alive &= keep;
             }
         }
 

@@ -77,6 +77,26 @@ def test_knn_full_size_properties(ops, cuda_device):
     assert bool((d[..., 1:] >= d[..., :-1] - 1e-3).all())                         # ascending distances
 
 
+def test_knn_large_cloud_c4_shape(ops, cuda_device):
+    """BASELINE C4 shape: N = 10 000 points, k = 16 (one cloud in 150-d, two in 3-d), bit-exact against the oracle."""
+    from oracle import knn as oknn
+    x3 = torch.randn(2, 10000, 3, generator=torch.Generator().manual_seed(10))
+    assert torch.equal(_knn_gpu(ops, x3, 16, cuda_device), oknn.knn_indices(x3, 16, nthreads=os.cpu_count() or 8))
+    x150 = torch.randn(1, 10000, 150, generator=torch.Generator().manual_seed(11))
+    assert torch.equal(_knn_gpu(ops, x150, 16, cuda_device), oknn.knn_indices(x150, 16, nthreads=os.cpu_count() or 8))
+
+
+def test_knn_clustered_data_exercises_pruning(ops, cuda_device):
+    """tight clusters far apart: most candidates are pruned after the first dims; results must stay bit-exact."""
+    from oracle import knn as oknn
+    g = torch.Generator().manual_seed(12)
+    centres = torch.randn(16, 150, generator=g) * 20
+    x = (centres[torch.randint(0, 16, (2, 1500), generator=g)] + torch.randn(2, 1500, 150, generator=g) * 0.05)
+    assert torch.equal(_knn_gpu(ops, x, 5, cuda_device), oknn.knn_indices(x, 5, nthreads=8))
+    x[:, 100:140] = x[:, 0:40]                                  # exact duplicates across tiles
+    assert torch.equal(_knn_gpu(ops, x, 8, cuda_device), oknn.knn_indices(x, 8, nthreads=8))
+
+
 def test_knn_rejects_bad_k(ops, cuda_device):
     x = torch.randn(40, 3, device=cuda_device)
     with pytest.raises(RuntimeError):
