@@ -11,10 +11,10 @@
 // per pair-dimension, the minimum the bit-exact direct form allows.  TC independent chains per thread give the ILP.
 // Zero padding (candidate and query padded to a multiple of 4 dims with 0) is exact: fma(0,0,acc) == acc.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace nt {
 
-constexpr int KNN_THREADS = 64;   // 2 warps per CTA, 8 CTAs per SM: C2 gives 1024 CTAs on 1184 resident slots (7 vs 6.92 per SM)
 constexpr int KNN_TC = 32;        // candidates per tile (independent fma chains per thread)
 constexpr int KNN_DC = 16;        // dims per query-register chunk
 constexpr int KNN_PRUNE_EVERY = 2;  // re-evaluate the warp-level alive mask every 2 chunks (32 dims)
@@ -35,12 +35,12 @@ __device__ __forceinline__ void topk_insert(float (&ld)[K], int (&li)[K], float 
 
 // One dim-chunk (NG float4 groups) of the fma chains of the candidates whose bit is set in `alive` (warp-uniform).
 // Candidates are handled in pairs so two independent chains interleave inside every branch.
-template <int NG>
+template <int NG, bool PRUNE>
 __device__ __forceinline__ void chain_chunk(float (&acc)[KNN_TC], unsigned alive, const float *__restrict__ tile, int Dp,
                                             int d0, const float (&qv)[KNN_DC]) {
 #pragma unroll
     for (int c = 0; c < KNN_TC; c += 2) {
-        if ((alive >> c) & 3u) {
+        if (!PRUNE || ((alive >> c) & 3u)) {
             const float4 *r0 = reinterpret_cast<const float4 *>(tile + c * Dp + d0);
             const float4 *r1 = reinterpret_cast<const float4 *>(tile + (c + 1) * Dp + d0);
             float a0 = acc[c], a1 = acc[c + 1];
@@ -82,8 +82,8 @@ __device__ __forceinline__ void load_query_chunk(const float *__restrict__ xq, i
 // decrease.  A candidate whose partial sum is already >= the current k-th best distance of EVERY lane of the warp can never
 // satisfy the strict insertion test `dist < kth` for any of them, so its remaining dimensions are skipped; the (partial)
 // value it keeps still fails that test.  Thresholds only tighten, so a stale alive bit is merely conservative.
-template <int K>
-__global__ void __launch_bounds__(KNN_THREADS, (K <= 16) ? 8 : 4)
+template <int K, int KNN_THREADS, bool PRUNE, bool PREFETCH>
+__global__ void __launch_bounds__(KNN_THREADS, (K <= 16) ? 512 / KNN_THREADS : 256 / KNN_THREADS)
 knn_kernel(const float *__restrict__ x, int N, int D, int ldx, int k, int32_t *__restrict__ idx) {
     extern __shared__ __align__(16) float tile[];   // [KNN_TC][Dp]
     const int Dp = (D + 3) & ~3;
@@ -104,7 +104,7 @@ knn_kernel(const float *__restrict__ x, int N, int D, int ldx, int k, int32_t *_
     const int n_chunks = full_chunks + (tail_groups ? 1 : 0);
 
     float qv[KNN_DC], qn[KNN_DC];
-    load_query_chunk(xq, 0, (0 < full_chunks) ? KNN_DC / 4 : tail_groups, D, q_ok, qvec, qn);
+    if (PREFETCH) load_query_chunk(xq, 0, (0 < full_chunks) ? KNN_DC / 4 : tail_groups, D, q_ok, qvec, qn);
 
     for (int c0 = 0; c0 < N; c0 += KNN_TC) {
         __syncthreads();
@@ -124,19 +124,22 @@ knn_kernel(const float *__restrict__ x, int N, int D, int ldx, int k, int32_t *_
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int d0 = ch * KNN_DC;
             const int groups = (ch < full_chunks) ? (KNN_DC / 4) : tail_groups;
+            if (PREFETCH) {
 #pragma unroll
-            for (int i = 0; i < KNN_DC; ++i) qv[i] = qn[i];
-            {   // prefetch the query values of the NEXT chunk (wrapping to chunk 0 for the next tile)
+                for (int i = 0; i < KNN_DC; ++i) qv[i] = qn[i];
+                // prefetch the query values of the NEXT chunk (wrapping to chunk 0 for the next tile)
                 const int nch = (ch + 1 < n_chunks) ? ch + 1 : 0;
                 load_query_chunk(xq, nch * KNN_DC, (nch < full_chunks) ? KNN_DC / 4 : tail_groups, D, q_ok, qvec, qn);
+            } else {
+                load_query_chunk(xq, d0, groups, D, q_ok, qvec, qv);
             }
             switch (groups) {
-                case 4: chain_chunk<4>(acc, alive, tile, Dp, d0, qv); break;
-                case 3: chain_chunk<3>(acc, alive, tile, Dp, d0, qv); break;
-                case 2: chain_chunk<2>(acc, alive, tile, Dp, d0, qv); break;
-                default: chain_chunk<1>(acc, alive, tile, Dp, d0, qv); break;
+                case 4: chain_chunk<4, PRUNE>(acc, alive, tile, Dp, d0, qv); break;
+                case 3: chain_chunk<3, PRUNE>(acc, alive, tile, Dp, d0, qv); break;
+                case 2: chain_chunk<2, PRUNE>(acc, alive, tile, Dp, d0, qv); break;
+                default: chain_chunk<1, PRUNE>(acc, alive, tile, Dp, d0, qv); break;
             }
-            if ((ch % KNN_PRUNE_EVERY) == KNN_PRUNE_EVERY - 1 && ch + 1 < n_chunks) {
+            if (PRUNE && (ch % KNN_PRUNE_EVERY) == KNN_PRUNE_EVERY - 1 && ch + 1 < n_chunks) {
                 const float thr = q_ok ? ld[K - 1] : -1.f;          // idle lanes never keep a candidate alive
                 unsigned keep = 0;
 #pragma unroll
@@ -160,18 +163,38 @@ knn_kernel(const float *__restrict__ x, int N, int D, int ldx, int k, int32_t *_
     }
 }
 
-template <int K>
-static int launch_knn(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
+template <int K, int THREADS, bool PRUNE, bool PREFETCH>
+static int launch_knn_cfg(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
     const int Dp = (D + 3) & ~3;
     size_t smem = (size_t)KNN_TC * Dp * sizeof(float);
     if (smem > 200 * 1024) return fail("nt_knn: feature dimension %s too large for the staging tile (D=%ld)", "", D);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(knn_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(knn_kernel<K, THREADS, PRUNE, PREFETCH>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail("nt_knn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    dim3 grid((N + KNN_THREADS - 1) / KNN_THREADS, B);
-    knn_kernel<K><<<grid, KNN_THREADS, smem, st>>>(x, N, D, ldx, k, idx);
+    dim3 grid((N + THREADS - 1) / THREADS, B);
+    knn_kernel<K, THREADS, PRUNE, PREFETCH><<<grid, THREADS, smem, st>>>(x, N, D, ldx, k, idx);
     return check_launch("nt_knn");
+}
+
+static int g_knn_variant = -1;      // developer knob (NT_KNN_VARIANT), read once
+
+template <int K>
+static int launch_knn(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
+    if (g_knn_variant < 0) {
+        const char *v = getenv("NT_KNN_VARIANT");
+        g_knn_variant = v ? atoi(v) : 0;
+    }
+    switch (g_knn_variant) {
+        case 1: return launch_knn_cfg<K, 64, false, false>(x, B, N, D, ldx, k, idx, st);
+        case 2: return launch_knn_cfg<K, 256, false, true>(x, B, N, D, ldx, k, idx, st);
+        case 3: return launch_knn_cfg<K, 64, true, true>(x, B, N, D, ldx, k, idx, st);
+        case 4: return launch_knn_cfg<K, 256, true, false>(x, B, N, D, ldx, k, idx, st);
+        case 5: return launch_knn_cfg<K, 128, false, false>(x, B, N, D, ldx, k, idx, st);
+        case 6: return launch_knn_cfg<K, 128, true, false>(x, B, N, D, ldx, k, idx, st);
+        default: return launch_knn_cfg<K, 256, false, false>(x, B, N, D, ldx, k, idx, st);
+    }
 }
 
 }  // namespace nt
