@@ -163,6 +163,130 @@ knn_kernel(const float *__restrict__ x, int N, int D, int ldx, int k, int32_t *_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Packed-FP32x2 variant (Blackwell FADD2 / FFMA2: add.rn.f32x2, fma.rn.f32x2).  Two candidates share one instruction, so
+// a pair-dimension costs 1 issue slot instead of 2; every half is an independent IEEE fma.rn, i.e. the same bits as the
+// scalar chain.  The candidate tile is stored TRANSPOSED ([dim][candidate], row stride 36 floats) so that one broadcast
+// LDS.128 delivers the same dimension of four consecutive candidates = two packed operands.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int KNN_TS = 36;     // transposed tile row stride (floats): 16-byte aligned rows, 4-way instead of 32-way store conflicts
+
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+template <int K, int KNN_THREADS>
+__global__ void __launch_bounds__(KNN_THREADS, (K <= 16) ? 512 / KNN_THREADS : 256 / KNN_THREADS)
+knn_kernel_x2(const float *__restrict__ x, int N, int D, int ldx, int k, int32_t *__restrict__ idx) {
+    extern __shared__ __align__(16) float tile[];   // [Dp][KNN_TS]
+    const int Dp = (D + 3) & ~3;
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * KNN_THREADS + threadIdx.x;
+    const bool q_ok = q < N;
+    const float *cloud = x + (size_t)b * N * ldx;
+    const float *xq = cloud + (size_t)(q_ok ? q : 0) * ldx;
+    const bool qvec = ((ldx & 3) == 0) && aligned16(x);
+
+    float ld[K];
+    int li[K];
+#pragma unroll
+    for (int e = 0; e < K; ++e) { ld[e] = 1e10f; li[e] = -1; }
+
+    const int full_chunks = Dp / KNN_DC;
+    const int tail_groups = (Dp - full_chunks * KNN_DC) >> 2;
+    const int n_chunks = full_chunks + (tail_groups ? 1 : 0);
+
+    for (int c0 = 0; c0 < N; c0 += KNN_TC) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < KNN_TC * Dp; i += KNN_THREADS) {
+            int c = i / Dp, d = i - c * Dp;
+            float v = 0.f;
+            if (c0 + c < N && d < D) v = __ldg(cloud + (size_t)(c0 + c) * ldx + d);
+            tile[d * KNN_TS + c] = v;
+        }
+        __syncthreads();
+
+        unsigned long long acc2[KNN_TC / 2];
+#pragma unroll
+        for (int c = 0; c < KNN_TC / 2; ++c) acc2[c] = 0ull;       // {0.f, 0.f}
+
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const int d0 = ch * KNN_DC;
+            const int groups = (ch < full_chunks) ? (KNN_DC / 4) : tail_groups;
+            float qv[KNN_DC];
+            if (ch < full_chunks && qvec && q_ok) {                  // straight-line fast path: 4 x LDG.128
+#pragma unroll
+                for (int g = 0; g < KNN_DC / 4; ++g) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(xq + d0 + 4 * g));
+                    qv[4 * g + 0] = v.x; qv[4 * g + 1] = v.y; qv[4 * g + 2] = v.z; qv[4 * g + 3] = v.w;
+                }
+            } else {
+                load_query_chunk(xq, d0, groups, D, q_ok, qvec, qv);
+            }
+            const int dims = groups * 4;
+#pragma unroll
+            for (int dd = 0; dd < KNN_DC; ++dd) {
+                if (dd < dims) {
+                    const unsigned long long nq2 = pack_f32x2(-qv[dd], -qv[dd]);
+                    const float4 *row = reinterpret_cast<const float4 *>(tile + (d0 + dd) * KNN_TS);
+#pragma unroll
+                    for (int c4 = 0; c4 < KNN_TC / 4; ++c4) {
+                        const float4 cv = row[c4];
+                        const unsigned long long da = add_f32x2(pack_f32x2(cv.x, cv.y), nq2);
+                        const unsigned long long db = add_f32x2(pack_f32x2(cv.z, cv.w), nq2);
+                        acc2[2 * c4] = fma_f32x2(da, da, acc2[2 * c4]);
+                        acc2[2 * c4 + 1] = fma_f32x2(db, db, acc2[2 * c4 + 1]);
+                    }
+                }
+            }
+        }
+
+#pragma unroll
+        for (int c2 = 0; c2 < KNN_TC / 2; ++c2) {
+            float a0, a1;
+            unpack_f32x2(acc2[c2], a0, a1);
+            if (c0 + 2 * c2 < N && a0 < ld[K - 1]) topk_insert<K>(ld, li, a0, c0 + 2 * c2);
+            if (c0 + 2 * c2 + 1 < N && a1 < ld[K - 1]) topk_insert<K>(ld, li, a1, c0 + 2 * c2 + 1);
+        }
+    }
+
+    if (q_ok) {
+        int32_t *o = idx + ((size_t)b * N + q) * k;
+#pragma unroll
+        for (int e = 0; e < K; ++e)
+            if (e < k) o[e] = li[e];
+    }
+}
+
+template <int K, int THREADS>
+static int launch_knn_x2(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
+    const int Dp = (D + 3) & ~3;
+    size_t smem = (size_t)KNN_TS * Dp * sizeof(float);
+    if (smem > 200 * 1024) return fail("nt_knn: feature dimension %s too large for the staging tile (D=%ld)", "", D);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(knn_kernel_x2<K, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail("nt_knn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    dim3 grid((N + THREADS - 1) / THREADS, B);
+    knn_kernel_x2<K, THREADS><<<grid, THREADS, smem, st>>>(x, N, D, ldx, k, idx);
+    return check_launch("nt_knn");
+}
+
 template <int K, int THREADS, bool PRUNE, bool PREFETCH>
 static int launch_knn_cfg(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
     const int Dp = (D + 3) & ~3;
@@ -187,12 +311,9 @@ static int launch_knn(const float *x, int B, int N, int D, int ldx, int k, int32
         g_knn_variant = v ? atoi(v) : 0;
     }
     switch (g_knn_variant) {
-        case 1: return launch_knn_cfg<K, 64, false, false>(x, B, N, D, ldx, k, idx, st);
-        case 2: return launch_knn_cfg<K, 256, false, true>(x, B, N, D, ldx, k, idx, st);
-        case 3: return launch_knn_cfg<K, 64, true, true>(x, B, N, D, ldx, k, idx, st);
         case 4: return launch_knn_cfg<K, 256, true, false>(x, B, N, D, ldx, k, idx, st);
-        case 5: return launch_knn_cfg<K, 128, false, false>(x, B, N, D, ldx, k, idx, st);
-        case 6: return launch_knn_cfg<K, 128, true, false>(x, B, N, D, ldx, k, idx, st);
+        case 7: return launch_knn_x2<K, 256>(x, B, N, D, ldx, k, idx, st);
+        case 8: return launch_knn_x2<K, 128>(x, B, N, D, ldx, k, idx, st);
         default: return launch_knn_cfg<K, 256, false, false>(x, B, N, D, ldx, k, idx, st);
     }
 }
