@@ -156,16 +156,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
             }
         }
         const uint8_t *wsrc = w_split + (size_t)tile_n * g.num_kb * ((size_t)g.n_tile * 128);
-        // register double-buffering: the global loads of K block kb+1 are issued right after block kb has been handed
-        // to the tensor core, so their latency overlaps the wait for the stage to drain
-        float v[4][8];
-        auto fetch = [&](int kb) {
+        // Register prefetch ring, depth 3: the gather is latency-bound (random rows of PQ miss L2 while the activation
+        // stream evicts it), so the loads of K blocks kb+1 .. kb+3 are in flight while block kb is packed and handed to
+        // the tensor core.  (Loop unrolled by 3 so every buffer is addressed statically.)
+        float v0[4][8], v1[4][8], v2[4][8];
+        auto fetch = [&](int kb, float (&v)[4][8]) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int k = (kb * 4 + j) * EPC;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
-                if (r_ok && k < p.K) {
+                if (r_ok && kb < g.num_kb && k < p.K) {
                     load_chunk<EPC>(ap, k, p.K, vec, v[j]);
                     if (PROD == NT_PROD_EDGE) {
                         if (aq) {
@@ -180,8 +181,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
                 }
             }
         };
-        fetch(0);
-        for (int kb = 0; kb < g.num_kb; ++kb) {
+        auto consume = [&](int kb, float (&v)[4][8]) {
             const int s = kb & 1, use = kb >> 1;
             mbar_wait(&empty[s], (use & 1) ^ 1);
             uint8_t *a_hi = stage_base[s], *a_lo = a_hi + TC_A_BYTES, *b_all = a_lo + TC_A_BYTES;
@@ -199,7 +199,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
             }
             fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&full[s]);
-            if (kb + 1 < g.num_kb) fetch(kb + 1);
+        };
+        fetch(0, v0); fetch(1, v1); fetch(2, v2);
+        for (int kb = 0; kb < g.num_kb; kb += 3) {
+            consume(kb, v0); fetch(kb + 3, v0);
+            if (kb + 1 < g.num_kb) { consume(kb + 1, v1); fetch(kb + 4, v1); }
+            if (kb + 2 < g.num_kb) { consume(kb + 2, v2); fetch(kb + 5, v2); }
         }
 
         // =========================== epilogue (thread = row, TMEM lane = row) ===========================
@@ -226,14 +231,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
         const int n_chunks = (g.n_tile + 31) / 32;
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int c0 = ch * 32;
-            float acc[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
             const int cl = col0 + c0 + lane;                             // the column this lane owns in row-wise passes
             const bool cl_ok = (c0 + lane) < g.n_tile && cl < p.n_out;
             float auxv[32];
             if (EPI == NT_EPI_BNRELU_BWD) {
-                // coalesced read of the aux rows (lane = column), transposed through smem so each thread gets its row
-#pragma unroll 8
+                // coalesced read of the aux rows (lane = column): all 32 (64 with the gathered operand) loads are issued
+                // back to back, BEFORE the TMEM load, then transposed through smem so each thread gets its own row
+#pragma unroll
                 for (int rr = 0; rr < 32; ++rr) {
                     float a = 0.f;
                     if (rr < wrows && cl_ok) {
@@ -245,8 +249,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
                             a = fmaxf(a, 0.f);
                         }
                     }
-                    tw[rr * 33 + lane] = a;
+                    auxv[rr] = a;
                 }
+            }
+            float acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+            if (EPI == NT_EPI_BNRELU_BWD) {
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) tw[rr * 33 + lane] = auxv[rr];
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) auxv[i] = tw[lane * 33 + i];

@@ -17,7 +17,8 @@
 namespace nt {
 using namespace tc;
 
-constexpr int TN_THREADS = 192;
+constexpr int TN_PRODUCER_WARPS = 8;             // warps 0-7: producers + epilogue; warp 8: MMA issuer; warp 9: TMEM
+constexpr int TN_THREADS = (TN_PRODUCER_WARPS + 2) * 32;
 constexpr int TN_RB = 16;                       // rows (K of the MMA) per stage = 2 tf32 k-steps of 8
 constexpr int TN_STAGES = 3;
 constexpr int TN_MAX_M = 256, TN_MAX_N = 256;
@@ -60,12 +61,12 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p)
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < m_tiles * p.n_pad) tmem_cols <<= 1;
 
-    if (warp == 4 && lane == 0) {
-        for (int s = 0; s < TN_STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+    if (warp == TN_PRODUCER_WARPS && lane == 0) {
+        for (int s = 0; s < TN_STAGES; ++s) { mbar_init(&full[s], TN_PRODUCER_WARPS * 32); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
         mbar_fence_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == TN_PRODUCER_WARPS + 1) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -75,21 +76,23 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p)
     const int64_t r_end = min(p.rows, r_begin + p.rows_per_split);
     const int n_stages = (int)((max((int64_t)0, r_end - r_begin) + TN_RB - 1) / TN_RB);
 
-    if (warp < 4) {
-        // =========================== producers: warp = K-chunk (4 rows), lane = output row (m or n) ===========================
-        const int j = warp;                                              // rows 4j .. 4j+3 of the 16-row stage
-        constexpr int MAXA = TN_MAX_M / 32, MAXB = TN_MAX_N / 32;          // output rows per lane
+    if (warp < TN_PRODUCER_WARPS) {
+        // ============ producers: (warp & 3) = K-chunk (4 rows), (warp >> 2) = which half of the 32-row groups, lane = row ============
+        const int j = warp & 3;                                          // rows 4j .. 4j+3 of the 16-row stage
+        const int half = warp >> 2;
+        constexpr int MAXA = TN_MAX_M / 32 / 2, MAXB = TN_MAX_N / 32 / 2;  // 32-row groups per thread
         const int ia = p.m_pad / 32, ib = (p.n_pad + 31) / 32;
-        float va[MAXA][4], vb[MAXB][4];
+        struct Regs { float a[MAXA][4]; float b[MAXB][4]; };
+        Regs v0, v1, v2;                                                 // prefetch ring, depth 3 (static addressing)
 
-        auto fetch = [&](int st) {
+        auto fetch = [&](int st, Regs &v) {
             const int64_t rbase = r_begin + (int64_t)st * TN_RB + 4 * j;
             const float *arow[4], *bp[4], *bq[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int64_t r = rbase + i;
                 arow[i] = bp[i] = bq[i] = nullptr;
-                if (r < r_end) {
+                if (st < n_stages && r < r_end) {
                     arow[i] = p.a + r * p.lda;
                     if (p.b_edge) edge_row_ptrs(p.e, r, bp[i], bq[i]);
                     else bp[i] = p.b + r * p.ldb;
@@ -97,59 +100,69 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p)
             }
 #pragma unroll
             for (int t = 0; t < MAXA; ++t) {
-                const int col = p.m0 + t * 32 + lane;
+                const int grp = half + 2 * t;
+                const int col = p.m0 + grp * 32 + lane;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) va[t][i] = (t < ia && arow[i] && col < p.m) ? __ldg(arow[i] + col) : 0.f;
+                for (int i = 0; i < 4; ++i) v.a[t][i] = (grp < ia && arow[i] && col < p.m) ? __ldg(arow[i] + col) : 0.f;
             }
 #pragma unroll
             for (int t = 0; t < MAXB; ++t) {
-                const int col = p.n0 + t * 32 + lane;
-                const bool c_ok = t < ib && (t * 32 + lane) < p.n_pad && col < p.n;
+                const int grp = half + 2 * t;
+                const int col = p.n0 + grp * 32 + lane;
+                const bool c_ok = grp < ib && (grp * 32 + lane) < p.n_pad && col < p.n;
                 const float mu = (c_ok && p.mu) ? __ldg(p.mu + col) : 0.f;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    float v = 0.f;
+                    float x = 0.f;
                     if (c_ok && bp[i]) {
-                        v = __ldg(bp[i] + col);
+                        x = __ldg(bp[i] + col);
                         if (p.b_edge) {
-                            if (bq[i]) v += __ldg(bq[i] + col);
-                            v = fmaxf(v, 0.f);
+                            if (bq[i]) x += __ldg(bq[i] + col);
+                            x = fmaxf(x, 0.f);
                         }
-                        v -= mu;
+                        x -= mu;
                     }
-                    vb[t][i] = v;
+                    v.b[t][i] = x;
                 }
             }
         };
-
-        if (n_stages > 0) fetch(0);
-        for (int st = 0; st < n_stages; ++st) {
+        auto consume = [&](int st, Regs &v) {
             const int s = st % TN_STAGES, use = st / TN_STAGES;
             mbar_wait(&empty[s], (use & 1) ^ 1);
             uint8_t *a_hi = smem + s * stage_bytes, *a_lo = a_hi + a_plane, *b_hi = a_lo + a_plane, *b_lo = b_hi + b_plane;
 #pragma unroll
-            for (int t = 0; t < MAXA; ++t)
-                if (t < ia) tn_store_chunk(a_hi, a_lo, j, p.m_pad, t * 32 + lane, va[t]);
+            for (int t = 0; t < MAXA; ++t) {
+                const int grp = half + 2 * t;
+                if (grp < ia) tn_store_chunk(a_hi, a_lo, j, p.m_pad, grp * 32 + lane, v.a[t]);
+            }
 #pragma unroll
-            for (int t = 0; t < MAXB; ++t)
-                if (t < ib && (t * 32 + lane) < p.n_pad) tn_store_chunk(b_hi, b_lo, j, p.n_pad, t * 32 + lane, vb[t]);
+            for (int t = 0; t < MAXB; ++t) {
+                const int grp = half + 2 * t;
+                if (grp < ib && (grp * 32 + lane) < p.n_pad) tn_store_chunk(b_hi, b_lo, j, p.n_pad, grp * 32 + lane, v.b[t]);
+            }
             fence_proxy_async();
             mbar_arrive(&full[s]);
-            if (st + 1 < n_stages) fetch(st + 1);
+        };
+        fetch(0, v0); fetch(1, v1); fetch(2, v2);
+        for (int st = 0; st < n_stages; st += 3) {
+            consume(st, v0); fetch(st + 3, v0);
+            if (st + 1 < n_stages) { consume(st + 1, v1); fetch(st + 4, v1); }
+            if (st + 2 < n_stages) { consume(st + 2, v2); fetch(st + 5, v2); }
         }
 
         // =========================== epilogue: TMEM -> coalesced partial tile ===========================
         float *tw = reinterpret_cast<float *>(smem) + warp * (32 * 33);          // stage memory is free now
+        const int quad = warp & 3;                                               // TMEM lane quadrant this warp may read
         float *dst_tile = p.partial + (size_t)blockIdx.x * p.m_pad * p.n_pad;
         if (n_stages > 0) {
             mbar_wait(tmem_full, 0);
             tc_fence_after();
         }
         for (int mt = 0; mt < m_tiles; ++mt) {
-            for (int c0 = 0; c0 < p.n_pad; c0 += 32) {
+            for (int c0 = half * 32; c0 < p.n_pad; c0 += 64) {                   // the two halves interleave the column chunks
                 float acc[32];
                 if (n_stages > 0) {
-                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * p.n_pad + c0), acc);
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * p.n_pad + c0), acc);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
@@ -158,14 +171,14 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p)
                 for (int i = 0; i < 32; ++i) tw[lane * 33 + i] = acc[i];
                 __syncwarp();
                 if (c0 + lane < p.n_pad) {
-                    float *dst = dst_tile + (size_t)(mt * 128 + warp * 32) * p.n_pad + c0 + lane;
+                    float *dst = dst_tile + (size_t)(mt * 128 + quad * 32) * p.n_pad + c0 + lane;
 #pragma unroll 8
                     for (int rr = 0; rr < 32; ++rr) dst[(size_t)rr * p.n_pad] = tw[rr * 33 + lane];
                 }
                 __syncwarp();
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == TN_PRODUCER_WARPS) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(128, (uint32_t)p.n_pad, 0, 0);        // K-major after the transposing producer
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, tmem_cols);
+    if (warp == TN_PRODUCER_WARPS + 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // out[m, n] (+)= sum_s partial[s, m - m0, n - n0]     (double accumulation; OutT = float or double)

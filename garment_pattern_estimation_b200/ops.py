@@ -15,6 +15,7 @@ Operators (reference call sites in parentheses, relative to /root/reference):
   * ``linear``           nn.Linear on rows (panel_dec_lin nn/nets.py:232, placement_decoder nn/nets.py:128)
 """
 import ctypes
+import os
 
 import torch
 
@@ -89,7 +90,7 @@ class EdgeSrc:
 
 
 GRAD_PRECISION = _lib.NT_PREC_TF32X3
-TN_ENGINE = 'simt'    # weight-gradient GEMM: 'tc' (tcgen05, deterministic) is correct but its transposing producer is still
+TN_ENGINE = os.environ.get('NT_TN_ENGINE', 'simt')    # weight-gradient GEMM: 'tc' (tcgen05, deterministic) is correct but its transposing producer is still
                       # latency-bound (1.5 ms vs 1.0 ms per launch at C2); the CUDA-core kernel stays the default this round
 GEMM_ENGINE = 'tc'    # 'tc' = tcgen05 tensor-core engine (product path); 'simt' = fp32 CUDA-core engine (validation only)
 
