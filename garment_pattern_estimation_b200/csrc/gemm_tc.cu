@@ -159,29 +159,31 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
         // Register prefetch ring, depth 3: the gather is latency-bound (random rows of PQ miss L2 while the activation
         // stream evicts it), so the loads of K blocks kb+1 .. kb+3 are in flight while block kb is packed and handed to
         // the tensor core.  (Loop unrolled by 3 so every buffer is addressed statically.)
-        float v0[4][8], v1[4][8], v2[4][8];
-        auto fetch = [&](int kb, float (&v)[4][8]) {
+        // NOTE: fetch() only LOADS (raw centre and neighbour values stay in separate registers); the add / ReLU that
+        // consumes them is deferred to consume(), otherwise the first use would stall on the loads right away.
+        struct Regs { float p[4][EPC]; float q[PROD == NT_PROD_EDGE ? 4 : 1][EPC]; };
+        Regs v0, v1, v2;
+        auto fetch = [&](int kb, Regs &v) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int k = (kb * 4 + j) * EPC;
+                float t[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
-                if (r_ok && kb < g.num_kb && k < p.K) {
-                    load_chunk<EPC>(ap, k, p.K, vec, v[j]);
-                    if (PROD == NT_PROD_EDGE) {
-                        if (aq) {
-                            float q[8];
-                            load_chunk<EPC>(aq, k, p.K, vec, q);
+                for (int e = 0; e < 8; ++e) t[e] = 0.f;
+                const bool live = r_ok && kb < g.num_kb && k < p.K;
+                if (live) load_chunk<EPC>(ap, k, p.K, vec, t);
 #pragma unroll
-                            for (int e = 0; e < EPC; ++e) v[j][e] += q[e];
-                        }
+                for (int e = 0; e < EPC; ++e) v.p[j][e] = t[e];
+                if (PROD == NT_PROD_EDGE) {
 #pragma unroll
-                        for (int e = 0; e < EPC; ++e) v[j][e] = fmaxf(v[j][e], 0.f);
-                    }
+                    for (int e = 0; e < 8; ++e) t[e] = 0.f;
+                    if (live && aq) load_chunk<EPC>(aq, k, p.K, vec, t);
+#pragma unroll
+                    for (int e = 0; e < EPC; ++e) v.q[j][e] = t[e];
                 }
             }
         };
-        auto consume = [&](int kb, float (&v)[4][8]) {
+        auto consume = [&](int kb, Regs &v) {
             const int s = kb & 1, use = kb >> 1;
             mbar_wait(&empty[s], (use & 1) ^ 1);
             uint8_t *a_hi = stage_base[s], *a_lo = a_hi + TC_A_BYTES, *b_all = a_lo + TC_A_BYTES;
@@ -192,8 +194,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+                float t[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) t[e] = 0.f;
+#pragma unroll
+                for (int e = 0; e < EPC; ++e)
+                    t[e] = (PROD == NT_PROD_EDGE) ? fmaxf(v.p[j][e] + v.q[j][e], 0.f) : v.p[j][e];
                 uint4 h, l;
-                pack_chunk(v[j], TF32, h, l);
+                pack_chunk(t, TF32, h, l);
                 *reinterpret_cast<uint4 *>(a_hi + j * (TC_M * 16) + r * 16) = h;
                 *reinterpret_cast<uint4 *>(a_lo + j * (TC_M * 16) + r * 16) = l;
             }

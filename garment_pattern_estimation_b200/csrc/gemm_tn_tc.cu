@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p)
         const int half = warp >> 2;
         constexpr int MAXA = TN_MAX_M / 32 / 2, MAXB = TN_MAX_N / 32 / 2;  // 32-row groups per thread
         const int ia = p.m_pad / 32, ib = (p.n_pad + 31) / 32;
-        struct Regs { float a[MAXA][4]; float b[MAXB][4]; };
+        struct Regs { float a[MAXA][4]; float b[MAXB][4]; float q[MAXB][4]; };   // raw loads; combined in consume()
         Regs v0, v1, v2;                                                 // prefetch ring, depth 3 (static addressing)
 
         auto fetch = [&](int st, Regs &v) {
@@ -110,19 +110,11 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p)
                 const int grp = half + 2 * t;
                 const int col = p.n0 + grp * 32 + lane;
                 const bool c_ok = grp < ib && (grp * 32 + lane) < p.n_pad && col < p.n;
-                const float mu = (c_ok && p.mu) ? __ldg(p.mu + col) : 0.f;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    float x = 0.f;
-                    if (c_ok && bp[i]) {
-                        x = __ldg(bp[i] + col);
-                        if (p.b_edge) {
-                            if (bq[i]) x += __ldg(bq[i] + col);
-                            x = fmaxf(x, 0.f);
-                        }
-                        x -= mu;
-                    }
-                    v.b[t][i] = x;
+                    // invalid rows / columns must end up exactly 0 after relu(b + q) - mu: encode them as b = mu, q = 0
+                    v.b[t][i] = (c_ok && bp[i]) ? __ldg(bp[i] + col) : 0.f;
+                    v.q[t][i] = (c_ok && bp[i] && p.b_edge && bq[i]) ? __ldg(bq[i] + col) : 0.f;
                 }
             }
         };
@@ -138,7 +130,20 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p)
 #pragma unroll
             for (int t = 0; t < MAXB; ++t) {
                 const int grp = half + 2 * t;
-                if (grp < ib && (grp * 32 + lane) < p.n_pad) tn_store_chunk(b_hi, b_lo, j, p.n_pad, grp * 32 + lane, v.b[t]);
+                if (grp < ib && (grp * 32 + lane) < p.n_pad) {
+                    const int col = p.n0 + grp * 32 + lane;
+                    const bool c_ok = col < p.n;
+                    const float mu = (c_ok && p.mu) ? __ldg(p.mu + col) : 0.f;
+                    float x[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int64_t r = r_begin + (int64_t)st * TN_RB + 4 * j + i;
+                        float y = v.b[t][i];
+                        if (p.b_edge) y = fmaxf(y + v.q[t][i], 0.f);
+                        x[i] = (c_ok && r < r_end) ? y - mu : 0.f;
+                    }
+                    tn_store_chunk(b_hi, b_lo, j, p.n_pad, grp * 32 + lane, x);
+                }
             }
             fence_proxy_async();
             mbar_arrive(&full[s]);
