@@ -166,53 +166,94 @@ __global__ void edge_stats_kernel(const float *pq, int ldpq, int qoff, const int
     }
 }
 
-__global__ void bn_relu_bwd_last_kernel(const float *a, int lda, const float *g, int ldg, const uint8_t *sel, int k,
-                                        const float *s, const float *mu, const float *rstd, const double *sums,
-                                        int64_t count, int64_t rows, int C, float *dz, int lddz, double *colsum) {
-    __shared__ float r0[8][33];
-    const int c = blockIdx.y * 32 + threadIdx.x;
-    const int64_t rbeg = (int64_t)blockIdx.x * CR_ROWS;
-    const int64_t rend = min(rows, rbeg + CR_ROWS);
-    float acc = 0.f;
-    if (c < C) {
+// Each thread owns 4 consecutive columns (one float4 when the row stride allows it) and walks its row chunk 8 rows apart;
+// block = (32 column-quads, 8 row lanes) -> a warp reads 512 contiguous bytes of a row.
+constexpr int BL_ROWS = 256;   // rows per block
+
+__global__ void __launch_bounds__(256) bn_relu_bwd_last_kernel(const float *__restrict__ a, int lda, const float *__restrict__ g,
+                                                               int ldg, const uint8_t *__restrict__ sel, int k,
+                                                               const float *__restrict__ s, const float *__restrict__ mu,
+                                                               const float *__restrict__ rstd, const double *__restrict__ sums,
+                                                               int64_t count, int64_t rows, int C, float *__restrict__ dz,
+                                                               int lddz, double *__restrict__ colsum) {
+    __shared__ float red[8][32][4];
+    const int c0 = (blockIdx.y * 32 + threadIdx.x) * 4;
+    const int64_t rbeg = (int64_t)blockIdx.x * BL_ROWS;
+    const int64_t rend = min(rows, rbeg + BL_ROWS);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < C) {
         const float inv = 1.0f / (float)count;
-        const float sc = s[c], m = mu[c], rs = rstd[c];
-        const float dbeta = (float)sums[c] * inv, dgamma = (float)sums[C + c] * inv;
+        float sc[4], m[4], rs[4], dbeta[4], dgamma[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = min(c0 + j, C - 1);
+            sc[j] = s[c]; m[j] = mu[c]; rs[j] = rstd[c];
+            dbeta[j] = (float)sums[c] * inv; dgamma[j] = (float)sums[C + c] * inv;
+        }
+        const bool vec = (c0 + 3 < C) && ((lda & 3) == 0) && ((lddz & 3) == 0) && aligned16(a) && aligned16(dz);
         for (int64_t r = rbeg + threadIdx.y; r < rend; r += 8) {
-            const float av = a[r * lda + c];
-            float out = 0.f;
-            if (av > 0.f) {
-                const int64_t node = r / k;
-                float gs = 0.f;
-                if (!sel || sel[node * C + c] == (uint8_t)(r - node * k)) gs = g[node * ldg + c];
-                out = sc * (gs - dbeta - (av - m) * rs * dgamma);
+            float av[4];
+            if (vec) {
+                const float4 t = *reinterpret_cast<const float4 *>(a + r * lda + c0);
+                av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) av[j] = (c0 + j < C) ? a[r * lda + c0 + j] : 0.f;
             }
-            dz[r * lddz + c] = out;
-            acc += out;
+            const int64_t node = r / k;
+            const uint8_t slot = (uint8_t)(r - node * k);
+            float out[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                out[j] = 0.f;
+                if (c0 + j < C && av[j] > 0.f) {
+                    float gs = 0.f;
+                    if (!sel || sel[node * C + c0 + j] == slot) gs = g[node * ldg + c0 + j];
+                    out[j] = sc[j] * (gs - dbeta[j] - (av[j] - m[j]) * rs[j] * dgamma[j]);
+                }
+                acc[j] += out[j];
+            }
+            if (vec) {
+                *reinterpret_cast<float4 *>(dz + r * lddz + c0) = make_float4(out[0], out[1], out[2], out[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c0 + j < C) dz[r * lddz + c0 + j] = out[j];
+            }
         }
     }
-    r0[threadIdx.y][threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.y == 0 && c < C && colsum) {
-        float s0 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s0 += r0[i][threadIdx.x];
-        atomicAdd(colsum + c, (double)s0);
+    for (int j = 0; j < 4; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.y == 0 && colsum) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (c0 + j >= C) continue;
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x][j];
+            atomicAdd(colsum + c0 + j, (double)t);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-__global__ void linear_bn_bwd_kernel(const double *rawc, const double *csum, int n_out, int C, const float *w,
-                                     const float *s, const float *beta, const float *rstd, int64_t count,
-                                     float *dW, float *db, float *dgamma, float *dbeta, float *k0, float *k1) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one WARP per input channel c: lanes stride over the n_out output rows, double partial sums reduced by shuffles
+__global__ void __launch_bounds__(256) linear_bn_bwd_kernel(const double *__restrict__ rawc, const double *__restrict__ csum,
+                                                            int n_out, int C, const float *__restrict__ w,
+                                                            const float *__restrict__ s, const float *__restrict__ beta,
+                                                            const float *__restrict__ rstd, int64_t count, float *__restrict__ dW,
+                                                            float *__restrict__ db, float *__restrict__ dgamma,
+                                                            float *__restrict__ dbeta, float *__restrict__ k0, float *__restrict__ k1) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (blockIdx.x == 0) {
         for (int o = threadIdx.x; o < n_out; o += blockDim.x) db[o] = (float)csum[o];
     }
     if (c >= C) return;
     const double sc = s[c], bc = beta[c];
     double db_acc = 0.0, dg_acc = 0.0;
-    for (int o = 0; o < n_out; ++o) {
+    for (int o = lane; o < n_out; o += 32) {
         const double cs = csum[o];
         const double rw = rawc[(int64_t)o * C + c];
         const double wv = w[(int64_t)o * C + c];
@@ -221,11 +262,18 @@ __global__ void linear_bn_bwd_kernel(const double *rawc, const double *csum, int
         db_acc += wv * cs;
         dg_acc += wv * rw;
     }
-    dg_acc *= (double)rstd[c];
-    dbeta[c] = (float)db_acc; dgamma[c] = (float)dg_acc;
-    const double inv = 1.0 / (double)count;
-    k0[c] = (float)(sc * db_acc * inv);
-    k1[c] = (float)(sc * (double)rstd[c] * dg_acc * inv);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        db_acc += __shfl_xor_sync(0xffffffffu, db_acc, off);
+        dg_acc += __shfl_xor_sync(0xffffffffu, dg_acc, off);
+    }
+    if (lane == 0) {
+        dg_acc *= (double)rstd[c];
+        dbeta[c] = (float)db_acc; dgamma[c] = (float)dg_acc;
+        const double inv = 1.0 / (double)count;
+        k0[c] = (float)(sc * db_acc * inv);
+        k1[c] = (float)(sc * (double)rstd[c] * dg_acc * inv);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -318,7 +366,7 @@ extern "C" int nt_bn_relu_bwd_last(const float *a, int lda, const float *g, int 
     NT_REQUIRE(a && g && s && mu && rstd && sums && dz && k >= 1 && count >= 1 && C >= 1, "nt_bn_relu_bwd_last: bad arguments");
     NT_REQUIRE(lda >= C && ldg >= C && lddz >= C && rows % k == 0, "nt_bn_relu_bwd_last: bad strides");
     if (rows == 0) return 0;
-    dim3 grid(blocks_for(rows, CR_ROWS), (C + 31) / 32), block(32, 8);
+    dim3 grid(blocks_for(rows, BL_ROWS), (C + 127) / 128), block(32, 8);
     bn_relu_bwd_last_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         a, lda, g, ldg, sel, k, s, mu, rstd, sums, count, rows, C, dz, lddz, colsum);
     return check_launch("nt_bn_relu_bwd_last");
@@ -330,7 +378,7 @@ extern "C" int nt_linear_bn_bwd(const double *rawc, const double *csum, int n_ou
     NT_REQUIRE(rawc && csum && dW && db && n_out >= 1 && C >= 1, "nt_linear_bn_bwd: bad arguments");
     NT_REQUIRE(w && s && beta && rstd && dgamma && dbeta && k0 && k1 && count >= 1,
                "nt_linear_bn_bwd: BN operands missing");
-    linear_bn_bwd_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    linear_bn_bwd_kernel<<<(C + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         rawc, csum, n_out, C, w, s, beta, rstd, count, dW, db, dgamma, dbeta, k0, k1);
     return check_launch("nt_linear_bn_bwd");
 }

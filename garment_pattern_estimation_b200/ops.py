@@ -90,8 +90,8 @@ class EdgeSrc:
 
 
 GRAD_PRECISION = _lib.NT_PREC_TF32X3
-TN_ENGINE = os.environ.get('NT_TN_ENGINE', 'simt')    # weight-gradient GEMM: 'tc' (tcgen05, deterministic) is correct but its transposing producer is still
-                      # latency-bound (1.5 ms vs 1.0 ms per launch at C2); the CUDA-core kernel stays the default this round
+TN_ENGINE = os.environ.get('NT_TN_ENGINE', 'tc')      # weight-gradient GEMM: 'tc' = tcgen05 + deterministic split reduction (0.6 ms per
+                      # launch at C2), 'simt' = fp32 CUDA-core kernel with atomics (1.0 ms; validation only)
 GEMM_ENGINE = 'tc'    # 'tc' = tcgen05 tensor-core engine (product path); 'simt' = fp32 CUDA-core engine (validation only)
 
 

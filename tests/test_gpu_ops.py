@@ -307,6 +307,6 @@ def test_tc_weight_gradient_gemm_matches_float64(ops, cuda_device, rows, m, n):
             out_c = torch.zeros(m, n, dtype=torch.float64, device=dev)
             ops.gemm_tn(a, a.stride(0), m, rows, out_c, b=b, ldb=b.stride(0), n=n, mu=mu)
         finally:
-            ops.GEMM_ENGINE, ops.TN_ENGINE = 'tc', 'simt'
+            ops.GEMM_ENGINE, ops.TN_ENGINE = 'tc', 'tc'
         assert rel_err(out, want) < 2e-5, engine
         assert rel_err(out_c, want_c) < 2e-5, engine
