@@ -35,6 +35,7 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+FLOP_SINK = None      # dict: kernel group -> useful flops (bench.py roofline_tensor)
 EVENT_SINK = None     # set to a dict to collect (start, end) CUDA-event pairs per kernel group (bench.py roofline)
 
 
@@ -129,8 +130,10 @@ def gemm_nt(rows, K, n_out, w, ldw, epilogue, a=None, lda=0, edge=None, bias=Non
         g.vmax, g.vmin, g.imax, g.imin = (_p(t) for t in agg)
     g.aux, g.ldaux, g.aux_edge = _p(aux), int(ldaux), int(bool(aux_edge))
     g.k0, g.k1, g.mu, g.colsum = _p(k0), _p(k1), _p(mu), _p(colsum)
-    _call('nt_gemm_nt', _lib.load().nt_gemm_nt, ctypes.byref(g), _stream(),
-          group='nt_gemm_nt[%s,%s]' % (_EPI_NAMES[epilogue], 'edge' if g.producer == NT_PROD_EDGE else 'plain'))
+    group = 'nt_gemm_nt[%s,%s]' % (_EPI_NAMES[epilogue], 'edge' if g.producer == NT_PROD_EDGE else 'plain')
+    if FLOP_SINK is not None:
+        FLOP_SINK[group] = FLOP_SINK.get(group, 0.0) + 2.0 * rows * K * n_out
+    _call('nt_gemm_nt', _lib.load().nt_gemm_nt, ctypes.byref(g), _stream(), group=group)
 
 
 def gemm_tn(a, lda, m, rows, out, b=None, ldb=0, n=0, edge=None, mu=None):
@@ -143,6 +146,9 @@ def gemm_tn(a, lda, m, rows, out, b=None, ldb=0, n=0, edge=None, mu=None):
         bop = (None, 0, n, rows, _p(edge.pq), edge.ldpq, edge.qoff, _p(edge.idx), edge.k, edge.n_per_cloud)
     else:
         bop = (_p(b), ldb, n, rows, None, 0, 0, None, 1, 1)
+    if FLOP_SINK is not None:
+        name = 'nt_gemm_tn_centered' if mu is not None else 'nt_gemm_tn'
+        FLOP_SINK[name] = FLOP_SINK.get(name, 0.0) + 2.0 * rows * m * n
     if mu is not None:
         assert out.dtype == torch.float64
         _call('nt_gemm_tn_centered', lib.nt_gemm_tn_centered, _p(a), lda, m, *bop, _p(mu), _p(out), out.stride(0),
