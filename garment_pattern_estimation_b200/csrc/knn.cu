@@ -67,6 +67,9 @@ __device__ __forceinline__ void load_query_chunk(const float *__restrict__ xq, i
             const int d = d0 + 4 * g;
             if (qvec && d + 3 < D) {
                 v = __ldg(reinterpret_cast<const float4 *>(xq + d));
+            } else if (qvec && d + 2 == D) {
+                const float2 t = __ldg(reinterpret_cast<const float2 *>(xq + d));
+                v.x = t.x; v.y = t.y;
             } else {
                 if (d + 0 < D) v.x = __ldg(xq + d + 0);
                 if (d + 1 < D) v.y = __ldg(xq + d + 1);
@@ -82,17 +85,21 @@ __device__ __forceinline__ void load_query_chunk(const float *__restrict__ xq, i
 // decrease.  A candidate whose partial sum is already >= the current k-th best distance of EVERY lane of the warp can never
 // satisfy the strict insertion test `dist < kth` for any of them, so its remaining dimensions are skipped; the (partial)
 // value it keeps still fails that test.  Thresholds only tighten, so a stale alive bit is merely conservative.
-template <int K, int KNN_THREADS, bool PRUNE, bool PREFETCH>
+// DT > 0: the feature count is a compile-time constant (rows 16-byte aligned, checked at launch) so every bounds test of
+// the query / tile loads folds away -- with a runtime D those guards were ~25 % of the issued instructions (ncu, round 1).
+template <int K, int KNN_THREADS, bool PRUNE, bool PREFETCH, int DT>
 __global__ void __launch_bounds__(KNN_THREADS, (K <= 16) ? 512 / KNN_THREADS : 256 / KNN_THREADS)
-knn_kernel(const float *__restrict__ x, int N, int D, int ldx, int k, int32_t *__restrict__ idx) {
+knn_kernel(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int32_t *__restrict__ idx) {
     extern __shared__ __align__(16) float tile[];   // [KNN_TC][Dp]
+    const int D = DT ? DT : D_rt;
     const int Dp = (D + 3) & ~3;
     const int b = blockIdx.y;
     const int q = blockIdx.x * KNN_THREADS + threadIdx.x;
     const bool q_ok = q < N;
     const float *cloud = x + (size_t)b * N * ldx;
     const float *xq = cloud + (size_t)(q_ok ? q : 0) * ldx;
-    const bool qvec = ((ldx & 3) == 0) && aligned16(x);
+    const bool qvec = DT ? true : (((ldx & 3) == 0) && aligned16(x));
+    const bool q_ld = DT ? true : q_ok;     // with DT idle lanes read row 0 (in bounds) instead of branching
 
     float ld[K];
     int li[K];
@@ -104,7 +111,7 @@ knn_kernel(const float *__restrict__ x, int N, int D, int ldx, int k, int32_t *_
     const int n_chunks = full_chunks + (tail_groups ? 1 : 0);
 
     float qv[KNN_DC], qn[KNN_DC];
-    if (PREFETCH) load_query_chunk(xq, 0, (0 < full_chunks) ? KNN_DC / 4 : tail_groups, D, q_ok, qvec, qn);
+    if (PREFETCH) load_query_chunk(xq, 0, (0 < full_chunks) ? KNN_DC / 4 : tail_groups, D, q_ld, qvec, qn);
 
     for (int c0 = 0; c0 < N; c0 += KNN_TC) {
         __syncthreads();
@@ -129,9 +136,9 @@ knn_kernel(const float *__restrict__ x, int N, int D, int ldx, int k, int32_t *_
                 for (int i = 0; i < KNN_DC; ++i) qv[i] = qn[i];
                 // prefetch the query values of the NEXT chunk (wrapping to chunk 0 for the next tile)
                 const int nch = (ch + 1 < n_chunks) ? ch + 1 : 0;
-                load_query_chunk(xq, nch * KNN_DC, (nch < full_chunks) ? KNN_DC / 4 : tail_groups, D, q_ok, qvec, qn);
+                load_query_chunk(xq, nch * KNN_DC, (nch < full_chunks) ? KNN_DC / 4 : tail_groups, D, q_ld, qvec, qn);
             } else {
-                load_query_chunk(xq, d0, groups, D, q_ok, qvec, qv);
+                load_query_chunk(xq, d0, groups, D, q_ld, qvec, qv);
             }
             switch (groups) {
                 case 4: chain_chunk<4, PRUNE>(acc, alive, tile, Dp, d0, qv); break;
@@ -287,19 +294,27 @@ static int launch_knn_x2(const float *x, int B, int N, int D, int ldx, int k, in
     return check_launch("nt_knn");
 }
 
-template <int K, int THREADS, bool PRUNE, bool PREFETCH>
-static int launch_knn_cfg(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
+template <int K, int THREADS, bool PRUNE, bool PREFETCH, int DT>
+static int launch_knn_dt(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
     const int Dp = (D + 3) & ~3;
     size_t smem = (size_t)KNN_TC * Dp * sizeof(float);
     if (smem > 200 * 1024) return fail("nt_knn: feature dimension %s too large for the staging tile (D=%ld)", "", D);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(knn_kernel<K, THREADS, PRUNE, PREFETCH>,
+        cudaError_t e = cudaFuncSetAttribute(knn_kernel<K, THREADS, PRUNE, PREFETCH, DT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail("nt_knn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
     dim3 grid((N + THREADS - 1) / THREADS, B);
-    knn_kernel<K, THREADS, PRUNE, PREFETCH><<<grid, THREADS, smem, st>>>(x, N, D, ldx, k, idx);
+    knn_kernel<K, THREADS, PRUNE, PREFETCH, DT><<<grid, THREADS, smem, st>>>(x, N, D, ldx, k, idx);
     return check_launch("nt_knn");
+}
+
+template <int K, int THREADS, bool PRUNE, bool PREFETCH>
+static int launch_knn_cfg(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
+    // specialised feature counts of the shipped configs (EConv_feature = 150); needs 16-byte aligned rows
+    const bool aligned = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+    if (D == 150 && aligned && !PRUNE && !PREFETCH) return launch_knn_dt<K, THREADS, false, false, 150>(x, B, N, D, ldx, k, idx, st);
+    return launch_knn_dt<K, THREADS, PRUNE, PREFETCH, 0>(x, B, N, D, ldx, k, idx, st);
 }
 
 static int g_knn_variant = -1;      // developer knob (NT_KNN_VARIANT), read once
