@@ -294,6 +294,136 @@ static int launch_knn_x2(const float *x, int B, int N, int D, int ldx, int k, in
     return check_launch("nt_knn");
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Two queries per thread (default).  ncu on the one-query kernel: FP32 pipe 43 % busy and identical run time for the
+// scalar, the packed-FP32x2 and the guard-free variants -> the limiter is the shared-memory -> register return path
+// (128 B/clk/SM): a broadcast LDS.128 still writes 512 B of registers per warp, i.e. 4 cycles per 8 FP instructions.
+// Reusing every candidate word for TWO queries halves that traffic (16 FP instructions per LDS.128) and puts the bound
+// back on the FP32 pipe.  Candidates are processed 16 at a time so the 2 x 16 fma chains still fit in registers.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int KNN_HC = 16;     // candidates per half tile
+
+template <int NG>
+__device__ __forceinline__ void chain_chunk_q2(float (&a0)[KNN_HC], float (&a1)[KNN_HC], const float *__restrict__ tile, int Dp,
+                                               int d0, const float (&q0)[KNN_DC], const float (&q1)[KNN_DC]) {
+#pragma unroll
+    for (int c = 0; c < KNN_HC; ++c) {
+        const float4 *row = reinterpret_cast<const float4 *>(tile + c * Dp + d0);
+        float x = a0[c], y = a1[c];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const float4 cv = row[g];
+            float d, e;
+            d = __fsub_rn(cv.x, q0[4 * g + 0]); e = __fsub_rn(cv.x, q1[4 * g + 0]); x = __fmaf_rn(d, d, x); y = __fmaf_rn(e, e, y);
+            d = __fsub_rn(cv.y, q0[4 * g + 1]); e = __fsub_rn(cv.y, q1[4 * g + 1]); x = __fmaf_rn(d, d, x); y = __fmaf_rn(e, e, y);
+            d = __fsub_rn(cv.z, q0[4 * g + 2]); e = __fsub_rn(cv.z, q1[4 * g + 2]); x = __fmaf_rn(d, d, x); y = __fmaf_rn(e, e, y);
+            d = __fsub_rn(cv.w, q0[4 * g + 3]); e = __fsub_rn(cv.w, q1[4 * g + 3]); x = __fmaf_rn(d, d, x); y = __fmaf_rn(e, e, y);
+        }
+        a0[c] = x; a1[c] = y;
+    }
+}
+
+template <int K, int KNN_THREADS, int DT>
+__global__ void __launch_bounds__(KNN_THREADS, (K <= 8) ? 512 / KNN_THREADS : 256 / KNN_THREADS)
+knn_kernel_q2(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int32_t *__restrict__ idx) {
+    extern __shared__ __align__(16) float tile[];   // [KNN_TC][Dp]
+    const int D = DT ? DT : D_rt;
+    const int Dp = (D + 3) & ~3;
+    const int b = blockIdx.y;
+    const int qa = blockIdx.x * (2 * KNN_THREADS) + threadIdx.x;
+    const int qb = qa + KNN_THREADS;
+    const bool a_ok = qa < N, b_ok = qb < N;
+    const float *cloud = x + (size_t)b * N * ldx;
+    const float *xa = cloud + (size_t)(a_ok ? qa : 0) * ldx;
+    const float *xb = cloud + (size_t)(b_ok ? qb : 0) * ldx;
+    const bool qvec = DT ? true : (((ldx & 3) == 0) && aligned16(x));
+    const bool la = DT ? true : a_ok, lb = DT ? true : b_ok;
+
+    float lda_[K], ldb_[K];
+    int lia[K], lib[K];
+#pragma unroll
+    for (int e = 0; e < K; ++e) { lda_[e] = 1e10f; lia[e] = -1; ldb_[e] = 1e10f; lib[e] = -1; }
+
+    const int full_chunks = Dp / KNN_DC;
+    const int tail_groups = (Dp - full_chunks * KNN_DC) >> 2;
+    const int n_chunks = full_chunks + (tail_groups ? 1 : 0);
+
+    for (int c0 = 0; c0 < N; c0 += KNN_TC) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < KNN_TC * Dp; i += KNN_THREADS) {
+            int c = i / Dp, d = i - c * Dp;
+            float v = 0.f;
+            if (c0 + c < N && d < D) v = __ldg(cloud + (size_t)(c0 + c) * ldx + d);
+            tile[i] = v;
+        }
+        __syncthreads();
+
+#pragma unroll 1
+        for (int h = 0; h < KNN_TC / KNN_HC; ++h) {
+            const float *half_tile = tile + h * KNN_HC * Dp;
+            const int cbase = c0 + h * KNN_HC;
+            if (cbase >= N) break;
+            float a0[KNN_HC], a1[KNN_HC];
+#pragma unroll
+            for (int c = 0; c < KNN_HC; ++c) { a0[c] = 0.f; a1[c] = 0.f; }
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                const int d0 = ch * KNN_DC;
+                const int groups = (ch < full_chunks) ? (KNN_DC / 4) : tail_groups;
+                float q0[KNN_DC], q1[KNN_DC];
+                load_query_chunk(xa, d0, groups, D, la, qvec, q0);
+                load_query_chunk(xb, d0, groups, D, lb, qvec, q1);
+                switch (groups) {
+                    case 4: chain_chunk_q2<4>(a0, a1, half_tile, Dp, d0, q0, q1); break;
+                    case 3: chain_chunk_q2<3>(a0, a1, half_tile, Dp, d0, q0, q1); break;
+                    case 2: chain_chunk_q2<2>(a0, a1, half_tile, Dp, d0, q0, q1); break;
+                    default: chain_chunk_q2<1>(a0, a1, half_tile, Dp, d0, q0, q1); break;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < KNN_HC; ++c) {
+                if (cbase + c < N) {
+                    if (a0[c] < lda_[K - 1]) topk_insert<K>(lda_, lia, a0[c], cbase + c);
+                    if (a1[c] < ldb_[K - 1]) topk_insert<K>(ldb_, lib, a1[c], cbase + c);
+                }
+            }
+        }
+    }
+
+    if (a_ok) {
+        int32_t *o = idx + ((size_t)b * N + qa) * k;
+#pragma unroll
+        for (int e = 0; e < K; ++e)
+            if (e < k) o[e] = lia[e];
+    }
+    if (b_ok) {
+        int32_t *o = idx + ((size_t)b * N + qb) * k;
+#pragma unroll
+        for (int e = 0; e < K; ++e)
+            if (e < k) o[e] = lib[e];
+    }
+}
+
+template <int K, int THREADS, int DT>
+static int launch_knn_q2(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
+    const int Dp = (D + 3) & ~3;
+    size_t smem = (size_t)KNN_TC * Dp * sizeof(float);
+    if (smem > 200 * 1024) return fail("nt_knn: feature dimension %s too large for the staging tile (D=%ld)", "", D);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(knn_kernel_q2<K, THREADS, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail("nt_knn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    dim3 grid((N + 2 * THREADS - 1) / (2 * THREADS), B);
+    knn_kernel_q2<K, THREADS, DT><<<grid, THREADS, smem, st>>>(x, N, D, ldx, k, idx);
+    return check_launch("nt_knn");
+}
+
+template <int K, int THREADS>
+static int launch_knn_q2_any(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
+    const bool aligned = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+    if (D == 150 && aligned) return launch_knn_q2<K, THREADS, 150>(x, B, N, D, ldx, k, idx, st);
+    return launch_knn_q2<K, THREADS, 0>(x, B, N, D, ldx, k, idx, st);
+}
+
 template <int K, int THREADS, bool PRUNE, bool PREFETCH, int DT>
 static int launch_knn_dt(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
     const int Dp = (D + 3) & ~3;
@@ -328,8 +458,10 @@ static int launch_knn(const float *x, int B, int N, int D, int ldx, int k, int32
     switch (g_knn_variant) {
         case 4: return launch_knn_cfg<K, 256, true, false>(x, B, N, D, ldx, k, idx, st);
         case 7: return launch_knn_x2<K, 256>(x, B, N, D, ldx, k, idx, st);
-        case 8: return launch_knn_x2<K, 128>(x, B, N, D, ldx, k, idx, st);
-        default: return launch_knn_cfg<K, 256, false, false>(x, B, N, D, ldx, k, idx, st);
+        case 9: return launch_knn_cfg<K, 256, false, false>(x, B, N, D, ldx, k, idx, st);
+        case 10: return launch_knn_q2_any<K, 64>(x, B, N, D, ldx, k, idx, st);
+        case 11: return launch_knn_q2_any<K, 256>(x, B, N, D, ldx, k, idx, st);
+        default: return launch_knn_q2_any<K, 128>(x, B, N, D, ldx, k, idx, st);
     }
 }
 
