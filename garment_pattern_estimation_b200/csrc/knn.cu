@@ -323,9 +323,13 @@ __device__ __forceinline__ void chain_chunk_q2(float (&a0)[KNN_HC], float (&a1)[
     }
 }
 
+// blockIdx.z selects a slice of the CANDIDATE range (split S = gridDim.z): with one thread per query pair the grid would
+// only hold B*N/64 warps (1024 at C2, 7 per SM), so the scan of every query is split over S CTAs that each write a partial
+// sorted list; knn_merge_kernel then takes the k lexicographically smallest (distance, index) pairs -- still exact.
 template <int K, int KNN_THREADS, int DT>
 __global__ void __launch_bounds__(KNN_THREADS, (K <= 8) ? 512 / KNN_THREADS : 256 / KNN_THREADS)
-knn_kernel_q2(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int32_t *__restrict__ idx) {
+knn_kernel_q2(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int32_t *__restrict__ idx,
+              float *__restrict__ part_d, int32_t *__restrict__ part_i, int cand_per_split) {
     extern __shared__ __align__(16) float tile[];   // [KNN_TC][Dp]
     const int D = DT ? DT : D_rt;
     const int Dp = (D + 3) & ~3;
@@ -348,12 +352,14 @@ knn_kernel_q2(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int3
     const int tail_groups = (Dp - full_chunks * KNN_DC) >> 2;
     const int n_chunks = full_chunks + (tail_groups ? 1 : 0);
 
-    for (int c0 = 0; c0 < N; c0 += KNN_TC) {
+    const int c_begin = blockIdx.z * cand_per_split;
+    const int c_end = min(N, c_begin + cand_per_split);
+    for (int c0 = c_begin; c0 < c_end; c0 += KNN_TC) {
         __syncthreads();
         for (int i = threadIdx.x; i < KNN_TC * Dp; i += KNN_THREADS) {
             int c = i / Dp, d = i - c * Dp;
             float v = 0.f;
-            if (c0 + c < N && d < D) v = __ldg(cloud + (size_t)(c0 + c) * ldx + d);
+            if (c0 + c < c_end && d < D) v = __ldg(cloud + (size_t)(c0 + c) * ldx + d);
             tile[i] = v;
         }
         __syncthreads();
@@ -362,7 +368,7 @@ knn_kernel_q2(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int3
         for (int h = 0; h < KNN_TC / KNN_HC; ++h) {
             const float *half_tile = tile + h * KNN_HC * Dp;
             const int cbase = c0 + h * KNN_HC;
-            if (cbase >= N) break;
+            if (cbase >= c_end) break;
             float a0[KNN_HC], a1[KNN_HC];
 #pragma unroll
             for (int c = 0; c < KNN_HC; ++c) { a0[c] = 0.f; a1[c] = 0.f; }
@@ -381,7 +387,7 @@ knn_kernel_q2(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int3
             }
 #pragma unroll
             for (int c = 0; c < KNN_HC; ++c) {
-                if (cbase + c < N) {
+                if (cbase + c < c_end) {
                     if (a0[c] < lda_[K - 1]) topk_insert<K>(lda_, lia, a0[c], cbase + c);
                     if (a1[c] < ldb_[K - 1]) topk_insert<K>(ldb_, lib, a1[c], cbase + c);
                 }
@@ -389,22 +395,68 @@ knn_kernel_q2(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int3
         }
     }
 
-    if (a_ok) {
-        int32_t *o = idx + ((size_t)b * N + qa) * k;
+    if (gridDim.z == 1) {
+        if (a_ok) {
+            int32_t *o = idx + ((size_t)b * N + qa) * k;
 #pragma unroll
-        for (int e = 0; e < K; ++e)
-            if (e < k) o[e] = lia[e];
-    }
-    if (b_ok) {
-        int32_t *o = idx + ((size_t)b * N + qb) * k;
+            for (int e = 0; e < K; ++e)
+                if (e < k) o[e] = lia[e];
+        }
+        if (b_ok) {
+            int32_t *o = idx + ((size_t)b * N + qb) * k;
 #pragma unroll
-        for (int e = 0; e < K; ++e)
-            if (e < k) o[e] = lib[e];
+            for (int e = 0; e < K; ++e)
+                if (e < k) o[e] = lib[e];
+        }
+    } else {      // partial lists: [query][split][K]
+        if (a_ok) {
+            const size_t o = (((size_t)b * N + qa) * gridDim.z + blockIdx.z) * K;
+#pragma unroll
+            for (int e = 0; e < K; ++e) { part_d[o + e] = lda_[e]; part_i[o + e] = lia[e]; }
+        }
+        if (b_ok) {
+            const size_t o = (((size_t)b * N + qb) * gridDim.z + blockIdx.z) * K;
+#pragma unroll
+            for (int e = 0; e < K; ++e) { part_d[o + e] = ldb_[e]; part_i[o + e] = lib[e]; }
+        }
     }
 }
 
+// exact merge of S sorted partial lists per query: slices are visited in ascending candidate order, so the stable
+// strict-greater insertion reproduces the sequential scan (equal distances keep the lower index first)
+template <int K>
+__global__ void knn_merge_kernel(const float *__restrict__ part_d, const int32_t *__restrict__ part_i, int64_t M, int S, int k,
+                                 int32_t *__restrict__ idx) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= M) return;
+    float ld[K];
+    int li[K];
+#pragma unroll
+    for (int e = 0; e < K; ++e) { ld[e] = 1e10f; li[e] = -1; }
+    for (int s = 0; s < S; ++s) {
+        const size_t o = ((size_t)q * S + s) * K;
+        for (int e = 0; e < K; ++e) {
+            const float d = part_d[o + e];
+            if (d < ld[K - 1]) topk_insert<K>(ld, li, d, part_i[o + e]);
+            else break;                                      // the slice list is ascending
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < K; ++e)
+        if (e < k) idx[q * k + e] = li[e];
+}
+
+static int knn_split_for(int B, int N, int threads) {
+    // enough CTAs for ~2 resident waves of warps; every slice a multiple of the 32-candidate tile
+    const long ctas = (long)B * ((N + 2 * threads - 1) / (2 * threads));
+    int S = 1;
+    while (S < 8 && ctas * S * (threads / 32) < 2 * 148 * 8 && (N / (2 * S)) >= 2 * KNN_TC) S *= 2;
+    return S;
+}
+
 template <int K, int THREADS, int DT>
-static int launch_knn_q2(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
+static int launch_knn_q2(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *workspace, int S,
+                         cudaStream_t st) {
     const int Dp = (D + 3) & ~3;
     size_t smem = (size_t)KNN_TC * Dp * sizeof(float);
     if (smem > 200 * 1024) return fail("nt_knn: feature dimension %s too large for the staging tile (D=%ld)", "", D);
@@ -412,16 +464,27 @@ static int launch_knn_q2(const float *x, int B, int N, int D, int ldx, int k, in
         cudaError_t e = cudaFuncSetAttribute(knn_kernel_q2<K, THREADS, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail("nt_knn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    dim3 grid((N + 2 * THREADS - 1) / (2 * THREADS), B);
-    knn_kernel_q2<K, THREADS, DT><<<grid, THREADS, smem, st>>>(x, N, D, ldx, k, idx);
-    return check_launch("nt_knn");
+    if (!workspace) S = 1;
+    const int per = ((N + S - 1) / S + KNN_TC - 1) / KNN_TC * KNN_TC;
+    S = (N + per - 1) / per;
+    const int64_t M = (int64_t)B * N;
+    float *part_d = reinterpret_cast<float *>(workspace);
+    int32_t *part_i = reinterpret_cast<int32_t *>(part_d + (size_t)M * S * K);
+    dim3 grid((N + 2 * THREADS - 1) / (2 * THREADS), B, S);
+    knn_kernel_q2<K, THREADS, DT><<<grid, THREADS, smem, st>>>(x, N, D, ldx, k, idx, part_d, part_i, per);
+    int rc = check_launch("nt_knn");
+    if (rc || S == 1) return rc;
+    knn_merge_kernel<K><<<(unsigned)((M + 255) / 256), 256, 0, st>>>(part_d, part_i, M, S, k, idx);
+    return check_launch("nt_knn(merge)");
 }
 
 template <int K, int THREADS>
-static int launch_knn_q2_any(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
+static int launch_knn_q2_any(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *workspace, int S,
+                             cudaStream_t st) {
     const bool aligned = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
-    if (D == 150 && aligned) return launch_knn_q2<K, THREADS, 150>(x, B, N, D, ldx, k, idx, st);
-    return launch_knn_q2<K, THREADS, 0>(x, B, N, D, ldx, k, idx, st);
+    if (S <= 0) S = knn_split_for(B, N, THREADS);
+    if (D == 150 && aligned) return launch_knn_q2<K, THREADS, 150>(x, B, N, D, ldx, k, idx, workspace, S, st);
+    return launch_knn_q2<K, THREADS, 0>(x, B, N, D, ldx, k, idx, workspace, S, st);
 }
 
 template <int K, int THREADS, bool PRUNE, bool PREFETCH, int DT>
@@ -450,7 +513,7 @@ static int launch_knn_cfg(const float *x, int B, int N, int D, int ldx, int k, i
 static int g_knn_variant = -1;      // developer knob (NT_KNN_VARIANT), read once
 
 template <int K>
-static int launch_knn(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
+static int launch_knn(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *ws, cudaStream_t st) {
     if (g_knn_variant < 0) {
         const char *v = getenv("NT_KNN_VARIANT");
         g_knn_variant = v ? atoi(v) : 0;
@@ -459,15 +522,24 @@ static int launch_knn(const float *x, int B, int N, int D, int ldx, int k, int32
         case 4: return launch_knn_cfg<K, 256, true, false>(x, B, N, D, ldx, k, idx, st);
         case 7: return launch_knn_x2<K, 256>(x, B, N, D, ldx, k, idx, st);
         case 9: return launch_knn_cfg<K, 256, false, false>(x, B, N, D, ldx, k, idx, st);
-        case 10: return launch_knn_q2_any<K, 64>(x, B, N, D, ldx, k, idx, st);
-        case 11: return launch_knn_q2_any<K, 256>(x, B, N, D, ldx, k, idx, st);
-        default: return launch_knn_q2_any<K, 128>(x, B, N, D, ldx, k, idx, st);
+        case 10: return launch_knn_q2_any<K, 64>(x, B, N, D, ldx, k, idx, ws, 2, st);
+        case 11: return launch_knn_q2_any<K, 128>(x, B, N, D, ldx, k, idx, ws, 2, st);
+        case 12: return launch_knn_q2_any<K, 64>(x, B, N, D, ldx, k, idx, ws, 4, st);
+        case 13: return launch_knn_q2_any<K, 128>(x, B, N, D, ldx, k, idx, ws, 4, st);
+        case 14: return launch_knn_q2_any<K, 128>(x, B, N, D, ldx, k, idx, ws, 1, st);
+        default: return launch_knn_q2_any<K, 64>(x, B, N, D, ldx, k, idx, ws, 0, st);
     }
 }
 
 }  // namespace nt
 
-extern "C" int nt_knn(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *stream) {
+extern "C" int64_t nt_knn_workspace_bytes(int B, int N, int k) {
+    if (B < 1 || N < 1 || k < 1) return 0;
+    const int K = k <= 5 ? 5 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32));
+    return (int64_t)B * N * 8 /*max split*/ * K * 8 /*dist + index*/;
+}
+
+extern "C" int nt_knn(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *workspace, void *stream) {
     using namespace nt;
     NT_REQUIRE(x && idx, "nt_knn: null pointer");
     NT_REQUIRE(B >= 0 && N >= 0 && D >= 1 && ldx >= D, "nt_knn: bad shape");
@@ -476,8 +548,8 @@ extern "C" int nt_knn(const float *x, int B, int N, int D, int ldx, int k, int32
     NT_REQUIRE(B <= 65535, "nt_knn: at most 65535 clouds per call");
     if (B == 0 || N == 0) return 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (k <= 5) return launch_knn<5>(x, B, N, D, ldx, k, idx, st);
-    if (k <= 8) return launch_knn<8>(x, B, N, D, ldx, k, idx, st);
-    if (k <= 16) return launch_knn<16>(x, B, N, D, ldx, k, idx, st);
-    return launch_knn<32>(x, B, N, D, ldx, k, idx, st);
+    if (k <= 5) return launch_knn<5>(x, B, N, D, ldx, k, idx, workspace, st);
+    if (k <= 8) return launch_knn<8>(x, B, N, D, ldx, k, idx, workspace, st);
+    if (k <= 16) return launch_knn<16>(x, B, N, D, ldx, k, idx, workspace, st);
+    return launch_knn<32>(x, B, N, D, ldx, k, idx, workspace, st);
 }

@@ -168,7 +168,9 @@ def knn_graph(x, B, N, k):
     if x.shape[0] != B * N:
         raise RuntimeError('knn_graph: expected {} rows, got {}'.format(B * N, x.shape[0]))
     idx = torch.empty(B * N, k, dtype=torch.int32, device=x.device)
-    _call('nt_knn', _lib.load().nt_knn, _p(x), B, N, x.shape[1], ldx, k, _p(idx), _stream(),
+    lib = _lib.load()
+    ws = torch.empty(int(lib.nt_knn_workspace_bytes(B, N, k)), dtype=torch.uint8, device=x.device)
+    _call('nt_knn', lib.nt_knn, _p(x), B, N, x.shape[1], ldx, k, _p(idx), _p(ws), _stream(),
           group='nt_knn[D=%d]' % x.shape[1])
     return idx
 

@@ -36,8 +36,11 @@ int64_t nt_launch_count(void);
  * For every point of every cloud: the k nearest points of the SAME cloud by squared L2 over D features, self
  * included, ascending by (distance, index); distance = sequential fp32 fma chain over d = 0..D-1 (bit-exact with
  * oracle/knn_oracle.c).  x: [B*N, >=D] with row stride ldx.  idx: [B*N, k] int32, local to the cloud.
- * Requires 1 <= k <= 32 and k <= N. */
-int nt_knn(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *stream);
+ * Requires 1 <= k <= 32 and k <= N.
+ * workspace: nt_knn_workspace_bytes(B, N, k) bytes of device memory (partial lists when the candidate scan is split over
+ * several CTAs to fill the GPU); NULL = never split. */
+int64_t nt_knn_workspace_bytes(int B, int N, int k);
+int nt_knn(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *workspace, void *stream);
 
 /* ---- generic fused row GEMM:  out = epilogue( producer(A) . W^T )   (W: [n_out, K] like nn.Linear.weight) --
  * Serves the Linear layers of MLP() (nn/net_blocks.py:43-47) inside DynamicEdgeConv.message (edge rows) and

@@ -51,11 +51,11 @@ def test_bad_arguments_return_error_codes_not_crashes():
     """argument validation happens before any CUDA call, so it can be exercised on a CPU box"""
     from garment_pattern_estimation_b200 import _lib
     lib = _lib.load()
-    assert lib.nt_knn(None, 1, 10, 3, 3, 5, None, None) != 0
+    assert lib.nt_knn(None, 1, 10, 3, 3, 5, None, None, None) != 0
     assert b'null' in lib.nt_last_error()
     buf = (ctypes.c_float * 64)()
     ibuf = (ctypes.c_int32 * 64)()
-    assert lib.nt_knn(ctypes.cast(buf, ctypes.c_void_p), 1, 4, 3, 3, 64, ctypes.cast(ibuf, ctypes.c_void_p), None) != 0
+    assert lib.nt_knn(ctypes.cast(buf, ctypes.c_void_p), 1, 4, 3, 3, 64, ctypes.cast(ibuf, ctypes.c_void_p), None, None) != 0
     assert b'k must be' in lib.nt_last_error()
     assert lib.nt_sparsemax_fwd(ctypes.cast(buf, ctypes.c_void_p), 2, 33, ctypes.cast(buf, ctypes.c_void_p), None) != 0
     with pytest.raises(RuntimeError):
