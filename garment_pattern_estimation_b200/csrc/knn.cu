@@ -171,6 +171,94 @@ knn_kernel(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int32_t
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// High-occupancy variant: 16 candidates per tile so the thread fits in 64 registers and 32 warps are resident per SM.
+// ------------------------------------------------------------------------------------------------------------------
+template <int K, int DT>
+__global__ void __launch_bounds__(256, 4)
+knn_kernel_occ(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int32_t *__restrict__ idx) {
+    constexpr int TC = 16;
+    extern __shared__ __align__(16) float tile[];   // [TC][Dp]
+    const int D = DT ? DT : D_rt;
+    const int Dp = (D + 3) & ~3;
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    const bool q_ok = q < N;
+    const float *cloud = x + (size_t)b * N * ldx;
+    const float *xq = cloud + (size_t)(q_ok ? q : 0) * ldx;
+    const bool qvec = DT ? true : (((ldx & 3) == 0) && aligned16(x));
+    const bool q_ld = DT ? true : q_ok;
+    float ld[K];
+    int li[K];
+#pragma unroll
+    for (int e = 0; e < K; ++e) { ld[e] = 1e10f; li[e] = -1; }
+    const int n_groups = Dp >> 2;
+    for (int c0 = 0; c0 < N; c0 += TC) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < TC * Dp; i += 256) {
+            int c = i / Dp, d = i - c * Dp;
+            float v = 0.f;
+            if (c0 + c < N && d < D) v = __ldg(cloud + (size_t)(c0 + c) * ldx + d);
+            tile[i] = v;
+        }
+        __syncthreads();
+        float acc[TC];
+#pragma unroll
+        for (int c = 0; c < TC; ++c) acc[c] = 0.f;
+#pragma unroll 2
+        for (int g = 0; g < n_groups; ++g) {
+            float qv4[KNN_DC];
+            // one float4 of the query per step (4 dims), 16 chains advance by 4 dims each
+            {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int d = 4 * g;
+                if (q_ld) {
+                    if (qvec && d + 3 < D) v = __ldg(reinterpret_cast<const float4 *>(xq + d));
+                    else if (qvec && d + 2 == D) { const float2 t = __ldg(reinterpret_cast<const float2 *>(xq + d)); v.x = t.x; v.y = t.y; }
+                    else {
+                        if (d + 0 < D) v.x = __ldg(xq + d + 0);
+                        if (d + 1 < D) v.y = __ldg(xq + d + 1);
+                        if (d + 2 < D) v.z = __ldg(xq + d + 2);
+                        if (d + 3 < D) v.w = __ldg(xq + d + 3);
+                    }
+                }
+                qv4[0] = v.x; qv4[1] = v.y; qv4[2] = v.z; qv4[3] = v.w;
+            }
+#pragma unroll
+            for (int c = 0; c < TC; ++c) {
+                const float4 cv = *reinterpret_cast<const float4 *>(tile + c * Dp + 4 * g);
+                float a = acc[c], t;
+                t = __fsub_rn(cv.x, qv4[0]); a = __fmaf_rn(t, t, a);
+                t = __fsub_rn(cv.y, qv4[1]); a = __fmaf_rn(t, t, a);
+                t = __fsub_rn(cv.z, qv4[2]); a = __fmaf_rn(t, t, a);
+                t = __fsub_rn(cv.w, qv4[3]); a = __fmaf_rn(t, t, a);
+                acc[c] = a;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < TC; ++c)
+            if (c0 + c < N && acc[c] < ld[K - 1]) topk_insert<K>(ld, li, acc[c], c0 + c);
+    }
+    if (q_ok) {
+        int32_t *o = idx + ((size_t)b * N + q) * k;
+#pragma unroll
+        for (int e = 0; e < K; ++e)
+            if (e < k) o[e] = li[e];
+    }
+}
+
+template <int K>
+static int launch_knn_occ(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
+    const int Dp = (D + 3) & ~3;
+    size_t smem = (size_t)16 * Dp * sizeof(float);
+    if (smem > 48 * 1024) return fail("nt_knn: feature dimension %s too large (D=%ld)", "", D);
+    const bool aligned = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+    dim3 grid((N + 255) / 256, B);
+    if (D == 150 && aligned) knn_kernel_occ<K, 150><<<grid, 256, smem, st>>>(x, N, D, ldx, k, idx);
+    else knn_kernel_occ<K, 0><<<grid, 256, smem, st>>>(x, N, D, ldx, k, idx);
+    return check_launch("nt_knn");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Packed-FP32x2 variant (Blackwell FADD2 / FFMA2: add.rn.f32x2, fma.rn.f32x2).  Two candidates share one instruction, so
 // a pair-dimension costs 1 issue slot instead of 2; every half is an independent IEEE fma.rn, i.e. the same bits as the
 // scalar chain.  The candidate tile is stored TRANSPOSED ([dim][candidate], row stride 36 floats) so that one broadcast
@@ -527,6 +615,7 @@ static int launch_knn(const float *x, int B, int N, int D, int ldx, int k, int32
         case 12: return launch_knn_q2_any<K, 64>(x, B, N, D, ldx, k, idx, ws, 4, st);
         case 13: return launch_knn_q2_any<K, 128>(x, B, N, D, ldx, k, idx, ws, 4, st);
         case 14: return launch_knn_q2_any<K, 128>(x, B, N, D, ldx, k, idx, ws, 1, st);
+        case 15: return launch_knn_occ<K>(x, B, N, D, ldx, k, idx, st);
         default: return launch_knn_q2_any<K, 64>(x, B, N, D, ldx, k, idx, ws, 0, st);
     }
 }
