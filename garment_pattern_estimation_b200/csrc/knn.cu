@@ -89,7 +89,8 @@ __device__ __forceinline__ void load_query_chunk(const float *__restrict__ xq, i
 // the query / tile loads folds away -- with a runtime D those guards were ~25 % of the issued instructions (ncu, round 1).
 template <int K, int KNN_THREADS, bool PRUNE, bool PREFETCH, int DT>
 __global__ void __launch_bounds__(KNN_THREADS, (K <= 16) ? 512 / KNN_THREADS : 256 / KNN_THREADS)
-knn_kernel(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int32_t *__restrict__ idx) {
+knn_kernel(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int32_t *__restrict__ idx,
+           float *__restrict__ part_d, int32_t *__restrict__ part_i, int cand_per_split) {
     extern __shared__ __align__(16) float tile[];   // [KNN_TC][Dp]
     const int D = DT ? DT : D_rt;
     const int Dp = (D + 3) & ~3;
@@ -113,12 +114,15 @@ knn_kernel(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int32_t
     float qv[KNN_DC], qn[KNN_DC];
     if (PREFETCH) load_query_chunk(xq, 0, (0 < full_chunks) ? KNN_DC / 4 : tail_groups, D, q_ld, qvec, qn);
 
-    for (int c0 = 0; c0 < N; c0 += KNN_TC) {
+    // blockIdx.z = slice of the candidate range (see knn_merge_kernel): finer work items even out the SM load
+    const int c_begin = blockIdx.z * cand_per_split;
+    const int c_end = min(N, c_begin + cand_per_split);
+    for (int c0 = c_begin; c0 < c_end; c0 += KNN_TC) {
         __syncthreads();
         for (int i = threadIdx.x; i < KNN_TC * Dp; i += KNN_THREADS) {
             int c = i / Dp, d = i - c * Dp;
             float v = 0.f;
-            if (c0 + c < N && d < D) v = __ldg(cloud + (size_t)(c0 + c) * ldx + d);
+            if (c0 + c < c_end && d < D) v = __ldg(cloud + (size_t)(c0 + c) * ldx + d);
             tile[i] = v;
         }
         __syncthreads();
@@ -126,7 +130,7 @@ knn_kernel(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int32_t
         float acc[KNN_TC];
 #pragma unroll
         for (int c = 0; c < KNN_TC; ++c) acc[c] = 0.f;
-        unsigned alive = (c0 + KNN_TC <= N) ? 0xffffffffu : ((1u << (N - c0)) - 1u);
+        unsigned alive = (c0 + KNN_TC <= c_end) ? 0xffffffffu : ((1u << (c_end - c0)) - 1u);
 
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int d0 = ch * KNN_DC;
@@ -158,16 +162,46 @@ knn_kernel(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int32_t
 
 #pragma unroll
         for (int c = 0; c < KNN_TC; ++c) {
-            if (c0 + c < N && acc[c] < ld[K - 1]) topk_insert<K>(ld, li, acc[c], c0 + c);
+            if (c0 + c < c_end && acc[c] < ld[K - 1]) topk_insert<K>(ld, li, acc[c], c0 + c);
         }
     }
 
     if (q_ok) {
-        int32_t *o = idx + ((size_t)b * N + q) * k;
+        if (gridDim.z == 1) {
+            int32_t *o = idx + ((size_t)b * N + q) * k;
 #pragma unroll
-        for (int e = 0; e < K; ++e)
-            if (e < k) o[e] = li[e];
+            for (int e = 0; e < K; ++e)
+                if (e < k) o[e] = li[e];
+        } else {
+            const size_t o = (((size_t)b * N + q) * gridDim.z + blockIdx.z) * K;
+#pragma unroll
+            for (int e = 0; e < K; ++e) { part_d[o + e] = ld[e]; part_i[o + e] = li[e]; }
+        }
     }
+}
+
+// exact merge of S sorted partial lists per query: slices are visited in ascending candidate order, so the stable
+// strict-greater insertion reproduces the sequential scan (equal distances keep the lower index first)
+template <int K>
+__global__ void knn_merge_kernel(const float *__restrict__ part_d, const int32_t *__restrict__ part_i, int64_t M, int S, int k,
+                                 int32_t *__restrict__ idx) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= M) return;
+    float ld[K];
+    int li[K];
+#pragma unroll
+    for (int e = 0; e < K; ++e) { ld[e] = 1e10f; li[e] = -1; }
+    for (int s = 0; s < S; ++s) {
+        const size_t o = ((size_t)q * S + s) * K;
+        for (int e = 0; e < K; ++e) {
+            const float d = part_d[o + e];
+            if (d < ld[K - 1]) topk_insert<K>(ld, li, d, part_i[o + e]);
+            else break;                                      // the slice list is ascending
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < K; ++e)
+        if (e < k) idx[q * k + e] = li[e];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -510,30 +544,6 @@ knn_kernel_q2(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int3
     }
 }
 
-// exact merge of S sorted partial lists per query: slices are visited in ascending candidate order, so the stable
-// strict-greater insertion reproduces the sequential scan (equal distances keep the lower index first)
-template <int K>
-__global__ void knn_merge_kernel(const float *__restrict__ part_d, const int32_t *__restrict__ part_i, int64_t M, int S, int k,
-                                 int32_t *__restrict__ idx) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= M) return;
-    float ld[K];
-    int li[K];
-#pragma unroll
-    for (int e = 0; e < K; ++e) { ld[e] = 1e10f; li[e] = -1; }
-    for (int s = 0; s < S; ++s) {
-        const size_t o = ((size_t)q * S + s) * K;
-        for (int e = 0; e < K; ++e) {
-            const float d = part_d[o + e];
-            if (d < ld[K - 1]) topk_insert<K>(ld, li, d, part_i[o + e]);
-            else break;                                      // the slice list is ascending
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < K; ++e)
-        if (e < k) idx[q * k + e] = li[e];
-}
-
 static int knn_split_for(int B, int N, int threads) {
     // enough CTAs for ~2 resident waves of warps; every slice a multiple of the 32-candidate tile
     const long ctas = (long)B * ((N + 2 * threads - 1) / (2 * threads));
@@ -576,7 +586,8 @@ static int launch_knn_q2_any(const float *x, int B, int N, int D, int ldx, int k
 }
 
 template <int K, int THREADS, bool PRUNE, bool PREFETCH, int DT>
-static int launch_knn_dt(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
+static int launch_knn_dt(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *workspace, int S,
+                         cudaStream_t st) {
     const int Dp = (D + 3) & ~3;
     size_t smem = (size_t)KNN_TC * Dp * sizeof(float);
     if (smem > 200 * 1024) return fail("nt_knn: feature dimension %s too large for the staging tile (D=%ld)", "", D);
@@ -585,17 +596,40 @@ static int launch_knn_dt(const float *x, int B, int N, int D, int ldx, int k, in
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail("nt_knn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    dim3 grid((N + THREADS - 1) / THREADS, B);
-    knn_kernel<K, THREADS, PRUNE, PREFETCH, DT><<<grid, THREADS, smem, st>>>(x, N, D, ldx, k, idx);
-    return check_launch("nt_knn");
+    if (!workspace || S < 1) S = 1;
+    const int per = ((N + S - 1) / S + KNN_TC - 1) / KNN_TC * KNN_TC;
+    S = (N + per - 1) / per;
+    const int64_t M = (int64_t)B * N;
+    float *part_d = reinterpret_cast<float *>(workspace);
+    int32_t *part_i = reinterpret_cast<int32_t *>(part_d + (size_t)M * S * K);
+    dim3 grid((N + THREADS - 1) / THREADS, B, S);
+    knn_kernel<K, THREADS, PRUNE, PREFETCH, DT><<<grid, THREADS, smem, st>>>(x, N, D, ldx, k, idx, part_d, part_i, per);
+    int rc = check_launch("nt_knn");
+    if (rc || S == 1) return rc;
+    knn_merge_kernel<K><<<(unsigned)((M + 255) / 256), 256, 0, st>>>(part_d, part_i, M, S, k, idx);
+    return check_launch("nt_knn(merge)");
+}
+
+// Candidate split: the one-thread-per-query grid has only B*N/THREADS CTAs (256 at C2 for 296 resident slots: 108 SMs get
+// two CTAs, 40 get one).  Splitting the scan into S slices makes ~7 work items per slot, which the hardware CTA scheduler
+// balances dynamically; capped so a slice keeps at least 4 tiles.
+static int knn_auto_split(int B, int N, int threads) {
+    const long ctas = (long)B * ((N + threads - 1) / threads);
+    const long slots = 148L * (512 / threads);
+    int S = 1;
+    while (S < 8 && ctas * S < 6 * slots && N / (2 * S) >= 4 * KNN_TC) S *= 2;
+    return S;
 }
 
 template <int K, int THREADS, bool PRUNE, bool PREFETCH>
-static int launch_knn_cfg(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
+static int launch_knn_cfg(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *workspace, int S,
+                          cudaStream_t st) {
     // specialised feature counts of the shipped configs (EConv_feature = 150); needs 16-byte aligned rows
     const bool aligned = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
-    if (D == 150 && aligned && !PRUNE && !PREFETCH) return launch_knn_dt<K, THREADS, false, false, 150>(x, B, N, D, ldx, k, idx, st);
-    return launch_knn_dt<K, THREADS, PRUNE, PREFETCH, 0>(x, B, N, D, ldx, k, idx, st);
+    if (S <= 0) S = knn_auto_split(B, N, THREADS);
+    if (D == 150 && aligned && !PRUNE && !PREFETCH)
+        return launch_knn_dt<K, THREADS, false, false, 150>(x, B, N, D, ldx, k, idx, workspace, S, st);
+    return launch_knn_dt<K, THREADS, PRUNE, PREFETCH, 0>(x, B, N, D, ldx, k, idx, workspace, S, st);
 }
 
 static int g_knn_variant = -1;      // developer knob (NT_KNN_VARIANT), read once
@@ -607,16 +641,14 @@ static int launch_knn(const float *x, int B, int N, int D, int ldx, int k, int32
         g_knn_variant = v ? atoi(v) : 0;
     }
     switch (g_knn_variant) {
-        case 4: return launch_knn_cfg<K, 256, true, false>(x, B, N, D, ldx, k, idx, st);
-        case 7: return launch_knn_x2<K, 256>(x, B, N, D, ldx, k, idx, st);
-        case 9: return launch_knn_cfg<K, 256, false, false>(x, B, N, D, ldx, k, idx, st);
-        case 10: return launch_knn_q2_any<K, 64>(x, B, N, D, ldx, k, idx, ws, 2, st);
-        case 11: return launch_knn_q2_any<K, 128>(x, B, N, D, ldx, k, idx, ws, 2, st);
-        case 12: return launch_knn_q2_any<K, 64>(x, B, N, D, ldx, k, idx, ws, 4, st);
-        case 13: return launch_knn_q2_any<K, 128>(x, B, N, D, ldx, k, idx, ws, 4, st);
-        case 14: return launch_knn_q2_any<K, 128>(x, B, N, D, ldx, k, idx, ws, 1, st);
-        case 15: return launch_knn_occ<K>(x, B, N, D, ldx, k, idx, st);
-        default: return launch_knn_q2_any<K, 64>(x, B, N, D, ldx, k, idx, ws, 0, st);
+        // experiments kept for the record; all bit-exact, none faster than the default
+        case 4: return launch_knn_cfg<K, 256, true, false>(x, B, N, D, ldx, k, idx, ws, 1, st);     // warp-level pruning
+        case 7: return launch_knn_x2<K, 256>(x, B, N, D, ldx, k, idx, st);                           // packed FP32x2
+        case 9: return launch_knn_cfg<K, 256, false, false>(x, B, N, D, ldx, k, idx, ws, 1, st);    // no candidate split
+        case 13: return launch_knn_q2_any<K, 128>(x, B, N, D, ldx, k, idx, ws, 4, st);              // two queries per thread
+        case 15: return launch_knn_occ<K>(x, B, N, D, ldx, k, idx, st);                              // 64 registers, 32 warps/SM
+        case 16: return launch_knn_cfg<K, 256, false, false>(x, B, N, D, ldx, k, idx, ws, 4, st);
+        default: return launch_knn_cfg<K, 256, false, false>(x, B, N, D, ldx, k, idx, ws, 0, st);   // auto split (8 at C2)
     }
 }
 
