@@ -90,7 +90,7 @@ class EdgeSrc:
         self.qoff = H if idx is not None else 0
 
 
-GRAD_PRECISION = _lib.NT_PREC_TF32X3
+GRAD_PRECISION = _lib.NT_PREC_BF16X3 if os.environ.get('NT_GRAD_PRECISION', 'tf32x3') == 'bf16x3' else _lib.NT_PREC_TF32X3
 TN_ENGINE = os.environ.get('NT_TN_ENGINE', 'tc')      # weight-gradient GEMM: 'tc' = tcgen05 + deterministic split reduction (0.6 ms per
                       # launch at C2), 'simt' = fp32 CUDA-core kernel with atomics (1.0 ms; validation only)
 GEMM_ENGINE = 'tc'    # 'tc' = tcgen05 tensor-core engine (product path); 'simt' = fp32 CUDA-core engine (validation only)
