@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
                     float a = 0.f;
                     if (rr < wrows && cl_ok) {
                         const float *pp = rowp[warp * 32 + rr];
-                        a = p.aux_edge ? __ldg(pp + cl) : __ldcs(pp + cl);
+                        a = pp[cl];
                         if (p.aux_edge) {
                             const float *qq = rowq[warp * 32 + rr];
                             if (qq) a += __ldg(qq + cl);
@@ -235,11 +235,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
                 __syncwarp();
                 if (cl_ok) {
                     float *dst = p.out + wrow0 * (int64_t)p.ldo + cl;
-                    // activations / gradients stream through L2 (evict-first) so the re-read operands (PQ rows, W) stay resident
-                        for (int rr = 0; rr < wrows; ++rr) {
-                            if (EPI == NT_EPI_BIAS) dst[(int64_t)rr * p.ldo] = tw[rr * 33 + lane];
-                            else __stcs(dst + (int64_t)rr * p.ldo, tw[rr * 33 + lane]);
-                        }
+                    for (int rr = 0; rr < wrows; ++rr) dst[(int64_t)rr * p.ldo] = tw[rr * 33 + lane];
                 }
                 __syncwarp();
             }

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_last_kernel(const float *__re
         for (int64_t r = rbeg + threadIdx.y; r < rend; r += 8) {
             float av[4];
             if (vec) {
-                const float4 t = __ldcs(reinterpret_cast<const float4 *>(a + r * lda + c0));
+                const float4 t = *reinterpret_cast<const float4 *>(a + r * lda + c0);
                 av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
             } else {
 #pragma unroll
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_last_kernel(const float *__re
                 acc[j] += out[j];
             }
             if (vec) {
-                __stcs(reinterpret_cast<float4 *>(dz + r * lddz + c0), make_float4(out[0], out[1], out[2], out[3]));
+                *reinterpret_cast<float4 *>(dz + r * lddz + c0) = make_float4(out[0], out[1], out[2], out[3]);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
