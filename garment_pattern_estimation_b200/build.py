@@ -42,8 +42,17 @@ def nvcc_path():
     return None
 
 
+def _compile_one(nvcc, src, obj, flags, verbose):
+    cmd = [nvcc] + flags + ['-I', INCLUDE, '-c', src, '-o', obj]
+    if verbose:
+        print(' '.join(cmd))
+    subprocess.check_call(cmd)
+
+
 def build(force=False, verbose=False, extra_flags=()):
-    """Compile every .cu under csrc/ into lib/libnt_b200.so.  Returns the library path."""
+    """Compile every .cu under csrc/ (in parallel, one object per source, re-using up-to-date objects) and link them into
+    lib/libnt_b200.so.  Returns the library path."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB_DIR, exist_ok=True)
     stamp = os.path.join(LIB_DIR, 'libnt_b200.stamp')
     fp = _fingerprint()
@@ -52,10 +61,35 @@ def build(force=False, verbose=False, extra_flags=()):
     nvcc = nvcc_path()
     if nvcc is None:
         raise RuntimeError('nvcc not found: cannot build libnt_b200.so (the product has no CPU fallback)')
-    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ['-I', INCLUDE, '-o', LIB_PATH] + sources()
+    obj_dir = os.path.join(LIB_DIR, 'obj')
+    os.makedirs(obj_dir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != '--shared'] + list(extra_flags)
+    headers = hashlib.sha256()
+    for path in [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith('.cuh')] + \
+            [os.path.join(INCLUDE, 'nt_b200.h')]:
+        with open(path, 'rb') as f:
+            headers.update(f.read())
+    headers.update(' '.join(flags).encode())
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + '.o')
+        with open(src, 'rb') as f:
+            key = hashlib.sha256(headers.digest() + f.read()).hexdigest()
+        keyfile = obj + '.key'
+        objs.append(obj)
+        if force or not (os.path.exists(obj) and os.path.exists(keyfile) and open(keyfile).read() == key):
+            jobs.append((src, obj, keyfile, key))
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 4))) as pool:
+        futures = [pool.submit(_compile_one, nvcc, src, obj, flags, verbose) for src, obj, _, _ in jobs]
+        for fut in futures:
+            fut.result()
+    for _, obj, keyfile, key in jobs:
+        with open(keyfile, 'w') as f:
+            f.write(key)
+    link = [nvcc, '--shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB_PATH] + objs
     if verbose:
-        print(' '.join(cmd))
-    subprocess.check_call(cmd)
+        print(' '.join(link))
+    subprocess.check_call(link)
     with open(stamp, 'w') as f:
         f.write(fp)
     return LIB_PATH

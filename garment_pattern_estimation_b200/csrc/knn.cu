@@ -652,12 +652,19 @@ static int launch_knn(const float *x, int B, int N, int D, int ldx, int k, int32
     }
 }
 
+// tensor-core filter + exact re-rank path (knn_tc.cu)
+bool knn_tc_eligible(int N, int D, const void *workspace);
+int64_t knn_tc_workspace_bytes(int B, int N, int k);
+int knn_tc_run(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *workspace, cudaStream_t st);
+
 }  // namespace nt
 
 extern "C" int64_t nt_knn_workspace_bytes(int B, int N, int k) {
     if (B < 1 || N < 1 || k < 1) return 0;
     const int K = k <= 5 ? 5 : (k <= 8 ? 8 : (k <= 16 ? 16 : 32));
-    return (int64_t)B * N * 8 /*max split*/ * K * 8 /*dist + index*/;
+    const int64_t split_bytes = (int64_t)B * N * 8 /*max split*/ * K * 8 /*dist + index*/;
+    const int64_t tc_bytes = nt::knn_tc_workspace_bytes(B, N, k);
+    return split_bytes > tc_bytes ? split_bytes : tc_bytes;
 }
 
 extern "C" int nt_knn(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *workspace, void *stream) {
@@ -669,6 +676,8 @@ extern "C" int nt_knn(const float *x, int B, int N, int D, int ldx, int k, int32
     NT_REQUIRE(B <= 65535, "nt_knn: at most 65535 clouds per call");
     if (B == 0 || N == 0) return 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // feature-space graphs (D >= 8): bf16 tcgen05 filter + exact fp32 re-rank, bit-identical to the direct form below
+    if (knn_tc_eligible(N, D, workspace)) return knn_tc_run(x, B, N, D, ldx, k, idx, workspace, st);
     if (k <= 5) return launch_knn<5>(x, B, N, D, ldx, k, idx, workspace, st);
     if (k <= 8) return launch_knn<8>(x, B, N, D, ldx, k, idx, workspace, st);
     if (k <= 16) return launch_knn<16>(x, B, N, D, ldx, k, idx, workspace, st);

@@ -1,0 +1,594 @@
+// Tensor-core kNN (sm_100a): approximate filter on tcgen05 + exact fp32 re-ranking.  Same contract as knn.cu -- the
+// result is bit-identical to the sequential fp32 fma chain of oracle/knn_oracle.c -- at a fraction of the FP32-ALU work.
+//
+// Replaces torch_cluster.knn as reached from DynamicEdgeConv.forward (reference nn/net_blocks.py:127-135,174) for the
+// feature-space graph of the second EdgeConv layer (D = EConv_feature = 150), where the direct form costs 2*D FP32
+// instructions per pair (449 N^2 flop per cloud, the scaling term of the inference sweep).
+//
+// Idea.  d(i,j) = n_i + n_j - 2 x_i.x_j.  A single bf16 tcgen05 GEMM gives  s~_ij = x^_i . x^_j  (x^ = bf16(x)) with a
+// PROVABLE error: |x^ - x| <= 2^-8 |x|, products of bf16 numbers are exact in the fp32 accumulator, hence
+//     | (n_i + n_j - 2 s~_ij) - chain_ij |  <=  C (n_i + n_j),   C = 8.2e-3
+// (2 * (2u + u^2) / 2 = 7.83e-3 from the operand rounding, < 5e-5 from the fp32 accumulation, the norms and the rounding
+// of the reference chain itself; the rest is margin).  Per query i the kernel keeps
+//     optimistic  score  so_ij = s~_ij - n_j (1 - C) / 2      (upper bound of the true "closeness" up to a row constant)
+//     pessimistic score  sp_ij = so_ij - C n_j                (lower bound)
+// The k-th largest sp seen so far (sigma) bounds the true k-th distance from above, so every true neighbour satisfies
+//     so_ij >= sigma - C n_i.
+// Candidates passing that test (about k + 2 per query on real features) are appended to a per-query list; a second kernel
+// evaluates the exact fp32 chain for them only and selects the k smallest (distance, index) pairs.  Queries whose list
+// overflowed or came up short (NaNs, > 1e10 distances, masses of duplicates) are redone by a brute-force exact kernel, so
+// the result never depends on the filter being tight -- only the speed does.
+//
+// The term -n_j (1 - C) / 2 rides inside the GEMM: three spare K slots of the (zero-padded) last K block carry it as an
+// exact 3-term bf16 split on the candidate side and 1.0 on the query side.
+//
+// Filter kernel (one CTA per SM, 10 warps):
+//   warp 9     loader: cp.async.bulk of pre-split operand blocks (8 KB = 128 rows x 32 bf16 in the UMMA no-swizzle
+//              K-major core-matrix layout) -- the 2 resident query tiles once, candidate blocks through an 8-stage ring;
+//   warp 8     single-thread tcgen05.mma issue, M128 N128 K16, into a double-buffered TMEM accumulator (2 x 256 columns:
+//              two query tiles x 128 candidates);
+//   warps 0-7  epilogue (thread = query row = TMEM lane): tcgen05.ld 32 columns, one compare per pair against the running
+//              threshold; the rare hits are handled in a batched, warp-convergent loop (sorted top-k of sp in registers).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <math.h>
+#include <stdlib.h>
+
+namespace nt {
+using namespace tc;
+
+constexpr float KT_C = 8.2e-3f;
+constexpr int KT_ROWS = 128;            // rows per operand tile
+constexpr int KT_BLK = 8192;            // bytes per (tile, K block): 4 chunks x 128 rows x 16 B
+constexpr int KT_MAXKB = 5;             // D + 3 <= 160
+constexpr int KT_STAGES = 8;
+constexpr int KT_THREADS = 10 * 32;
+constexpr int KT_SURV = 128;            // survivors per query the re-rank kernel handles before falling back
+constexpr size_t KT_CHUNK_BYTES = (size_t)768 << 20;   // workspace budget per chunk of clouds
+
+struct KnnTcPlan {
+    int T, Np, KB, S, tps, QP, cap, Bc;
+    size_t off_norms, off_xs, off_xa, off_meta, off_buf, off_fb, total;
+};
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// KB_sizing: K blocks used for SIZING (KT_MAXKB when D is unknown), KB: the real one (layout strides).
+static KnnTcPlan knn_tc_plan(int B, int N, int KB, int KB_sizing, int k) {
+    KnnTcPlan p;
+    p.T = (N + KT_ROWS - 1) / KT_ROWS;
+    p.Np = p.T * KT_ROWS;
+    p.KB = KB;
+    p.QP = (p.T + 1) / 2;
+    p.cap = k <= 8 ? 128 : 256;
+    int S = 1;
+    while (S < 8 && (long)B * p.QP * S < 2 * 148 && p.T / (2 * S) >= 4) S *= 2;
+    p.tps = (p.T + S - 1) / S;
+    p.S = (p.T + p.tps - 1) / p.tps;
+    const size_t per_cloud_sizing = (size_t)p.Np * 4 + (size_t)p.T * KB_sizing * KT_BLK + (size_t)p.T * KT_BLK +
+                                    (size_t)p.Np * p.S * 8 + (size_t)p.Np * p.S * p.cap * 8 + (size_t)N * 4 + 6 * 256;
+    long bc = (long)(KT_CHUNK_BYTES / per_cloud_sizing);
+    p.Bc = (int)(bc < 1 ? 1 : (bc > B ? B : bc));
+    size_t o = 256;                                             // header: [0] = fallback counter
+    p.off_norms = o; o = align256(o + (size_t)p.Bc * p.Np * 4);
+    p.off_xs = o;    o = align256(o + (size_t)p.Bc * p.T * KB_sizing * KT_BLK);
+    p.off_xa = o;    o = align256(o + (size_t)p.Bc * p.T * KT_BLK);
+    p.off_meta = o;  o = align256(o + (size_t)p.Bc * p.Np * p.S * 8);
+    p.off_buf = o;   o = align256(o + (size_t)p.Bc * p.Np * p.S * p.cap * 8);
+    p.off_fb = o;    o = align256(o + (size_t)p.Bc * N * 4);
+    p.total = o;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// exact distance of the contract: acc = fma(c_d - q_d, c_d - q_d, acc), d = 0..D-1 (never contracted / reassociated)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float chain_dist(const float *__restrict__ xc, const float *__restrict__ xq, int D, bool vec) {
+    float acc = 0.f;
+    int d = 0;
+    if (vec) {
+        for (; d + 3 < D; d += 4) {
+            const float4 c = __ldg(reinterpret_cast<const float4 *>(xc + d));
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(xq + d));
+            float t;
+            t = __fsub_rn(c.x, q.x); acc = __fmaf_rn(t, t, acc);
+            t = __fsub_rn(c.y, q.y); acc = __fmaf_rn(t, t, acc);
+            t = __fsub_rn(c.z, q.z); acc = __fmaf_rn(t, t, acc);
+            t = __fsub_rn(c.w, q.w); acc = __fmaf_rn(t, t, acc);
+        }
+    }
+    for (; d < D; ++d) {
+        const float t = __fsub_rn(__ldg(xc + d), __ldg(xq + d));
+        acc = __fmaf_rn(t, t, acc);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
+    return make_uint4(bf16_bits(v[0]) | (bf16_bits(v[1]) << 16), bf16_bits(v[2]) | (bf16_bits(v[3]) << 16),
+                      bf16_bits(v[4]) | (bf16_bits(v[5]) << 16), bf16_bits(v[6]) | (bf16_bits(v[7]) << 16));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// operand preparation: one thread per (padded) point row
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) knn_tc_prepare_kernel(const float *__restrict__ x, int N, int D, int ldx, int T, int KB,
+                                                            long total_rows, float *__restrict__ norms,
+                                                            uint8_t *__restrict__ xs, uint8_t *__restrict__ xa) {
+    const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= total_rows) return;
+    const int Np = T * KT_ROWS;
+    const int b = (int)(row / Np), rr = (int)(row - (long)b * Np);
+    const int t = rr / KT_ROWS, r = rr - t * KT_ROWS;
+    const bool valid = rr < N;
+    const float *src = x + ((size_t)b * N + (valid ? rr : 0)) * (size_t)ldx;
+    const bool vec = ((ldx & 3) == 0) && aligned16(x);
+    float n = 0.f;
+    float last[8];
+    for (int kb = 0; kb < KB; ++kb) {
+        uint4 *dst = reinterpret_cast<uint4 *>(xs + ((size_t)((size_t)b * T + t) * KB + kb) * KT_BLK);
+        uint4 *dsta = reinterpret_cast<uint4 *>(xa + ((size_t)b * T + t) * KT_BLK);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v[8];
+            const int d0 = kb * 32 + j * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            if (valid) {
+                if (vec && d0 + 7 < D) {
+                    const float4 a = __ldg(reinterpret_cast<const float4 *>(src + d0));
+                    const float4 c = __ldg(reinterpret_cast<const float4 *>(src + d0 + 4));
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) if (d0 + e < D) v[e] = __ldg(src + d0 + e);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) n = __fmaf_rn(v[e], v[e], n);
+            if (kb == KB - 1 && j == 3) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) last[e] = v[e];
+            } else {
+                const uint4 pk = pack8_bf16(v);
+                dst[j * KT_ROWS + r] = pk;
+                if (kb == KB - 1) dsta[j * KT_ROWS + r] = pk;
+            }
+        }
+    }
+    // last chunk of the last K block: up to 5 data dims + the 3 augmentation slots
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(xs + ((size_t)((size_t)b * T + t) * KB + (KB - 1)) * KT_BLK);
+        uint4 *dsta = reinterpret_cast<uint4 *>(xa + ((size_t)b * T + t) * KT_BLK);
+        float vb[8], va[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { vb[e] = last[e]; va[e] = last[e]; }
+        float h1, h2 = 0.f, h3 = 0.f;
+        if (valid) {
+            const float a = -0.5f * n * (1.0f - KT_C);
+            h1 = __bfloat162float(__float2bfloat16_rn(a));
+            const float r1 = a - h1;
+            h2 = __bfloat162float(__float2bfloat16_rn(r1));
+            const float r2 = r1 - h2;
+            h3 = __bfloat162float(__float2bfloat16_rn(r2));
+        } else {
+            h1 = -3.0e38f;                       // padding rows can never pass the filter
+        }
+        vb[5] = h1; vb[6] = h2; vb[7] = h3;
+        va[5] = 1.f; va[6] = 1.f; va[7] = 1.f;
+        dst[3 * KT_ROWS + r] = pack8_bf16(vb);
+        dsta[3 * KT_ROWS + r] = pack8_bf16(va);
+    }
+    norms[row] = valid ? n : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// filter kernel
+// ------------------------------------------------------------------------------------------------------------------
+struct KnnTcArgs {
+    const float *norms; const uint8_t *xs; const uint8_t *xa;
+    int2 *meta; int2 *buf;
+    int N, T, Np, KB, S, tps, QP, k, cap;
+};
+
+__device__ __forceinline__ float select32(const float (&v)[32], int e) {
+    float a[16], b[8], c[4], d[2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (e & 16) ? v[i + 16] : v[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (e & 8) ? a[i + 8] : a[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (e & 4) ? b[i + 4] : b[i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) d[i] = (e & 2) ? c[i + 2] : c[i];
+    return (e & 1) ? d[1] : d[0];
+}
+
+// Drops the entries of a thread's candidate list that the current threshold already excludes.  Returns the new count, or -1
+// when fewer than 32 free slots remain afterwards (the query is then redone by the exact fallback kernel).
+__device__ __noinline__ int knn_tc_compact(int2 *buf, int cnt, float thr, int cap) {
+    int m = 0;
+    for (int e = 0; e < cnt; ++e) {
+        const int2 t = buf[e];
+        if (__int_as_float(t.x) >= thr) buf[m++] = t;
+    }
+    return (m > cap - 32) ? -1 : m;
+}
+
+template <int KL>
+__global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(KnnTcArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *sA = smem;                                               // [2 query tiles][KB][8 KB]
+    uint8_t *sB = sA + 2 * a.KB * KT_BLK;                             // [KT_STAGES][8 KB]
+    float *snrm = reinterpret_cast<float *>(sB + KT_STAGES * KT_BLK); // [2 parity][2 halves][128]
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(snrm + 512);      // [KT_MAXKB]
+    uint64_t *b_full = a_full + KT_MAXKB;                             // [KT_STAGES]
+    uint64_t *b_empty = b_full + KT_STAGES;                           // [KT_STAGES]
+    uint64_t *t_full = b_empty + KT_STAGES;                           // [2]
+    uint64_t *t_empty = t_full + 2;                                   // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int item = blockIdx.x;
+    const int s = item % a.S; item /= a.S;
+    const int qp = item % a.QP;
+    const int b = item / a.QP;
+    const int ct_begin = s * a.tps;
+    const int ct_end = min(a.T, ct_begin + a.tps);
+    const int n_ct = ct_end - ct_begin;                               // >= 1 by construction of the plan
+    int rot = 0;                                                      // start with the query tiles' own neighbourhood
+    if (2 * qp >= ct_begin && 2 * qp < ct_end) rot = 2 * qp - ct_begin;
+
+    if (warp == 8 && lane == 0) {
+        for (int i = 0; i < KT_MAXKB; ++i) mbar_init(&a_full[i], 1);
+        for (int i = 0; i < KT_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 256); }
+        mbar_fence_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint8_t *xs_cloud = a.xs + (size_t)b * a.T * a.KB * KT_BLK;
+
+    if (warp == 9) {
+        // =========================== loader ===========================
+        if (lane == 0) {
+            for (int kb = 0; kb < a.KB; ++kb) {
+                mbar_arrive_expect_tx(&a_full[kb], 2 * KT_BLK);
+                for (int h = 0; h < 2; ++h) {
+                    const int tile = min(2 * qp + h, a.T - 1);
+                    const uint8_t *src = (kb == a.KB - 1) ? a.xa + ((size_t)b * a.T + tile) * KT_BLK
+                                                          : xs_cloud + ((size_t)tile * a.KB + kb) * KT_BLK;
+                    bulk_g2s(sA + (size_t)(h * a.KB + kb) * KT_BLK, src, KT_BLK, &a_full[kb]);
+                }
+            }
+            int it = 0;
+            for (int i = 0; i < n_ct; ++i) {
+                const int ct = ct_begin + (i + rot) % n_ct;
+                for (int kb = 0; kb < a.KB; ++kb, ++it) {
+                    const int st = it % KT_STAGES, use = it / KT_STAGES;
+                    mbar_wait(&b_empty[st], (use & 1) ^ 1);
+                    mbar_arrive_expect_tx(&b_full[st], KT_BLK);
+                    bulk_g2s(sB + (size_t)st * KT_BLK, xs_cloud + ((size_t)ct * a.KB + kb) * KT_BLK, KT_BLK, &b_full[st]);
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+            const uint32_t lbo = KT_ROWS * 16, sbo = 128;
+            int it = 0;
+            for (int i = 0; i < n_ct; ++i) {
+                const int acc = i & 1, ause = i >> 1;
+                mbar_wait(&t_empty[acc], (ause & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < a.KB; ++kb, ++it) {
+                    const int st = it % KT_STAGES, use = it / KT_STAGES;
+                    if (i == 0) mbar_wait(&a_full[kb], 0);
+                    mbar_wait(&b_full[st], use & 1);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(sB + (size_t)st * KT_BLK);
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const uint64_t db = make_smem_desc(b_addr + kk * 2 * lbo, lbo, sbo);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t a_addr = smem_u32(sA + (size_t)(h * a.KB + kb) * KT_BLK);
+                            const uint64_t da = make_smem_desc(a_addr + kk * 2 * lbo, lbo, sbo);
+                            umma_bf16(tmem_base + (uint32_t)(acc * 256 + h * 128), da, db, idesc, (kb | kk) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&b_empty[st]);
+                }
+                umma_commit(&t_full[acc]);
+            }
+        }
+    } else {
+        // =========================== epilogue: thread = query row ===========================
+        const int h = warp >> 2, quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const int qtile = 2 * qp + h;
+        const int q = qtile * KT_ROWS + r;
+        const bool q_ok = qtile < a.T && q < a.N;
+        const float *norms_c = a.norms + (size_t)b * a.Np;
+        const float cni = q_ok ? KT_C * norms_c[q] : 0.f;
+        const int n_lim = q_ok ? a.N : 0;
+        float thr = q_ok ? -INFINITY : INFINITY;
+        float top[KL];                               // ascending; top[0] = k-th largest pessimistic score so far
+#pragma unroll
+        for (int e = 0; e < KL; ++e) top[e] = (e < a.k) ? -INFINITY : INFINITY;
+        int cnt = 0, ovf = 0;
+        int2 *mybuf = a.buf + (((size_t)b * a.Np + (size_t)(q_ok ? q : 0)) * a.S + s) * (size_t)a.cap;
+
+        for (int i = 0; i < n_ct; ++i) {
+            const int ct = ct_begin + (i + rot) % n_ct;
+            const int acc = i & 1, ause = i >> 1;
+            float *nrm = snrm + (i & 1) * 256 + h * 128;
+            nrm[r] = KT_C * __ldg(norms_c + ct * KT_ROWS + r);
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
+            mbar_wait(&t_full[acc], ause & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256 + h * 128 + ch * 32), v);
+                uint32_t m = 0;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) m |= (v[e] >= thr) ? (1u << e) : 0u;
+                if (m) {
+                    if (cnt > a.cap - 32) {
+                        cnt = knn_tc_compact(mybuf, cnt, thr, a.cap);
+                        if (cnt < 0) { cnt = 0; ovf = 1; }
+                    }
+                    while (m) {
+                        const int e = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float val = select32(v, e);
+                        const int j = ct * KT_ROWS + ch * 32 + e;
+                        if (j < n_lim && val >= thr) {
+                            mybuf[cnt++] = make_int2(__float_as_int(val), j);
+                            const float p = val - nrm[ch * 32 + e];
+                            if (p > top[0]) {
+                                top[0] = p;
+#pragma unroll
+                                for (int u = 0; u < KL - 1; ++u) {
+                                    const float lo = fminf(top[u], top[u + 1]), hi = fmaxf(top[u], top[u + 1]);
+                                    top[u] = lo; top[u + 1] = hi;
+                                }
+                                thr = top[0] - cni;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&t_empty[acc]);
+        }
+        if (q_ok) a.meta[((size_t)b * a.Np + q) * a.S + s] = make_int2(__float_as_int(top[0]), cnt | (ovf << 30));
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// re-rank: one warp per query
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) knn_tc_rerank_kernel(const float *__restrict__ x, int N, int D, int ldx, int k,
+                                                           int Np, int S, int cap, long n_queries,
+                                                           const float *__restrict__ norms, const int2 *__restrict__ meta,
+                                                           const int2 *__restrict__ buf, int32_t *__restrict__ idx,
+                                                           int *__restrict__ fb_count, int32_t *__restrict__ fb_list) {
+    __shared__ float s_d[8][KT_SURV];
+    __shared__ int s_j[8][KT_SURV];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long gq = (long)blockIdx.x * 8 + warp;                      // chunk-local query id = b * N + q
+    if (gq >= n_queries) return;
+    const int b = (int)(gq / N), q = (int)(gq - (long)b * N);
+    const size_t row = (size_t)b * Np + q;
+    float *sd = s_d[warp];
+    int *sj = s_j[warp];
+
+    // slot summaries
+    float sigma = -INFINITY;
+    int cnt_l = 0, bad = 0;
+    if (lane < S) {
+        const int2 mt = meta[row * S + lane];
+        sigma = __int_as_float(mt.x);
+        cnt_l = mt.y & 0x3fffffff;
+        bad = (mt.y >> 30) & 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sigma = fmaxf(sigma, __shfl_xor_sync(0xffffffffu, sigma, o));
+    bad = __any_sync(0xffffffffu, bad);
+    const float thr = sigma - KT_C * norms[row];
+
+    int ns = 0;
+    if (!bad) {
+        for (int sl = 0; sl < S && !bad; ++sl) {
+            const int c = __shfl_sync(0xffffffffu, cnt_l, sl);
+            const int2 *bp = buf + (row * S + sl) * (size_t)cap;
+            for (int e0 = 0; e0 < c; e0 += 32) {
+                const int e = e0 + lane;
+                int2 t = make_int2(0, 0);
+                bool keep = false;
+                if (e < c) { t = bp[e]; keep = __int_as_float(t.x) >= thr; }
+                const unsigned mk = __ballot_sync(0xffffffffu, keep);
+                const int pos = ns + __popc(mk & ((1u << lane) - 1u));
+                if (ns + __popc(mk) > KT_SURV) { bad = 1; break; }
+                if (keep) sj[pos] = t.y;
+                ns += __popc(mk);
+            }
+        }
+    }
+    if (!bad && ns < k) bad = 1;
+    __syncwarp();
+    if (!bad) {
+        const float *cloud = x + (size_t)b * N * (size_t)ldx;
+        const float *xq = cloud + (size_t)q * ldx;
+        const bool vec = ((ldx & 3) == 0) && aligned16(x);
+        for (int e = lane; e < ns; e += 32) {
+            const float d = chain_dist(cloud + (size_t)sj[e] * ldx, xq, D, vec);
+            sd[e] = (d == d) ? d : INFINITY;                 // NaN never enters the reference's list either
+        }
+        __syncwarp();
+        int32_t *out = idx + gq * k;
+        for (int t = 0; t < k; ++t) {
+            float bd = INFINITY;
+            int bj = 0x7fffffff, bt = -1;
+            for (int e = lane; e < ns; e += 32) {
+                const float d = sd[e];
+                const int j = sj[e];
+                if (d < bd || (d == bd && j < bj)) { bd = d; bj = j; bt = e; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+                if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; bt = ot; }
+            }
+            if (bt < 0 || !(bd < 1e10f)) { bad = 1; break; }
+            if (lane == 0) { out[t] = bj; sd[bt] = INFINITY; sj[bt] = 0x7fffffff; }
+            __syncwarp();
+        }
+    }
+    if (bad && lane == 0) {
+        const int pos = atomicAdd(fb_count, 1);
+        fb_list[pos] = (int32_t)gq;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// exact brute-force fallback for the flagged queries (one CTA per query, looping over the list)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) knn_tc_fallback_kernel(const float *__restrict__ x, int N, int D, int ldx, int k,
+                                                             int32_t *__restrict__ idx, const int *__restrict__ fb_count,
+                                                             const int32_t *__restrict__ fb_list) {
+    __shared__ float w_d[4];
+    __shared__ int w_j[4], w_o[4];
+    __shared__ int win_owner;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int total = *fb_count;
+    const bool vec = ((ldx & 3) == 0) && aligned16(x);
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const long gq = fb_list[w];
+        const int b = (int)(gq / N), q = (int)(gq - (long)b * N);
+        const float *cloud = x + (size_t)b * N * (size_t)ldx;
+        const float *xq = cloud + (size_t)q * ldx;
+        float ld[32];
+        int li[32];
+        for (int e = 0; e < k; ++e) { ld[e] = 1e10f; li[e] = -1; }
+        for (int j = tid; j < N; j += 128) {
+            const float d = chain_dist(cloud + (size_t)j * ldx, xq, D, vec);
+            if (ld[k - 1] > d) {
+                int e = k - 1;
+                while (e > 0 && ld[e - 1] > d) { ld[e] = ld[e - 1]; li[e] = li[e - 1]; --e; }
+                ld[e] = d; li[e] = j;
+            }
+        }
+        int head = 0;
+        for (int t = 0; t < k; ++t) {
+            float bd = (head < k && li[head] >= 0) ? ld[head] : INFINITY;
+            int bj = (head < k && li[head] >= 0) ? li[head] : 0x7fffffff;
+            int bo = tid;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                const int oo = __shfl_xor_sync(0xffffffffu, bo, o);
+                if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; bo = oo; }
+            }
+            if (lane == 0) { w_d[warp] = bd; w_j[warp] = bj; w_o[warp] = bo; }
+            __syncthreads();
+            if (tid == 0) {
+                float fd = w_d[0]; int fj = w_j[0], fo = w_o[0];
+                for (int u = 1; u < 4; ++u)
+                    if (w_d[u] < fd || (w_d[u] == fd && w_j[u] < fj)) { fd = w_d[u]; fj = w_j[u]; fo = w_o[u]; }
+                idx[gq * k + t] = (fd < 1e10f) ? fj : -1;
+                win_owner = (fd < 1e10f) ? fo : -1;
+            }
+            __syncthreads();
+            if (tid == win_owner) ++head;
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+static int g_knn_tc_enabled = -1;
+
+bool knn_tc_eligible(int N, int D, const void *workspace) {
+    if (g_knn_tc_enabled < 0) {
+        const char *v = getenv("NT_KNN_TC");
+        g_knn_tc_enabled = v ? atoi(v) : 1;
+    }
+    return g_knn_tc_enabled && workspace && D >= 8 && D + 3 <= 32 * KT_MAXKB && N >= 200;
+}
+
+int64_t knn_tc_workspace_bytes(int B, int N, int k) {
+    if (N < 200) return 0;
+    return (int64_t)knn_tc_plan(B, N, KT_MAXKB, KT_MAXKB, k).total;
+}
+
+template <int KL>
+static int knn_tc_launch_filter(const KnnTcArgs &a, int items, cudaStream_t st) {
+    const size_t smem = (size_t)(2 * a.KB + KT_STAGES) * KT_BLK + 512 * 4 + (KT_MAXKB + 2 * KT_STAGES + 4) * 8 + 16;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(knn_tc_filter_kernel<KL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)((2 * KT_MAXKB + KT_STAGES) * KT_BLK + 4096));
+        if (e != cudaSuccess) return fail("nt_knn(tc): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    knn_tc_filter_kernel<KL><<<items, KT_THREADS, smem, st>>>(a);
+    return check_launch("nt_knn(tc filter)");
+}
+
+int knn_tc_run(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *workspace, cudaStream_t st) {
+    const int KB = (D + 3 + 31) / 32;
+    const KnnTcPlan p = knn_tc_plan(B, N, KB, KT_MAXKB, k);
+    uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
+    if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0) return fail("%s", "nt_knn: workspace must be 256-byte aligned");
+    int *fb_count = reinterpret_cast<int *>(ws);
+    float *norms = reinterpret_cast<float *>(ws + p.off_norms);
+    uint8_t *xs = ws + p.off_xs, *xa = ws + p.off_xa;
+    int2 *meta = reinterpret_cast<int2 *>(ws + p.off_meta);
+    int2 *buf = reinterpret_cast<int2 *>(ws + p.off_buf);
+    int32_t *fb_list = reinterpret_cast<int32_t *>(ws + p.off_fb);
+    for (int b0 = 0; b0 < B; b0 += p.Bc) {
+        const int Bc = (B - b0 < p.Bc) ? (B - b0) : p.Bc;
+        const float *xc = x + (size_t)b0 * N * (size_t)ldx;
+        int32_t *idxc = idx + (size_t)b0 * N * k;
+        cudaError_t e = cudaMemsetAsync(fb_count, 0, 256, st);
+        if (e != cudaSuccess) return fail("nt_knn(tc): cudaMemsetAsync: %s", cudaGetErrorString(e));
+        const long rows = (long)Bc * p.Np;
+        knn_tc_prepare_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(xc, N, D, ldx, p.T, KB, rows, norms, xs, xa);
+        int rc = check_launch("nt_knn(tc prepare)");
+        if (rc) return rc;
+        KnnTcArgs a;
+        a.norms = norms; a.xs = xs; a.xa = xa; a.meta = meta; a.buf = buf;
+        a.N = N; a.T = p.T; a.Np = p.Np; a.KB = KB; a.S = p.S; a.tps = p.tps; a.QP = p.QP; a.k = k; a.cap = p.cap;
+        const int items = Bc * p.QP * p.S;
+        rc = k <= 8 ? knn_tc_launch_filter<8>(a, items, st)
+                    : (k <= 16 ? knn_tc_launch_filter<16>(a, items, st) : knn_tc_launch_filter<32>(a, items, st));
+        if (rc) return rc;
+        const long nq = (long)Bc * N;
+        knn_tc_rerank_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(xc, N, D, ldx, k, p.Np, p.S, p.cap, nq, norms, meta, buf,
+                                                                      idxc, fb_count, fb_list);
+        rc = check_launch("nt_knn(tc rerank)");
+        if (rc) return rc;
+        knn_tc_fallback_kernel<<<296, 128, 0, st>>>(xc, N, D, ldx, k, idxc, fb_count, fb_list);
+        rc = check_launch("nt_knn(tc fallback)");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace nt

@@ -97,6 +97,48 @@ def test_knn_clustered_data_exercises_pruning(ops, cuda_device):
     assert torch.equal(_knn_gpu(ops, x, 8, cuda_device), oknn.knn_indices(x, 8, nthreads=8))
 
 
+# ---- tensor-core filter + exact re-rank path (csrc/knn_tc.cu; taken for 8 <= D <= 157, N >= 200) -----------------------
+@pytest.mark.parametrize('B,N,D,k', [(2, 2048, 150, 5), (3, 640, 157, 5), (2, 1000, 112, 5), (2, 500, 8, 3), (1, 3000, 150, 16),
+                                      (2, 384, 150, 32), (5, 200, 33, 1), (1, 1153, 96, 9)])
+def test_knn_tensor_core_filter_bit_exact(ops, cuda_device, B, N, D, k):
+    from oracle import knn as oknn
+    x = torch.randn(B, N, D, generator=torch.Generator().manual_seed(7 * B + N + D + k))
+    assert torch.equal(_knn_gpu(ops, x, k, cuda_device), oknn.knn_indices(x, k, nthreads=8))
+
+
+def test_knn_tensor_core_filter_hard_inputs(ops, cuda_device):
+    """inputs on which the bf16 filter cannot separate the candidates: the exact fallback must take over, bit-exact."""
+    from oracle import knn as oknn
+    g = torch.Generator().manual_seed(21)
+    # (a) a large common offset: norms ~1.5e8, distances ~3e2 -> every candidate is inside the error band
+    x = 1000.0 + torch.randn(2, 400, 150, generator=g)
+    assert torch.equal(_knn_gpu(ops, x, 5, cuda_device), oknn.knn_indices(x, 5, nthreads=8))
+    # (b) masses of exact duplicates (ties on distance 0 far beyond k) and a few distinct points
+    base = torch.randn(7, 150, generator=g)
+    x = base[torch.randint(0, 7, (2, 600), generator=g)].clone()
+    x[:, ::50] += torch.randn(2, 12, 150, generator=g)
+    assert torch.equal(_knn_gpu(ops, x, 8, cuda_device), oknn.knn_indices(x, 8, nthreads=8))
+    # (c) spatially ORDERED points (every new candidate is nearer than the previous ones for a while) and outliers
+    t = torch.linspace(0, 1, 1500).view(1, 1500, 1)
+    x = torch.cat([t * torch.randn(1, 1, 150, generator=g) * 30, ], dim=-1) + 0.01 * torch.randn(1, 1500, 150, generator=g)
+    x[0, 700] *= 50
+    assert torch.equal(_knn_gpu(ops, x, 5, cuda_device), oknn.knn_indices(x, 5, nthreads=8))
+    # (d) tiny magnitudes and an all-zero cloud
+    x = 1e-20 * torch.randn(1, 300, 64, generator=g)
+    assert torch.equal(_knn_gpu(ops, x, 4, cuda_device), oknn.knn_indices(x, 4, nthreads=8))
+    x = torch.zeros(1, 256, 16)
+    assert torch.equal(_knn_gpu(ops, x, 6, cuda_device), oknn.knn_indices(x, 6, nthreads=8))
+
+
+def test_knn_tensor_core_filter_on_model_features(ops, cuda_device):
+    """layer-2 graph on real EdgeConv features (shipped-checkpoint scale: norms ~1e3, outliers ~3e4)."""
+    from oracle import knn as oknn
+    g = torch.Generator().manual_seed(33)
+    feat = torch.relu(torch.randn(2, 2048, 150, generator=g)) * torch.rand(1, 1, 150, generator=g) * 8
+    feat[:, ::97] *= 6.0
+    assert torch.equal(_knn_gpu(ops, feat, 5, cuda_device), oknn.knn_indices(feat, 5, nthreads=8))
+
+
 def test_knn_rejects_bad_k(ops, cuda_device):
     x = torch.randn(40, 3, device=cuda_device)
     with pytest.raises(RuntimeError):
