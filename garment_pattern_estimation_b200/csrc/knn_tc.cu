@@ -376,22 +376,32 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(KnnTcArgs 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// re-rank: one warp per query
+// re-rank: one warp per query.  The candidate rows are read COALESCED (lane = feature dimension), the differences
+// c_d - q_d staged in shared memory, and the sequential fp32 chain then runs one lane per candidate out of shared memory
+// -- one global-memory latency per batch of 8 candidates instead of one per 4 dimensions.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) knn_tc_rerank_kernel(const float *__restrict__ x, int N, int D, int ldx, int k,
-                                                           int Np, int S, int cap, long n_queries,
-                                                           const float *__restrict__ norms, const int2 *__restrict__ meta,
-                                                           const int2 *__restrict__ buf, int32_t *__restrict__ idx,
-                                                           int *__restrict__ fb_count, int32_t *__restrict__ fb_list) {
-    __shared__ float s_d[8][KT_SURV];
-    __shared__ int s_j[8][KT_SURV];
+constexpr int KR_WARPS = 4;             // warps (queries) per CTA
+constexpr int KR_BATCH = 8;             // candidates per staging batch
+constexpr int KR_LD = 161;              // odd row stride of the staging tile (D <= 157): conflict-free in both phases
+constexpr int KR_DREG = 5;              // ceil(160 / 32) query values per lane
+
+__global__ void __launch_bounds__(KR_WARPS * 32) knn_tc_rerank_kernel(const float *__restrict__ x, int N, int D, int ldx, int k,
+                                                                     int Np, int S, int cap, long n_queries,
+                                                                     const float *__restrict__ norms,
+                                                                     const int2 *__restrict__ meta, const int2 *__restrict__ buf,
+                                                                     int32_t *__restrict__ idx, int *__restrict__ fb_count,
+                                                                     int32_t *__restrict__ fb_list) {
+    __shared__ float s_d[KR_WARPS][KT_SURV];
+    __shared__ int s_j[KR_WARPS][KT_SURV];
+    __shared__ float s_t[KR_WARPS][KR_BATCH * KR_LD];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long gq = (long)blockIdx.x * 8 + warp;                      // chunk-local query id = b * N + q
+    const long gq = (long)blockIdx.x * KR_WARPS + warp;               // chunk-local query id = b * N + q
     if (gq >= n_queries) return;
     const int b = (int)(gq / N), q = (int)(gq - (long)b * N);
     const size_t row = (size_t)b * Np + q;
     float *sd = s_d[warp];
     int *sj = s_j[warp];
+    float *stg = s_t[warp];
 
     // slot summaries
     float sigma = -INFINITY;
@@ -402,6 +412,11 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(const float *__restr
         cnt_l = mt.y & 0x3fffffff;
         bad = (mt.y >> 30) & 1;
     }
+    const float *cloud = x + (size_t)b * N * (size_t)ldx;
+    const float *xq = cloud + (size_t)q * ldx;
+    float qv[KR_DREG];
+#pragma unroll
+    for (int i = 0; i < KR_DREG; ++i) qv[i] = (lane + 32 * i < D) ? __ldg(xq + lane + 32 * i) : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sigma = fmaxf(sigma, __shfl_xor_sync(0xffffffffu, sigma, o));
     bad = __any_sync(0xffffffffu, bad);
@@ -428,14 +443,35 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(const float *__restr
     if (!bad && ns < k) bad = 1;
     __syncwarp();
     if (!bad) {
-        const float *cloud = x + (size_t)b * N * (size_t)ldx;
-        const float *xq = cloud + (size_t)q * ldx;
-        const bool vec = ((ldx & 3) == 0) && aligned16(x);
-        for (int e = lane; e < ns; e += 32) {
-            const float d = chain_dist(cloud + (size_t)sj[e] * ldx, xq, D, vec);
-            sd[e] = (d == d) ? d : INFINITY;                 // NaN never enters the reference's list either
+        for (int base = 0; base < ns; base += KR_BATCH) {
+            const int nb = min(KR_BATCH, ns - base);
+            // phase A: coalesced loads of up to 8 candidate rows (all issued before the first use), differences to smem
+            float cv[KR_BATCH][KR_DREG];
+#pragma unroll
+            for (int c = 0; c < KR_BATCH; ++c) {
+                const float *rp = cloud + (size_t)sj[base + (c < nb ? c : 0)] * ldx;
+#pragma unroll
+                for (int i = 0; i < KR_DREG; ++i) cv[c][i] = (c < nb && lane + 32 * i < D) ? __ldg(rp + lane + 32 * i) : 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < KR_BATCH; ++c) {
+#pragma unroll
+                for (int i = 0; i < KR_DREG; ++i) stg[c * KR_LD + lane + 32 * i] = __fsub_rn(cv[c][i], qv[i]);
+            }
+            __syncwarp();
+            // phase B: lane c runs the sequential chain of candidate c
+            if (lane < nb) {
+                const float *tp = stg + lane * KR_LD;
+                float acc = 0.f;
+#pragma unroll 8
+                for (int d = 0; d < D; ++d) {
+                    const float t = tp[d];
+                    acc = __fmaf_rn(t, t, acc);
+                }
+                sd[base + lane] = (acc == acc) ? acc : INFINITY;      // NaN never enters the reference's list either
+            }
+            __syncwarp();
         }
-        __syncwarp();
         int32_t *out = idx + gq * k;
         for (int t = 0; t < k; ++t) {
             float bd = INFINITY;
@@ -580,7 +616,7 @@ int knn_tc_run(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx
                     : (k <= 16 ? knn_tc_launch_filter<16>(a, items, st) : knn_tc_launch_filter<32>(a, items, st));
         if (rc) return rc;
         const long nq = (long)Bc * N;
-        knn_tc_rerank_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(xc, N, D, ldx, k, p.Np, p.S, p.cap, nq, norms, meta, buf,
+        knn_tc_rerank_kernel<<<(unsigned)((nq + KR_WARPS - 1) / KR_WARPS), KR_WARPS * 32, 0, st>>>(xc, N, D, ldx, k, p.Np, p.S, p.cap, nq, norms, meta, buf,
                                                                       idxc, fb_count, fb_list);
         rc = check_launch("nt_knn(tc rerank)");
         if (rc) return rc;
