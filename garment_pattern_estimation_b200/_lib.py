@@ -52,6 +52,8 @@ _SIGNATURES = {
                            c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'nt_edge_stats': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    'nt_edge_activation': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_int,
+                                   c_void_p, c_void_p]),
     'nt_maxmin_finish': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                  c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'nt_bn_apply': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
     uint64_t *tmem_full = empty + TC_STAGES;                          // [1]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
     float *red = reinterpret_cast<float *>(tail + 64);                // [2][256]
+    float *colv = red + 512;                                          // [4][256]: bias | k0 | k1 | mu of this column tile
 
     constexpr int EPC = TF32 ? 4 : 8;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -66,6 +67,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
 
     if (tid < 128) {
         for (int i = tid; i < 512; i += 128) red[i] = 0.f;
+        for (int i = tid; i < 256; i += 128) {
+            const int c = tile_n * g.n_tile + i;
+            const bool ok = i < g.n_tile && c < p.n_out;
+            colv[i] = (ok && p.bias) ? __ldg(p.bias + c) : 0.f;
+            colv[256 + i] = (ok && EPI == NT_EPI_BNRELU_BWD) ? __ldg(p.k0 + c) : 0.f;
+            colv[512 + i] = (ok && EPI == NT_EPI_BNRELU_BWD) ? __ldg(p.k1 + c) : 0.f;
+            colv[768 + i] = (ok && EPI == NT_EPI_BNRELU_BWD) ? __ldg(p.mu + c) : 0.f;
+        }
     }
     if (warp == 4 && lane == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 128 + 1); mbar_init(&empty[s], 1); }
@@ -175,8 +184,114 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
             __syncwarp();                        // every warp only reads the 32 entries it wrote itself
         }
         const int n_chunks = (g.n_tile + 31) / 32;
+        // vectorised row-wise access (thread = row, 32 consecutive columns = 128 contiguous bytes) needs 16-byte aligned rows
+        const bool vec_io = (!p.out || (((p.ldo & 3) == 0) && aligned16(p.out))) &&
+                            (EPI != NT_EPI_BNRELU_BWD ||
+                             (p.aux_edge ? (((p.ae.ldpq & 3) == 0) && ((p.ae.qoff & 3) == 0) && aligned16(p.ae.pq))
+                                         : (((p.ldaux & 3) == 0) && aligned16(p.aux))));
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int c0 = ch * 32;
+            if (vec_io && c0 + 32 <= g.n_tile && col0 + c0 + 32 <= p.n_out) {
+                // ================= fast path: all 32 columns of the chunk exist =================
+                const int cg = col0 + c0;                                // first global column of the chunk
+                float auxv[32];
+                if (EPI == NT_EPI_BNRELU_BWD) {
+                    // this thread's own aux row: 8 x 16-byte loads (+8 for the gathered operand), issued before the TMEM load
+                    const float *pp = rowp[r], *qq = rowq[r];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid) {
+                            a = __ldg(reinterpret_cast<const float4 *>(pp + cg) + i);
+                            if (p.aux_edge) {
+                                if (qq) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4 *>(qq + cg) + i);
+                                    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                                }
+                                a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+                            }
+                        }
+                        auxv[4 * i] = a.x; auxv[4 * i + 1] = a.y; auxv[4 * i + 2] = a.z; auxv[4 * i + 3] = a.w;
+                    }
+                }
+                float acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(colv + c0 + 4 * i);
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                    if (EPI == NT_EPI_BNRELU_BWD) {
+                        const float4 k04 = *reinterpret_cast<const float4 *>(colv + 256 + c0 + 4 * i);
+                        const float4 k14 = *reinterpret_cast<const float4 *>(colv + 512 + c0 + 4 * i);
+                        const float4 mu4 = *reinterpret_cast<const float4 *>(colv + 768 + c0 + 4 * i);
+                        const float k0v[4] = {k04.x, k04.y, k04.z, k04.w}, k1v[4] = {k14.x, k14.y, k14.z, k14.w};
+                        const float muv[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float a = auxv[4 * i + e];
+                            acc[4 * i + e] = (valid && a > 0.f) ? (acc[4 * i + e] - k0v[e] - (a - muv[e]) * k1v[e]) : 0.f;
+                        }
+                    } else if (EPI == NT_EPI_BIAS) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[4 * i + e] += bb[e];
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[4 * i + e] = valid ? fmaxf(acc[4 * i + e] + bb[e], 0.f) : 0.f;
+                    }
+                }
+                if (p.out && valid) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.out + grow * (int64_t)p.ldo + cg);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                }
+                if (EPI == NT_EPI_RELU_MAXMIN) {
+                    // max / min over the k edge rows of every centre point; the same pass yields the column statistics
+                    // (a thread always lands on the same column: 128 % 32 == 0)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) vt[r * 33 + i] = acc[i];
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const int kk = p.k_agg;
+                    const int nodes_here = rows_here / kk;
+                    const int64_t node0 = row0 / kk;
+                    float t1 = 0.f, t2 = 0.f;
+                    for (int t = tid; t < nodes_here * 32; t += 128) {
+                        const int nd = t >> 5, cc = t & 31;
+                        float x = vt[(nd * kk) * 33 + cc];
+                        float mx = x, mn = x;
+                        int ix = 0, in = 0;
+                        t1 += x; t2 = fmaf(x, x, t2);
+                        for (int sl = 1; sl < kk; ++sl) {
+                            x = vt[(nd * kk + sl) * 33 + cc];
+                            if (x > mx) { mx = x; ix = sl; }
+                            if (x < mn) { mn = x; in = sl; }
+                            t1 += x; t2 = fmaf(x, x, t2);
+                        }
+                        const int64_t o = (node0 + nd) * (int64_t)p.n_out + cg + cc;
+                        p.vmax[o] = mx; p.vmin[o] = mn; p.imax[o] = (uint8_t)ix; p.imin[o] = (uint8_t)in;
+                    }
+                    if (p.stats) { atomicAdd(&red[c0 + lane], t1); atomicAdd(&red[256 + c0 + lane], t2); }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                } else if (EPI != NT_EPI_BIAS) {
+                    const bool want = (EPI == NT_EPI_BNRELU_BWD) ? (p.colsum != nullptr) : (p.stats != nullptr);
+                    if (want) {
+                        // column sums of this warp's 32 rows through the per-warp transposition tile (lane = column)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) tw[lane * 33 + i] = acc[i];
+                        __syncwarp();
+                        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const float x = tw[rr * 33 + lane];
+                            t1 += x;
+                            if (EPI != NT_EPI_BNRELU_BWD) t2 = fmaf(x, x, t2);
+                        }
+                        atomicAdd(&red[c0 + lane], t1);
+                        if (EPI != NT_EPI_BNRELU_BWD) atomicAdd(&red[256 + c0 + lane], t2);
+                        __syncwarp();
+                    }
+                }
+                continue;
+            }
             const int cl = col0 + c0 + lane;                             // the column this lane owns in row-wise passes
             const bool cl_ok = (c0 + lane) < g.n_tile && cl < p.n_out;
             float auxv[32];
@@ -330,11 +445,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
 template <int PROD, int EPI, bool TF32>
 static int launch_tc(const NTParams &p, const void *w_split, cudaStream_t st) {
     const TCGeom g = tc_geometry(p.n_out, p.K, TF32 ? NT_PREC_TF32X3 : NT_PREC_BF16X3);
-    const size_t smem = TC_STAGES * tc_stage_bytes(g.n_tile) + 64 + 2 * 256 * sizeof(float);
+    const size_t smem = TC_STAGES * tc_stage_bytes(g.n_tile) + 64 + 6 * 256 * sizeof(float);
     static bool configured = false;     // per instantiation; the attribute is idempotent, races are harmless
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel<PROD, EPI, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(TC_STAGES * tc_stage_bytes(256) + 64 + 2 * 256 * sizeof(float)));
+                                             (int)(TC_STAGES * tc_stage_bytes(256) + 64 + 6 * 256 * sizeof(float)));
         if (e != cudaSuccess) return fail("nt_gemm_nt(tc): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }

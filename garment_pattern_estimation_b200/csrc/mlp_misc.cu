@@ -166,6 +166,60 @@ __global__ void edge_stats_kernel(const float *pq, int ldpq, int qoff, const int
     }
 }
 
+// Materialises the first edge activation a1[e, :] = relu(P[centre(e), :] + Q[nbr(e), :]) (float4 per thread, block = 32
+// column quads x 8 row lanes) and accumulates its BatchNorm statistics on the way.  Every later consumer (the next GEMM's
+// A operand, the weight-gradient GEMM, the BN/ReLU backward epilogue) then streams a1 instead of re-gathering two random
+// rows of PQ per edge (ncu, round 1: the gathered variants of those kernels ran 2x slower than the plain ones).
+constexpr int EA_ROWS = 128;   // rows per block
+
+__global__ void __launch_bounds__(256) edge_activation_kernel(const float *__restrict__ pq, int ldpq, int qoff,
+                                                              const int32_t *__restrict__ idx, int k, int n_per_cloud,
+                                                              int64_t rows, int H, float *__restrict__ out, int ldo,
+                                                              double *__restrict__ stats) {
+    __shared__ float red[8][32][8];
+    const int c0 = (blockIdx.y * 32 + threadIdx.x) * 4;
+    const int64_t rbeg = (int64_t)blockIdx.x * EA_ROWS;
+    const int64_t rend = min(rows, rbeg + EA_ROWS);
+    const bool vec = ((ldpq & 3) == 0) && ((qoff & 3) == 0) && ((ldo & 3) == 0) && aligned16(pq) && aligned16(out) && c0 + 3 < H;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < H) {
+        for (int64_t r = rbeg + threadIdx.y; r < rend; r += 8) {
+            const int64_t centre = r / k;
+            const int64_t j = (centre / n_per_cloud) * (int64_t)n_per_cloud + __ldg(idx + r);
+            const float *pp = pq + centre * ldpq + c0, *qp = pq + j * ldpq + qoff + c0;
+            float v[4];
+            if (vec) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(pp)), b = __ldg(reinterpret_cast<const float4 *>(qp));
+                v[0] = fmaxf(a.x + b.x, 0.f); v[1] = fmaxf(a.y + b.y, 0.f); v[2] = fmaxf(a.z + b.z, 0.f); v[3] = fmaxf(a.w + b.w, 0.f);
+                *reinterpret_cast<float4 *>(out + r * ldo + c0) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    v[e] = (c0 + e < H) ? fmaxf(__ldg(pp + e) + __ldg(qp + e), 0.f) : 0.f;
+                    if (c0 + e < H) out[r * ldo + c0 + e] = v[e];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { s1[e] += v[e]; s2[e] = fmaf(v[e], v[e], s2[e]); }
+        }
+    }
+    if (!stats) return;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { red[threadIdx.y][threadIdx.x][e] = s1[e]; red[threadIdx.y][threadIdx.x][4 + e] = s2[e]; }
+    __syncthreads();
+    if (threadIdx.y == 0 && c0 < H) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (c0 + e >= H) break;
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { t1 += red[i][threadIdx.x][e]; t2 += red[i][threadIdx.x][4 + e]; }
+            atomicAdd(stats + c0 + e, (double)t1);
+            atomicAdd(stats + H + c0 + e, (double)t2);
+        }
+    }
+}
+
 // Each thread owns 4 consecutive columns (one float4 when the row stride allows it) and walks its row chunk 8 rows apart;
 // block = (32 column-quads, 8 row lanes) -> a warp reads 512 contiguous bytes of a row.
 constexpr int BL_ROWS = 256;   // rows per block
@@ -357,6 +411,17 @@ extern "C" int nt_edge_stats(const float *pq, int ldpq, int qoff, const int32_t 
     edge_stats_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pq, ldpq, qoff, idx, k, n_per_cloud,
                                                                                 rows, H, stats);
     return check_launch("nt_edge_stats");
+}
+
+extern "C" int nt_edge_activation(const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
+                                  int64_t rows, int H, float *out, int ldo, double *stats, void *stream) {
+    NT_REQUIRE(pq && idx && out && rows >= 0 && H >= 1 && ldpq >= H && ldo >= H, "nt_edge_activation: bad arguments");
+    NT_REQUIRE(k >= 1 && n_per_cloud >= 1, "nt_edge_activation: edge operand needs k and n_per_cloud");
+    if (rows == 0) return 0;
+    dim3 grid(blocks_for(rows, EA_ROWS), (H + 127) / 128), block(32, 8);
+    edge_activation_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pq, ldpq, qoff, idx, k, n_per_cloud,
+                                                                                     rows, H, out, ldo, stats);
+    return check_launch("nt_edge_activation");
 }
 
 extern "C" int nt_bn_relu_bwd_last(const float *a, int lda, const float *g, int ldg, const uint8_t *sel, int k,

@@ -93,6 +93,10 @@ class EdgeSrc:
 GRAD_PRECISION = _lib.NT_PREC_BF16X3 if os.environ.get('NT_GRAD_PRECISION', 'tf32x3') == 'bf16x3' else _lib.NT_PREC_TF32X3
 TN_ENGINE = os.environ.get('NT_TN_ENGINE', 'tc')      # weight-gradient GEMM: 'tc' = tcgen05 + deterministic split reduction (0.6 ms per
                       # launch at C2), 'simt' = fp32 CUDA-core kernel with atomics (1.0 ms; validation only)
+# EdgeConv: materialise the first edge activation a1 = relu(P[i] + Q[j]) once ([E, H] fp32) instead of re-gathering two
+# random PQ rows per edge in every consumer (next GEMM, weight-gradient GEMM, BN/ReLU backward epilogue).  '0' keeps the
+# gather fused into those kernels (smaller footprint, ~2x slower consumers).
+EDGE_MATERIALIZE = os.environ.get('NT_EDGE_MATERIALIZE', '1') != '0'
 GEMM_ENGINE = 'tc'    # 'tc' = tcgen05 tensor-core engine (product path); 'simt' = fp32 CUDA-core engine (validation only)
 
 
@@ -258,11 +262,17 @@ class _FusedMLPFunction(torch.autograd.Function):
                                       _p(wn), _p(bn_), n_next, _p(w_f), _p(w_ft), _p(b_f), _stream())
             return vec, w_f, w_ft, b_f
 
-        # ---- BN_1 statistics of a_1 = relu(P + Q) (no GEMM at row level)
+        # ---- BN_1 statistics of a_1 = relu(P + Q) (no GEMM at row level); edge mode also materialises a_1
         stats = torch.zeros(2 * H1, dtype=torch.float64, device=dev) if training else None
-        if training:
+        a1 = None
+        if mode == 'edge' and EDGE_MATERIALIZE:
+            a1 = _rowbuf(R, H1, dev)
+            _call('nt_edge_activation', _lib.load().nt_edge_activation, _p(pq), src.ldpq, src.qoff, _p(src.idx), src.k,
+                  src.n_per_cloud, R, H1, _p(a1), a1.stride(0), _p(stats), _stream())
+        elif training:
             _call('nt_edge_stats', _lib.load().nt_edge_stats, _p(pq), src.ldpq, src.qoff, _p(src.idx), src.k, src.n_per_cloud, R, H1,
                                          _p(stats), _stream())
+        first_in = dict(edge=src) if a1 is None else dict(a=a1, lda=a1.stride(0))
         bn_vec = [None] * L
         w_fts = [None] * L            # w_fts[l] = (W_l . diag(s_l))^T, l >= 1
         bn_vec[0], w_f, w_fts[1], b_f = fold(0, stats, 1)
@@ -274,8 +284,8 @@ class _FusedMLPFunction(torch.autograd.Function):
             stats = torch.zeros(2 * Hn, dtype=torch.float64, device=dev) if training else None
             out = _rowbuf(R, Hn, dev)
             if l == 1:
-                gemm_nt(R, widths[0], Hn, w_f, widths[0], NT_EPI_RELU_STATS, edge=src, bias=b_f, out=out,
-                        ldo=out.stride(0), stats=stats)
+                gemm_nt(R, widths[0], Hn, w_f, widths[0], NT_EPI_RELU_STATS, bias=b_f, out=out,
+                        ldo=out.stride(0), stats=stats, **first_in)
             else:
                 gemm_nt(R, widths[l - 1], Hn, w_f, widths[l - 1], NT_EPI_RELU_STATS, a=acts[l], lda=acts[l].stride(0),
                         bias=b_f, out=out, ldo=out.stride(0), stats=stats)
@@ -285,7 +295,7 @@ class _FusedMLPFunction(torch.autograd.Function):
         # ---- last layer
         HL, Kin = widths[L - 1], widths[L - 2]
         stats = torch.zeros(2 * HL, dtype=torch.float64, device=dev) if training else None
-        last_in = dict(edge=src) if L == 2 else dict(a=acts[L - 1], lda=acts[L - 1].stride(0))
+        last_in = first_in if L == 2 else dict(a=acts[L - 1], lda=acts[L - 1].stride(0))
         need_bwd = training and any(ctx.needs_input_grad)
         if mode == 'edge':
             tail = 0 if tail_src is None else tail_src.shape[1]
@@ -320,7 +330,7 @@ class _FusedMLPFunction(torch.autograd.Function):
         ctx.meta = None
         if need_bwd:
             ctx.meta = dict(mode=mode, k=k, N=N, L=L, widths=widths, M=M, C=C, R=R, tail=tail, ldx=ldx)
-            ctx.save_for_backward(x, idx, pq, Wc, sel, vsel, *Ws, *[a for a in acts[2:]], *bn_vec, *w_fts[1:], *betas)
+            ctx.save_for_backward(x, idx, pq, Wc, sel, vsel, a1, *Ws, *[a for a in acts[2:]], *bn_vec, *w_fts[1:], *betas)
         return out
 
     @staticmethod
@@ -331,9 +341,10 @@ class _FusedMLPFunction(torch.autograd.Function):
             raise RuntimeError('fused_mlp: backward through an eval-mode (running-statistics) forward is not supported')
         mode, k, N, L, widths, M, C, R, tail = (m[key] for key in ('mode', 'k', 'N', 'L', 'widths', 'M', 'C', 'R', 'tail'))
         sv = ctx.saved_tensors
-        x, idx, pq, Wc, sel, vsel = sv[:6]
+        x, idx, pq, Wc, sel, vsel, a1 = sv[:7]
+        sv = sv[1:]                                                       # (a1 shifts the remaining slots by one)
         Ws = list(sv[6:6 + L])
-        acts = [None, None] + list(sv[6 + L:6 + L + (L - 1)])             # acts[2..L]
+        acts = [None, a1] + list(sv[6 + L:6 + L + (L - 1)])               # acts[1] (edge mode, materialised), acts[2..L]
         bn_vec = list(sv[6 + 2 * L - 1:6 + 3 * L - 1])
         w_fts = [None] + list(sv[6 + 3 * L - 1:6 + 4 * L - 2])            # w_fts[1..L-1]
         betas = list(sv[6 + 4 * L - 2:6 + 5 * L - 2])
@@ -363,7 +374,7 @@ class _FusedMLPFunction(torch.autograd.Function):
             Hout, Hin = widths[l], widths[l - 1]
             pmean, prstd, ps, pt = bn_vec[l - 1]
             raw = torch.zeros(Hout, Hin, **f64)            # dz^T . (a_l - mean_l), accumulated in double
-            if l == 1:
+            if l == 1 and a1 is None:
                 gemm_tn(dz, dz.stride(0), Hout, R, raw, n=Hin, edge=src, mu=pmean)
             else:
                 gemm_tn(dz, dz.stride(0), Hout, R, raw, b=acts[l], ldb=acts[l].stride(0), n=Hin, mu=pmean)
@@ -376,7 +387,7 @@ class _FusedMLPFunction(torch.autograd.Function):
             grads_W[l], grads_b[l] = dW, db
             grads_g[l - 1], grads_beta[l - 1] = vecs[0], vecs[1]
             csum_prev = torch.zeros(Hin, **f64)
-            if l == 1:
+            if l == 1 and a1 is None:
                 dz_prev = _rowbuf(R, Hin, dev)
                 gemm_nt(R, Hout, Hin, w_fts[l], Hout, NT_EPI_BNRELU_BWD, a=dz, lda=dz.stride(0), edge=src, out=dz_prev,
                         ldo=dz_prev.stride(0), aux_edge=True, k0=vecs[2], k1=vecs[3], mu=pmean, colsum=csum_prev)

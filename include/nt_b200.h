@@ -129,6 +129,12 @@ int nt_bn_fold(const double *stats, int64_t count, int C, const float *gamma, co
 int nt_edge_stats(const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
                   int64_t rows, int H, double *stats, void *stream);
 
+/* Materialised first edge activation: out[e, 0:H] = relu(pq[centre(e), 0:H] + pq[nbr(e), qoff:qoff+H]) for `rows` edge rows
+ * (DynamicEdgeConv.message input after the algebraic split of the first Linear, nn/net_blocks.py:127-135), with the
+ * BatchNorm statistics of nt_edge_stats accumulated in the same pass when stats != NULL. */
+int nt_edge_activation(const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
+                       int64_t rows, int H, float *out, int ldo, double *stats, void *stream);
+
 /* EdgeConv aggregation finish (DynamicEdgeConv aggr='max', nn/net_blocks.py:127-135): out[m, c] =
  * s[c] >= 0 ? s*vmax + t : s*vmin + t; sel = slot that produced it, vsel = the pre-BN value it had (both optional,
  * [M, C], kept for the backward).  Optionally appends `tail` columns copied from tail_src (the skip connection,
