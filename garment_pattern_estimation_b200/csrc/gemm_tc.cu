@@ -88,18 +88,28 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        // =========================== A-operand producers (thread = row) ===========================
+        // =========================== A-operand producers ===========================
+        // Lane mapping: chunk jj = lane >> 3 (16 bytes of K) of the rows warp*32 + 8*i + (lane & 7), i = 0..3.  One warp load
+        // then touches 8 rows x 64 contiguous bytes (8 L1 lines) instead of 32 rows x 16 bytes (32 lines) -- ncu showed the
+        // L1TEX tag stage as the busiest unit of the thread-per-row mapping -- and the 16-byte shared-memory stores of a
+        // quarter-warp land in 128 contiguous bytes (conflict-free).
         const int r = tid;
         const bool r_ok = r < rows_here;
-        const float *ap = nullptr, *aq = nullptr;
+        const int jj = lane >> 3;
+        int prow[4];
+        bool p_ok[4];
+        const float *ap[4], *aq[4];
         bool vec = false;
-        if (r_ok) {
-            if (PROD == NT_PROD_PLAIN) {
-                ap = p.a + (row0 + r) * (int64_t)p.lda;
-                vec = ((p.lda & 3) == 0) && aligned16(p.a);
-            } else {
-                edge_row_ptrs(p.e, row0 + r, ap, aq);
-                vec = ((p.e.ldpq & 3) == 0) && ((p.e.qoff & 3) == 0) && aligned16(p.e.pq);
+        if (PROD == NT_PROD_PLAIN) vec = ((p.lda & 3) == 0) && aligned16(p.a);
+        else vec = ((p.e.ldpq & 3) == 0) && ((p.e.qoff & 3) == 0) && aligned16(p.e.pq);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            prow[i] = warp * 32 + 8 * i + (lane & 7);
+            p_ok[i] = prow[i] < rows_here;
+            ap[i] = aq[i] = nullptr;
+            if (p_ok[i]) {
+                if (PROD == NT_PROD_PLAIN) ap[i] = p.a + (row0 + prow[i]) * (int64_t)p.lda;
+                else edge_row_ptrs(p.e, row0 + prow[i], ap[i], aq[i]);
             }
         }
         const uint8_t *wsrc = w_split + (size_t)tile_n * g.num_kb * ((size_t)g.n_tile * 128);
@@ -111,22 +121,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
         struct Regs { float p[4][EPC]; float q[PROD == NT_PROD_EDGE ? 4 : 1][EPC]; };
         Regs v0, v1, v2;
         auto fetch = [&](int kb, Regs &v) {
+            const int k = (kb * 4 + jj) * EPC;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = (kb * 4 + j) * EPC;
+            for (int i = 0; i < 4; ++i) {
                 float t[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) t[e] = 0.f;
-                const bool live = r_ok && kb < g.num_kb && k < p.K;
-                if (live) load_chunk<EPC>(ap, k, p.K, vec, t);
+                const bool live = p_ok[i] && kb < g.num_kb && k < p.K;
+                if (live) load_chunk<EPC>(ap[i], k, p.K, vec, t);
 #pragma unroll
-                for (int e = 0; e < EPC; ++e) v.p[j][e] = t[e];
+                for (int e = 0; e < EPC; ++e) v.p[i][e] = t[e];
                 if (PROD == NT_PROD_EDGE) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) t[e] = 0.f;
-                    if (live && aq) load_chunk<EPC>(aq, k, p.K, vec, t);
+                    if (live && aq[i]) load_chunk<EPC>(aq[i], k, p.K, vec, t);
 #pragma unroll
-                    for (int e = 0; e < EPC; ++e) v.q[j][e] = t[e];
+                    for (int e = 0; e < EPC; ++e) v.q[i][e] = t[e];
                 }
             }
         };
@@ -140,17 +150,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
                 bulk_g2s(b_all, wsrc + (size_t)kb * bytes, bytes, &full[s]);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int i = 0; i < 4; ++i) {
                 float t[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) t[e] = 0.f;
 #pragma unroll
                 for (int e = 0; e < EPC; ++e)
-                    t[e] = (PROD == NT_PROD_EDGE) ? fmaxf(v.p[j][e] + v.q[j][e], 0.f) : v.p[j][e];
+                    t[e] = (PROD == NT_PROD_EDGE) ? fmaxf(v.p[i][e] + v.q[i][e], 0.f) : v.p[i][e];
                 uint4 h, l;
                 pack_chunk(t, TF32, h, l);
-                *reinterpret_cast<uint4 *>(a_hi + j * (TC_M * 16) + r * 16) = h;
-                *reinterpret_cast<uint4 *>(a_lo + j * (TC_M * 16) + r * 16) = l;
+                *reinterpret_cast<uint4 *>(a_hi + jj * (TC_M * 16) + prow[i] * 16) = h;
+                *reinterpret_cast<uint4 *>(a_lo + jj * (TC_M * 16) + prow[i] * 16) = l;
             }
             fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&full[s]);
@@ -166,7 +176,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         float *vt = reinterpret_cast<float *>(smem);                    // [128][33] staging (aliases stage 0)
-        float *tw = reinterpret_cast<float *>(stage_base[1]) + warp * (32 * 33);   // per-warp 32x33 transposition tile
+        // per-warp transposition tile: 32 x 36 floats (16-byte accesses, fast path) or 32 x 33 (scalar path) in the same region;
+        // 4 x 4608 B = 18432 B = the smallest possible stage (n_tile = 16)
+        float *tw4 = reinterpret_cast<float *>(stage_base[1]) + warp * (32 * 36);
+        float *tw = tw4;
         const bool valid = r_ok;
         const int64_t grow = row0 + r;
         const int64_t wrow0 = row0 + warp * 32;                          // first row of this warp
@@ -193,26 +206,40 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
             const int c0 = ch * 32;
             if (vec_io && c0 + 32 <= g.n_tile && col0 + c0 + 32 <= p.n_out) {
                 // ================= fast path: all 32 columns of the chunk exist =================
+                // Global traffic is COALESCED (a warp request = 4 rows x 128 contiguous bytes: lane -> row 4m + (lane >> 3),
+                // 16-byte column group lane & 7) and exchanged with the thread-per-row register layout of the TMEM load through a
+                // per-warp 32 x 36 transposition tile with conflict-free 16-byte accesses.
                 const int cg = col0 + c0;                                // first global column of the chunk
+                const int sub = lane >> 3, q4 = (lane & 7) * 4;
                 float auxv[32];
                 if (EPI == NT_EPI_BNRELU_BWD) {
-                    // this thread's own aux row: 8 x 16-byte loads (+8 for the gathered operand), issued before the TMEM load
-                    const float *pp = rowp[r], *qq = rowq[r];
+                    float4 ld[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int m = 0; m < 8; ++m) {
+                        const int rr = 4 * m + sub;
                         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid) {
-                            a = __ldg(reinterpret_cast<const float4 *>(pp + cg) + i);
+                        if (rr < wrows) {
+                            a = __ldg(reinterpret_cast<const float4 *>(rowp[warp * 32 + rr] + cg + q4));
                             if (p.aux_edge) {
+                                const float *qq = rowq[warp * 32 + rr];
                                 if (qq) {
-                                    const float4 b = __ldg(reinterpret_cast<const float4 *>(qq + cg) + i);
+                                    const float4 b = __ldg(reinterpret_cast<const float4 *>(qq + cg + q4));
                                     a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
                                 }
                                 a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
                             }
                         }
+                        ld[m] = a;
+                    }
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) *reinterpret_cast<float4 *>(tw4 + (4 * m + sub) * 36 + q4) = ld[m];
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 a = *reinterpret_cast<const float4 *>(tw4 + lane * 36 + 4 * i);
                         auxv[4 * i] = a.x; auxv[4 * i + 1] = a.y; auxv[4 * i + 2] = a.z; auxv[4 * i + 3] = a.w;
                     }
+                    __syncwarp();
                 }
                 float acc[32];
                 tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
@@ -239,10 +266,38 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
                         for (int e = 0; e < 4; ++e) acc[4 * i + e] = valid ? fmaxf(acc[4 * i + e] + bb[e], 0.f) : 0.f;
                     }
                 }
-                if (p.out && valid) {
-                    float4 *dst = reinterpret_cast<float4 *>(p.out + grow * (int64_t)p.ldo + cg);
+                const bool want = (EPI == NT_EPI_BIAS || EPI == NT_EPI_RELU_MAXMIN)
+                                      ? false
+                                      : ((EPI == NT_EPI_BNRELU_BWD) ? (p.colsum != nullptr) : (p.stats != nullptr));
+                if (p.out || want) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4 *>(tw4 + lane * 36 + 4 * i) =
+                            make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                    __syncwarp();
+                    if (p.out) {
+                        float *dst = p.out + wrow0 * (int64_t)p.ldo + cg + q4;
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) {
+                            const int rr = 4 * m + sub;
+                            if (rr < wrows)
+                                *reinterpret_cast<float4 *>(dst + (int64_t)rr * p.ldo) =
+                                    *reinterpret_cast<const float4 *>(tw4 + rr * 36 + q4);
+                        }
+                    }
+                    if (want) {
+                        // column sums of this warp's 32 rows (lane = column; invalid rows hold zeros)
+                        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const float x = tw4[rr * 36 + lane];
+                            t1 += x;
+                            if (EPI != NT_EPI_BNRELU_BWD) t2 = fmaf(x, x, t2);
+                        }
+                        atomicAdd(&red[c0 + lane], t1);
+                        if (EPI != NT_EPI_BNRELU_BWD) atomicAdd(&red[256 + c0 + lane], t2);
+                    }
+                    __syncwarp();
                 }
                 if (EPI == NT_EPI_RELU_MAXMIN) {
                     // max / min over the k edge rows of every centre point; the same pass yields the column statistics
@@ -271,24 +326,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_nt_tc_kernel(NTParams p, c
                     }
                     if (p.stats) { atomicAdd(&red[c0 + lane], t1); atomicAdd(&red[256 + c0 + lane], t2); }
                     asm volatile("bar.sync 1, 128;" ::: "memory");
-                } else if (EPI != NT_EPI_BIAS) {
-                    const bool want = (EPI == NT_EPI_BNRELU_BWD) ? (p.colsum != nullptr) : (p.stats != nullptr);
-                    if (want) {
-                        // column sums of this warp's 32 rows through the per-warp transposition tile (lane = column)
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) tw[lane * 33 + i] = acc[i];
-                        __syncwarp();
-                        float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-                        for (int rr = 0; rr < 32; ++rr) {
-                            const float x = tw[rr * 33 + lane];
-                            t1 += x;
-                            if (EPI != NT_EPI_BNRELU_BWD) t2 = fmaf(x, x, t2);
-                        }
-                        atomicAdd(&red[c0 + lane], t1);
-                        if (EPI != NT_EPI_BNRELU_BWD) atomicAdd(&red[256 + c0 + lane], t2);
-                        __syncwarp();
-                    }
                 }
                 continue;
             }
