@@ -45,6 +45,7 @@ __device__ __forceinline__ void tn_store_chunk(uint8_t *hi_plane, uint8_t *lo_pl
     *reinterpret_cast<uint4 *>(lo_plane + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+template <bool EDGE>
 __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     // plane = [4 K-chunks][rows_pad][16 B]  (K-major core matrices: LBO = rows_pad*16, SBO = 128)
@@ -82,77 +83,153 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TNTCParams p)
         const int half = warp >> 2;
         constexpr int MAXA = TN_MAX_M / 32 / 2, MAXB = TN_MAX_N / 32 / 2;  // 32-row groups per thread
         const int ia = p.m_pad / 32, ib = (p.n_pad + 31) / 32;
-        struct Regs { float a[MAXA][4]; float b[MAXB][4]; float q[MAXB][4]; };   // raw loads; combined in consume()
-        Regs v0, v1, v2;                                                 // prefetch ring, depth 3 (static addressing)
+        if constexpr (EDGE) {
+            struct Regs { float a[MAXA][4]; float b[MAXB][4]; float q[MAXB][4]; };   // raw loads; combined in consume()
+            Regs v0, v1, v2;                                                 // prefetch ring, depth 3 (static addressing)
 
-        auto fetch = [&](int st, Regs &v) {
-            const int64_t rbase = r_begin + (int64_t)st * TN_RB + 4 * j;
-            const float *arow[4], *bp[4], *bq[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t r = rbase + i;
-                arow[i] = bp[i] = bq[i] = nullptr;
-                if (st < n_stages && r < r_end) {
-                    arow[i] = p.a + r * p.lda;
-                    if (p.b_edge) edge_row_ptrs(p.e, r, bp[i], bq[i]);
-                    else bp[i] = p.b + r * p.ldb;
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < MAXA; ++t) {
-                const int grp = half + 2 * t;
-                const int col = p.m0 + grp * 32 + lane;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v.a[t][i] = (grp < ia && arow[i] && col < p.m) ? __ldg(arow[i] + col) : 0.f;
-            }
-#pragma unroll
-            for (int t = 0; t < MAXB; ++t) {
-                const int grp = half + 2 * t;
-                const int col = p.n0 + grp * 32 + lane;
-                const bool c_ok = grp < ib && (grp * 32 + lane) < p.n_pad && col < p.n;
-#pragma unroll
+            auto fetch = [&](int st, Regs &v) {
+                const int64_t rbase = r_begin + (int64_t)st * TN_RB + 4 * j;
+                const float *arow[4], *bp[4], *bq[4];
+    #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    // invalid rows / columns must end up exactly 0 after relu(b + q) - mu: encode them as b = mu, q = 0
-                    v.b[t][i] = (c_ok && bp[i]) ? __ldg(bp[i] + col) : 0.f;
-                    v.q[t][i] = (c_ok && bp[i] && p.b_edge && bq[i]) ? __ldg(bq[i] + col) : 0.f;
+                    const int64_t r = rbase + i;
+                    arow[i] = bp[i] = bq[i] = nullptr;
+                    if (st < n_stages && r < r_end) {
+                        arow[i] = p.a + r * p.lda;
+                        if (p.b_edge) edge_row_ptrs(p.e, r, bp[i], bq[i]);
+                        else bp[i] = p.b + r * p.ldb;
+                    }
                 }
+    #pragma unroll
+                for (int t = 0; t < MAXA; ++t) {
+                    const int grp = half + 2 * t;
+                    const int col = p.m0 + grp * 32 + lane;
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i) v.a[t][i] = (grp < ia && arow[i] && col < p.m) ? __ldg(arow[i] + col) : 0.f;
+                }
+    #pragma unroll
+                for (int t = 0; t < MAXB; ++t) {
+                    const int grp = half + 2 * t;
+                    const int col = p.n0 + grp * 32 + lane;
+                    const bool c_ok = grp < ib && (grp * 32 + lane) < p.n_pad && col < p.n;
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        // invalid rows / columns must end up exactly 0 after relu(b + q) - mu: encode them as b = mu, q = 0
+                        v.b[t][i] = (c_ok && bp[i]) ? __ldg(bp[i] + col) : 0.f;
+                        v.q[t][i] = (c_ok && bp[i] && p.b_edge && bq[i]) ? __ldg(bq[i] + col) : 0.f;
+                    }
+                }
+            };
+            auto consume = [&](int st, Regs &v) {
+                const int s = st % TN_STAGES, use = st / TN_STAGES;
+                mbar_wait(&empty[s], (use & 1) ^ 1);
+                uint8_t *a_hi = smem + s * stage_bytes, *a_lo = a_hi + a_plane, *b_hi = a_lo + a_plane, *b_lo = b_hi + b_plane;
+    #pragma unroll
+                for (int t = 0; t < MAXA; ++t) {
+                    const int grp = half + 2 * t;
+                    if (grp < ia) tn_store_chunk(a_hi, a_lo, j, p.m_pad, grp * 32 + lane, v.a[t]);
+                }
+    #pragma unroll
+                for (int t = 0; t < MAXB; ++t) {
+                    const int grp = half + 2 * t;
+                    if (grp < ib && (grp * 32 + lane) < p.n_pad) {
+                        const int col = p.n0 + grp * 32 + lane;
+                        const bool c_ok = col < p.n;
+                        const float mu = (c_ok && p.mu) ? __ldg(p.mu + col) : 0.f;
+                        float x[4];
+    #pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int64_t r = r_begin + (int64_t)st * TN_RB + 4 * j + i;
+                            float y = v.b[t][i];
+                            if (p.b_edge) y = fmaxf(y + v.q[t][i], 0.f);
+                            x[i] = (c_ok && r < r_end) ? y - mu : 0.f;
+                        }
+                        tn_store_chunk(b_hi, b_lo, j, p.n_pad, grp * 32 + lane, x);
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&full[s]);
+            };
+            fetch(0, v0); fetch(1, v1); fetch(2, v2);
+            for (int st = 0; st < n_stages; st += 3) {
+                consume(st, v0); fetch(st + 3, v0);
+                if (st + 1 < n_stages) { consume(st + 1, v1); fetch(st + 4, v1); }
+                if (st + 2 < n_stages) { consume(st + 2, v2); fetch(st + 5, v2); }
             }
-        };
-        auto consume = [&](int st, Regs &v) {
-            const int s = st % TN_STAGES, use = st / TN_STAGES;
-            mbar_wait(&empty[s], (use & 1) ^ 1);
-            uint8_t *a_hi = smem + s * stage_bytes, *a_lo = a_hi + a_plane, *b_hi = a_lo + a_plane, *b_lo = b_hi + b_plane;
+        } else {
+            // ---- plain operands: everything loop-invariant hoisted (column masks, centring values, base pointers); a stage
+            // whose 16 rows all exist takes a path without per-row tests (ncu, round 1: two thirds of this kernel's issued
+            // instructions were predicate / address arithmetic)
+            struct Regs { float a[MAXA][4]; float b[MAXB][4]; };
+            Regs v0, v1, v2;
+            bool a_ld[MAXA], a_st[MAXA], b_ld[MAXB], b_st[MAXB];
+            float muv[MAXB];
 #pragma unroll
             for (int t = 0; t < MAXA; ++t) {
                 const int grp = half + 2 * t;
-                if (grp < ia) tn_store_chunk(a_hi, a_lo, j, p.m_pad, grp * 32 + lane, v.a[t]);
+                a_st[t] = grp < ia;
+                a_ld[t] = a_st[t] && (p.m0 + grp * 32 + lane) < p.m;
             }
 #pragma unroll
             for (int t = 0; t < MAXB; ++t) {
                 const int grp = half + 2 * t;
-                if (grp < ib && (grp * 32 + lane) < p.n_pad) {
-                    const int col = p.n0 + grp * 32 + lane;
-                    const bool c_ok = col < p.n;
-                    const float mu = (c_ok && p.mu) ? __ldg(p.mu + col) : 0.f;
-                    float x[4];
+                b_st[t] = grp < ib && (grp * 32 + lane) < p.n_pad;
+                b_ld[t] = b_st[t] && (p.n0 + grp * 32 + lane) < p.n;
+                muv[t] = (b_ld[t] && p.mu) ? __ldg(p.mu + p.n0 + grp * 32 + lane) : 0.f;
+            }
+            const float *abase = p.a + (r_begin + 4 * j) * (int64_t)p.lda + p.m0 + half * 32 + lane;
+            const float *bbase = p.b + (r_begin + 4 * j) * (int64_t)p.ldb + p.n0 + half * 32 + lane;
+            const int n_full = (int)(max((int64_t)0, r_end - r_begin) / TN_RB);       // stages with all 16 rows present
+            auto fetch = [&](int st, Regs &v) {
+                if (st >= n_stages) return;
+                const float *ar = abase + (int64_t)st * TN_RB * p.lda;
+                const float *br = bbase + (int64_t)st * TN_RB * p.ldb;
+                if (st < n_full) {
+#pragma unroll
+                    for (int t = 0; t < MAXA; ++t)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v.a[t][i] = a_ld[t] ? __ldg(ar + (int64_t)i * p.lda + t * 64) : 0.f;
+#pragma unroll
+                    for (int t = 0; t < MAXB; ++t)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v.b[t][i] = b_ld[t] ? __ldg(br + (int64_t)i * p.ldb + t * 64) : muv[t];
+                } else {
+                    const int64_t rbase = r_begin + (int64_t)st * TN_RB + 4 * j;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int64_t r = r_begin + (int64_t)st * TN_RB + 4 * j + i;
-                        float y = v.b[t][i];
-                        if (p.b_edge) y = fmaxf(y + v.q[t][i], 0.f);
-                        x[i] = (c_ok && r < r_end) ? y - mu : 0.f;
+                        const bool r_ok = rbase + i < r_end;
+#pragma unroll
+                        for (int t = 0; t < MAXA; ++t) v.a[t][i] = (a_ld[t] && r_ok) ? __ldg(ar + (int64_t)i * p.lda + t * 64) : 0.f;
+#pragma unroll
+                        for (int t = 0; t < MAXB; ++t) v.b[t][i] = (b_ld[t] && r_ok) ? __ldg(br + (int64_t)i * p.ldb + t * 64) : muv[t];
                     }
-                    tn_store_chunk(b_hi, b_lo, j, p.n_pad, grp * 32 + lane, x);
                 }
+            };
+            auto consume = [&](int st, Regs &v) {
+                const int s = st % TN_STAGES, use = st / TN_STAGES;
+                mbar_wait(&empty[s], (use & 1) ^ 1);
+                uint8_t *a_hi = smem + s * stage_bytes, *a_lo = a_hi + a_plane, *b_hi = a_lo + a_plane, *b_lo = b_hi + b_plane;
+#pragma unroll
+                for (int t = 0; t < MAXA; ++t)
+                    if (a_st[t]) tn_store_chunk(a_hi, a_lo, j, p.m_pad, (half + 2 * t) * 32 + lane, v.a[t]);
+#pragma unroll
+                for (int t = 0; t < MAXB; ++t) {
+                    if (b_st[t]) {
+                        float x[4];                      // missing rows / columns were loaded as mu: exactly 0 after centring
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) x[i] = v.b[t][i] - muv[t];
+                        tn_store_chunk(b_hi, b_lo, j, p.n_pad, (half + 2 * t) * 32 + lane, x);
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&full[s]);
+            };
+            fetch(0, v0); fetch(1, v1); fetch(2, v2);
+            for (int st = 0; st < n_stages; st += 3) {
+                consume(st, v0); fetch(st + 3, v0);
+                if (st + 1 < n_stages) { consume(st + 1, v1); fetch(st + 4, v1); }
+                if (st + 2 < n_stages) { consume(st + 2, v2); fetch(st + 5, v2); }
             }
-            fence_proxy_async();
-            mbar_arrive(&full[s]);
-        };
-        fetch(0, v0); fetch(1, v1); fetch(2, v2);
-        for (int st = 0; st < n_stages; st += 3) {
-            consume(st, v0); fetch(st + 3, v0);
-            if (st + 1 < n_stages) { consume(st + 1, v1); fetch(st + 4, v1); }
-            if (st + 2 < n_stages) { consume(st + 2, v2); fetch(st + 5, v2); }
         }
 
         // =========================== epilogue: TMEM -> coalesced partial tile ===========================
@@ -256,12 +333,15 @@ int gemm_tn_tc(const float *a, int lda, int m, const float *b, int ldb, int n, i
             const size_t smem = TN_STAGES * stage_bytes + 128;
             static bool configured = false;
             if (!configured) {
-                cudaError_t err = cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                cudaError_t err = cudaFuncSetAttribute(gemm_tn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                if (err == cudaSuccess)
+                    err = cudaFuncSetAttribute(gemm_tn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
                 if (err != cudaSuccess) return fail("nt_gemm_tn(tc): cudaFuncSetAttribute: %s", cudaGetErrorString(err));
                 configured = true;
             }
             if (smem > 227 * 1024) return fail("nt_gemm_tn(tc): tile does not fit shared memory%s", "");
-            gemm_tn_tc_kernel<<<splits, TN_THREADS, smem, st>>>(p);
+            if (b_edge) gemm_tn_tc_kernel<true><<<splits, TN_THREADS, smem, st>>>(p);
+            else gemm_tn_tc_kernel<false><<<splits, TN_THREADS, smem, st>>>(p);
             int rc = check_launch("nt_gemm_tn(tc)");
             if (rc) return rc;
             const int total = p.m_pad * p.n_pad;

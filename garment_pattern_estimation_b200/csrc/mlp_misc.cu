@@ -348,6 +348,169 @@ __global__ void edge_scatter_kernel(const float *dz, int lddz, const int32_t *id
     dpq[m * lddpq + h] = sum;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Node-centric float4 versions of the three edge-sized element-wise kernels (used when every row is 16-byte aligned).
+// A thread owns 4 consecutive columns of one centre point and walks its k edge rows with up to 4 independent 16-byte
+// loads in flight; per-node operands (centre row of PQ, upstream gradient, selected slots) are read once instead of k
+// times and no 64-bit division is left in the loops.  Block = (32 column quads, 8 node lanes).
+constexpr int NV_NODES = 32;   // nodes per block
+
+__device__ __forceinline__ float4 ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+__global__ void __launch_bounds__(256) edge_activation_v4_kernel(const float *__restrict__ pq, int ldpq, int qoff,
+                                                                 const int32_t *__restrict__ idx, int k, int n_per_cloud,
+                                                                 int64_t nodes, int H, float *__restrict__ out, int ldo,
+                                                                 double *__restrict__ stats) {
+    __shared__ float red[8][32][8];
+    const int c0 = (blockIdx.y * 32 + threadIdx.x) * 4;
+    const int64_t nbeg = (int64_t)blockIdx.x * NV_NODES;
+    const int64_t nend = min(nodes, nbeg + NV_NODES);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < H) {
+        for (int64_t node = nbeg + threadIdx.y; node < nend; node += 8) {
+            const float4 pc = ld4(pq + node * ldpq + c0);
+            const int64_t base = (node / n_per_cloud) * (int64_t)n_per_cloud;
+            const int32_t *ip = idx + node * k;
+            float *op = out + node * k * (int64_t)ldo + c0;
+            for (int s0 = 0; s0 < k; s0 += 4) {
+                float4 q[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (s0 + u < k) q[u] = ld4(pq + (base + __ldg(ip + s0 + u)) * ldpq + qoff + c0);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (s0 + u < k) {
+                        float4 v;
+                        v.x = fmaxf(pc.x + q[u].x, 0.f); v.y = fmaxf(pc.y + q[u].y, 0.f);
+                        v.z = fmaxf(pc.z + q[u].z, 0.f); v.w = fmaxf(pc.w + q[u].w, 0.f);
+                        *reinterpret_cast<float4 *>(op + (int64_t)(s0 + u) * ldo) = v;
+                        s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+                        s2[0] = fmaf(v.x, v.x, s2[0]); s2[1] = fmaf(v.y, v.y, s2[1]);
+                        s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
+                    }
+                }
+            }
+        }
+    }
+    if (!stats) return;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { red[threadIdx.y][threadIdx.x][e] = s1[e]; red[threadIdx.y][threadIdx.x][4 + e] = s2[e]; }
+    __syncthreads();
+    if (threadIdx.y == 0 && c0 < H) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { t1 += red[i][threadIdx.x][e]; t2 += red[i][threadIdx.x][4 + e]; }
+            atomicAdd(stats + c0 + e, (double)t1);
+            atomicAdd(stats + H + c0 + e, (double)t2);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_relu_bwd_last_v4_kernel(const float *__restrict__ a, int lda, const float *__restrict__ g,
+                                                                  int ldg, const uint8_t *__restrict__ sel, int k,
+                                                                  const float *__restrict__ s, const float *__restrict__ mu,
+                                                                  const float *__restrict__ rstd, const double *__restrict__ sums,
+                                                                  int64_t count, int64_t nodes, int C, float *__restrict__ dz,
+                                                                  int lddz, double *__restrict__ colsum) {
+    __shared__ float red[8][32][4];
+    const int c0 = (blockIdx.y * 32 + threadIdx.x) * 4;     // C % 4 == 0 is NOT required: the tail quad is masked per column
+    const int64_t nbeg = (int64_t)blockIdx.x * NV_NODES;
+    const int64_t nend = min(nodes, nbeg + NV_NODES);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < C) {
+        const float inv = 1.0f / (float)count;
+        float sc[4], k0[4], k1[4], m[4];
+        bool ok[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = min(c0 + j, C - 1);
+            ok[j] = c0 + j < C;
+            sc[j] = s[c]; m[j] = mu[c];
+            k0[j] = (float)sums[c] * inv;                        // dbeta / count
+            k1[j] = rstd[c] * ((float)sums[C + c] * inv);        // rstd * dgamma / count
+        }
+        for (int64_t node = nbeg + threadIdx.y; node < nend; node += 8) {
+            float gv[4];                                         // upstream gradient rows may have any stride: scalar loads
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gv[j] = ok[j] ? __ldg(g + node * ldg + c0 + j) : 0.f;
+            int slot_sel[4] = {-1, -1, -1, -1};                  // -1: every slot receives the gradient (no aggregation)
+            if (sel) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) slot_sel[j] = ok[j] ? (int)sel[node * C + c0 + j] : 0;
+            }
+            const float *ap = a + node * k * (int64_t)lda + c0;
+            float *op = dz + node * k * (int64_t)lddz + c0;
+            for (int s0 = 0; s0 < k; s0 += 4) {
+                float4 av[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (s0 + u < k) av[u] = ld4(ap + (int64_t)(s0 + u) * lda);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (s0 + u < k) {
+                        const float x[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
+                        float o[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float gs = (slot_sel[j] < 0 || slot_sel[j] == s0 + u) ? gv[j] : 0.f;
+                            // same association as the scalar kernel: sc * (gs - dbeta' - ((x - m) * rstd) * dgamma')
+                            o[j] = (ok[j] && x[j] > 0.f) ? sc[j] * (gs - k0[j] - (x[j] - m[j]) * k1[j]) : 0.f;
+                            acc[j] += o[j];
+                        }
+                        *reinterpret_cast<float4 *>(op + (int64_t)(s0 + u) * lddz) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.y == 0 && colsum) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (c0 + j >= C) continue;
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x][j];
+            atomicAdd(colsum + c0 + j, (double)t);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) edge_scatter_v4_kernel(const float *__restrict__ dz, int lddz, const int32_t *__restrict__ idx,
+                                                              int k, int n_per_cloud, int64_t M, int H, float *__restrict__ dpq,
+                                                              int lddpq) {
+    const int c0 = (blockIdx.y * 32 + threadIdx.x) * 4;
+    if (c0 >= H) return;
+    const int64_t nbeg = (int64_t)blockIdx.x * NV_NODES;
+    const int64_t nend = min(M, nbeg + NV_NODES);
+    for (int64_t node = nbeg + threadIdx.y; node < nend; node += 8) {
+        const int64_t base = (node / n_per_cloud) * (int64_t)n_per_cloud;
+        const int32_t *ip = idx + node * k;
+        const float *zp = dz + node * k * (int64_t)lddz + c0;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s0 = 0; s0 < k; s0 += 4) {
+            float4 v[4];
+            int j[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (s0 + u < k) { v[u] = ld4(zp + (int64_t)(s0 + u) * lddz); j[u] = __ldg(ip + s0 + u); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (s0 + u < k) {
+                    sum.x += v[u].x; sum.y += v[u].y; sum.z += v[u].z; sum.w += v[u].w;
+                    if (v[u].x != 0.f || v[u].y != 0.f || v[u].z != 0.f || v[u].w != 0.f)
+                        atomicAdd(reinterpret_cast<float4 *>(dpq + (base + j[u]) * lddpq + H + c0), v[u]);
+                }
+            }
+        }
+        *reinterpret_cast<float4 *>(dpq + node * lddpq + c0) = sum;
+    }
+}
+
 static inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace nt
@@ -418,9 +581,16 @@ extern "C" int nt_edge_activation(const float *pq, int ldpq, int qoff, const int
     NT_REQUIRE(pq && idx && out && rows >= 0 && H >= 1 && ldpq >= H && ldo >= H, "nt_edge_activation: bad arguments");
     NT_REQUIRE(k >= 1 && n_per_cloud >= 1, "nt_edge_activation: edge operand needs k and n_per_cloud");
     if (rows == 0) return 0;
-    dim3 grid(blocks_for(rows, EA_ROWS), (H + 127) / 128), block(32, 8);
-    edge_activation_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pq, ldpq, qoff, idx, k, n_per_cloud,
-                                                                                     rows, H, out, ldo, stats);
+    dim3 block(32, 8);
+    if ((H & 3) == 0 && (ldpq & 3) == 0 && (qoff & 3) == 0 && (ldo & 3) == 0 && aligned16(pq) && aligned16(out) && rows % k == 0) {
+        dim3 grid(blocks_for(rows / k, NV_NODES), (H + 127) / 128);
+        edge_activation_v4_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pq, ldpq, qoff, idx, k, n_per_cloud,
+                                                                                            rows / k, H, out, ldo, stats);
+    } else {
+        dim3 grid(blocks_for(rows, EA_ROWS), (H + 127) / 128);
+        edge_activation_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pq, ldpq, qoff, idx, k, n_per_cloud,
+                                                                                         rows, H, out, ldo, stats);
+    }
     return check_launch("nt_edge_activation");
 }
 
@@ -431,9 +601,17 @@ extern "C" int nt_bn_relu_bwd_last(const float *a, int lda, const float *g, int 
     NT_REQUIRE(a && g && s && mu && rstd && sums && dz && k >= 1 && count >= 1 && C >= 1, "nt_bn_relu_bwd_last: bad arguments");
     NT_REQUIRE(lda >= C && ldg >= C && lddz >= C && rows % k == 0, "nt_bn_relu_bwd_last: bad strides");
     if (rows == 0) return 0;
-    dim3 grid(blocks_for(rows, BL_ROWS), (C + 127) / 128), block(32, 8);
-    bn_relu_bwd_last_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        a, lda, g, ldg, sel, k, s, mu, rstd, sums, count, rows, C, dz, lddz, colsum);
+    dim3 block(32, 8);
+    const int Cp = (C + 3) & ~3;      // the float4 kernel touches whole column quads: rows must be padded to a multiple of 4
+    if ((lda & 3) == 0 && (lddz & 3) == 0 && lda >= Cp && lddz >= Cp && aligned16(a) && aligned16(dz)) {
+        dim3 grid(blocks_for(rows / k, NV_NODES), (C + 127) / 128);
+        bn_relu_bwd_last_v4_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            a, lda, g, ldg, sel, k, s, mu, rstd, sums, count, rows / k, C, dz, lddz, colsum);
+    } else {
+        dim3 grid(blocks_for(rows, BL_ROWS), (C + 127) / 128);
+        bn_relu_bwd_last_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            a, lda, g, ldg, sel, k, s, mu, rstd, sums, count, rows, C, dz, lddz, colsum);
+    }
     return check_launch("nt_bn_relu_bwd_last");
 }
 
@@ -453,7 +631,13 @@ extern "C" int nt_edge_scatter(const float *dz, int lddz, const int32_t *idx, in
     NT_REQUIRE(dz && idx && dpq && k >= 1 && n_per_cloud >= 1 && M >= 0 && H >= 1 && lddz >= H && lddpq >= 2 * H,
                "nt_edge_scatter: bad arguments");
     if (M == 0) return 0;
-    edge_scatter_kernel<<<blocks_for(M * H, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dz, lddz, idx, k, n_per_cloud, M, H, dpq, lddpq);
+    if ((H & 3) == 0 && (lddz & 3) == 0 && (lddpq & 3) == 0 && aligned16(dz) && aligned16(dpq)) {
+        dim3 grid(blocks_for(M, NV_NODES), (H + 127) / 128), block(32, 8);
+        edge_scatter_v4_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dz, lddz, idx, k, n_per_cloud, M, H,
+                                                                                         dpq, lddpq);
+    } else {
+        edge_scatter_kernel<<<blocks_for(M * H, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            dz, lddz, idx, k, n_per_cloud, M, H, dpq, lddpq);
+    }
     return check_launch("nt_edge_scatter");
 }
