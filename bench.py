@@ -273,11 +273,14 @@ def main():
     # ---- per-kernel-group device times (CUDA events on the launching stream) for the roofline of the dominant kernel
     ops.EVENT_SINK = {}
     ops.FLOP_SINK = {}
+    ops.BYTES_SINK = {}
     for i in range(3):
         train_step(*resident[i % 4])
     torch.cuda.synchronize()
     gemm_flops = {name: v / 3.0 for name, v in ops.FLOP_SINK.items()}
+    gemm_bytes = {name: v / 3.0 for name, v in ops.BYTES_SINK.items()}
     ops.FLOP_SINK = None
+    ops.BYTES_SINK = None
     groups = {name: sum(s.elapsed_time(e) for s, e in evs) / 3.0 for name, evs in ops.EVENT_SINK.items()}
     counts = {name: len(evs) / 3.0 for name, evs in ops.EVENT_SINK.items()}
     ops.EVENT_SINK = None
@@ -296,34 +299,54 @@ def main():
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
 
+    # ---- roofline of the DOMINANT kernel group of the step (largest share of device time among this library's kernels).
+    # The fused row GEMMs stream edge-sized fp32 operands once and write the result once: HBM is the binding roofline
+    # (K <= 200, so arithmetic intensity is ~100 flop/B even with the 3-product split).  achieved = algorithmic bytes of
+    # the group's launches (operand rows + result rows + weights, counted in ops.gemm_nt / ops.gemm_tn) / their summed
+    # CUDA-event time = launch-weighted average of bytes-per-launch / launch-duration.
+    sm_clock = (clocks or {}).get('sm_mhz') or peaks.get('sm_max_mhz', 1965.0)
+    dom = max(gemm_bytes, key=lambda n: groups.get(n, 0.0)) if gemm_bytes else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'dominant_traffic.json')) as f:
+            tj = json.load(f)
+            traffic = tj.get(dom, {}).get('dram_bytes_per_launch') if isinstance(tj.get(dom), dict) else None
+    except (OSError, ValueError):
+        pass
+    kernel_names = {'nt_gemm_nt[bnrelu_bwd,plain]': 'nt::gemm_nt_tc_kernel<PLAIN, BNRELU_BWD, TF32x3> (data-gradient GEMM fused '
+                                                    'with the BatchNorm/ReLU backward)',
+                    'nt_gemm_tn_centered': 'nt::gemm_tn_tc_kernel (weight-gradient GEMM with centred operand)'}
+    roofline = None
+    if dom:
+        dom_ms, dom_n = groups[dom], max(counts.get(dom, 1.0), 1.0)
+        gbs = gemm_bytes[dom] / (dom_ms * 1e-3) / 1e9
+        roofline = {
+            'kernel': kernel_names.get(dom, dom) + '; {:.0f} launches per step, C2 shape'.format(dom_n),
+            'group': dom, 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+            'traffic': traffic, 'peak_source': peak_src, 'launch_ms': dom_ms / dom_n,
+            'algorithmic_bytes_per_launch': gemm_bytes[dom] / dom_n, 'share_of_step': dom_ms / ms_per_step,
+            'note': 'algorithmic bytes = fp32 operand rows read once + result rows written once + weights; the same group '
+                    'reaches {:.1f} TFLOP/s of useful fp32-equivalent math (see roofline_tensor)'.format(
+                        gemm_flops.get(dom, 0.0) / (dom_ms * 1e-3) / 1e12),
+        }
+
+    # ---- kNN on the 150-d EdgeConv features: bf16 tcgen05 filter + exact fp32 re-rank (csrc/knn_tc.cu).  Reported as
+    # direct-form-equivalent work: the bit-exact chain costs (3C-1) N^2 flop per cloud on the FP32 pipe.
     knn_name = 'nt_knn[D=150]'
     knn_ms = groups.get(knn_name, 0.0) / max(counts.get(knn_name, 1.0), 1.0)      # average launch duration
     feat = 150
-    alg_bytes = B * (4 * feat * N + 4 * N * k)            # read the [N,150] fp32 features once + write int32 indices
     pair_dims = B * N * N * feat
-    flops = B * N * N * (3 * feat - 1)                    # (3C-1) N^2 per cloud
-    sm_clock = (clocks or {}).get('sm_mhz') or peaks.get('sm_max_mhz', 1965.0)
+    flops = B * N * N * (3 * feat - 1)
     fp32_peak = SMS * FP32_LANES_PER_SM * 2 * sm_clock * 1e6 / 1e12
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'knn_traffic.json')) as f:
-            traffic = json.load(f).get('dram_bytes_per_launch')
-    except (OSError, ValueError):
-        pass
-    roofline = {
-        'kernel': 'nt::knn_kernel<5> on the 150-d EdgeConv features (kNN-L2), {} clouds x {} pts per launch'.format(B, N),
-        'bound': 'hbm', 'achieved': alg_bytes / (knn_ms * 1e-3) / 1e9 if knn_ms else None, 'peak': hbm_peak,
-        'unit': 'GB/s', 'frac': (alg_bytes / (knn_ms * 1e-3) / 1e9 / hbm_peak) if knn_ms else None,
-        'traffic': traffic, 'peak_source': peak_src, 'launch_ms': knn_ms,
-        'share_of_step': groups.get(knn_name, 0.0) / ms_per_step if ms_per_step else None,
-        'note': 'the bit-exact direct-form distance is FP32-ALU bound (SURVEY.md F9: 718+ flop/B), so the HBM fraction '
-                'is small by construction; the binding roofline is `compute`',
-        'compute': {'bound': 'fp32_alu', 'achieved': flops / (knn_ms * 1e-3) / 1e12 if knn_ms else None,
-                    'peak': fp32_peak, 'unit': 'TFLOP/s',
-                    'frac': (flops / (knn_ms * 1e-3) / 1e12 / fp32_peak) if knn_ms else None,
-                    'pair_dims_per_s': pair_dims / (knn_ms * 1e-3) if knn_ms else None,
-                    'peak_source': 'nominal 148 SM x 128 lanes x 2 x {:.0f} MHz (median SM clock during the run)'
-                    .format(sm_clock)},
+    roofline_knn = {
+        'kernel': 'nt_knn D=150: knn_tc_prepare + knn_tc_filter (tcgen05 bf16, M128 N128 K16) + knn_tc_rerank (exact fp32 chain) '
+                  '+ knn_tc_fallback; {} clouds x {} pts per call'.format(B, N),
+        'launch_ms': knn_ms, 'share_of_step': groups.get(knn_name, 0.0) / ms_per_step if ms_per_step else None,
+        'direct_form_equivalent': {'tflops': flops / (knn_ms * 1e-3) / 1e12 if knn_ms else None, 'fp32_alu_peak': fp32_peak,
+                                   'ratio_to_fp32_alu_peak': (flops / (knn_ms * 1e-3) / 1e12 / fp32_peak) if knn_ms else None,
+                                   'pair_dims_per_s': pair_dims / (knn_ms * 1e-3) if knn_ms else None},
+        'note': 'results are bit-identical to the sequential fp32 fma chain; the filter does 2*160*N^2 bf16 tensor flops per '
+                'cloud instead of 449 N^2 FP32-ALU flops, so the ratio to the FP32-ALU peak may exceed 1',
     }
 
     # tensor-core GEMM group (tcgen05, TF32x3): useful flops (2*rows*K*n_out, one product -- the 3x split is overhead)
@@ -338,7 +361,7 @@ def main():
         'ms_per_step': tc_ms, 'useful_gflop_per_step': tc_flops / 1e9,
         'note': 'peak = measured sustained bf16 cuBLAS GEMM (MEASURED_PEAKS.json); these kernels run kind::tf32 (half the '
                 'bf16 rate) with a 3-product error-compensated split, so 1/6 of that peak is the precision-imposed ceiling; '
-                'they are currently bound by the gather/epilogue side, not by the tensor pipe (profiles/)',
+                'they are bound by HBM streaming and instruction issue of the operand split, not by the tensor pipe (profiles/)',
     }
 
     cpu_baseline = None
@@ -356,7 +379,8 @@ def main():
         'e2e': {'value': e2e_value, 'unit': 'clouds/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps,
-        'clocks': clocks, 'roofline': roofline, 'roofline_tensor': roofline_tensor, 'cpu_baseline': cpu_baseline,
+        'clocks': clocks, 'roofline': roofline, 'roofline_tensor': roofline_tensor, 'roofline_knn': roofline_knn,
+        'cpu_baseline': cpu_baseline,
         'kernel_ms_per_step': {kk: round(v, 4) for kk, v in sorted(groups.items(), key=lambda kv: -kv[1])},
     }
     print(json.dumps(line))

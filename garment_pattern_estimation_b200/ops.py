@@ -36,6 +36,7 @@ def _stream():
 
 
 FLOP_SINK = None      # dict: kernel group -> useful flops (bench.py roofline_tensor)
+BYTES_SINK = None     # dict: kernel group -> algorithmic HBM bytes (operands read once + results written once; bench.py roofline)
 EVENT_SINK = None     # set to a dict to collect (start, end) CUDA-event pairs per kernel group (bench.py roofline)
 
 
@@ -137,6 +138,9 @@ def gemm_nt(rows, K, n_out, w, ldw, epilogue, a=None, lda=0, edge=None, bias=Non
     group = 'nt_gemm_nt[%s,%s]' % (_EPI_NAMES[epilogue], 'edge' if g.producer == NT_PROD_EDGE else 'plain')
     if FLOP_SINK is not None:
         FLOP_SINK[group] = FLOP_SINK.get(group, 0.0) + 2.0 * rows * K * n_out
+    if BYTES_SINK is not None:
+        cols = K + (n_out if out is not None else 0) + (n_out if epilogue == NT_EPI_BNRELU_BWD else 0)
+        BYTES_SINK[group] = BYTES_SINK.get(group, 0.0) + 4.0 * rows * cols + 4.0 * n_out * K
     _call('nt_gemm_nt', _lib.load().nt_gemm_nt, ctypes.byref(g), _stream(), group=group)
 
 
@@ -153,6 +157,9 @@ def gemm_tn(a, lda, m, rows, out, b=None, ldb=0, n=0, edge=None, mu=None):
     if FLOP_SINK is not None:
         name = 'nt_gemm_tn_centered' if mu is not None else 'nt_gemm_tn'
         FLOP_SINK[name] = FLOP_SINK.get(name, 0.0) + 2.0 * rows * m * n
+    if BYTES_SINK is not None:
+        name = 'nt_gemm_tn_centered' if mu is not None else 'nt_gemm_tn'
+        BYTES_SINK[name] = BYTES_SINK.get(name, 0.0) + 4.0 * rows * (m + n) + 4.0 * m * n
     if mu is not None:
         assert out.dtype == torch.float64
         _call('nt_gemm_tn_centered', lib.nt_gemm_tn_centered, _p(a), lda, m, *bop, _p(mu), _p(out), out.stride(0),
