@@ -40,6 +40,7 @@ _SIGNATURES = {
     'nt_knn_workspace_bytes': (c_int64, [c_int, c_int, c_int]),
     'nt_knn': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'nt_gemm_nt': (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
+    'nt_set_nt_engine': (c_int, [c_int]),
     'nt_gemm_weights_bytes': (c_int64, [c_int, c_int, c_int]),
     'nt_gemm_prepare_weights': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'nt_gemm_tn_workspace_bytes': (c_int64, []),

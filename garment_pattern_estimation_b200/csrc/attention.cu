@@ -51,75 +51,148 @@ __global__ void sparsemax_bwd_kernel(const float *__restrict__ out, const float 
     if (live) gz[row * P + lane] = nz ? gv - mean : 0.f;
 }
 
-// enc[b, p, f] += scale * sum_{n in chunk} w[b, n, p] * feat[b, n, f]
-constexpr int AP_CHUNK = 128;   // points per CTA
+// ---------------------------------------------------------------------------------------------------------------------
+// Attention pooling.  Three small contractions per cloud (N points, P <= 32 panels, F features):
+//   forward   enc[p, f]  = scale * sum_n w[n, p] * feat[n, f]
+//   backward  gfeat[n,f] = scale * sum_p w[n, p] * genc[p, f]        gw[n, p] = scale * sum_f genc[p, f] * feat[n, f]
+// They are bandwidth-trivial (feat is read once), so the kernels stage 64-point chunks of feat / w (and genc of the cloud)
+// in shared memory with coalesced loads, rows padded to a multiple of 4 floats, and run register-tiled FMA loops on
+// 16-byte shared-memory reads.
+// ---------------------------------------------------------------------------------------------------------------------
 constexpr int AP_MAXP = 32;
+constexpr int AP_PTS = 64;           // points per staged chunk
+constexpr int AP_THREADS = 256;
+constexpr int AP_FWD_CHUNKS = 4;     // chunks per CTA in the forward (fewer atomics on enc)
 
-__global__ void __launch_bounds__(256) attn_pool_fwd_kernel(const float *__restrict__ w, const float *__restrict__ feat,
-                                                            int ldf, int N, int P, int F, float scale,
-                                                            float *__restrict__ enc) {
-    __shared__ float ws[AP_CHUNK][AP_MAXP + 1];
-    const int b = blockIdx.y;
-    const int n0 = blockIdx.x * AP_CHUNK;
-    const int nn = min(AP_CHUNK, N - n0);
-    for (int i = threadIdx.x; i < nn * P; i += blockDim.x) {
-        int n = i / P, p = i - n * P;
-        ws[n][p] = w[((int64_t)b * N + n0 + n) * P + p];
-    }
-    __syncthreads();
-    for (int f = threadIdx.x; f < F; f += blockDim.x) {
-        float acc[AP_MAXP];
-#pragma unroll
-        for (int p = 0; p < AP_MAXP; ++p) acc[p] = 0.f;
-        const float *fp = feat + ((int64_t)b * N + n0) * ldf + f;
-        for (int n = 0; n < nn; ++n) {
-            const float fv = __ldg(fp + (int64_t)n * ldf);
-#pragma unroll
-            for (int p = 0; p < AP_MAXP; ++p)
-                if (p < P) acc[p] = fmaf(ws[n][p], fv, acc[p]);
-        }
-#pragma unroll
-        for (int p = 0; p < AP_MAXP; ++p)
-            if (p < P) atomicAdd(enc + ((int64_t)b * P + p) * F + f, acc[p] * scale);
+__device__ __forceinline__ void ap_stage(float *dst, int pitch, const float *src, int ld, int rows, int cols, int rows_pad) {
+    // dst[r][c] = src[r][c] for r < rows, c < cols; zero elsewhere (r < rows_pad, c < pitch); coalesced along c
+    for (int i = threadIdx.x; i < rows_pad * pitch; i += AP_THREADS) {
+        const int r = i / pitch, c = i - r * pitch;
+        dst[i] = (r < rows && c < cols) ? __ldg(src + (int64_t)r * ld + c) : 0.f;
     }
 }
 
-constexpr int APB_CHUNK = 32;   // points per CTA in the backward
-
-__global__ void __launch_bounds__(256) attn_pool_bwd_kernel(const float *__restrict__ genc, const float *__restrict__ w,
-                                                            const float *__restrict__ feat, int ldf, int N, int P,
-                                                            int F, float scale, float *__restrict__ gw,
-                                                            float *__restrict__ gfeat, int ldgf, int accumulate) {
-    extern __shared__ float sm[];            // genc[b]: [P][F]  then  w chunk: [APB_CHUNK][P]
-    float *ge = sm;
-    float *wc = sm + P * F;
+// grid (ceil(N / (64*4)), B); dynamic smem: feat_s[64][Fp] + w_s[64][Pp]
+__global__ void __launch_bounds__(AP_THREADS) attn_pool_fwd_kernel(const float *__restrict__ w, const float *__restrict__ feat,
+                                                                   int ldf, int N, int P, int F, float scale,
+                                                                   float *__restrict__ enc) {
+    extern __shared__ __align__(16) float sm[];
+    const int Fp = (F + 3) & ~3, Pp = (P + 3) & ~3;
+    float *feat_s = sm, *w_s = sm + AP_PTS * Fp;
     const int b = blockIdx.y;
-    const int n0 = blockIdx.x * APB_CHUNK;
-    const int nn = min(APB_CHUNK, N - n0);
-    for (int i = threadIdx.x; i < P * F; i += blockDim.x) ge[i] = genc[(int64_t)b * P * F + i];
-    for (int i = threadIdx.x; i < nn * P; i += blockDim.x) wc[i] = w[((int64_t)b * N + n0) * P + i];
-    __syncthreads();
-    // gfeat[b, n, f] = scale * sum_p w[n, p] * genc[p, f]
-    if (gfeat) {
-        for (int f = threadIdx.x; f < F; f += blockDim.x) {
-            for (int n = 0; n < nn; ++n) {
-                float acc = 0.f;
-                for (int p = 0; p < P; ++p) acc = fmaf(wc[n * P + p], ge[p * F + f], acc);
-                float *dst = gfeat + ((int64_t)b * N + n0 + n) * ldgf + f;
-                *dst = accumulate ? (*dst + acc * scale) : (acc * scale);
+    const int nf4 = Fp >> 2, np4 = Pp >> 2, items = nf4 * np4;     // work item = 4 features x 4 panels
+    float acc[2][16];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[j][e] = 0.f;
+    for (int ch = 0; ch < AP_FWD_CHUNKS; ++ch) {
+        const int n0 = (blockIdx.x * AP_FWD_CHUNKS + ch) * AP_PTS;
+        if (n0 >= N) break;
+        const int nn = min(AP_PTS, N - n0);
+        __syncthreads();
+        ap_stage(feat_s, Fp, feat + ((int64_t)b * N + n0) * ldf, ldf, nn, F, AP_PTS);
+        ap_stage(w_s, Pp, w + ((int64_t)b * N + n0) * P, P, nn, P, AP_PTS);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int item = threadIdx.x + j * AP_THREADS;
+            if (item >= items) continue;
+            const int f4 = item % nf4, p4 = item / nf4;
+            const float *fs = feat_s + 4 * f4, *ws = w_s + 4 * p4;
+            for (int n = 0; n < AP_PTS; ++n) {
+                const float4 fv = *reinterpret_cast<const float4 *>(fs + n * Fp);
+                const float4 wv = *reinterpret_cast<const float4 *>(ws + n * Pp);
+                const float ff[4] = {fv.x, fv.y, fv.z, fv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                for (int pi = 0; pi < 4; ++pi)
+#pragma unroll
+                    for (int fi = 0; fi < 4; ++fi) acc[j][pi * 4 + fi] = fmaf(ww[pi], ff[fi], acc[j][pi * 4 + fi]);
             }
         }
     }
-    // gw[b, n, p] = scale * sum_f genc[p, f] * feat[n, f]   (one warp per (n, p) pair)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int item = threadIdx.x + j * AP_THREADS;
+        if (item >= items) continue;
+        const int f4 = item % nf4, p4 = item / nf4;
+#pragma unroll
+        for (int pi = 0; pi < 4; ++pi)
+#pragma unroll
+            for (int fi = 0; fi < 4; ++fi) {
+                const int p = 4 * p4 + pi, f = 4 * f4 + fi;
+                if (p < P && f < F) atomicAdd(enc + ((int64_t)b * P + p) * F + f, acc[j][pi * 4 + fi] * scale);
+            }
+    }
+}
+
+// grid (ceil(N / 64), B); dynamic smem: feat_s[64][Fp] (re-used for the gfeat tile) + ge_s[Pp][Fp] + w_s[64][Pp]
+__global__ void __launch_bounds__(AP_THREADS) attn_pool_bwd_kernel(const float *__restrict__ genc, const float *__restrict__ w,
+                                                                   const float *__restrict__ feat, int ldf, int N, int P,
+                                                                   int F, float scale, float *__restrict__ gw,
+                                                                   float *__restrict__ gfeat, int ldgf, int accumulate) {
+    extern __shared__ __align__(16) float sm[];
+    const int Fp = (F + 3) & ~3, Pp = (P + 3) & ~3;
+    float *feat_s = sm, *ge_s = sm + AP_PTS * Fp, *w_s = ge_s + Pp * Fp;
+    const int b = blockIdx.y;
+    const int n0 = blockIdx.x * AP_PTS;
+    const int nn = min(AP_PTS, N - n0);
+    const int nf4 = Fp >> 2, np4 = Pp >> 2;
+    ap_stage(ge_s, Fp, genc + (int64_t)b * P * F, F, P, F, Pp);
+    ap_stage(w_s, Pp, w + ((int64_t)b * N + n0) * P, P, nn, P, AP_PTS);
+    if (gw) ap_stage(feat_s, Fp, feat + ((int64_t)b * N + n0) * ldf, ldf, nn, F, AP_PTS);
+    __syncthreads();
+    // gw[n, p4 .. p4+3] = scale * sum_f genc[p, f] * feat[n, f]: work item = (point, 4 panels); the lanes of a warp cover
+    // 32 / np4 points x np4 panel groups, so feat rows and genc rows are both read as a few broadcast 16-byte accesses
     if (gw) {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-        for (int pair = warp; pair < nn * P; pair += nwarps) {
-            const int n = pair / P, p = pair - n * P;
-            const float *fp = feat + ((int64_t)b * N + n0 + n) * ldf;
-            float acc = 0.f;
-            for (int f = lane; f < F; f += 32) acc = fmaf(ge[p * F + f], __ldg(fp + f), acc);
-            acc = warp_sum(acc);
-            if (lane == 0) gw[((int64_t)b * N + n0 + n) * P + p] = acc * scale;
+        for (int item = threadIdx.x; item < AP_PTS * np4; item += AP_THREADS) {
+            const int n = item / np4, p4 = item - n * np4;
+            if (n >= nn) continue;
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            const float *fs = feat_s + n * Fp, *gs = ge_s + 4 * p4 * Fp;
+            for (int f4 = 0; f4 < nf4; ++f4) {
+                const float4 fv = *reinterpret_cast<const float4 *>(fs + 4 * f4);
+#pragma unroll
+                for (int pi = 0; pi < 4; ++pi) {
+                    const float4 gv = *reinterpret_cast<const float4 *>(gs + pi * Fp + 4 * f4);
+                    a[pi] = fmaf(gv.x, fv.x, a[pi]); a[pi] = fmaf(gv.y, fv.y, a[pi]);
+                    a[pi] = fmaf(gv.z, fv.z, a[pi]); a[pi] = fmaf(gv.w, fv.w, a[pi]);
+                }
+            }
+#pragma unroll
+            for (int pi = 0; pi < 4; ++pi)
+                if (4 * p4 + pi < P) gw[((int64_t)b * N + n0 + n) * P + 4 * p4 + pi] = a[pi] * scale;
+        }
+    }
+    if (gfeat) {
+        __syncthreads();                 // feat_s is free now: it receives the gfeat tile for a coalesced store
+        // gfeat[n .. n+1, f4 .. f4+3] = scale * sum_p w[n, p] * genc[p, f]: work item = (2 points, 4 features)
+        for (int item = threadIdx.x; item < (AP_PTS / 2) * nf4; item += AP_THREADS) {
+            const int f4 = item % nf4, n2 = item / nf4;
+            float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+            const float *w0 = w_s + (2 * n2) * Pp, *w1 = w0 + Pp, *gs = ge_s + 4 * f4;
+            for (int p4 = 0; p4 < np4; ++p4) {
+                const float4 wa = *reinterpret_cast<const float4 *>(w0 + 4 * p4);
+                const float4 wb = *reinterpret_cast<const float4 *>(w1 + 4 * p4);
+                const float wav[4] = {wa.x, wa.y, wa.z, wa.w}, wbv[4] = {wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int pi = 0; pi < 4; ++pi) {
+                    const float4 gv = *reinterpret_cast<const float4 *>(gs + (4 * p4 + pi) * Fp);
+                    a0[0] = fmaf(wav[pi], gv.x, a0[0]); a0[1] = fmaf(wav[pi], gv.y, a0[1]);
+                    a0[2] = fmaf(wav[pi], gv.z, a0[2]); a0[3] = fmaf(wav[pi], gv.w, a0[3]);
+                    a1[0] = fmaf(wbv[pi], gv.x, a1[0]); a1[1] = fmaf(wbv[pi], gv.y, a1[1]);
+                    a1[2] = fmaf(wbv[pi], gv.z, a1[2]); a1[3] = fmaf(wbv[pi], gv.w, a1[3]);
+                }
+            }
+            *reinterpret_cast<float4 *>(feat_s + (2 * n2) * Fp + 4 * f4) = make_float4(a0[0], a0[1], a0[2], a0[3]);
+            *reinterpret_cast<float4 *>(feat_s + (2 * n2 + 1) * Fp + 4 * f4) = make_float4(a1[0], a1[1], a1[2], a1[3]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nn * F; i += AP_THREADS) {
+            const int n = i / F, f = i - n * F;
+            float *dst = gfeat + ((int64_t)b * N + n0 + n) * ldgf + f;
+            const float v = feat_s[n * Fp + f] * scale;
+            *dst = accumulate ? (*dst + v) : v;
         }
     }
 }
@@ -144,13 +217,26 @@ extern "C" int nt_sparsemax_bwd(const float *out, const float *g, int64_t rows, 
     return check_launch("nt_sparsemax_bwd");
 }
 
+static size_t ap_fwd_smem(int P, int F) { return ((size_t)AP_PTS * ((F + 3) & ~3) + (size_t)AP_PTS * ((P + 3) & ~3)) * sizeof(float); }
+static size_t ap_bwd_smem(int P, int F) {
+    const size_t Fp = (F + 3) & ~3, Pp = (P + 3) & ~3;
+    return ((size_t)AP_PTS * Fp + Pp * Fp + (size_t)AP_PTS * Pp) * sizeof(float);
+}
+
 extern "C" int nt_attn_pool_fwd(const float *w, const float *feat, int ldf, int B, int N, int P, int F, float scale,
                                 float *enc, void *stream) {
     NT_REQUIRE(w && feat && enc && B >= 0 && N >= 1 && P >= 1 && P <= AP_MAXP && F >= 1 && ldf >= F,
                "nt_attn_pool_fwd: bad arguments (P <= 32)");
+    NT_REQUIRE(B <= 65535, "nt_attn_pool_fwd: at most 65535 clouds per call");
     if (B == 0) return 0;
-    dim3 grid((N + AP_CHUNK - 1) / AP_CHUNK, B);
-    attn_pool_fwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, feat, ldf, N, P, F, scale, enc);
+    const size_t smem = ap_fwd_smem(P, F);
+    NT_REQUIRE(((F + 3) / 4) * ((P + 3) / 4) <= 2 * AP_THREADS && smem <= 200 * 1024, "nt_attn_pool_fwd: P*F too large");
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(attn_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail("nt_attn_pool_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    dim3 grid((N + AP_PTS * AP_FWD_CHUNKS - 1) / (AP_PTS * AP_FWD_CHUNKS), B);
+    attn_pool_fwd_kernel<<<grid, AP_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(w, feat, ldf, N, P, F, scale, enc);
     return check_launch("nt_attn_pool_fwd");
 }
 
@@ -160,15 +246,16 @@ extern "C" int nt_attn_pool_bwd(const float *genc, const float *w, const float *
     NT_REQUIRE(genc && w && feat && B >= 0 && N >= 1 && P >= 1 && P <= AP_MAXP && F >= 1 && ldf >= F,
                "nt_attn_pool_bwd: bad arguments (P <= 32)");
     NT_REQUIRE(!gfeat || ldgf >= F, "nt_attn_pool_bwd: bad gfeat stride");
+    NT_REQUIRE(B <= 65535, "nt_attn_pool_bwd: at most 65535 clouds per call");
     if (B == 0) return 0;
-    size_t smem = ((size_t)P * F + (size_t)APB_CHUNK * P) * sizeof(float);
+    const size_t smem = ap_bwd_smem(P, F);
+    NT_REQUIRE(smem <= 200 * 1024, "nt_attn_pool_bwd: P*F too large");
     if (smem > 48 * 1024) {
-        NT_REQUIRE(smem <= 200 * 1024, "nt_attn_pool_bwd: P*F too large");
         cudaError_t e = cudaFuncSetAttribute(attn_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail("nt_attn_pool_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    dim3 grid((N + APB_CHUNK - 1) / APB_CHUNK, B);
-    attn_pool_bwd_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(genc, w, feat, ldf, N, P, F, scale,
-                                                                                     gw, gfeat, ldgf, accumulate_gfeat);
+    dim3 grid((N + AP_PTS - 1) / AP_PTS, B);
+    attn_pool_bwd_kernel<<<grid, AP_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(genc, w, feat, ldf, N, P, F, scale,
+                                                                                            gw, gfeat, ldgf, accumulate_gfeat);
     return check_launch("nt_attn_pool_bwd");
 }

@@ -510,14 +510,27 @@ static int dispatch_tc(const NTParams &p, int producer, int epilogue, const void
     }
 }
 
-static int g_nt_engine = -1;       // developer knob NT_NT_ENGINE: 1 = one tile per CTA (this file), 2 = persistent (gemm_tc2.cu)
+// Engine choice for the TF32x3 row GEMMs.  0 = auto (default): the streaming engine (gemm_tc3.cu) for eligible calls with at
+// least TC3_MIN_ROWS rows, the one-tile-per-CTA engine (this file) otherwise; 1 = always this file; 2 = persistent engine
+// of gemm_tc2.cu (experiment); 3 = streaming engine whenever eligible, whatever the row count (tests).
+// Set by nt_set_nt_engine() or, before the first call, by the developer knob NT_NT_ENGINE.
+static std::atomic<int> g_nt_engine{-1};
+constexpr int64_t TC3_MIN_ROWS = 32768;
 
 int launch_nt_tc(const NTParams &p, int producer, int epilogue, int precision, const void *w_split, cudaStream_t st) {
-    if (g_nt_engine < 0) {
+    int engine = g_nt_engine.load(std::memory_order_relaxed);
+    if (engine < 0) {
         const char *v = getenv("NT_NT_ENGINE");
-        g_nt_engine = v ? atoi(v) : 1;
+        engine = v ? atoi(v) : 0;
+        g_nt_engine.store(engine, std::memory_order_relaxed);
     }
-    if (g_nt_engine == 2 && precision == NT_PREC_TF32X3) return launch_nt_tc2(p, producer, epilogue, w_split, st);
+    if (precision == NT_PREC_TF32X3) {
+        if (engine == 2) return launch_nt_tc2(p, producer, epilogue, w_split, st);
+        if (engine == 3 || (engine == 0 && p.rows >= TC3_MIN_ROWS)) {
+            const int rc = launch_nt_tc3(p, producer, epilogue, w_split, st);
+            if (rc >= 0) return rc;
+        }
+    }
     return precision == NT_PREC_TF32X3 ? dispatch_tc<true>(p, producer, epilogue, w_split, st)
                                        : dispatch_tc<false>(p, producer, epilogue, w_split, st);
 }
@@ -525,6 +538,12 @@ int launch_nt_tc(const NTParams &p, int producer, int epilogue, int precision, c
 }  // namespace nt
 
 using namespace nt;
+
+extern "C" int nt_set_nt_engine(int engine) {
+    NT_REQUIRE(engine >= 0 && engine <= 3, "nt_set_nt_engine: engine must be 0 (auto), 1, 2 or 3");
+    g_nt_engine.store(engine, std::memory_order_relaxed);
+    return 0;
+}
 
 extern "C" int64_t nt_gemm_weights_bytes(int n_out, int K, int precision) {
     if (n_out < 1 || K < 1) return 0;

@@ -1,0 +1,389 @@
+// Streaming engine for the big fused row GEMMs (same contract as gemm_tc.cu / nt_gemm_nt), sm_100a.
+//
+//   out = epilogue( A . W^T )      A: [rows, K] fp32 rows in HBM (plain producer), W: [n_out <= 224, K], TF32x3
+//
+// These GEMMs have K, n_out <= 200: they are streaming kernels (read A once, write the result once; BNRELU_BWD also reads
+// the saved activation once), so the design goal is bytes in flight, not flops.  One persistent CTA per SM loops over
+// 128-row tiles with four decoupled pipelines:
+//
+//   warps 0-3   A loaders/converters.  Every thread keeps P3_DEPTH k-blocks (16 columns each) of ITS OWN 4 x 16-byte row
+//               chunks in flight with cp.async.cg (global -> shared, no registers, zero-fill for ragged rows / K tails):
+//               6 x 8 KB per CTA are always outstanding, independent of what the epilogue is doing and across tile
+//               boundaries.  A landed k-block is split hi/lo (TF32x3) from shared memory into the UMMA core-matrix stage.
+//   warp 12     single-thread tcgen05.mma issue into one of TWO TMEM accumulators (2 x 256 columns).
+//   warps 4-7   epilogue group 0 (tiles 0, 2, 4, ... of this CTA; TMEM accumulator 0)
+//   warps 8-11  epilogue group 1 (tiles 1, 3, 5, ...;              TMEM accumulator 1)
+//               each group has two tile periods to drain its accumulator; all global traffic of the epilogue is
+//               coalesced 16-byte accesses exchanged with the thread-per-row TMEM layout through a 32 x 36 transposition
+//               tile per warp, and the BNRELU_BWD aux rows of chunk c+1 are loaded while chunk c is processed.
+//
+// The one-tile-per-CTA engine (gemm_tc.cu) remains the general path (gathered operands, unaligned rows, n_out > 224, small
+// row counts); launch_nt_tc3 returns -1 when a call is not eligible.
+#include "gemm_tc_shared.cuh"
+
+namespace nt {
+
+constexpr int P3_EPI0_WARP = 4;
+constexpr int P3_MMA_WARP = 12;
+constexpr int P3_THREADS = 13 * 32;
+constexpr int P3_STAGES = 3;
+constexpr int P3_DEPTH = 6;                        // k-blocks in flight per producer thread
+constexpr int P3_SLAB = 4 * TC_M * 16;             // raw k-block: [4 chunks][128 rows][16 B]
+constexpr int P3_TW = 32 * 36;                     // floats of one per-warp transposition tile
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__host__ __device__ inline size_t tc3_smem_bytes(int n_tile) {
+    return P3_STAGES * tc_stage_bytes(n_tile) + (size_t)P3_DEPTH * P3_SLAB + 8 * P3_TW * 4 + 4 * 256 * 4 + 512 * 4 + 128;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, const uint8_t *__restrict__ w_split, TCGeom g) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const size_t stage_bytes = tc_stage_bytes(g.n_tile);
+    uint8_t *raw = smem + P3_STAGES * stage_bytes;
+    float *tw_all = reinterpret_cast<float *>(raw + P3_DEPTH * P3_SLAB);          // 8 x [32][36]
+    float *colv = tw_all + 8 * P3_TW;                                              // [4][256]: bias | k0 | k1 | mu
+    float *red = colv + 4 * 256;                                                   // [2][256] column statistics
+    uint64_t *full = reinterpret_cast<uint64_t *>(red + 512);                      // [3]
+    uint64_t *empty = full + P3_STAGES;                                            // [3]
+    uint64_t *tmem_full = empty + P3_STAGES;                                       // [2]
+    uint64_t *tmem_empty = tmem_full + 2;                                          // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_row_tiles = (p.rows + p.rows_per_tile - 1) / p.rows_per_tile;
+    const int my_tiles = (int)((n_row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);      // tiles blockIdx.x, +grid, ...
+
+    for (int i = tid; i < 512; i += P3_THREADS) red[i] = 0.f;
+    for (int i = tid; i < 256; i += P3_THREADS) {
+        const bool ok = i < p.n_out;
+        colv[i] = (ok && p.bias) ? __ldg(p.bias + i) : 0.f;
+        colv[256 + i] = (ok && EPI == NT_EPI_BNRELU_BWD) ? __ldg(p.k0 + i) : 0.f;
+        colv[512 + i] = (ok && EPI == NT_EPI_BNRELU_BWD) ? __ldg(p.k1 + i) : 0.f;
+        colv[768 + i] = (ok && EPI == NT_EPI_BNRELU_BWD) ? __ldg(p.mu + i) : 0.f;
+    }
+    if (warp == P3_MMA_WARP && lane == 0) {
+        for (int s = 0; s < P3_STAGES; ++s) { mbar_init(&full[s], 128 + 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+        mbar_fence_init();
+    }
+    if (warp == P3_MMA_WARP) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int total_it = my_tiles * g.num_kb;
+
+    if (warp < 4) {
+        // =========================== A loaders / converters ===========================
+        // lane -> 16-byte chunk jj = lane >> 3 of the rows warp*32 + 8*i + (lane & 7): a warp request touches 8 rows x 64
+        // contiguous bytes, and the 16-byte shared-memory accesses of a quarter-warp cover 128 contiguous bytes.
+        const int jj = lane >> 3;
+        int prow[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) prow[i] = warp * 32 + 8 * i + (lane & 7);
+        const uint32_t raw_u32 = smem_u32(raw);
+        const uint32_t slot_off = (uint32_t)(jj * (TC_M * 16));
+
+        // fetch stream position (tile, k-block) -- advanced incrementally, it runs P3_DEPTH iterations ahead of consume
+        int f_it = 0, f_kb = 0;
+        int64_t f_row0 = (int64_t)blockIdx.x * p.rows_per_tile;
+        auto issue = [&]() {
+            if (f_it < total_it) {
+                const int rows_here = (int)min((int64_t)p.rows_per_tile, p.rows - f_row0);
+                const int k = (f_kb * 4 + jj) * 4;
+                const uint32_t dst0 = raw_u32 + (uint32_t)((f_it % P3_DEPTH) * P3_SLAB) + slot_off;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool live = prow[i] < rows_here && k < p.K;
+                    const uint32_t nbytes = live ? (uint32_t)min(16, (p.K - k) * 4) : 0u;
+                    const float *src = live ? p.a + (f_row0 + prow[i]) * (int64_t)p.lda + k : p.a;
+                    cp_async16(dst0 + (uint32_t)(prow[i] * 16), src, nbytes);
+                }
+                ++f_it;
+                if (++f_kb == g.num_kb) { f_kb = 0; f_row0 += (int64_t)gridDim.x * p.rows_per_tile; }
+            }
+            cp_async_commit();                       // exactly one group per call, possibly empty
+        };
+#pragma unroll 1
+        for (int d = 0; d < P3_DEPTH; ++d) issue();
+
+        int s = 0, use = 0, kb = 0, slab = 0;
+#pragma unroll 1
+        for (int it = 0; it < total_it; ++it) {
+            cp_async_wait<P3_DEPTH - 1>();           // this thread's chunks of k-block `it` have landed
+            mbar_wait(&empty[s], (use & 1) ^ 1);
+            uint8_t *a_hi = smem + s * stage_bytes, *a_lo = a_hi + TC_A_BYTES, *b_all = a_lo + TC_A_BYTES;
+            if (tid == 0) {
+                const uint32_t bytes = (uint32_t)g.n_tile * 128u;
+                mbar_arrive_expect_tx(&full[s], bytes);
+                bulk_g2s(b_all, w_split + (size_t)kb * bytes, bytes, &full[s]);
+            }
+            const uint8_t *rs = raw + slab * P3_SLAB + slot_off;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 x = *reinterpret_cast<const float4 *>(rs + prow[i] * 16);
+                uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                split_tf32(x.x, h0, l0); split_tf32(x.y, h1, l1); split_tf32(x.z, h2, l2); split_tf32(x.w, h3, l3);
+                *reinterpret_cast<uint4 *>(a_hi + slot_off + prow[i] * 16) = make_uint4(h0, h1, h2, h3);
+                *reinterpret_cast<uint4 *>(a_lo + slot_off + prow[i] * 16) = make_uint4(l0, l1, l2, l3);
+            }
+            fence_proxy_async();                     // generic-proxy smem writes -> visible to the tensor core
+            mbar_arrive(&full[s]);
+            issue();                                 // refill the raw slab this thread has just read
+            if (++s == P3_STAGES) { s = 0; ++use; }
+            if (++kb == g.num_kb) kb = 0;
+            if (++slab == P3_DEPTH) slab = 0;
+        }
+        cp_async_wait<0>();
+    } else if (warp == P3_MMA_WARP) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_M, (uint32_t)g.n_tile, 0, 0);
+            const uint32_t lbo_a = TC_M * 16, lbo_b = (uint32_t)g.n_tile * 16, sbo = 128;
+            int s = 0, use = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int as = ti & 1, ause = ti >> 1;
+                mbar_wait(&tmem_empty[as], (ause & 1) ^ 1);         // the epilogue group has drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(as * 256);
+                for (int kb = 0; kb < g.num_kb; ++kb) {
+                    mbar_wait(&full[s], use & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + s * stage_bytes), a_lo = a_hi + TC_A_BYTES;
+                    const uint32_t b_hi = a_lo + TC_A_BYTES, b_lo = b_hi + 4 * lbo_b;
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const uint64_t dah = make_smem_desc(a_hi + kk * 2 * lbo_a, lbo_a, sbo);
+                        const uint64_t dal = make_smem_desc(a_lo + kk * 2 * lbo_a, lbo_a, sbo);
+                        const uint64_t dbh = make_smem_desc(b_hi + kk * 2 * lbo_b, lbo_b, sbo);
+                        const uint64_t dbl = make_smem_desc(b_lo + kk * 2 * lbo_b, lbo_b, sbo);
+                        umma_tf32(d, dah, dbh, idesc, (kb | kk) ? 1u : 0u);
+                        umma_tf32(d, dah, dbl, idesc, 1u);
+                        umma_tf32(d, dal, dbh, idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);            // stage reusable once these MMAs have read it
+                    if (++s == P3_STAGES) { s = 0; ++use; }
+                }
+                umma_commit(&tmem_full[as]);           // accumulator complete -> epilogue group `as`
+            }
+        }
+    } else {
+        // =========================== epilogue groups (thread = row of the tile, TMEM lane = row) ===========================
+        const int grp = (warp - P3_EPI0_WARP) >> 2;                // 0: warps 4-7, 1: warps 8-11
+        const int quad = warp & 3;                                  // TMEM lane quadrant this warp may read
+        const int et = quad * 32 + lane;                            // 0..127 inside the group = row of the tile
+        float *twg = tw_all + grp * (4 * P3_TW);                    // the group's four tiles are contiguous: row r at r*36
+        float *tw4 = twg + quad * P3_TW;
+        const int sub = lane >> 3, q4 = (lane & 7) * 4;
+        const int n_chunks = (g.n_tile + 31) / 32;
+        for (int ti = grp; ti < my_tiles; ti += 2) {
+            const int as = grp, ause = ti >> 1;
+            const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * p.rows_per_tile;
+            const int rows_here = (int)min((int64_t)p.rows_per_tile, p.rows - row0);
+            const bool valid = et < rows_here;
+            const int64_t wrow0 = row0 + quad * 32;                  // first row of this warp
+            const int wrows = max(0, min(32, rows_here - quad * 32));
+            const float *auxw = (EPI == NT_EPI_BNRELU_BWD) ? p.aux + wrow0 * (int64_t)p.ldaux : nullptr;
+            float4 ld[8];
+            // coalesced aux read of one 32-column chunk: lane -> row 4m + sub, columns q4 .. q4+3
+            auto load_aux = [&](int ch) {
+                const int cg = ch * 32, nv = min(32, p.n_out - cg);
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const int rr = 4 * m + sub;
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rr < wrows) {
+                        const float *src = auxw + (int64_t)rr * p.ldaux + cg + q4;
+                        if (q4 + 3 < nv) {
+                            a = __ldg(reinterpret_cast<const float4 *>(src));
+                        } else if (q4 < nv) {
+                            a.x = __ldg(src);
+                            if (q4 + 1 < nv) a.y = __ldg(src + 1);
+                            if (q4 + 2 < nv) a.z = __ldg(src + 2);
+                        }
+                    }
+                    ld[m] = a;
+                }
+            };
+            if (EPI == NT_EPI_BNRELU_BWD) load_aux(0);               // does not depend on the accumulator
+            mbar_wait(&tmem_full[as], ause & 1);
+            tc_fence_after();
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                const int c0 = ch * 32;
+                const int nv = min(32, p.n_out - c0);                // valid columns of this chunk (>= 1)
+                float auxv[32];
+                if (EPI == NT_EPI_BNRELU_BWD) {
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) *reinterpret_cast<float4 *>(tw4 + (4 * m + sub) * 36 + q4) = ld[m];
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 a = *reinterpret_cast<const float4 *>(tw4 + lane * 36 + 4 * i);
+                        auxv[4 * i] = a.x; auxv[4 * i + 1] = a.y; auxv[4 * i + 2] = a.z; auxv[4 * i + 3] = a.w;
+                    }
+                    __syncwarp();
+                    if (ch + 1 < n_chunks) load_aux(ch + 1);         // in flight while this chunk is processed
+                }
+                float acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + c0), acc);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(colv + c0 + 4 * i);
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                    if (EPI == NT_EPI_BNRELU_BWD) {
+                        const float4 k04 = *reinterpret_cast<const float4 *>(colv + 256 + c0 + 4 * i);
+                        const float4 k14 = *reinterpret_cast<const float4 *>(colv + 512 + c0 + 4 * i);
+                        const float4 mu4 = *reinterpret_cast<const float4 *>(colv + 768 + c0 + 4 * i);
+                        const float k0v[4] = {k04.x, k04.y, k04.z, k04.w}, k1v[4] = {k14.x, k14.y, k14.z, k14.w};
+                        const float muv[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float a = auxv[4 * i + e];
+                            acc[4 * i + e] = (valid && a > 0.f) ? (acc[4 * i + e] - k0v[e] - (a - muv[e]) * k1v[e]) : 0.f;
+                        }
+                    } else if (EPI == NT_EPI_BIAS) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[4 * i + e] += bb[e];
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[4 * i + e] = valid ? fmaxf(acc[4 * i + e] + bb[e], 0.f) : 0.f;
+                    }
+                }
+                const bool want = (EPI == NT_EPI_BIAS) ? false
+                                                       : ((EPI == NT_EPI_BNRELU_BWD) ? (p.colsum != nullptr) : (p.stats != nullptr));
+                if (p.out || want || EPI == NT_EPI_RELU_MAXMIN) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4 *>(tw4 + lane * 36 + 4 * i) =
+                            make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                    __syncwarp();
+                    if (p.out) {
+                        float *dst = p.out + wrow0 * (int64_t)p.ldo + c0 + q4;
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) {
+                            const int rr = 4 * m + sub;
+                            if (rr < wrows) {
+                                const float4 v = *reinterpret_cast<const float4 *>(tw4 + rr * 36 + q4);
+                                float *d = dst + (int64_t)rr * p.ldo;
+                                if (q4 + 3 < nv) {
+                                    *reinterpret_cast<float4 *>(d) = v;
+                                } else if (q4 < nv) {
+                                    d[0] = v.x;
+                                    if (q4 + 1 < nv) d[1] = v.y;
+                                    if (q4 + 2 < nv) d[2] = v.z;
+                                }
+                            }
+                        }
+                    }
+                    if (EPI == NT_EPI_RELU_MAXMIN) {
+                        // max / min over the k edge rows of every centre point (nodes straddle warps: group barrier); the same
+                        // pass yields the column statistics (a thread always lands on the same column: 128 % 32 == 0)
+                        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                        const int kk = p.k_agg;
+                        const int nodes_here = rows_here / kk;
+                        const int64_t node0 = row0 / kk;
+                        float t1 = 0.f, t2 = 0.f;
+                        if (lane < nv) {
+                            for (int t = et; t < nodes_here * 32; t += 128) {
+                                const int nd = t >> 5;
+                                float x = twg[(nd * kk) * 36 + lane];
+                                float mx = x, mn = x;
+                                int ix = 0, in = 0;
+                                t1 += x; t2 = fmaf(x, x, t2);
+                                for (int sl = 1; sl < kk; ++sl) {
+                                    x = twg[(nd * kk + sl) * 36 + lane];
+                                    if (x > mx) { mx = x; ix = sl; }
+                                    if (x < mn) { mn = x; in = sl; }
+                                    t1 += x; t2 = fmaf(x, x, t2);
+                                }
+                                const int64_t o = (node0 + nd) * (int64_t)p.n_out + c0 + lane;
+                                p.vmax[o] = mx; p.vmin[o] = mn; p.imax[o] = (uint8_t)ix; p.imin[o] = (uint8_t)in;
+                            }
+                            if (p.stats) { atomicAdd(&red[c0 + lane], t1); atomicAdd(&red[256 + c0 + lane], t2); }
+                        }
+                        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    } else {
+                        if (want && lane < nv) {
+                            // column sums of this warp's 32 rows (lane = column; invalid rows hold zeros)
+                            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                            for (int rr = 0; rr < 32; ++rr) {
+                                const float x = tw4[rr * 36 + lane];
+                                t1 += x;
+                                if (EPI != NT_EPI_BNRELU_BWD) t2 = fmaf(x, x, t2);
+                            }
+                            atomicAdd(&red[c0 + lane], t1);
+                            if (EPI != NT_EPI_BNRELU_BWD) atomicAdd(&red[256 + c0 + lane], t2);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[as]);
+        }
+        // flush the per-CTA column statistics once (they accumulate over all of this CTA's tiles, both groups)
+        if (EPI != NT_EPI_BIAS) {
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            for (int c = (warp - P3_EPI0_WARP) * 32 + lane; c < p.n_out; c += 256) {
+                if (EPI == NT_EPI_BNRELU_BWD) {
+                    if (p.colsum) atomicAdd(p.colsum + c, (double)red[c]);
+                } else if (p.stats) {
+                    atomicAdd(p.stats + c, (double)red[c]);
+                    atomicAdd(p.stats + p.n_out + c, (double)red[256 + c]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == P3_MMA_WARP) tmem_dealloc(tmem_base, 512);
+}
+
+template <int EPI>
+static int launch_tc3(const NTParams &p, const void *w_split, const TCGeom &g, int sms, cudaStream_t st) {
+    const size_t smem = tc3_smem_bytes(g.n_tile);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc3_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail("nt_gemm_nt(tc3): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const int64_t n_row_tiles = (p.rows + p.rows_per_tile - 1) / p.rows_per_tile;
+    const int ctas = (int)(n_row_tiles < sms ? n_row_tiles : sms);
+    gemm_nt_tc3_kernel<EPI><<<ctas, P3_THREADS, smem, st>>>(p, reinterpret_cast<const uint8_t *>(w_split), g);
+    return check_launch("nt_gemm_nt(tc3)");
+}
+
+// -1: not eligible (the caller falls back to the one-tile-per-CTA engine)
+int launch_nt_tc3(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st) {
+    if (producer != NT_PROD_PLAIN || p.n_out > 224) return -1;
+    const TCGeom g = tc_geometry(p.n_out, p.K, NT_PREC_TF32X3);
+    if (g.n_tiles != 1 || tc3_smem_bytes(g.n_tile) > 227 * 1024) return -1;
+    if ((p.lda & 3) != 0 || !aligned16(p.a)) return -1;
+    if (p.out && ((p.ldo & 3) != 0 || !aligned16(p.out))) return -1;
+    if (epilogue == NT_EPI_BNRELU_BWD && (p.aux_edge || (p.ldaux & 3) != 0 || !aligned16(p.aux))) return -1;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
+            return fail("nt_gemm_nt(tc3): cannot query the SM count%s", "");
+        sms = n;
+    }
+    switch (epilogue) {
+        case NT_EPI_BIAS: return launch_tc3<NT_EPI_BIAS>(p, w_split, g, sms, st);
+        case NT_EPI_RELU_STATS: return launch_tc3<NT_EPI_RELU_STATS>(p, w_split, g, sms, st);
+        case NT_EPI_RELU_MAXMIN: return launch_tc3<NT_EPI_RELU_MAXMIN>(p, w_split, g, sms, st);
+        default: return launch_tc3<NT_EPI_BNRELU_BWD>(p, w_split, g, sms, st);
+    }
+}
+
+}  // namespace nt

@@ -70,5 +70,7 @@ __device__ __forceinline__ void load_chunk(const float *src, int k, int K, bool 
 
 // persistent engine entry (gemm_tc2.cu)
 int launch_nt_tc2(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st);
+// streaming engine entry (gemm_tc3.cu); returns -1 when the call is not eligible (caller falls back to gemm_tc.cu)
+int launch_nt_tc3(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st);
 
 }  // namespace nt

@@ -656,6 +656,8 @@ static int launch_knn(const float *x, int B, int N, int D, int ldx, int k, int32
 bool knn_tc_eligible(int N, int D, const void *workspace);
 int64_t knn_tc_workspace_bytes(int B, int N, int k);
 int knn_tc_run(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *workspace, cudaStream_t st);
+// xyz graphs (knn3.cu)
+int knn3_run(const float *x, int B, int N, int ldx, int k, int32_t *idx, cudaStream_t st);
 
 }  // namespace nt
 
@@ -678,6 +680,9 @@ extern "C" int nt_knn(const float *x, int B, int N, int D, int ldx, int k, int32
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // feature-space graphs (D >= 8): bf16 tcgen05 filter + exact fp32 re-rank, bit-identical to the direct form below
     if (knn_tc_eligible(N, D, workspace)) return knn_tc_run(x, B, N, D, ldx, k, idx, workspace, st);
+    // coordinate-space graphs (D = 3): register top-k over a shared-memory copy of the cloud (knn3.cu); NT_KNN_VARIANT keeps
+    // the generic kernels reachable for comparison
+    if (D == 3 && getenv("NT_KNN_VARIANT") == nullptr) return knn3_run(x, B, N, ldx, k, idx, st);
     if (k <= 5) return launch_knn<5>(x, B, N, D, ldx, k, idx, workspace, st);
     if (k <= 8) return launch_knn<8>(x, B, N, D, ldx, k, idx, workspace, st);
     if (k <= 16) return launch_knn<16>(x, B, N, D, ldx, k, idx, workspace, st);

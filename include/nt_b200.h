@@ -92,6 +92,11 @@ typedef struct nt_gemm_args {
 
 int nt_gemm_nt(const nt_gemm_args *args, void *stream);
 
+/* Engine used for the TF32x3 row GEMMs: 0 = auto (streaming persistent engine for large aligned calls, one-tile-per-CTA
+ * engine otherwise; default), 1 = one tile per CTA, 2 = persistent experiment, 3 = streaming engine whenever eligible.
+ * Process-wide; results are bit-identical across engines (same operand split, same accumulation order). */
+int nt_set_nt_engine(int engine);
+
 /* Tensor-core operand preparation: splits W [n_out, K] (fp32) into bf16 hi/lo planes laid out as UMMA core matrices per
  * (column tile, K block of 32 bf16 / 16 tf32 elements).  w_split must hold nt_gemm_weights_bytes(n_out, K) bytes, 16-byte aligned. */
 int64_t nt_gemm_weights_bytes(int n_out, int K, int precision);
