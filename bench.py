@@ -172,6 +172,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='eager launches instead of parallel.GraphedTrainStep')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -195,14 +196,14 @@ def main():
 
     import garment_pattern_estimation_b200 as g
     from garment_pattern_estimation_b200 import _lib, ops
-    from garment_pattern_estimation_b200.parallel import FlatDataParallel
+    from garment_pattern_estimation_b200.parallel import FlatDataParallel, GraphedTrainStep
 
     B, N, k = WORKLOAD['batch_per_gpu'], WORKLOAD['points'], WORKLOAD['k']
     dc, nc, lc = att_configs(k)
     torch.manual_seed(SEED_INIT)
     model = g.GarmentSegmentPattern3D(dc, nc, lc).to(dev).train()
     wrapper = FlatDataParallel(model, device_ids=[dev], auto_reduce=False)
-    opt = torch.optim.Adam(model.parameters(), lr=2e-3)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-3, capturable=True)
 
     # 4 distinct synthetic batches per rank, in pinned host memory (e2e) and resident copies (value)
     host, resident = [], []
@@ -214,7 +215,7 @@ def main():
         resident.append((hx.to(dev), {kk: v.to(dev) for kk, v in hgt.items()}))
     h2d_bytes = host[0][0].numel() * 4 + sum(v.numel() * v.element_size() for v in host[0][1].values())
 
-    def train_step(x, gt):
+    def eager_step(x, gt):
         out = wrapper(x)
         loss, _, _ = model.loss(out, gt)
         loss.backward()
@@ -222,6 +223,25 @@ def main():
         opt.step()
         wrapper.zero_grad()
         return loss
+
+    # The product's training-step API: the whole step captured once into a CUDA graph (parallel.GraphedTrainStep) and
+    # replayed per batch; with more than one rank the all-reduce + optimizer step stay outside the graph.
+    graphed, graph_note = None, 'eager launches (--no-graph)'
+    launches_per_eager_step = None
+    if not args.no_graph:
+        l0 = _lib.launch_count()
+        eager_step(*resident[0])
+        launches_per_eager_step = _lib.launch_count() - l0
+        try:
+            graphed = GraphedTrainStep(wrapper, opt, resident[0][0], resident[0][1], warmup=3)
+            graph_note = ('parallel.GraphedTrainStep: forward + loss + backward{} replayed as one CUDA graph'
+                          .format(' + Adam' if graphed.capture_update else ' (all-reduce + Adam eager)'))
+        except Exception as e:  # noqa: BLE001 -- capture problems must not hide the eager number
+            graphed, graph_note = None, 'eager launches (graph capture failed: {})'.format(str(e)[:120])
+            torch.cuda.synchronize()
+
+    def train_step(x, gt):
+        return graphed(x, gt) if graphed is not None else eager_step(x, gt)
 
     def barrier():
         if world > 1:
@@ -253,6 +273,8 @@ def main():
     if rank == 0:
         sampler.start()
     ms_total, launches = timed(lambda i: train_step(*resident[i % 4]), args.steps)
+    if graphed is not None:      # replayed kernel nodes do not pass through the library's host entry points: count = the
+        launches = launches_per_eager_step * args.steps      # libnt_b200 launches of one eager step (captured 1:1) x steps
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * B / (ms_per_step * 1e-3)
@@ -260,9 +282,12 @@ def main():
     # ---- e2e: host buffers, H2D of inputs and D2H of the loss every step
     def e2e_step(i):
         hx, hgt = host[i % 4]
-        x = hx.to(dev, non_blocking=True)
-        gt = {kk: v.to(dev, non_blocking=True) for kk, v in hgt.items()}
-        loss = train_step(x, gt)
+        if graphed is not None:                      # H2D straight into the graph's static input buffers
+            loss = graphed(hx, hgt)
+        else:
+            x = hx.to(dev, non_blocking=True)
+            gt = {kk: v.to(dev, non_blocking=True) for kk, v in hgt.items()}
+            loss = eager_step(x, gt)
         return float(loss.item())                    # device -> host read of the step's result
 
     for i in range(2):
@@ -275,7 +300,7 @@ def main():
     ops.FLOP_SINK = {}
     ops.BYTES_SINK = {}
     for i in range(3):
-        train_step(*resident[i % 4])
+        eager_step(*resident[i % 4])          # eager: CUDA events cannot bracket the nodes of a replayed graph
     torch.cuda.synchronize()
     gemm_flops = {name: v / 3.0 for name, v in ops.FLOP_SINK.items()}
     gemm_bytes = {name: v / 3.0 for name, v in ops.BYTES_SINK.items()}
@@ -378,7 +403,7 @@ def main():
         'config': workload_config(world),
         'e2e': {'value': e2e_value, 'unit': 'clouds/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': e2e_ms / args.steps},
-        'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps,
+        'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps, 'launch_mode': graph_note,
         'clocks': clocks, 'roofline': roofline, 'roofline_tensor': roofline_tensor, 'roofline_knn': roofline_knn,
         'cpu_baseline': cpu_baseline,
         'kernel_ms_per_step': {kk: round(v, 4) for kk, v in sorted(groups.items(), key=lambda kv: -kv[1])},

@@ -65,10 +65,22 @@ constexpr int AP_THREADS = 256;
 constexpr int AP_FWD_CHUNKS = 4;     // chunks per CTA in the forward (fewer atomics on enc)
 
 __device__ __forceinline__ void ap_stage(float *dst, int pitch, const float *src, int ld, int rows, int cols, int rows_pad) {
-    // dst[r][c] = src[r][c] for r < rows, c < cols; zero elsewhere (r < rows_pad, c < pitch); coalesced along c
-    for (int i = threadIdx.x; i < rows_pad * pitch; i += AP_THREADS) {
-        const int r = i / pitch, c = i - r * pitch;
-        dst[i] = (r < rows && c < cols) ? __ldg(src + (int64_t)r * ld + c) : 0.f;
+    // dst[r][c] = src[r][c] for r < rows, c < cols; zero elsewhere (r < rows_pad, c < pitch).  Warp = 4 rows at a time, lane =
+    // column (coalesced); the 4 row loads of a column group are issued back to back so that every thread keeps several
+    // independent global loads in flight (the staging phase is latency-bound otherwise).
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = AP_THREADS / 32;
+    for (int r0 = warp * 4; r0 < rows_pad; r0 += nwarps * 4) {
+        for (int c = lane; c < pitch; c += 32) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u;
+                v[u] = (r < rows && c < cols) ? __ldg(src + (int64_t)r * ld + c) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r0 + u < rows_pad) dst[(r0 + u) * pitch + c] = v[u];
+        }
     }
 }
 
@@ -188,11 +200,13 @@ __global__ void __launch_bounds__(AP_THREADS) attn_pool_bwd_kernel(const float *
             *reinterpret_cast<float4 *>(feat_s + (2 * n2 + 1) * Fp + 4 * f4) = make_float4(a1[0], a1[1], a1[2], a1[3]);
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < nn * F; i += AP_THREADS) {
-            const int n = i / F, f = i - n * F;
-            float *dst = gfeat + ((int64_t)b * N + n0 + n) * ldgf + f;
-            const float v = feat_s[n * Fp + f] * scale;
-            *dst = accumulate ? (*dst + v) : v;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int n = warp; n < nn; n += AP_THREADS / 32) {
+            float *dst = gfeat + ((int64_t)b * N + n0 + n) * ldgf;
+            for (int f = lane; f < F; f += 32) {
+                const float v = feat_s[n * Fp + f] * scale;
+                dst[f] = accumulate ? (dst[f] + v) : v;
+            }
         }
     }
 }

@@ -120,3 +120,85 @@ class FlatDataParallel(nn.Module):
             raise RuntimeError('global batch {} is not divisible by world size {}'.format(B, self.world_size))
         per = B // self.world_size
         return batch_tensor[self.rank * per:(self.rank + 1) * per]
+
+
+class GraphedTrainStep:
+    """One training step (forward -> loss -> backward [-> gradient all-reduce] -> optimizer.step -> zero_grad) captured ONCE
+    into a CUDA graph and replayed per batch: the ~450 kernel launches of a step (libnt_b200 kernels, cuDNN LSTM, loss,
+    Adam) cost one host call, so the step time is the GPU time even when the host is slow or shared between ranks.
+
+    The reference's loop (nn/trainer.py:92-103) is the eager equivalent; numerics are identical because the graph replays
+    exactly the kernels the eager step launches.  Requirements of CUDA-graph capture:
+      * fixed batch shape (the shape of ``example_x`` / ``example_gt``); other shapes fall back to ``eager_step``;
+      * an optimizer whose step is capturable (``torch.optim.Adam(..., capturable=True)``);
+      * ``wrapper`` is a FlatDataParallel (its flat gradient buffer keeps every ``.grad`` at a static address).
+    With more than one rank the NCCL all-reduce and the optimizer step stay OUTSIDE the graph (``capture_update=False`` is
+    forced), i.e. the graph holds forward + loss + backward.
+
+    Construction runs ``warmup`` eager forward/backward passes on the example batch on a side stream (required before
+    capture; BatchNorm running statistics see these batches like any other training batch) and creates the optimizer state
+    with one step on all-zero gradients (parameters do not move for Adam / SGD without weight decay).
+    """
+
+    def __init__(self, wrapper, optimizer, example_x, example_gt, warmup=3, capture_update=True, forward_kwargs=None):
+        if not example_x.is_cuda:
+            raise RuntimeError('GraphedTrainStep needs CUDA tensors (the B200 hot path has no CPU fallback)')
+        self.wrapper, self.optimizer = wrapper, optimizer
+        self.model = wrapper.module
+        self.forward_kwargs = dict(forward_kwargs or {})
+        self.capture_update = bool(capture_update) and wrapper.world_size == 1
+        self.static_x = example_x.clone()
+        self.static_gt = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_gt.items()}
+        side = torch.cuda.Stream(device=example_x.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._forward_backward()
+                wrapper.zero_grad()
+            if self.capture_update:
+                # Optimizer state (Adam moments, step counters) must EXIST before capture, otherwise its lazy initialisation
+                # would be recorded into the graph and re-run on every replay.  One step on all-zero gradients creates it
+                # without moving the parameters (true for Adam / SGD without weight decay); step counters are rewound.
+                optimizer.step()
+                for st in optimizer.state.values():
+                    if torch.is_tensor(st.get('step')):
+                        st['step'].zero_()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._forward_backward()
+            if self.capture_update:
+                self._update()
+
+    def _forward_backward(self):
+        out = self.wrapper(self.static_x, **self.forward_kwargs)
+        loss, _, _ = self.model.loss(out, self.static_gt)
+        loss.backward()
+        return loss.detach()
+
+    def _update(self):
+        self.wrapper.reduce_gradients()
+        self.optimizer.step()
+        self.wrapper.zero_grad()
+
+    def eager_step(self, x, gt):
+        out = self.wrapper(x, **self.forward_kwargs)
+        loss, _, _ = self.model.loss(out, gt)
+        loss.backward()
+        self._update()
+        return loss.detach()
+
+    def __call__(self, x, gt):
+        """x / gt: device (or pinned host) tensors of the captured shapes.  Returns the loss tensor of this step (a static
+        buffer: read it before the next call)."""
+        if tuple(x.shape) != tuple(self.static_x.shape):
+            return self.eager_step(x.to(self.static_x.device), gt)
+        self.static_x.copy_(x, non_blocking=True)
+        for k, v in self.static_gt.items():
+            if torch.is_tensor(v):
+                v.copy_(gt[k], non_blocking=True)
+        self.graph.replay()
+        if not self.capture_update:
+            self._update()
+        return self.static_loss

@@ -22,4 +22,19 @@ elif what == 'edgeconv':
     for _ in range(2):
         out = conv(x, cloud_shape=(B, N))
         out.sum().backward()
+elif what == 'model':
+    # two eager training steps of the attention model at the C2 shape (every kernel of the step, in launch order)
+    import bench
+    import garment_pattern_estimation_b200 as g
+    dc, nc, lc = bench.att_configs(k)
+    torch.manual_seed(bench.SEED_INIT)
+    model = g.GarmentSegmentPattern3D(dc, nc, lc).to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=2e-3)
+    x, gt = bench.synthetic_batch(B, N, seed=1234)
+    x, gt = x.to(dev), {kk: v.to(dev) for kk, v in gt.items()}
+    for _ in range(2):
+        loss, _, _ = model.loss(model(x), gt)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
 torch.cuda.synchronize()
