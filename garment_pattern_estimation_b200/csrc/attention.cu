@@ -154,26 +154,34 @@ __global__ void __launch_bounds__(AP_THREADS) attn_pool_bwd_kernel(const float *
     ap_stage(w_s, Pp, w + ((int64_t)b * N + n0) * P, P, nn, P, AP_PTS);
     if (gw) ap_stage(feat_s, Fp, feat + ((int64_t)b * N + n0) * ldf, ldf, nn, F, AP_PTS);
     __syncthreads();
-    // gw[n, p4 .. p4+3] = scale * sum_f genc[p, f] * feat[n, f]: work item = (point, 4 panels); the lanes of a warp cover
-    // 32 / np4 points x np4 panel groups, so feat rows and genc rows are both read as a few broadcast 16-byte accesses
+    // gw[n, p8 .. p8+7] = scale * sum_f genc[p, f] * feat[n, f]: work item = (point, 8 panels) with the POINT index fastest, so the
+    // 32 lanes of a warp read 32 different feat rows (pitch Fp = 4 mod 8 float4s: conflict-free quarter-warps) and ONE genc row
+    // address (broadcast).  (ncu of the previous (point, 4 panels)-with-panels-fastest mapping: short-scoreboard bound, 3-way
+    // bank conflicts on the genc rows.)
     if (gw) {
-        for (int item = threadIdx.x; item < AP_PTS * np4; item += AP_THREADS) {
-            const int n = item / np4, p4 = item - n * np4;
+        const int np8 = (Pp + 7) >> 3;
+        for (int item = threadIdx.x; item < AP_PTS * np8; item += AP_THREADS) {
+            const int n = item % AP_PTS, p8 = item / AP_PTS;
             if (n >= nn) continue;
-            float a[4] = {0.f, 0.f, 0.f, 0.f};
-            const float *fs = feat_s + n * Fp, *gs = ge_s + 4 * p4 * Fp;
+            float a[8];
+#pragma unroll
+            for (int pi = 0; pi < 8; ++pi) a[pi] = 0.f;
+            const float *fs = feat_s + n * Fp;
+            const int prow0 = 8 * p8;
             for (int f4 = 0; f4 < nf4; ++f4) {
                 const float4 fv = *reinterpret_cast<const float4 *>(fs + 4 * f4);
 #pragma unroll
-                for (int pi = 0; pi < 4; ++pi) {
-                    const float4 gv = *reinterpret_cast<const float4 *>(gs + pi * Fp + 4 * f4);
-                    a[pi] = fmaf(gv.x, fv.x, a[pi]); a[pi] = fmaf(gv.y, fv.y, a[pi]);
-                    a[pi] = fmaf(gv.z, fv.z, a[pi]); a[pi] = fmaf(gv.w, fv.w, a[pi]);
+                for (int pi = 0; pi < 8; ++pi) {
+                    if (prow0 + pi < Pp) {
+                        const float4 gv = *reinterpret_cast<const float4 *>(ge_s + (prow0 + pi) * Fp + 4 * f4);
+                        a[pi] = fmaf(gv.x, fv.x, a[pi]); a[pi] = fmaf(gv.y, fv.y, a[pi]);
+                        a[pi] = fmaf(gv.z, fv.z, a[pi]); a[pi] = fmaf(gv.w, fv.w, a[pi]);
+                    }
                 }
             }
 #pragma unroll
-            for (int pi = 0; pi < 4; ++pi)
-                if (4 * p4 + pi < P) gw[((int64_t)b * N + n0 + n) * P + 4 * p4 + pi] = a[pi] * scale;
+            for (int pi = 0; pi < 8; ++pi)
+                if (prow0 + pi < P) gw[((int64_t)b * N + n0 + n) * P + prow0 + pi] = a[pi] * scale;
         }
     }
     if (gfeat) {

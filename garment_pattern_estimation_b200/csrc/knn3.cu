@@ -34,9 +34,11 @@ __global__ void __launch_bounds__(K3_THREADS) knn3_kernel(const float *__restric
             cand[i] = make_float4(pc[0], pc[1], pc[2], 0.f);
         }
         __syncthreads();
-        auto visit = [&](int c, const float4 p) {
+        auto dist = [&](const float4 p) {
             const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
-            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        };
+        auto offer = [&](int c, float d) {
             if (d < bd[K - 1]) {
                 bd[K - 1] = d; bi[K - 1] = c0 + c;
 #pragma unroll
@@ -50,10 +52,14 @@ __global__ void __launch_bounds__(K3_THREADS) knn3_kernel(const float *__restric
         };
         int c = 0;
         for (; c + 4 <= cn; c += 4) {
-            const float4 p0 = cand[c], p1 = cand[c + 1], p2 = cand[c + 2], p3 = cand[c + 3];
-            visit(c, p0); visit(c + 1, p1); visit(c + 2, p2); visit(c + 3, p3);
+            // four distances, ONE test against the current k-th best (the common case rejects all four); candidates that
+            // pass are still offered one by one in index order, so the result is that of the sequential scan
+            const float d0 = dist(cand[c]), d1 = dist(cand[c + 1]), d2 = dist(cand[c + 2]), d3 = dist(cand[c + 3]);
+            if (fminf(fminf(d0, d1), fminf(d2, d3)) < bd[K - 1]) {
+                offer(c, d0); offer(c + 1, d1); offer(c + 2, d2); offer(c + 3, d3);
+            }
         }
-        for (; c < cn; ++c) visit(c, cand[c]);
+        for (; c < cn; ++c) offer(c, dist(cand[c]));
     }
     if (q_ok) {
         int32_t *o = idx + ((int64_t)b * N + q) * k;

@@ -184,18 +184,20 @@ __global__ void __launch_bounds__(256) edge_activation_kernel(const float *__res
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     if (c0 < H) {
         for (int64_t r = rbeg + threadIdx.y; r < rend; r += 8) {
-            const int64_t centre = r / k;
-            const int64_t j = (centre / n_per_cloud) * (int64_t)n_per_cloud + __ldg(idx + r);
-            const float *pp = pq + centre * ldpq + c0, *qp = pq + j * ldpq + qoff + c0;
+            // idx == nullptr: plain rows, a_1 = relu(pq[r]) (no neighbour term)
+            const int64_t centre = idx ? r / k : r;
+            const int64_t j = idx ? (centre / n_per_cloud) * (int64_t)n_per_cloud + __ldg(idx + r) : 0;
+            const float *pp = pq + centre * ldpq + c0, *qp = idx ? pq + j * ldpq + qoff + c0 : nullptr;
             float v[4];
             if (vec) {
-                const float4 a = __ldg(reinterpret_cast<const float4 *>(pp)), b = __ldg(reinterpret_cast<const float4 *>(qp));
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(pp));
+                const float4 b = qp ? __ldg(reinterpret_cast<const float4 *>(qp)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 v[0] = fmaxf(a.x + b.x, 0.f); v[1] = fmaxf(a.y + b.y, 0.f); v[2] = fmaxf(a.z + b.z, 0.f); v[3] = fmaxf(a.w + b.w, 0.f);
                 *reinterpret_cast<float4 *>(out + r * ldo + c0) = make_float4(v[0], v[1], v[2], v[3]);
             } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    v[e] = (c0 + e < H) ? fmaxf(__ldg(pp + e) + __ldg(qp + e), 0.f) : 0.f;
+                    v[e] = (c0 + e < H) ? fmaxf(__ldg(pp + e) + (qp ? __ldg(qp + e) : 0.f), 0.f) : 0.f;
                     if (c0 + e < H) out[r * ldo + c0 + e] = v[e];
                 }
             }
@@ -480,6 +482,162 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_last_v4_kernel(const float *_
     }
 }
 
+// ---- two nodes per thread and iteration, every load of both nodes issued before the first use (k <= 8) ----------------------
+// The one-node loops above expose three dependent memory latencies per iteration (index -> gathered row -> next node); ncu showed
+// both kernels latency-bound (long scoreboard, 26-44 % of the DRAM peak).  Here a thread keeps up to 2 x (1 + k) 16-byte loads in
+// flight.  (Instantiated for k <= 5, the shipped k_neighbors; larger k keeps the one-node kernels.)
+
+template <int NX_K>
+__global__ void __launch_bounds__(256, 2) edge_activation_x2_kernel(const float *__restrict__ pq, int ldpq, int qoff,
+                                                                 const int32_t *__restrict__ idx, int k, int n_per_cloud,
+                                                                 int64_t nodes, int H, float *__restrict__ out, int ldo,
+                                                                 double *__restrict__ stats) {
+    __shared__ float red[8][32][8];
+    const int c0 = (blockIdx.y * 32 + threadIdx.x) * 4;
+    const int64_t nbeg = (int64_t)blockIdx.x * NV_NODES;
+    const int64_t nend = min(nodes, nbeg + NV_NODES);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < H) {
+        for (int64_t nodeA = nbeg + threadIdx.y; nodeA < nend; nodeA += 16) {
+            const int64_t nodeB = nodeA + 8;
+            const bool hasB = nodeB < nend;
+            const int32_t *ipA = idx + nodeA * k, *ipB = idx + (hasB ? nodeB : nodeA) * k;
+            int jA[NX_K], jB[NX_K];
+#pragma unroll
+            for (int u = 0; u < NX_K; ++u)
+                if (u < k) { jA[u] = __ldg(ipA + u); jB[u] = __ldg(ipB + u); }
+            const float4 pcA = ld4(pq + nodeA * ldpq + c0);
+            const float4 pcB = ld4(pq + (hasB ? nodeB : nodeA) * ldpq + c0);
+            const int64_t baseA = (nodeA / n_per_cloud) * (int64_t)n_per_cloud;
+            const int64_t baseB = ((hasB ? nodeB : nodeA) / n_per_cloud) * (int64_t)n_per_cloud;
+            float4 qA[NX_K], qB[NX_K];
+#pragma unroll
+            for (int u = 0; u < NX_K; ++u)
+                if (u < k) {
+                    qA[u] = ld4(pq + (baseA + jA[u]) * ldpq + qoff + c0);
+                    qB[u] = ld4(pq + (baseB + jB[u]) * ldpq + qoff + c0);
+                }
+            float *opA = out + nodeA * k * (int64_t)ldo + c0;
+            float *opB = out + nodeB * k * (int64_t)ldo + c0;
+#pragma unroll
+            for (int u = 0; u < NX_K; ++u)
+                if (u < k) {
+                    float4 v;
+                    v.x = fmaxf(pcA.x + qA[u].x, 0.f); v.y = fmaxf(pcA.y + qA[u].y, 0.f);
+                    v.z = fmaxf(pcA.z + qA[u].z, 0.f); v.w = fmaxf(pcA.w + qA[u].w, 0.f);
+                    *reinterpret_cast<float4 *>(opA + (int64_t)u * ldo) = v;
+                    s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+                    s2[0] = fmaf(v.x, v.x, s2[0]); s2[1] = fmaf(v.y, v.y, s2[1]);
+                    s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
+                    if (hasB) {
+                        v.x = fmaxf(pcB.x + qB[u].x, 0.f); v.y = fmaxf(pcB.y + qB[u].y, 0.f);
+                        v.z = fmaxf(pcB.z + qB[u].z, 0.f); v.w = fmaxf(pcB.w + qB[u].w, 0.f);
+                        *reinterpret_cast<float4 *>(opB + (int64_t)u * ldo) = v;
+                        s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+                        s2[0] = fmaf(v.x, v.x, s2[0]); s2[1] = fmaf(v.y, v.y, s2[1]);
+                        s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
+                    }
+                }
+        }
+    }
+    if (!stats) return;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { red[threadIdx.y][threadIdx.x][e] = s1[e]; red[threadIdx.y][threadIdx.x][4 + e] = s2[e]; }
+    __syncthreads();
+    if (threadIdx.y == 0 && c0 < H) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { t1 += red[i][threadIdx.x][e]; t2 += red[i][threadIdx.x][4 + e]; }
+            atomicAdd(stats + c0 + e, (double)t1);
+            atomicAdd(stats + H + c0 + e, (double)t2);
+        }
+    }
+}
+
+template <int NX_K>
+__global__ void __launch_bounds__(256, 2) bn_relu_bwd_last_x2_kernel(const float *__restrict__ a, int lda, const float *__restrict__ g,
+                                                                  int ldg, const uint8_t *__restrict__ sel, int k,
+                                                                  const float *__restrict__ s, const float *__restrict__ mu,
+                                                                  const float *__restrict__ rstd, const double *__restrict__ sums,
+                                                                  int64_t count, int64_t nodes, int C, float *__restrict__ dz,
+                                                                  int lddz, double *__restrict__ colsum) {
+    __shared__ float red[8][32][4];
+    const int c0 = (blockIdx.y * 32 + threadIdx.x) * 4;
+    const int64_t nbeg = (int64_t)blockIdx.x * NV_NODES;
+    const int64_t nend = min(nodes, nbeg + NV_NODES);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < C) {
+        const float inv = 1.0f / (float)count;
+        float sc[4], k0[4], k1[4], m[4];
+        bool ok[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = min(c0 + j, C - 1);
+            ok[j] = c0 + j < C;
+            sc[j] = s[c]; m[j] = mu[c];
+            k0[j] = (float)sums[c] * inv;
+            k1[j] = rstd[c] * ((float)sums[C + c] * inv);
+        }
+        for (int64_t nodeA = nbeg + threadIdx.y; nodeA < nend; nodeA += 16) {
+            const bool hasB = nodeA + 8 < nend;
+            const int64_t nodeB = hasB ? nodeA + 8 : nodeA;        // loads of a missing node B alias node A (never stored)
+            float gv[2][4];
+            int ss[2][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                gv[0][j] = ok[j] ? __ldg(g + nodeA * ldg + c0 + j) : 0.f;
+                gv[1][j] = ok[j] ? __ldg(g + nodeB * ldg + c0 + j) : 0.f;
+                ss[0][j] = ss[1][j] = -1;                            // -1: every slot receives the gradient (no aggregation)
+                if (sel) {
+                    ss[0][j] = ok[j] ? (int)sel[nodeA * C + c0 + j] : 0;
+                    ss[1][j] = ok[j] ? (int)sel[nodeB * C + c0 + j] : 0;
+                }
+            }
+            float4 av[2][NX_K];
+#pragma unroll
+            for (int u = 0; u < NX_K; ++u)
+                if (u < k) {
+                    av[0][u] = ld4(a + (nodeA * k + u) * (int64_t)lda + c0);
+                    av[1][u] = ld4(a + (nodeB * k + u) * (int64_t)lda + c0);
+                }
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                if (w == 1 && !hasB) break;
+                float *op = dz + (w == 0 ? nodeA : nodeB) * k * (int64_t)lddz + c0;
+#pragma unroll
+                for (int u = 0; u < NX_K; ++u)
+                    if (u < k) {
+                        const float x[4] = {av[w][u].x, av[w][u].y, av[w][u].z, av[w][u].w};
+                        float o[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float gs = (ss[w][j] < 0 || ss[w][j] == u) ? gv[w][j] : 0.f;
+                            // same association as the scalar kernel: sc * (gs - dbeta' - ((x - m) * rstd) * dgamma')
+                            o[j] = (ok[j] && x[j] > 0.f) ? sc[j] * (gs - k0[j] - (x[j] - m[j]) * k1[j]) : 0.f;
+                            acc[j] += o[j];
+                        }
+                        *reinterpret_cast<float4 *>(op + (int64_t)u * lddz) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.y == 0 && colsum) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (c0 + j >= C) continue;
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x][j];
+            atomicAdd(colsum + c0 + j, (double)t);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) edge_scatter_v4_kernel(const float *__restrict__ dz, int lddz, const int32_t *__restrict__ idx,
                                                               int k, int n_per_cloud, int64_t M, int H, float *__restrict__ dpq,
                                                               int lddpq) {
@@ -578,14 +736,18 @@ extern "C" int nt_edge_stats(const float *pq, int ldpq, int qoff, const int32_t 
 
 extern "C" int nt_edge_activation(const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
                                   int64_t rows, int H, float *out, int ldo, double *stats, void *stream) {
-    NT_REQUIRE(pq && idx && out && rows >= 0 && H >= 1 && ldpq >= H && ldo >= H, "nt_edge_activation: bad arguments");
-    NT_REQUIRE(k >= 1 && n_per_cloud >= 1, "nt_edge_activation: edge operand needs k and n_per_cloud");
+    NT_REQUIRE(pq && out && rows >= 0 && H >= 1 && ldpq >= H && ldo >= H, "nt_edge_activation: bad arguments");
+    NT_REQUIRE(!idx || (k >= 1 && n_per_cloud >= 1), "nt_edge_activation: edge operand needs k and n_per_cloud");
     if (rows == 0) return 0;
     dim3 block(32, 8);
-    if ((H & 3) == 0 && (ldpq & 3) == 0 && (qoff & 3) == 0 && (ldo & 3) == 0 && aligned16(pq) && aligned16(out) && rows % k == 0) {
+    if (idx && (H & 3) == 0 && (ldpq & 3) == 0 && (qoff & 3) == 0 && (ldo & 3) == 0 && aligned16(pq) && aligned16(out) && rows % k == 0) {
         dim3 grid(blocks_for(rows / k, NV_NODES), (H + 127) / 128);
-        edge_activation_v4_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pq, ldpq, qoff, idx, k, n_per_cloud,
-                                                                                            rows / k, H, out, ldo, stats);
+        if (k <= 5)
+            edge_activation_x2_kernel<5><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pq, ldpq, qoff, idx, k, n_per_cloud,
+                                                                                                   rows / k, H, out, ldo, stats);
+        else
+            edge_activation_v4_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pq, ldpq, qoff, idx, k, n_per_cloud,
+                                                                                                rows / k, H, out, ldo, stats);
     } else {
         dim3 grid(blocks_for(rows, EA_ROWS), (H + 127) / 128);
         edge_activation_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pq, ldpq, qoff, idx, k, n_per_cloud,
@@ -605,8 +767,12 @@ extern "C" int nt_bn_relu_bwd_last(const float *a, int lda, const float *g, int 
     const int Cp = (C + 3) & ~3;      // the float4 kernel touches whole column quads: rows must be padded to a multiple of 4
     if ((lda & 3) == 0 && (lddz & 3) == 0 && lda >= Cp && lddz >= Cp && aligned16(a) && aligned16(dz)) {
         dim3 grid(blocks_for(rows / k, NV_NODES), (C + 127) / 128);
-        bn_relu_bwd_last_v4_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-            a, lda, g, ldg, sel, k, s, mu, rstd, sums, count, rows / k, C, dz, lddz, colsum);
+        if (k <= 5)
+            bn_relu_bwd_last_x2_kernel<5><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+                a, lda, g, ldg, sel, k, s, mu, rstd, sums, count, rows / k, C, dz, lddz, colsum);
+        else
+            bn_relu_bwd_last_v4_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+                a, lda, g, ldg, sel, k, s, mu, rstd, sums, count, rows / k, C, dz, lddz, colsum);
     } else {
         dim3 grid(blocks_for(rows, BL_ROWS), (C + 127) / 128);
         bn_relu_bwd_last_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(

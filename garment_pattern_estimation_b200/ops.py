@@ -272,7 +272,7 @@ class _FusedMLPFunction(torch.autograd.Function):
         # ---- BN_1 statistics of a_1 = relu(P + Q) (no GEMM at row level); edge mode also materialises a_1
         stats = torch.zeros(2 * H1, dtype=torch.float64, device=dev) if training else None
         a1 = None
-        if mode == 'edge' and EDGE_MATERIALIZE:
+        if EDGE_MATERIALIZE:           # both row modes: every consumer then streams a plain, 16-byte aligned operand
             a1 = _rowbuf(R, H1, dev)
             _call('nt_edge_activation', _lib.load().nt_edge_activation, _p(pq), src.ldpq, src.qoff, _p(src.idx), src.k,
                   src.n_per_cloud, R, H1, _p(a1), a1.stride(0), _p(stats), _stream())

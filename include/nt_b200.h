@@ -136,7 +136,8 @@ int nt_edge_stats(const float *pq, int ldpq, int qoff, const int32_t *idx, int k
 
 /* Materialised first edge activation: out[e, 0:H] = relu(pq[centre(e), 0:H] + pq[nbr(e), qoff:qoff+H]) for `rows` edge rows
  * (DynamicEdgeConv.message input after the algebraic split of the first Linear, nn/net_blocks.py:127-135), with the
- * BatchNorm statistics of nt_edge_stats accumulated in the same pass when stats != NULL. */
+ * BatchNorm statistics of nt_edge_stats accumulated in the same pass when stats != NULL.  idx == NULL: plain rows,
+ * out[r] = relu(pq[r, 0:H]) (first activation of the per-point MLP, nn/net_blocks.py:43-47). */
 int nt_edge_activation(const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
                        int64_t rows, int H, float *out, int ldo, double *stats, void *stream);
 
