@@ -168,7 +168,7 @@ def workload_config(n_gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -275,7 +275,6 @@ def main():
     ms_total, launches = timed(lambda i: train_step(*resident[i % 4]), args.steps)
     if graphed is not None:      # replayed kernel nodes do not pass through the library's host entry points: count = the
         launches = launches_per_eager_step * args.steps      # libnt_b200 launches of one eager step (captured 1:1) x steps
-    clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
@@ -294,6 +293,7 @@ def main():
         e2e_step(i)
     e2e_ms, _ = timed(e2e_step, args.steps)
     e2e_value = world * B / (e2e_ms / args.steps * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None          # sampled (100 ms period) across both timed regions
 
     # ---- per-kernel-group device times (CUDA events on the launching stream) for the roofline of the dominant kernel
     ops.EVENT_SINK = {}
@@ -338,8 +338,9 @@ def main():
             traffic = tj.get(dom, {}).get('dram_bytes_per_launch') if isinstance(tj.get(dom), dict) else None
     except (OSError, ValueError):
         pass
-    kernel_names = {'nt_gemm_nt[bnrelu_bwd,plain]': 'nt::gemm_nt_tc_kernel<PLAIN, BNRELU_BWD, TF32x3> (data-gradient GEMM fused '
-                                                    'with the BatchNorm/ReLU backward)',
+    kernel_names = {'nt_gemm_nt[bnrelu_bwd,plain]': 'nt::gemm_nt_tc3_kernel<BNRELU_BWD> (streaming tcgen05 TF32x3 data-gradient GEMM '
+                                                    'fused with the BatchNorm/ReLU backward; the two per-point launches of the '
+                                                    'group run nt::gemm_nt_tc_kernel)',
                     'nt_gemm_tn_centered': 'nt::gemm_tn_tc_kernel (weight-gradient GEMM with centred operand)'}
     roofline = None
     if dom:
@@ -350,8 +351,12 @@ def main():
             'group': dom, 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
             'traffic': traffic, 'peak_source': peak_src, 'launch_ms': dom_ms / dom_n,
             'algorithmic_bytes_per_launch': gemm_bytes[dom] / dom_n, 'share_of_step': dom_ms / ms_per_step,
+            'traffic_source': 'profiles/dominant_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the '
+                              'launches of the group in one eager step)',
             'note': 'algorithmic bytes = fp32 operand rows read once + result rows written once + weights; the same group '
-                    'reaches {:.1f} TFLOP/s of useful fp32-equivalent math (see roofline_tensor)'.format(
+                    'reaches {:.1f} TFLOP/s of useful fp32-equivalent math (see roofline_tensor).  What caps the fraction is '
+                    'L2 throughput: every 128-row tile re-streams the TF32 hi/lo weight planes (346 KB) from L2, 3.4x the '
+                    'tile\'s own HBM bytes (DESIGN.md section 4)'.format(
                         gemm_flops.get(dom, 0.0) / (dom_ms * 1e-3) / 1e12),
         }
 

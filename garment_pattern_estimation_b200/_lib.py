@@ -73,6 +73,8 @@ _SIGNATURES = {
                                  c_void_p]),
     'nt_attn_pool_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                                  c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'nt_global_pool_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'nt_global_pool_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))

@@ -219,6 +219,60 @@ __global__ void __launch_bounds__(AP_THREADS) attn_pool_bwd_kernel(const float *
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Global pooling over the points of each cloud (torch_geometric.nn.global_{mean,max,add}_pool on the dense equal-size
+// layout the reference always builds, nn/net_blocks.py:145-150,182-187).  block (32, 8): lane = feature column (coalesced rows),
+// threadIdx.y strides over the points; one CTA per (32-column slab, cloud).  max also records the arg-max point for the backward
+// (first maximum wins, like scatter-max).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) global_pool_fwd_kernel(const float *__restrict__ x, int ldx, int N, int F, int mode,
+                                                              float *__restrict__ out, int32_t *__restrict__ arg) {
+    __shared__ float sv[8][32];
+    __shared__ int si[8][32];
+    const int f = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y;
+    float acc = (mode == NT_POOL_MAX) ? -INFINITY : 0.f;
+    int best = 0;
+    if (f < F) {
+        const float *xp = x + (int64_t)b * N * ldx + f;
+        for (int n = threadIdx.y; n < N; n += 8) {
+            const float v = __ldg(xp + (int64_t)n * ldx);
+            if (mode == NT_POOL_MAX) {
+                if (v > acc) { acc = v; best = n; }
+            } else {
+                acc += v;
+            }
+        }
+    }
+    sv[threadIdx.y][threadIdx.x] = acc;
+    si[threadIdx.y][threadIdx.x] = best;
+    __syncthreads();
+    if (threadIdx.y == 0 && f < F) {
+        for (int i = 1; i < 8; ++i) {
+            const float v = sv[i][threadIdx.x];
+            if (mode == NT_POOL_MAX) {
+                const int n = si[i][threadIdx.x];
+                if (v > acc || (v == acc && n < best)) { acc = v; best = n; }
+            } else {
+                acc += v;
+            }
+        }
+        if (mode == NT_POOL_MEAN) acc /= (float)N;
+        out[(int64_t)b * F + f] = acc;
+        if (arg) arg[(int64_t)b * F + f] = best;
+    }
+}
+
+__global__ void __launch_bounds__(256) global_pool_bwd_kernel(const float *__restrict__ g, const int32_t *__restrict__ arg, int N,
+                                                              int F, int mode, float *__restrict__ gx, int ldgx) {
+    const int f = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y;
+    if (f >= F) return;
+    const float gv = g[(int64_t)b * F + f] * (mode == NT_POOL_MEAN ? 1.0f / (float)N : 1.0f);
+    const int a = (mode == NT_POOL_MAX) ? arg[(int64_t)b * F + f] : -1;
+    float *gp = gx + (int64_t)b * N * ldgx + f;
+    for (int n = blockIdx.z * 8 + threadIdx.y; n < N; n += 8 * gridDim.z)
+        gp[(int64_t)n * ldgx] = (mode == NT_POOL_MAX) ? (n == a ? gv : 0.f) : gv;
+}
+
 }  // namespace nt
 
 using namespace nt;
@@ -280,4 +334,27 @@ extern "C" int nt_attn_pool_bwd(const float *genc, const float *w, const float *
     attn_pool_bwd_kernel<<<grid, AP_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(genc, w, feat, ldf, N, P, F, scale,
                                                                                             gw, gfeat, ldgf, accumulate_gfeat);
     return check_launch("nt_attn_pool_bwd");
+}
+
+extern "C" int nt_global_pool_fwd(const float *x, int ldx, int B, int N, int F, int mode, float *out, int32_t *argmax,
+                                  void *stream) {
+    NT_REQUIRE(x && out && B >= 0 && N >= 1 && F >= 1 && ldx >= F, "nt_global_pool_fwd: bad arguments");
+    NT_REQUIRE(mode == NT_POOL_MEAN || mode == NT_POOL_MAX || mode == NT_POOL_ADD, "nt_global_pool_fwd: unknown mode");
+    NT_REQUIRE(B <= 65535, "nt_global_pool_fwd: at most 65535 clouds per call");
+    if (B == 0) return 0;
+    dim3 grid((F + 31) / 32, B), block(32, 8);
+    global_pool_fwd_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, ldx, N, F, mode, out, argmax);
+    return check_launch("nt_global_pool_fwd");
+}
+
+extern "C" int nt_global_pool_bwd(const float *g, const int32_t *argmax, int B, int N, int F, int mode, float *gx, int ldgx,
+                                  void *stream) {
+    NT_REQUIRE(g && gx && B >= 0 && N >= 1 && F >= 1 && ldgx >= F, "nt_global_pool_bwd: bad arguments");
+    NT_REQUIRE(mode == NT_POOL_MEAN || mode == NT_POOL_MAX || mode == NT_POOL_ADD, "nt_global_pool_bwd: unknown mode");
+    NT_REQUIRE(mode != NT_POOL_MAX || argmax, "nt_global_pool_bwd: max pooling needs the arg-max of the forward");
+    NT_REQUIRE(B <= 65535, "nt_global_pool_bwd: at most 65535 clouds per call");
+    if (B == 0) return 0;
+    dim3 grid((F + 31) / 32, B, (N + 255) / 256 > 64 ? 64 : (N + 255) / 256), block(32, 8);
+    global_pool_bwd_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, argmax, N, F, mode, gx, ldgx);
+    return check_launch("nt_global_pool_bwd");
 }

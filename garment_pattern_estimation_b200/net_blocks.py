@@ -75,21 +75,21 @@ class DynamicEdgeConv(nn.Module):
 # ----------------------------------------------------------------------------------------------------------
 # global pools (torch_geometric.nn.global_*_pool; nn/net_blocks.py:145-150) on the dense equal-size layout
 # ----------------------------------------------------------------------------------------------------------
-def _dense(x, batch, size):
+def _cloud_shape(x, batch, size):
     B = int(size) if size is not None else int(batch.max().item()) + 1
-    return x.view(B, x.shape[0] // B, x.shape[-1])
+    return B, x.shape[0] // B
 
 
 def global_mean_pool(x, batch, size=None):
-    return _dense(x, batch, size).mean(dim=1)
+    return ops.global_pool(x, *_cloud_shape(x, batch, size), 'mean')
 
 
 def global_max_pool(x, batch, size=None):
-    return _dense(x, batch, size).max(dim=1).values
+    return ops.global_pool(x, *_cloud_shape(x, batch, size), 'max')
 
 
 def global_add_pool(x, batch, size=None):
-    return _dense(x, batch, size).sum(dim=1)
+    return ops.global_pool(x, *_cloud_shape(x, batch, size), 'add')
 
 
 # ----------------------------------------------------------------------------------------------------------

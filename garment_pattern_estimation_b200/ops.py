@@ -505,6 +505,41 @@ def attention_pool(weights, feats, B, N, scale):
     return _AttnPoolFunction.apply(weights, feats, B, N, float(scale))
 
 
+_POOL_MODES = {'mean': 0, 'max': 1, 'add': 2}
+
+
+class _GlobalPoolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, B, N, mode):
+        _require_cuda(x)
+        x, ldx = _rows2d(x)
+        F = x.shape[1]
+        out = torch.empty(B, F, dtype=torch.float32, device=x.device)
+        arg = torch.empty(B, F, dtype=torch.int32, device=x.device) if mode == 1 else None
+        _call('nt_global_pool_fwd', _lib.load().nt_global_pool_fwd, _p(x), ldx, B, N, F, mode, _p(out), _p(arg), _stream())
+        ctx.save_for_backward(arg)
+        ctx.dims = (B, N, F, mode)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        arg, = ctx.saved_tensors
+        B, N, F, mode = ctx.dims
+        g = g.contiguous()
+        gx = torch.empty(B * N, F, dtype=torch.float32, device=g.device)
+        _call('nt_global_pool_bwd', _lib.load().nt_global_pool_bwd, _p(g), _p(arg), B, N, F, mode, _p(gx), F, _stream())
+        return gx, None, None, None
+
+
+def global_pool(x, B, N, mode):
+    """torch_geometric.nn.global_{mean,max,add}_pool on the dense equal-size layout: [B*N, F] -> [B, F]."""
+    if mode not in _POOL_MODES:
+        raise ValueError('{} pooling is not supported'.format(mode))
+    if x.shape[0] != B * N:
+        raise RuntimeError('global_pool: expected {} rows, got {}'.format(B * N, x.shape[0]))
+    return _GlobalPoolFunction.apply(x, int(B), int(N), _POOL_MODES[mode])
+
+
 class _LinearFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):

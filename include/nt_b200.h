@@ -192,6 +192,17 @@ int nt_attn_pool_fwd(const float *w, const float *feat, int ldf, int B, int N, i
 int nt_attn_pool_bwd(const float *genc, const float *w, const float *feat, int ldf, int B, int N, int P, int F,
                      float scale, float *gw, float *gfeat, int ldgf, int accumulate_gfeat, void *stream);
 
+/* Global pooling over the N points of each of B equal-size clouds (torch_geometric.nn.global_{mean,max,add}_pool as used by
+ * EdgeConvFeatures, nn/net_blocks.py:145-150,182-187): out[b, f] = mean / max / sum over n of x[b*N + n, f].
+ * argmax ([B, F] int32, may be NULL unless the backward of max is needed) receives the first maximal point.
+ * Backward: gx[b*N + n, f] = g[b, f] / N (mean), g[b, f] (add), g[b, f] * [n == argmax[b, f]] (max); gx is overwritten. */
+#define NT_POOL_MEAN 0
+#define NT_POOL_MAX 1
+#define NT_POOL_ADD 2
+int nt_global_pool_fwd(const float *x, int ldx, int B, int N, int F, int mode, float *out, int32_t *argmax, void *stream);
+int nt_global_pool_bwd(const float *g, const int32_t *argmax, int B, int N, int F, int mode, float *gx, int ldgx,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,30 @@ def att_configs():
     return data_config, nn_config, loss_config
 
 
+def baseline_configs():
+    """(data_config, nn_config, loss_config) of the shipped baseline model (models/baseline/lstm_stitch_tags.yaml): global
+    mean pool + pattern LSTM + panel LSTM.  The loss section is reduced to the four regression terms (the stitch / free-class
+    terms need the stitch ground truth of the dataset, out of the hot path)."""
+    import yaml
+    with open(os.path.join(REFERENCE_ROOT, 'models', 'baseline', 'lstm_stitch_tags.yaml')) as f:
+        cfg = yaml.safe_load(f)
+    data_config = dict(cfg['dataset'])
+    data_config['max_pattern_len'] = 23
+    nn_config = dict(cfg['NN'])
+    loss_config = dict(nn_config.pop('loss'))
+    loss_config.update(loss_components=['shape', 'loop', 'rotation', 'translation'], quality_components=[])
+    nn_config.pop('pre-trained', None)
+    return data_config, nn_config, loss_config
+
+
+def baseline_checkpoint_state():
+    """model_state_dict of models/baseline/lstm_stitch_tags.pth without the DataParallel 'module.' prefix."""
+    import torch
+    ck = torch.load(os.path.join(REFERENCE_ROOT, 'models', 'baseline', 'lstm_stitch_tags.pth'),
+                    map_location='cpu', weights_only=False)
+    return {k[len('module.'):] if k.startswith('module.') else k: v for k, v in ck['model_state_dict'].items()}
+
+
 def att_checkpoint_state():
     """model_state_dict of models/att/neural_tailor_panels.pth without the DataParallel 'module.' prefix."""
     import torch

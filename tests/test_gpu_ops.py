@@ -493,3 +493,26 @@ def test_edgeconv_large_clouds_through_the_streaming_engine(ops, cuda_device, en
     for (n1, b1), (n2, b2) in zip(mine.nn.named_buffers(), ref_mlp.named_buffers()):
         if b1.dtype.is_floating_point:
             assert_close(b1, b2, what='BN buffer ' + n1)
+
+
+@pytest.mark.parametrize('mode', ['mean', 'max', 'add'])
+@pytest.mark.parametrize('B,N,F', [(3, 257, 153), (1, 5, 7), (32, 2048, 150)])
+def test_global_pool_matches_torch(ops, cuda_device, mode, B, N, F):
+    dev = cuda_device
+    x = torch.randn(B * N, F, device=dev)
+    if mode == 'max':
+        x[1::7] = x[0]                       # exact ties: the first maximal point must receive the gradient (scatter-max)
+    x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    got = ops.global_pool(x1, B, N, mode)
+    v = x2.view(B, N, F)
+    want = {'mean': lambda: v.mean(1), 'add': lambda: v.sum(1), 'max': lambda: v.max(1).values}[mode]()
+    assert_close(got, want, tol=1e-5, what='global pool ' + mode)
+    g = torch.randn_like(want)
+    got.backward(g)
+    if mode == 'max':
+        first = (v == want.unsqueeze(1)).float().argmax(1)                   # first point attaining the maximum
+        ref = torch.zeros_like(v).scatter_(1, first.unsqueeze(1), g.unsqueeze(1)).view(B * N, F)
+    else:
+        want.backward(g)
+        ref = x2.grad
+    assert_close(x1.grad, ref, tol=1e-6, what='global pool grad ' + mode)

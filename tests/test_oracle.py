@@ -149,3 +149,67 @@ def test_oracle_equals_unmodified_reference_when_available():
         l2, d2, _ = mine.loss(o2, dict(gt))
         assert float(l1) == float(l2)
     mine.load_state_dict(ref_stubs.att_checkpoint_state(), strict=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# baseline model (global pool + pattern LSTM) and the non-local attention branch
+# ------------------------------------------------------------------------------------------------------------
+BASELINE_NN = {'feature_extractor': 'EdgeConvFeatures', 'conv_depth': 2, 'k_neighbors': 5, 'EConv_hidden': 200,
+               'EConv_hidden_depth': 2, 'EConv_feature': 150, 'EConv_aggr': 'max', 'global_pool': 'mean',
+               'skip_connections': False, 'graph_pooling': False, 'pool_ratio': 0.1, 'local_attention': True,
+               'panel_decoder': 'LSTMDecoderModule', 'panel_encoding_size': 250, 'panel_hidden_size': 250,
+               'panel_n_layers': 3, 'lstm_init': 'kaiming_normal_', 'pattern_decoder': 'LSTMDecoderModule',
+               'pattern_encoding_size': 250, 'pattern_hidden_size': 250, 'pattern_n_layers': 2}       # lstm_stitch_tags.yaml:96-122
+
+
+def test_oracle_reproduces_reference_golden_baseline_and_nonlocal(golden_dir):
+    from oracle import model as om
+    gold = torch.load(os.path.join(golden_dir, 'n2_variants.pt'))
+    x, gt = gold['x'], gold['gt']
+    for name, build in (('baseline', lambda: om.OracleFullPattern3D(dict(om.ATT_DATA_CONFIG), dict(BASELINE_NN), {})),
+                        ('att_nonlocal', lambda: om.OracleSegmentPattern3D(
+                            dict(om.ATT_DATA_CONFIG), dict(om.ATT_NN_CONFIG, local_attention=False), {}))):
+        v = gold['variants'][name]
+        torch.manual_seed(gold['seed_init'])
+        model = build().train()
+        chk = float(sum(t.double().abs().sum() for t in model.state_dict().values() if t.dtype.is_floating_point))
+        assert abs(chk - v['state_checksum']) <= 1e-9 * v['state_checksum'], name
+        kw = {'lstm_state': v['states']['panel']}
+        if 'pattern' in v['states']:
+            kw['pattern_lstm_state'] = v['states']['pattern']
+        out = model(x, **kw)
+        for key, want in v['out_train'].items():
+            assert_close(out[key], want, tol=1e-5, what='oracle {} {}'.format(name, key))
+        loss, _ = om.main_losses(out, gt)
+        assert abs(float(loss) - float(v['loss'])) <= 1e-5 * abs(float(v['loss'])), name
+        loss.backward()
+        named = dict(model.named_parameters())
+        for pname, dig in v['grads'].items():
+            g = named[pname].grad.reshape(-1)
+            assert abs(float(g.double().norm()) - dig['norm']) <= 1e-4 * max(dig['norm'], 1e-12), (name, pname)
+
+
+def test_oracle_encoder_global_pools_golden(golden_dir):
+    from oracle import model as om
+    gold = torch.load(os.path.join(golden_dir, 'n2_variants.pt'))
+    for pool, want in gold['encoder_pools'].items():
+        torch.manual_seed(gold['seed_init'])
+        enc = om.OracleEdgeConvFeatures(250, dict(BASELINE_NN, global_pool=pool)).eval()
+        with torch.no_grad():
+            got = enc(gold['x'])[0]
+        assert_close(got, want, tol=1e-5, what='oracle encoder global_pool=' + pool)
+
+
+def test_oracle_loads_shipped_baseline_checkpoint_if_present(golden_dir):
+    ck = os.path.join(golden_dir, '_ckpt', 'baseline_state.pt')
+    if not os.path.exists(ck):
+        pytest.skip('extracted checkpoint fixture absent')
+    from oracle import model as om
+    gold = torch.load(os.path.join(golden_dir, 'n2_baseline_ckpt.pt'))
+    model = om.OracleFullPattern3D(dict(om.ATT_DATA_CONFIG), dict(BASELINE_NN), {})
+    model.load_state_dict(torch.load(ck), strict=True)
+    model.eval()
+    with torch.no_grad():
+        out = model(gold['x'], lstm_state=gold['states']['panel'], pattern_lstm_state=gold['states']['pattern'])
+    for key, want in gold['out_eval'].items():
+        assert_close(out[key], want, tol=1e-5, what='oracle baseline ckpt ' + key)

@@ -9,6 +9,8 @@ def main(path, header=''):
     cnt = defaultdict(int)
     for r in csv.reader(open(path)):
         if len(r) > 5 and r[0].isdigit():
+            if len(r) > 12 and r[12] != 'gpu__time_duration.sum':      # launch lists that carry several metrics per launch
+                continue
             name = r[4]
             try:
                 ns = float(r[-1])
