@@ -89,13 +89,19 @@ def test_error_behaviour_matches_reference_conventions():
         enc(torch.randn(2, 16, 3))
 
 
-def test_global_pools_on_dense_layout():
+def test_global_pools_have_no_cpu_fallback():
+    """global_{mean,max,add}_pool run in libnt_b200 (nt_global_pool_*; numerics in tests/test_gpu_ops.py): CPU tensors are refused
+    with the documented RuntimeError, a bad pool name with the reference's ValueError (nn/net_blocks.py:152)."""
+    import pytest
     from garment_pattern_estimation_b200 import net_blocks as nb
+    from garment_pattern_estimation_b200 import ops
     x = torch.randn(3 * 7, 5)
     batch = torch.arange(3).repeat_interleave(7)
-    assert torch.allclose(nb.global_mean_pool(x, batch, 3), x.view(3, 7, 5).mean(1))
-    assert torch.allclose(nb.global_max_pool(x, batch), x.view(3, 7, 5).max(1).values)
-    assert torch.allclose(nb.global_add_pool(x, batch, 3), x.view(3, 7, 5).sum(1))
+    for pool in (nb.global_mean_pool, nb.global_max_pool, nb.global_add_pool):
+        with pytest.raises(RuntimeError):
+            pool(x, batch, 3)
+    with pytest.raises(ValueError):
+        ops.global_pool(x, 3, 7, 'median')
 
 
 def test_initial_state_distribution_matches_reference_draw():
