@@ -11,6 +11,6 @@ Layout
   parallel.py                 one-process-per-GPU data-parallel wrapper (flat-buffer NCCL allreduce)
 """
 from . import net_blocks, nets  # noqa: F401
-from .nets import GarmentFullPattern3D, GarmentSegmentPattern3D  # noqa: F401
+from .nets import GarmentFullPattern3D, GarmentSegmentPattern3D, StitchOnEdge3DPairs  # noqa: F401
 
 __all__ = ['net_blocks', 'nets', 'GarmentFullPattern3D', 'GarmentSegmentPattern3D']

@@ -87,3 +87,50 @@ class ComposedPatternLoss:
 
     def train(self, mode=True):
         self.training = mode
+
+
+class ComposedLoss:
+    """Loss of the stage-2 stitch model (reference ``ComposedLoss``, nn/metrics/composed_loss.py:10-127): binary
+    cross-entropy with logits on edge-pair scores (``edge_pair_class``) plus the no-grad quality metrics accuracy /
+    stitch precision / stitch recall.  Same call interface as above; the metrics are evaluated as device tensors
+    (no host synchronisation), with the reference's convention that an empty denominator yields 0."""
+
+    def __init__(self, data_config, in_config={}):
+        self.config = {'loss_components': [], 'quality_components': []}
+        self.config.update(in_config)
+        self.with_quality_eval = True
+        self.training = False
+        self.l_components = self.config['loss_components']
+        self.q_components = self.config['quality_components']
+        unsupported = [c for c in list(self.l_components) + list(self.q_components)
+                       if c not in ('edge_pair_class', 'edge_pair_stitch_recall')]
+        if unsupported:
+            raise NotImplementedError('loss / quality components {} are not part of ComposedLoss'.format(unsupported))
+
+    def __call__(self, preds, ground_truth, names=None, epoch=1000):
+        gt = ground_truth.to(preds.device)
+        loss_dict = {}
+        full = 0.
+        if 'edge_pair_class' in self.l_components:
+            pair_loss = F.binary_cross_entropy_with_logits(preds.reshape(-1), gt.reshape(-1).to(torch.float32))
+            loss_dict['edge_pair_class_loss'] = pair_loss
+            full = full + pair_loss
+        if self.with_quality_eval:
+            with torch.no_grad():
+                pred_cls = torch.round(torch.sigmoid(preds))
+                if 'edge_pair_class' in self.q_components:
+                    loss_dict['edge_pair_class_acc'] = (pred_cls == gt).sum().float() / gt.numel()
+                if 'edge_pair_stitch_recall' in self.q_components:
+                    is_stitch = gt == 1
+                    correct = ((pred_cls == 1) & is_stitch).sum().float()
+                    n_pred, n_gt = (pred_cls == 1).sum().float(), is_stitch.sum().float()
+                    zero = torch.zeros((), device=preds.device)
+                    loss_dict['stitch_precision'] = torch.where(n_pred > 0, correct / n_pred.clamp_min(1), zero)
+                    loss_dict['stitch_recall'] = torch.where(n_gt > 0, correct / n_gt.clamp_min(1), zero)
+        return full, loss_dict, False
+
+    def eval(self):
+        self.training = False
+
+    def train(self, mode=True):
+        self.training = mode

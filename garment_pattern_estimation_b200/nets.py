@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import net_blocks as blocks
 from . import ops
-from .losses import ComposedPatternLoss
+from .losses import ComposedLoss, ComposedPatternLoss
 
 
 class Sparsemax(nn.Module):
@@ -198,3 +198,31 @@ class GarmentSegmentPattern3D(GarmentFullPattern3D):
         if len(att_weights) > 0:
             panels.update(att_weights=att_weights)
         return panels
+
+
+class StitchOnEdge3DPairs(BaseModule):
+    """Stage 2 of NeuralTailor (nn/nets.py:303-353): is a pair of 3D edges connected by a stitch?  One MLP
+    ``pair features (16) -> 200 -> 200 -> 200 -> 1`` (Linear/ReLU/BatchNorm blocks) evaluated by the fused row-GEMM
+    kernels; ``forward(pairs[..., 16]) -> logits[...]``.  Building the edge pairs from a predicted pattern
+    (nn/data/pattern_converter.py:411-499) is host-side data preparation and stays with the reference."""
+
+    def __init__(self, data_config, config={}, in_loss_config={}):
+        super().__init__()
+        self.pair_feature_len = data_config['element_size']
+        self.config.update({'stitch_hidden_size': 200, 'stitch_mlp_n_layers': 3})
+        self.config.update(config)
+        self.config['loss'] = {
+            'loss_components': ['edge_pair_class'],
+            'quality_components': ['edge_pair_class', 'edge_pair_stitch_recall'],
+            'panel_origin_invariant_loss': False, 'panel_order_inariant_loss': False}
+        self.config['loss'].update(in_loss_config)
+        self.loss = ComposedLoss(data_config, self.config['loss'])
+        self.config['loss'] = self.loss.config
+        mid_layers = [self.config['stitch_hidden_size']] * self.config['stitch_mlp_n_layers']
+        self.mlp = blocks.MLP([self.pair_feature_len] + mid_layers + [1])
+
+    def forward(self, pairs_batch, **kwargs):
+        return_shape = list(pairs_batch.shape)
+        return_shape.pop(-1)
+        out = self.mlp(pairs_batch.contiguous().view(-1, pairs_batch.shape[-1]))
+        return out.view(return_shape)

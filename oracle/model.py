@@ -7,6 +7,7 @@ Follows (reference file:line, relative to /root/reference):
   * ``OracleLSTMDecoder``        nn/net_blocks.py:363-402   repeat encoding out_len x -> nn.LSTM -> Linear
   * ``OracleFullPattern3D``      nn/nets.py:41-184          baseline model (pattern LSTM -> panel LSTM -> placement)
   * ``OracleSegmentPattern3D``   nn/nets.py:187-299         attention model (per-point sparsemax -> 23 pooled encodings)
+  * ``OracleStitchOnEdge3DPairs`` nn/nets.py:303-353        stage-2 stitch model (MLP on edge-pair features)
   * ``panel_loop_loss``          nn/metrics/losses.py:19-51
   * ``main_losses``              nn/metrics/composed_loss.py:294-321 (the 4 components active in att.yaml:124)
 The module tree / parameter names reproduce the reference state_dict so the shipped checkpoints load
@@ -274,6 +275,23 @@ class OracleSegmentPattern3D(OracleFullPattern3D):
         if len(att) > 0:
             out['att_weights'] = att
         return out
+
+
+class OracleStitchOnEdge3DPairs(nn.Module):
+    """nn/nets.py:303-353 (stage-2 stitch model): MLP 16 -> 200 x 3 -> 1 on edge-pair features; loss =
+    BCEWithLogits (nn/metrics/composed_loss.py:83-88)."""
+
+    def __init__(self, pair_feature_len=16, hidden=200, n_layers=3):
+        super().__init__()
+        self.mlp = mlp([pair_feature_len] + [hidden] * n_layers + [1])
+
+    def forward(self, pairs, **kwargs):
+        shape = list(pairs.shape)[:-1]
+        return self.mlp(pairs.contiguous().view(-1, pairs.shape[-1])).view(shape)
+
+    @staticmethod
+    def loss(preds, gt):
+        return F.binary_cross_entropy_with_logits(preds.view(-1), gt.view(-1).float())
 
 
 def synthetic_ground_truth(B, seed=11, n_panels=23, panel_len=14, device='cpu'):

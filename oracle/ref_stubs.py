@@ -103,6 +103,14 @@ def baseline_checkpoint_state():
     return {k[len('module.'):] if k.startswith('module.') else k: v for k, v in ck['model_state_dict'].items()}
 
 
+def stitch_checkpoint_state():
+    """model_state_dict of models/att/neural_tailor_stitch_model.pth without the DataParallel 'module.' prefix."""
+    import torch
+    ck = torch.load(os.path.join(REFERENCE_ROOT, 'models', 'att', 'neural_tailor_stitch_model.pth'),
+                    map_location='cpu', weights_only=False)
+    return {k[len('module.'):] if k.startswith('module.') else k: v for k, v in ck['model_state_dict'].items()}
+
+
 def att_checkpoint_state():
     """model_state_dict of models/att/neural_tailor_panels.pth without the DataParallel 'module.' prefix."""
     import torch

@@ -213,3 +213,43 @@ def test_oracle_loads_shipped_baseline_checkpoint_if_present(golden_dir):
         out = model(gold['x'], lstm_state=gold['states']['panel'], pattern_lstm_state=gold['states']['pattern'])
     for key, want in gold['out_eval'].items():
         assert_close(out[key], want, tol=1e-5, what='oracle baseline ckpt ' + key)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# stage-2 stitch model
+# ------------------------------------------------------------------------------------------------------------
+def test_oracle_reproduces_reference_golden_stitch_model(golden_dir):
+    from oracle import model as om
+    gold = torch.load(os.path.join(golden_dir, 'n3_stitch.pt'))
+    model = om.OracleStitchOnEdge3DPairs()
+    model.load_state_dict(gold['ckpt']['state'], strict=True)
+    model.eval()
+    with torch.no_grad():
+        logits = model(gold['pairs'])
+    assert_close(logits, gold['ckpt']['logits'], tol=1e-5, what='oracle stitch logits (shipped weights)')
+    assert abs(float(model.loss(logits, gold['gt'])) - float(gold['ckpt']['loss'])) <= 1e-5 * float(gold['ckpt']['loss'])
+    torch.manual_seed(gold['seed_init'])
+    model = om.OracleStitchOnEdge3DPairs().train()
+    logits = model(gold['pairs'])
+    assert_close(logits, gold['train']['logits'], tol=1e-5, what='oracle stitch logits (train)')
+    loss = model.loss(logits, gold['gt'])
+    loss.backward()
+    for name, dig in gold['train']['grads'].items():
+        g = dict(model.named_parameters())[name].grad.reshape(-1)
+        assert abs(float(g.double().norm()) - dig['norm']) <= 1e-4 * max(dig['norm'], 1e-12), name
+
+
+def test_stitch_loss_and_quality_metrics_match_reference_golden(golden_dir):
+    """The product's ComposedLoss (device-side metrics, no host syncs) on the reference's own logits."""
+    from garment_pattern_estimation_b200.losses import ComposedLoss
+    gold = torch.load(os.path.join(golden_dir, 'n3_stitch.pt'))
+    loss_obj = ComposedLoss({'element_size': 16}, {'loss_components': ['edge_pair_class'],
+                                                   'quality_components': ['edge_pair_class', 'edge_pair_stitch_recall']})
+    for case in ('ckpt', 'train'):
+        total, parts, flag = loss_obj(gold[case]['logits'], gold['gt'])
+        assert flag is False and set(parts) == set(gold[case]['parts'])
+        assert abs(float(total) - float(gold[case]['loss'])) <= 1e-6 * abs(float(gold[case]['loss']))
+        for k, want in gold[case]['parts'].items():
+            assert abs(float(parts[k]) - float(want)) <= 1e-6 * max(abs(float(want)), 1e-6), (case, k)
+    with pytest.raises(NotImplementedError):
+        ComposedLoss({}, {'loss_components': ['shape']})
