@@ -5,11 +5,15 @@ The reference's PanelLoopLoss walks all B*23 panels in a Python loop with a devi
 a device scalar); here it is one masked reduction.  These are [B, 23, 14, 4]-sized tensors -- a few KB --
 so they stay in torch (plumbing), off the kernel budget.
 
-Everything the shipped att config does NOT enable (order / origin matching, stitch, free-class and segmentation losses,
-the no-grad quality metrics) is out of scope and raises NotImplementedError if requested.
+The no-grad quality metrics of the shipped configs ('shape', 'discrete', 'rotation', 'translation'; att.yaml:124-138) are
+evaluated by ``metrics.PatternQuality`` (vectorised, one host read).  What the shipped att config does NOT enable (order /
+origin matching, stitch, free-class and segmentation losses, stitch quality) is out of scope
+and raises NotImplementedError if requested.
 """
 import torch
 import torch.nn.functional as F
+
+from .metrics import PatternQuality
 
 _SUPPORTED = ('shape', 'loop', 'rotation', 'translation')
 
@@ -51,7 +55,8 @@ class ComposedPatternLoss:
             raise NotImplementedError('loss components {} are outside the B200 hot path'.format(unsupported))
         if self.config['panel_origin_invariant_loss'] or self.config['panel_order_inariant_loss']:
             raise NotImplementedError('GT origin/order matching is outside the B200 hot path (att.yaml disables both)')
-        self.with_quality_eval = False      # quality metrics are no-grad diagnostics, out of scope
+        self.with_quality_eval = True       # reference default (composed_loss.py:159); no-op without quality_components
+        self.quality = PatternQuality(data_config, self.q_components)
         self.training = False
         self.debug_prints = False
         self.max_panel_len = data_config['max_panel_len']
@@ -80,6 +85,10 @@ class ComposedPatternLoss:
         if 'translation' in self.l_components:
             loss_dict['translation_loss'] = F.mse_loss(preds['translations'], gt['translations'])
             full = full + loss_dict['translation_loss']
+        if self.with_quality_eval and self.q_components:
+            with torch.no_grad():
+                quality, _ = self.quality(preds, gt, gt['num_edges'].int().view(-1), names)
+                loss_dict.update(quality)
         return full, loss_dict, False
 
     def eval(self):

@@ -171,9 +171,22 @@ class GraphedTrainStep:
             if self.capture_update:
                 self._update()
 
+    def _loss(self, out, gt):
+        """The training loss only: the no-grad quality metrics (diagnostics; they need a host read) are switched off for the
+        step, like ``loss.with_quality_eval = False`` in the reference."""
+        loss_obj = self.model.loss
+        had = getattr(loss_obj, 'with_quality_eval', None)
+        if had:
+            loss_obj.with_quality_eval = False
+        try:
+            return loss_obj(out, gt)[0]
+        finally:
+            if had:
+                loss_obj.with_quality_eval = True
+
     def _forward_backward(self):
         out = self.wrapper(self.static_x, **self.forward_kwargs)
-        loss, _, _ = self.model.loss(out, self.static_gt)
+        loss = self._loss(out, self.static_gt)
         loss.backward()
         return loss.detach()
 
@@ -184,7 +197,7 @@ class GraphedTrainStep:
 
     def eager_step(self, x, gt):
         out = self.wrapper(x, **self.forward_kwargs)
-        loss, _, _ = self.model.loss(out, gt)
+        loss = self._loss(out, gt)
         loss.backward()
         self._update()
         return loss.detach()

@@ -271,3 +271,75 @@ except RuntimeError as e:
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-3000:]
     assert 'All keys matched' in out.stdout and 'forward reached the B200 blocks' in out.stdout
+
+
+# ------------------------------------------------------------------------------------------------------------
+# quality metrics of the pattern loss (vectorised, device-side) vs the unmodified reference
+# ------------------------------------------------------------------------------------------------------------
+def _check_loss_against(parts_ref, total_ref, total, parts, tol=2e-5):
+    import math
+    assert set(parts) == set(parts_ref)
+    assert abs(float(total) - float(total_ref)) <= tol * abs(float(total_ref))
+    for k, want in parts_ref.items():
+        got = parts[k]
+        if want is None:
+            assert got is None, k
+            continue
+        assert got is not None, k
+        w, gval = float(want), float(got)
+        if math.isnan(w):
+            assert math.isnan(gval), k
+        else:
+            assert abs(gval - w) <= tol * max(abs(w), 1e-3), (k, gval, w)
+
+
+def test_pattern_loss_with_quality_metrics_matches_reference_golden():
+    from garment_pattern_estimation_b200.losses import ComposedPatternLoss
+    gold = torch.load(os.path.join(ROOT, 'tests', 'golden', 'n1_quality.pt'))
+    dc, _, _ = _att()
+    dc['standardize'] = gold['standardize']
+    loss_obj = ComposedPatternLoss(dc, dict(gold['loss_config']))
+    assert loss_obj.with_quality_eval is True
+    for name, case in gold['cases'].items():
+        total, parts, flag = loss_obj(case['preds'], {k: v.clone() for k, v in case['gt'].items()}, epoch=3)
+        assert flag is False
+        _check_loss_against(case['parts'], case['loss'], total, parts)
+    loss_obj.with_quality_eval = False
+    _, parts, _ = loss_obj(gold['cases']['mixed']['preds'], gold['cases']['mixed']['gt'])
+    assert set(parts) == {'pattern_loss', 'loop_loss', 'rotation_loss', 'translation_loss'}
+    with pytest.raises(NotImplementedError):
+        ComposedPatternLoss(dc, dict(gold['loss_config'], quality_components=['stitch']))
+
+
+def test_quality_metrics_match_unmodified_reference_on_random_batches():
+    """Runs only where /root/reference exists: random prediction batches (padding rows, open loops, random panel counts)
+    through the reference's ComposedPatternLoss and through the vectorised one."""
+    from oracle import ref_stubs
+    if not ref_stubs.reference_available():
+        pytest.skip('reference tree not present on this machine')
+    from oracle import model as om
+    from garment_pattern_estimation_b200.losses import ComposedPatternLoss
+    ref_stubs.import_reference()
+    import metrics.composed_loss as cl
+    dc, _, lc = ref_stubs.att_configs()
+    lc = dict(lc, loss_components=['shape', 'loop', 'rotation', 'translation'],
+              quality_components=['shape', 'discrete', 'rotation', 'translation'])
+    ref_loss = cl.ComposedPatternLoss(dict(dc), dict(lc))
+    mine = ComposedPatternLoss(dict(dc), dict(lc))
+    st = dc['standardize']
+    pad = -torch.tensor(st['gt_shift']['outlines']) / torch.tensor(st['gt_scale']['outlines'])
+    for seed in range(4):
+        g = torch.Generator().manual_seed(100 + seed)
+        B = 3 + seed
+        gt = om.synthetic_ground_truth(B, seed=50 + seed)
+        live = torch.arange(14)[None, None, :] < gt['num_edges'][..., None]
+        pred = torch.where(live[..., None], gt['outlines'], pad.expand_as(gt['outlines']).clone())
+        noise = [0.003, 0.02, 0.06, 0.2][seed]
+        pred = pred + noise * torch.randn(pred.shape, generator=g)
+        drop = torch.rand(B, 23, generator=g) < 0.1                               # some panels vanish, some appear
+        pred = torch.where(drop[..., None, None], pad.expand_as(pred), pred)
+        preds = {'outlines': pred, 'rotations': torch.randn(B, 23, 4, generator=g),
+                 'translations': torch.randn(B, 23, 3, generator=g)}
+        t1, p1, _ = ref_loss({k: v.clone() for k, v in preds.items()}, {k: v.clone() for k, v in gt.items()}, epoch=1)
+        t2, p2, _ = mine(preds, gt, epoch=1)
+        _check_loss_against(p1, t1, t2, p2)
