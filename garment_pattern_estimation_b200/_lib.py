@@ -29,6 +29,7 @@ class GemmArgs(ctypes.Structure):
         ('aux', c_void_p), ('ldaux', c_int), ('aux_edge', c_int),
         ('k0', c_void_p), ('k1', c_void_p), ('mu', c_void_p),
         ('colsum', c_void_p),
+        ('scatter_dpq', c_void_p), ('ldscatter', c_int),
     ]
 
 
@@ -40,6 +41,7 @@ _SIGNATURES = {
     'nt_knn_workspace_bytes': (c_int64, [c_int, c_int, c_int]),
     'nt_knn': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'nt_gemm_nt': (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
+    'nt_gemm_nt_scatter_supported': (c_int, [ctypes.POINTER(GemmArgs)]),
     'nt_set_nt_engine': (c_int, [c_int]),
     'nt_gemm_weights_bytes': (c_int64, [c_int, c_int, c_int]),
     'nt_gemm_prepare_weights': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

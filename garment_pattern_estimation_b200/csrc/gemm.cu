@@ -289,13 +289,12 @@ __global__ void __launch_bounds__(G_THREADS) gemm_tn_kernel(TNParams p) {
 
 }  // namespace nt
 
-extern "C" int nt_gemm_nt(const nt_gemm_args *g, void *stream) {
+static int nt_fill_params(const nt_gemm_args *g, nt::NTParams &p) {
     using namespace nt;
     NT_REQUIRE(g, "nt_gemm_nt: null args");
     NT_REQUIRE(g->rows >= 0 && g->K >= 1 && g->n_out >= 1, "nt_gemm_nt: bad shape");
     NT_REQUIRE(g->w && g->ldw >= g->K, "nt_gemm_nt: bad weight");
-    if (g->rows == 0) return 0;
-    NTParams p{};
+    p = NTParams{};
     p.rows = g->rows; p.K = g->K; p.n_out = g->n_out; p.rows_per_tile = G_TM;
     p.a = g->a; p.lda = g->lda;
     p.e = EdgeSrc{g->pq, g->ldpq, g->qoff, g->idx, g->k > 0 ? g->k : 1, g->n_per_cloud > 0 ? g->n_per_cloud : 1};
@@ -304,11 +303,33 @@ extern "C" int nt_gemm_nt(const nt_gemm_args *g, void *stream) {
     p.vmax = g->vmax; p.vmin = g->vmin; p.imax = g->imax; p.imin = g->imin; p.k_agg = g->k;
     p.aux = g->aux; p.ldaux = g->ldaux; p.aux_edge = g->aux_edge; p.ae = p.e;
     p.k0 = g->k0; p.k1 = g->k1; p.mu = g->mu; p.colsum = g->colsum;
+    p.scatter = g->scatter_dpq; p.ldscatter = g->ldscatter;
     if (g->producer == NT_PROD_PLAIN) NT_REQUIRE(g->a && g->lda >= g->K, "nt_gemm_nt: bad plain operand");
     else if (g->producer == NT_PROD_EDGE) {
         NT_REQUIRE(g->pq && g->ldpq >= g->K, "nt_gemm_nt: bad edge operand");
         if (g->idx) NT_REQUIRE(g->k >= 1 && g->n_per_cloud >= 1, "nt_gemm_nt: edge operand needs k and n_per_cloud");
     } else return fail("nt_gemm_nt: unknown producer %s%ld", "", g->producer);
+    if (p.scatter) {
+        NT_REQUIRE(g->epilogue == NT_EPI_BNRELU_BWD, "nt_gemm_nt: scatter_dpq needs NT_EPI_BNRELU_BWD");
+        NT_REQUIRE(g->idx && g->k >= 1 && g->k <= G_TM && g->n_per_cloud >= 1 && g->rows % g->k == 0,
+                   "nt_gemm_nt: scatter_dpq needs idx, k, n_per_cloud and rows % k == 0");
+        p.rows_per_tile = (G_TM / g->k) * g->k;          // tiles hold whole centre points
+    }
+    return 0;
+}
+
+extern "C" int nt_gemm_nt_scatter_supported(const nt_gemm_args *g) {
+    using namespace nt;
+    NTParams p;
+    if (!g || nt_fill_params(g, p) != 0 || !p.scatter || g->w_split == nullptr) return 0;
+    return nt_tc_would_stream(p, g->producer, g->epilogue, g->precision) ? 1 : 0;
+}
+
+extern "C" int nt_gemm_nt(const nt_gemm_args *g, void *stream) {
+    using namespace nt;
+    NTParams p;
+    if (int rc = nt_fill_params(g, p)) return rc;
+    if (g->rows == 0) return 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool tc = g->w_split != nullptr;
     switch (g->epilogue) {
@@ -331,7 +352,8 @@ extern "C" int nt_gemm_nt(const nt_gemm_args *g, void *stream) {
             return g->producer == NT_PROD_PLAIN ? launch_nt<NT_PROD_PLAIN, NT_EPI_RELU_MAXMIN>(p, st)
                                                 : launch_nt<NT_PROD_EDGE, NT_EPI_RELU_MAXMIN>(p, st);
         case NT_EPI_BNRELU_BWD:
-            NT_REQUIRE(g->out && g->ldo >= g->n_out && g->k0 && g->k1 && g->mu, "nt_gemm_nt: bwd operands missing");
+            NT_REQUIRE((g->out ? g->ldo >= g->n_out : p.scatter != nullptr) && g->k0 && g->k1 && g->mu, "nt_gemm_nt: bwd operands missing");
+            NT_REQUIRE(!p.scatter || tc, "nt_gemm_nt: scatter_dpq needs the tensor-core engine");
             NT_REQUIRE(g->aux_edge ? (g->pq != nullptr) : (g->aux != nullptr), "nt_gemm_nt: aux operand missing");
             NT_REQUIRE(g->producer == NT_PROD_PLAIN, "nt_gemm_nt: NT_EPI_BNRELU_BWD needs the plain producer");
             if (tc) return launch_nt_tc(p, g->producer, g->epilogue, g->precision, g->w_split, st);

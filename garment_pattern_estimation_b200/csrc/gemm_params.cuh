@@ -32,11 +32,14 @@ struct NTParams {
     float *vmax, *vmin; uint8_t *imax, *imin; int k_agg;
     const float *aux; int ldaux; int aux_edge; EdgeSrc ae;
     const float *k0, *k1, *mu; double *colsum;
+    float *scatter; int ldscatter;               // fused edge scatter (BNRELU_BWD on the streaming engine only)
 };
 
 
 // tensor-core engine entry (gemm_tc.cu); w_split = weights pre-split by nt_gemm_prepare_weights
 int launch_nt_tc(const NTParams &p, int producer, int epilogue, int precision, const void *w_split, cudaStream_t st);
+// true if launch_nt_tc would hand this call to the streaming engine (gemm_tc3.cu)
+bool nt_tc_would_stream(const NTParams &p, int producer, int epilogue, int precision);
 
 // tensor-core weight-gradient engine (gemm_tn_tc.cu)
 int gemm_tn_tc(const float *a, int lda, int m, const float *b, int ldb, int n, int64_t rows, const EdgeSrc &e, int b_edge,

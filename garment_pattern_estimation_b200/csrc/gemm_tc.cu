@@ -517,20 +517,33 @@ static int dispatch_tc(const NTParams &p, int producer, int epilogue, const void
 static std::atomic<int> g_nt_engine{-1};
 constexpr int64_t TC3_MIN_ROWS = 32768;
 
-int launch_nt_tc(const NTParams &p, int producer, int epilogue, int precision, const void *w_split, cudaStream_t st) {
+static int nt_engine() {
     int engine = g_nt_engine.load(std::memory_order_relaxed);
     if (engine < 0) {
         const char *v = getenv("NT_NT_ENGINE");
         engine = v ? atoi(v) : 0;
         g_nt_engine.store(engine, std::memory_order_relaxed);
     }
+    return engine;
+}
+
+bool nt_tc_would_stream(const NTParams &p, int producer, int epilogue, int precision) {
+    const int engine = nt_engine();
+    if (precision != NT_PREC_TF32X3) return false;
+    if (!(engine == 3 || (engine == 0 && p.rows >= TC3_MIN_ROWS))) return false;
+    return tc3_eligible(p, producer, epilogue);
+}
+
+int launch_nt_tc(const NTParams &p, int producer, int epilogue, int precision, const void *w_split, cudaStream_t st) {
+    const int engine = nt_engine();
     if (precision == NT_PREC_TF32X3) {
-        if (engine == 2) return launch_nt_tc2(p, producer, epilogue, w_split, st);
+        if (engine == 2 && !p.scatter) return launch_nt_tc2(p, producer, epilogue, w_split, st);
         if (engine == 3 || (engine == 0 && p.rows >= TC3_MIN_ROWS)) {
             const int rc = launch_nt_tc3(p, producer, epilogue, w_split, st);
             if (rc >= 0) return rc;
         }
     }
+    if (p.scatter) return fail("nt_gemm_nt: the fused scatter epilogue needs the streaming engine (see nt_gemm_nt_scatter_supported)%s", "");
     return precision == NT_PREC_TF32X3 ? dispatch_tc<true>(p, producer, epilogue, w_split, st)
                                        : dispatch_tc<false>(p, producer, epilogue, w_split, st);
 }

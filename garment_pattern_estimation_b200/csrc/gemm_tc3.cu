@@ -42,7 +42,7 @@ __host__ __device__ inline size_t tc3_smem_bytes(int n_tile) {
     return P3_STAGES * tc_stage_bytes(n_tile) + (size_t)P3_DEPTH * P3_SLAB + 8 * P3_TW * 4 + 4 * 256 * 4 + 512 * 4 + 128;
 }
 
-template <int EPI>
+template <int EPI, bool SCAT>
 __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, const uint8_t *__restrict__ w_split, TCGeom g) {
     extern __shared__ __align__(128) uint8_t smem[];
     const size_t stage_bytes = tc_stage_bytes(g.n_tile);
@@ -213,6 +213,19 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
                 }
             };
             if (EPI == NT_EPI_BNRELU_BWD) load_aux(0);               // does not depend on the accumulator
+            // fused edge scatter: global neighbour row of each of this lane's 8 rows (4m + sub) of the warp slab
+            int jrow[SCAT ? 8 : 1];
+            if (SCAT) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const int rr = 4 * m + sub;
+                    jrow[m] = 0;
+                    if (rr < wrows) {
+                        const int64_t e = wrow0 + rr, centre = e / p.e.k;
+                        jrow[m] = (int)((centre / p.e.n_per_cloud) * (int64_t)p.e.n_per_cloud + __ldg(p.e.idx + e));
+                    }
+                }
+            }
             mbar_wait(&tmem_full[as], ause & 1);
             tc_fence_after();
             for (int ch = 0; ch < n_chunks; ++ch) {
@@ -258,7 +271,8 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
                 }
                 const bool want = (EPI == NT_EPI_BIAS) ? false
                                                        : ((EPI == NT_EPI_BNRELU_BWD) ? (p.colsum != nullptr) : (p.stats != nullptr));
-                if (p.out || want || EPI == NT_EPI_RELU_MAXMIN) {
+                constexpr bool scat = SCAT;
+                if (p.out || want || scat || EPI == NT_EPI_RELU_MAXMIN) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         *reinterpret_cast<float4 *>(tw4 + lane * 36 + 4 * i) =
@@ -281,6 +295,34 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
                                 }
                             }
                         }
+                    }
+                    if (scat) {
+                        // neighbour half: dpq[j, n_out + col] += dz[e, col] (16-byte reductions; zero vectors -- ReLU-masked
+                        // rows -- are skipped); n_out % 4 == 0 is an eligibility condition, so every live quad is whole
+                        float *qdst = p.scatter + p.n_out + c0 + q4;
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) {
+                            const int rr = 4 * m + sub;
+                            if (rr < wrows && q4 < nv) {
+                                const float4 v = *reinterpret_cast<const float4 *>(tw4 + rr * 36 + q4);
+                                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
+                                    atomicAdd(reinterpret_cast<float4 *>(qdst + (int64_t)jrow[SCAT ? m : 0] * p.ldscatter), v);
+                            }
+                        }
+                        // centre half: dpq[c, col] = sum over the k edge rows of centre c (tiles hold whole centres: plain store)
+                        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                        const int kk = p.e.k;
+                        const int nodes_here = rows_here / kk;
+                        const int64_t node0 = row0 / kk;
+                        if (lane < nv) {
+                            for (int t = et; t < nodes_here * 32; t += 128) {
+                                const int nd = t >> 5;
+                                float sum = 0.f;
+                                for (int sl = 0; sl < kk; ++sl) sum += twg[(nd * kk + sl) * 36 + lane];
+                                p.scatter[(node0 + nd) * (int64_t)p.ldscatter + c0 + lane] = sum;
+                            }
+                        }
+                        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                     }
                     if (EPI == NT_EPI_RELU_MAXMIN) {
                         // max / min over the k edge rows of every centre point (nodes straddle warps: group barrier); the same
@@ -348,29 +390,41 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
     if (warp == P3_MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
-template <int EPI>
+template <int EPI, bool SCAT = false>
 static int launch_tc3(const NTParams &p, const void *w_split, const TCGeom &g, int sms, cudaStream_t st) {
     const size_t smem = tc3_smem_bytes(g.n_tile);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc3_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc3_kernel<EPI, SCAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail("nt_gemm_nt(tc3): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     const int64_t n_row_tiles = (p.rows + p.rows_per_tile - 1) / p.rows_per_tile;
     const int ctas = (int)(n_row_tiles < sms ? n_row_tiles : sms);
-    gemm_nt_tc3_kernel<EPI><<<ctas, P3_THREADS, smem, st>>>(p, reinterpret_cast<const uint8_t *>(w_split), g);
+    gemm_nt_tc3_kernel<EPI, SCAT><<<ctas, P3_THREADS, smem, st>>>(p, reinterpret_cast<const uint8_t *>(w_split), g);
     return check_launch("nt_gemm_nt(tc3)");
+}
+
+bool tc3_eligible(const NTParams &p, int producer, int epilogue) {
+    if (producer != NT_PROD_PLAIN || p.n_out > 224) return false;
+    const TCGeom g = tc_geometry(p.n_out, p.K, NT_PREC_TF32X3);
+    if (g.n_tiles != 1 || tc3_smem_bytes(g.n_tile) > 227 * 1024) return false;
+    if ((p.lda & 3) != 0 || !aligned16(p.a)) return false;
+    if (p.out && ((p.ldo & 3) != 0 || !aligned16(p.out))) return false;
+    if (epilogue == NT_EPI_BNRELU_BWD && (p.aux_edge || (p.ldaux & 3) != 0 || !aligned16(p.aux))) return false;
+    if (p.scatter) {
+        if (epilogue != NT_EPI_BNRELU_BWD || !p.e.idx || p.e.k < 1 || p.e.k > TC_M || p.e.n_per_cloud < 1) return false;
+        if (p.rows >= (int64_t)1 << 31) return false;
+        if ((p.n_out & 3) != 0 || (p.ldscatter & 3) != 0 || p.ldscatter < 2 * p.n_out || !aligned16(p.scatter)) return false;
+        if (p.rows % p.e.k != 0 || p.rows_per_tile % p.e.k != 0) return false;
+    }
+    return true;
 }
 
 // -1: not eligible (the caller falls back to the one-tile-per-CTA engine)
 int launch_nt_tc3(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st) {
-    if (producer != NT_PROD_PLAIN || p.n_out > 224) return -1;
+    if (!tc3_eligible(p, producer, epilogue)) return -1;
     const TCGeom g = tc_geometry(p.n_out, p.K, NT_PREC_TF32X3);
-    if (g.n_tiles != 1 || tc3_smem_bytes(g.n_tile) > 227 * 1024) return -1;
-    if ((p.lda & 3) != 0 || !aligned16(p.a)) return -1;
-    if (p.out && ((p.ldo & 3) != 0 || !aligned16(p.out))) return -1;
-    if (epilogue == NT_EPI_BNRELU_BWD && (p.aux_edge || (p.ldaux & 3) != 0 || !aligned16(p.aux))) return -1;
     static int sms = 0;
     if (sms == 0) {
         int dev = 0, n = 0;
@@ -382,7 +436,9 @@ int launch_nt_tc3(const NTParams &p, int producer, int epilogue, const void *w_s
         case NT_EPI_BIAS: return launch_tc3<NT_EPI_BIAS>(p, w_split, g, sms, st);
         case NT_EPI_RELU_STATS: return launch_tc3<NT_EPI_RELU_STATS>(p, w_split, g, sms, st);
         case NT_EPI_RELU_MAXMIN: return launch_tc3<NT_EPI_RELU_MAXMIN>(p, w_split, g, sms, st);
-        default: return launch_tc3<NT_EPI_BNRELU_BWD>(p, w_split, g, sms, st);
+        default:
+            return p.scatter ? launch_tc3<NT_EPI_BNRELU_BWD, true>(p, w_split, g, sms, st)
+                             : launch_tc3<NT_EPI_BNRELU_BWD, false>(p, w_split, g, sms, st);
     }
 }
 

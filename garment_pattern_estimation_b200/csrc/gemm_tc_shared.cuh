@@ -72,5 +72,6 @@ __device__ __forceinline__ void load_chunk(const float *src, int k, int K, bool 
 int launch_nt_tc2(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st);
 // streaming engine entry (gemm_tc3.cu); returns -1 when the call is not eligible (caller falls back to gemm_tc.cu)
 int launch_nt_tc3(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st);
+bool tc3_eligible(const NTParams &p, int producer, int epilogue);
 
 }  // namespace nt

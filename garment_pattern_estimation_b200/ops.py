@@ -98,6 +98,10 @@ TN_ENGINE = os.environ.get('NT_TN_ENGINE', 'tc')      # weight-gradient GEMM: 't
 # random PQ rows per edge in every consumer (next GEMM, weight-gradient GEMM, BN/ReLU backward epilogue).  '0' keeps the
 # gather fused into those kernels (smaller footprint, ~2x slower consumers).
 EDGE_MATERIALIZE = os.environ.get('NT_EDGE_MATERIALIZE', '1') != '0'
+# EdgeConv backward: scatter dz_1 into the per-point gradient dPQ inside the epilogue of the last data-gradient GEMM (dz_1 is
+# never written) instead of a separate nt_edge_scatter pass.  Correct (tests) but OFF by default: measured at C2 the 16-byte
+# reductions in the epilogue cost the GEMM +0.13 ms per launch while the separate pass costs 0.10 ms (8.89 vs 8.83 ms/step).
+FUSED_SCATTER = os.environ.get('NT_FUSED_SCATTER', '0') != '0'
 GEMM_ENGINE = 'tc'    # 'tc' = tcgen05 tensor-core engine (product path); 'simt' = fp32 CUDA-core engine (validation only)
 
 
@@ -111,7 +115,11 @@ def prepare_weights(w, ldw, n_out, K, precision):
 
 
 def gemm_nt(rows, K, n_out, w, ldw, epilogue, a=None, lda=0, edge=None, bias=None, out=None, ldo=0, stats=None,
-            agg=None, k_agg=0, aux=None, ldaux=0, aux_edge=False, k0=None, k1=None, mu=None, colsum=None, grad_gemm=False):
+            agg=None, k_agg=0, aux=None, ldaux=0, aux_edge=False, k0=None, k1=None, mu=None, colsum=None, grad_gemm=False,
+            scatter=None):
+    """scatter: optional [M, 2*n_out] tensor (second half zeroed) for the fused edge scatter of NT_EPI_BNRELU_BWD (needs
+    `edge` for idx / k / n_per_cloud).  Returns False -- without launching anything -- when the library cannot fuse the
+    scatter for this call, True otherwise."""
     # TF32x3 (fp32-like, ~1e-6) everywhere: the tensor pipe is far from being the limiter of these gather-bound GEMMs,
     # and BatchNorm's backward is cancellation-heavy (sum_r da = 0), which amplifies BF16x3's 1e-5 to ~5e-3 on bias
     # gradients.  GRAD_PRECISION can be switched to NT_PREC_BF16X3 for the data-gradient GEMMs.
@@ -135,13 +143,19 @@ def gemm_nt(rows, K, n_out, w, ldw, epilogue, a=None, lda=0, edge=None, bias=Non
         g.vmax, g.vmin, g.imax, g.imin = (_p(t) for t in agg)
     g.aux, g.ldaux, g.aux_edge = _p(aux), int(ldaux), int(bool(aux_edge))
     g.k0, g.k1, g.mu, g.colsum = _p(k0), _p(k1), _p(mu), _p(colsum)
+    if scatter is not None:
+        g.scatter_dpq, g.ldscatter = _p(scatter), int(scatter.stride(0))
+        if not _lib.load().nt_gemm_nt_scatter_supported(ctypes.byref(g)):
+            return False
     group = 'nt_gemm_nt[%s,%s]' % (_EPI_NAMES[epilogue], 'edge' if g.producer == NT_PROD_EDGE else 'plain')
     if FLOP_SINK is not None:
         FLOP_SINK[group] = FLOP_SINK.get(group, 0.0) + 2.0 * rows * K * n_out
     if BYTES_SINK is not None:
         cols = K + (n_out if out is not None else 0) + (n_out if epilogue == NT_EPI_BNRELU_BWD else 0)
-        BYTES_SINK[group] = BYTES_SINK.get(group, 0.0) + 4.0 * rows * cols + 4.0 * n_out * K
+        extra = 4.0 * scatter.shape[0] * scatter.shape[1] if scatter is not None else 0.0
+        BYTES_SINK[group] = BYTES_SINK.get(group, 0.0) + 4.0 * rows * cols + 4.0 * n_out * K + extra
     _call('nt_gemm_nt', _lib.load().nt_gemm_nt, ctypes.byref(g), _stream(), group=group)
+    return True
 
 
 def gemm_tn(a, lda, m, rows, out, b=None, ldb=0, n=0, edge=None, mu=None):
@@ -377,6 +391,7 @@ class _FusedMLPFunction(torch.autograd.Function):
                                            _p(sums), R, R, HL, _p(dz), dz.stride(0), _p(csum), _stream())
 
         # ---- walk down the Linear layers L-1 .. 1
+        dpq = None
         for l in range(L - 1, 0, -1):
             Hout, Hin = widths[l], widths[l - 1]
             pmean, prstd, ps, pt = bn_vec[l - 1]
@@ -394,6 +409,13 @@ class _FusedMLPFunction(torch.autograd.Function):
             grads_W[l], grads_b[l] = dW, db
             grads_g[l - 1], grads_beta[l - 1] = vecs[0], vecs[1]
             csum_prev = torch.zeros(Hin, **f64)
+            if l == 1 and mode == 'edge' and a1 is not None and FUSED_SCATTER:
+                dpq = torch.zeros(M, 2 * H1, **f32)
+                if gemm_nt(R, Hout, Hin, w_fts[l], Hout, NT_EPI_BNRELU_BWD, a=dz, lda=dz.stride(0), edge=src, aux=acts[l],
+                           ldaux=acts[l].stride(0), k0=vecs[2], k1=vecs[3], mu=pmean, colsum=csum_prev, scatter=dpq):
+                    dz, csum = None, csum_prev
+                    continue
+                dpq = None
             if l == 1 and a1 is None:
                 dz_prev = _rowbuf(R, Hin, dev)
                 gemm_nt(R, Hout, Hin, w_fts[l], Hout, NT_EPI_BNRELU_BWD, a=dz, lda=dz.stride(0), edge=src, out=dz_prev,
@@ -408,8 +430,9 @@ class _FusedMLPFunction(torch.autograd.Function):
         grads_b[0] = csum.float()
         gx = None
         if mode == 'edge':
-            dpq = torch.zeros(M, 2 * H1, **f32)
-            _call('nt_edge_scatter', _lib.load().nt_edge_scatter, _p(dz), dz.stride(0), _p(idx), k, N, M, H1, _p(dpq), 2 * H1, _stream())
+            if dpq is None:
+                dpq = torch.zeros(M, 2 * H1, **f32)
+                _call('nt_edge_scatter', _lib.load().nt_edge_scatter, _p(dz), dz.stride(0), _p(idx), k, N, M, H1, _p(dpq), 2 * H1, _stream())
             dWc = torch.zeros(2 * H1, C, **f32)
             gemm_tn(dpq, 2 * H1, 2 * H1, M, dWc, b=x, ldb=m['ldx'], n=C)
             grads_W[0] = torch.cat([dWc[:H1], dWc[H1:] - dWc[:H1]], dim=1)

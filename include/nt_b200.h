@@ -88,9 +88,17 @@ typedef struct nt_gemm_args {
     const float *aux; int ldaux; int aux_edge;
     const float *k0, *k1, *mu;                       /* [n_out] each */
     double *colsum;                                  /* [n_out] */
+    /* NT_EPI_BNRELU_BWD, optional fused scatter of dz into the per-point gradient of the split first EdgeConv Linear (what
+     * nt_edge_scatter does in a second pass): scatter_dpq[c, 0:n_out] = sum of dz over the k edge rows of centre c (plain
+     * store), scatter_dpq[j, n_out:2*n_out] += dz[e] for the neighbour j = idx[e] of every edge e (atomic; the caller zeroes
+     * that half).  Uses idx / k / n_per_cloud; `out` may then be NULL (dz is never written).  Only for calls for which
+     * nt_gemm_nt_scatter_supported() returns 1; otherwise nt_gemm_nt fails. */
+    float *scatter_dpq; int ldscatter;
 } nt_gemm_args;
 
 int nt_gemm_nt(const nt_gemm_args *args, void *stream);
+/* 1 if nt_gemm_nt(args) would run the fused-scatter epilogue (streaming engine, aligned operands), 0 otherwise. */
+int nt_gemm_nt_scatter_supported(const nt_gemm_args *args);
 
 /* Engine used for the TF32x3 row GEMMs: 0 = auto (streaming persistent engine for large aligned calls, one-tile-per-CTA
  * engine otherwise; default), 1 = one tile per CTA, 2 = persistent experiment, 3 = streaming engine whenever eligible.

@@ -516,3 +516,38 @@ def test_global_pool_matches_torch(ops, cuda_device, mode, B, N, F):
         want.backward(g)
         ref = x2.grad
     assert_close(x1.grad, ref, tol=1e-6, what='global pool grad ' + mode)
+
+
+def test_fused_edge_scatter_matches_separate_scatter_pass(ops, cuda_device):
+    """EdgeConv backward with dz_1 scattered inside the epilogue of the last data-gradient GEMM (streaming engine) vs the
+    separate nt_edge_scatter pass: same gradients up to the summation order of the atomics."""
+    from garment_pattern_estimation_b200 import net_blocks as nb
+    dev = cuda_device
+    C, widths, k, B, N = 150, [200, 200, 150], 5, 3, 1000
+    torch.manual_seed(5)
+    conv = nb.DynamicEdgeConv(nb.MLP([2 * C] + widths), k=k).to(dev).train()
+    x = torch.randn(B * N, C, device=dev)
+    g = torch.randn(B * N, widths[-1], device=dev)
+    results = {}
+    try:
+        _set_engine(3)
+        for fused in (True, False):
+            ops.FUSED_SCATTER = fused
+            conv.zero_grad()
+            xi = x.clone().requires_grad_(True)
+            before = _launches()
+            conv(xi, cloud_shape=(B, N)).backward(g)
+            torch.cuda.synchronize()
+            results[fused] = (xi.grad.clone(), {n: p.grad.clone() for n, p in conv.named_parameters()}, _launches() - before)
+    finally:
+        ops.FUSED_SCATTER = False
+        _set_engine(0)
+    assert results[True][2] == results[False][2] - 1, 'the fused path must save exactly the nt_edge_scatter launch'
+    assert rel_err(results[True][0], results[False][0]) < 1e-5
+    for n in results[True][1]:
+        assert rel_err(results[True][1][n], results[False][1][n]) < 1e-5, n
+
+
+def _launches():
+    from garment_pattern_estimation_b200 import _lib
+    return _lib.launch_count()
