@@ -6,9 +6,10 @@ a device scalar); here it is one masked reduction.  These are [B, 
 so they stay in torch (plumbing), off the kernel budget.
 
 The no-grad quality metrics of the shipped configs ('shape', 'discrete', 'rotation', 'translation'; att.yaml:124-138) are
-evaluated by ``metrics.PatternQuality`` (vectorised, one host read).  What the shipped att config does NOT enable (order /
-origin matching, stitch, free-class and segmentation losses, stitch quality) is out of scope
-and raises NotImplementedError if requested.
+evaluated by ``metrics.PatternQuality`` (vectorised, one host read); the GT pre-processing of the reference's DEFAULT loss
+config -- panel order matching and edge-loop origin matching (composed_loss.py:429-570, 621-703) -- is vectorised below.
+Stitch, free-class and segmentation losses and the stitch quality metrics need the dataset's stitch ground truth and stay out
+of scope: they raise NotImplementedError if requested.
 """
 import torch
 import torch.nn.functional as F
@@ -36,6 +37,61 @@ def panel_loop_loss(outlines, num_edges=None, pad_xy=None):
     return (sums ** 2).sum() / (P * 2)
 
 
+
+# ----------------------------------------------------------------------------------------------------------
+# GT pre-processing of the reference loss (nn/metrics/composed_loss.py:429-570, 621-703), vectorised
+# ----------------------------------------------------------------------------------------------------------
+def match_panel_order(pred_features, gt_features):
+    """Greedy panel assignment of ``_panel_order_match`` (composed_loss.py:530-570): repeatedly take the globally closest
+    (predicted slot, GT panel) pair of every pattern and retire its row and column.  Returns permutation [B, P] (long):
+    predicted slot p is matched with GT panel permutation[b, p].  The reference loops over the batch inside each of the P
+    rounds; here a round is one argmin + two scatters for the whole batch."""
+    B, P = pred_features.shape[0], gt_features.shape[1]
+    dist = torch.cdist(pred_features.reshape(B, P, -1), gt_features.reshape(B, P, -1))
+    perm = torch.full((B, P), -1, dtype=torch.long, device=pred_features.device)
+    ar = torch.arange(B, device=pred_features.device)
+    for _ in range(P):
+        flat = dist.reshape(B, -1).argmin(dim=1)                 # first minimum, like the reference
+        rows, cols = flat // P, flat % P
+        perm[ar, rows] = cols
+        dist[ar, rows, :] = float('inf')
+        dist[ar, :, cols] = float('inf')
+    return perm
+
+
+def permute_panels(features, permutation):
+    """``_feature_permute`` (composed_loss.py:573-589): gather along the panel dimension."""
+    idx = permutation
+    while idx.dim() < features.dim():
+        idx = idx.unsqueeze(-1)
+    return torch.gather(features, 1, idx.expand(features.shape))
+
+
+def match_edge_origin(pred_outlines, gt_outlines, gt_num_edges):
+    """``_batch_edge_order_match`` (composed_loss.py:656-703): for every panel, the rotation of the GT edge loop (first
+    num_edges rows; padding rows stay) that is closest to the prediction.  Returns (rotated GT outlines, leading edge per
+    panel [B*P]).  The reference tries the rotations one by one per panel in Python; here all L candidate rotations of all
+    panels are one gather + one reduction (first minimum wins, as with the reference's strict ``<``)."""
+    shape = gt_outlines.shape
+    L = shape[-2]
+    pred = pred_outlines.reshape(-1, L, shape[-1])
+    gt = gt_outlines.reshape(-1, L, shape[-1])
+    n = gt_num_edges.reshape(-1).to(gt.device).long()
+    Q = gt.shape[0]
+    e = torch.arange(L, device=gt.device)
+    shift = e.view(1, L, 1)                                                   # candidate leading edge
+    pos = e.view(1, 1, L)
+    nn_ = n.view(Q, 1, 1).clamp_min(1)
+    src = torch.where(pos < n.view(Q, 1, 1), (pos + shift) % nn_, pos)        # [Q, shift, L] source row of every row
+    cand = torch.gather(gt.unsqueeze(1).expand(Q, L, L, shape[-1]), 2, src.unsqueeze(-1).expand(Q, L, L, shape[-1]))
+    dist = ((pred.unsqueeze(1) - cand) ** 2).sum(dim=(-1, -2))                # [Q, shift]
+    valid = (shift.view(1, L) < n.view(Q, 1)) | (shift.view(1, L) == 0)      # rotation 0 is always a candidate
+    dist = torch.where(valid, dist, torch.full_like(dist, float('inf')))
+    lead = dist.argmin(dim=1)
+    chosen = torch.gather(cand, 1, lead.view(Q, 1, 1, 1).expand(Q, 1, L, shape[-1])).squeeze(1)
+    return chosen.view(shape), lead
+
+
 class ComposedPatternLoss:
     """Callable with the reference's interface: ``loss(preds, ground_truth, names=None, epoch=1000)`` ->
     ``(loss, loss_dict, structure_update_flag)``; ``.config``, ``.with_quality_eval``, ``.train()`` / ``.eval()``."""
@@ -53,8 +109,10 @@ class ComposedPatternLoss:
         unsupported = [c for c in self.l_components if c not in _SUPPORTED]
         if unsupported:
             raise NotImplementedError('loss components {} are outside the B200 hot path'.format(unsupported))
-        if self.config['panel_origin_invariant_loss'] or self.config['panel_order_inariant_loss']:
-            raise NotImplementedError('GT origin/order matching is outside the B200 hot path (att.yaml disables both)')
+        if self.config['panel_order_inariant_loss'] and self.config['order_by'] not in ('placement', 'translation',
+                                                                                      'shape_translation'):
+            raise NotImplementedError("panel order matching by '{}' needs the stitch ground truth (outside the B200 hot "
+                                      "path)".format(self.config['order_by']))
         self.with_quality_eval = True       # reference default (composed_loss.py:159); no-op without quality_components
         self.quality = PatternQuality(data_config, self.q_components)
         self.training = False
@@ -71,6 +129,13 @@ class ComposedPatternLoss:
     def __call__(self, preds, ground_truth, names=None, epoch=1000):
         device = preds['outlines'].device
         gt = {k: (v.to(device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in ground_truth.items()}
+        # ---- GT pre-processing (composed_loss.py:239-253): panel order, then edge-loop origin
+        if self.config['panel_order_inariant_loss']:
+            gt = self._gt_order_match(preds, gt, epoch)
+        if self.config['panel_origin_invariant_loss']:
+            with torch.no_grad():
+                gt = dict(gt)
+                gt['outlines'], _ = match_edge_origin(preds['outlines'], gt['outlines'], gt['num_edges'].int().view(-1))
         loss_dict = {}
         full = 0.
         if 'shape' in self.l_components:
@@ -89,7 +154,39 @@ class ComposedPatternLoss:
             with torch.no_grad():
                 quality, _ = self.quality(preds, gt, gt['num_edges'].int().view(-1), names)
                 loss_dict.update(quality)
-        return full, loss_dict, False
+        # the loss structure changes at the epoch where order matching starts (composed_loss.py:278-280)
+        structure_update = bool(self.config['panel_order_inariant_loss'] and epoch == self.config['epoch_with_order_matching'])
+        return full, loss_dict, structure_update
+
+    def _gt_order_match(self, preds, gt, epoch):
+        """composed_loss.py:429-527 without the stitch-related entries."""
+        with torch.no_grad():
+            order_by = self.config['order_by']
+            if 'translations' not in preds or (order_by == 'placement' and 'rotations' not in preds):
+                raise ValueError('ComposedPatternLoss::Error::Ordering by {} requested but it is not predicted'.format(order_by))
+            if order_by == 'placement':
+                pf = torch.cat([preds['translations'], preds['rotations']], dim=-1)
+                gf = torch.cat([gt['translations'], gt['rotations']], dim=-1)
+            elif order_by == 'translation':
+                pf, gf = preds['translations'], gt['translations']
+            else:       # shape_translation
+                B, P = preds['outlines'].shape[0], preds['outlines'].shape[1]
+                pf = torch.cat([preds['translations'], preds['outlines'].reshape(B, P, -1)], dim=-1)
+                gf = torch.cat([gt['translations'], gt['outlines'].reshape(B, P, -1)], dim=-1)
+            B, P = pf.shape[0], gf.shape[1]
+            if epoch < self.config['epoch_with_order_matching']:      # random order until matching starts (:538-543)
+                perm = torch.stack([torch.randperm(P, dtype=torch.long, device=pf.device) for _ in range(B)])
+            else:
+                perm = match_panel_order(pf, gf)
+            out = dict(gt)
+            for key in ('outlines', 'num_edges', 'empty_panels_mask'):
+                if key in gt:
+                    out[key] = permute_panels(gt[key], perm)
+            if 'rotation' in self.l_components:
+                out['rotations'] = permute_panels(gt['rotations'], perm)
+            if 'translation' in self.l_components:
+                out['translations'] = permute_panels(gt['translations'], perm)
+        return out
 
     def eval(self):
         self.training = False

@@ -82,11 +82,14 @@ class GarmentFullPattern3D(BaseModule):
             config['pattern_hidden_size'] = config.get('pattern_encoding_size', self.config['pattern_encoding_size'])
         self.config.update(config)
 
-        # Loss: the four regression terms; GT origin/order matching defaults to OFF here (the reference defaults it ON
-        # but the shipped att config turns it off; matching is out of scope).
+        # Loss configuration: the reference's defaults (nn/nets.py:83-94; its dict literal lists panel_origin_invariant_loss
+        # twice, the later True wins).  Stitch-related entries are kept for config round-trips; the stitch losses themselves
+        # are outside the B200 hot path (requesting them raises NotImplementedError).
         loss_config = {
-            'loss_components': ['shape', 'loop', 'rotation', 'translation'], 'quality_components': [],
-            'loop_loss_weight': 1., 'panel_origin_invariant_loss': False, 'panel_order_inariant_loss': False,
+            'loss_components': ['shape', 'loop', 'rotation', 'translation'],
+            'quality_components': ['shape', 'discrete', 'rotation', 'translation'],
+            'loop_loss_weight': 1., 'stitch_tags_margin': 0.3, 'epoch_with_stitches': 40, 'stitch_supervised_weight': 0.1,
+            'stitch_hardnet_version': False, 'panel_origin_invariant_loss': True,
         }
         loss_config.update(in_loss_config)
         self.loss = ComposedPatternLoss(data_config, loss_config)

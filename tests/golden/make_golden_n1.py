@@ -92,6 +92,41 @@ def main():
     torch.save({'standardize': st, 'loss_config': lc, 'cases': cases}, out)
     print('n1_quality.pt', os.path.getsize(out) // 1024, 'KiB')
 
+    # ---- GT panel-order / edge-origin matching (the reference's DEFAULT loss configuration)
+    matching = {}
+    for name, extra in (('origin', dict(panel_origin_invariant_loss=True, panel_order_inariant_loss=False)),
+                        ('order_placement_origin', dict(panel_origin_invariant_loss=True, panel_order_inariant_loss=True,
+                                                        order_by='placement')),
+                        ('order_shape_translation', dict(panel_origin_invariant_loss=False, panel_order_inariant_loss=True,
+                                                         order_by='shape_translation'))):
+        cfg = dict(lc, **extra)
+        ref_loss = cl.ComposedPatternLoss(dict(dc), dict(cfg))
+        g = torch.Generator().manual_seed(4242)
+        B = 4
+        gt = closed_loop_gt(B, 77)
+        gt['empty_panels_mask'] = gt['num_edges'] == 0
+        live = torch.arange(14)[None, None, :] < gt['num_edges'][..., None]
+        outl = torch.where(live[..., None], gt['outlines'], pad.expand_as(gt['outlines']).clone())
+        perm = torch.stack([torch.randperm(23, generator=g) for _ in range(B)])
+        pred = torch.gather(outl, 1, perm[..., None, None].expand_as(outl)).clone()
+        ne = torch.gather(gt['num_edges'], 1, perm)
+        for b in range(B):
+            for p_ in range(23):
+                n = int(ne[b, p_])
+                if n >= 3:
+                    s0 = int(torch.randint(0, n, (1,), generator=g))
+                    pred[b, p_, :n] = torch.roll(pred[b, p_, :n], -s0, dims=0)
+        preds = {'outlines': pred + 0.01 * torch.randn(pred.shape, generator=g),
+                 'rotations': torch.gather(gt['rotations'], 1, perm[..., None].expand(B, 23, 4)) + 0.01 * torch.randn(B, 23, 4, generator=g),
+                 'translations': torch.gather(gt['translations'], 1, perm[..., None].expand(B, 23, 3)) + 0.01 * torch.randn(B, 23, 3, generator=g)}
+        total, parts, flag = ref_loss({k: v.clone() for k, v in preds.items()}, {k: v.clone() for k, v in gt.items()}, epoch=3)
+        matching[name] = {'loss_config': cfg, 'preds': preds, 'gt': gt, 'loss': total.clone(), 'flag': bool(flag),
+                          'parts': {k: (None if v is None else torch.as_tensor(v).clone()) for k, v in parts.items()}}
+        print(name, float(total), {k: (None if v is None else round(float(v), 5)) for k, v in parts.items()})
+    out = os.path.join(HERE, 'n1_matching.pt')
+    torch.save({'standardize': st, 'cases': matching}, out)
+    print('n1_matching.pt', os.path.getsize(out) // 1024, 'KiB')
+
 
 if __name__ == '__main__':
     main()

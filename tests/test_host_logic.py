@@ -343,3 +343,68 @@ def test_quality_metrics_match_unmodified_reference_on_random_batches():
         t1, p1, _ = ref_loss({k: v.clone() for k, v in preds.items()}, {k: v.clone() for k, v in gt.items()}, epoch=1)
         t2, p2, _ = mine(preds, gt, epoch=1)
         _check_loss_against(p1, t1, t2, p2)
+
+
+@pytest.mark.parametrize('loss_cfg', [
+    dict(panel_origin_invariant_loss=True, panel_order_inariant_loss=False),
+    dict(panel_origin_invariant_loss=True, panel_order_inariant_loss=True, order_by='placement'),
+    dict(panel_origin_invariant_loss=False, panel_order_inariant_loss=True, order_by='shape_translation'),
+    dict(panel_origin_invariant_loss=True, panel_order_inariant_loss=True, order_by='translation', epoch_with_order_matching=5),
+])
+def test_gt_order_and_origin_matching_match_unmodified_reference(loss_cfg):
+    """SURVEY.md section 8f row N1, second half (runs only where /root/reference exists): the vectorised panel-order and
+    edge-loop-origin matching against the reference's per-panel Python loops -- loss terms, quality metrics and the
+    structure-update flag, at epochs before / at / after the start of order matching."""
+    from oracle import ref_stubs
+    if not ref_stubs.reference_available():
+        pytest.skip('reference tree not present on this machine')
+    from oracle import model as om
+    from garment_pattern_estimation_b200.losses import ComposedPatternLoss
+    ref_stubs.import_reference()
+    import metrics.composed_loss as cl
+    dc, _, lc = ref_stubs.att_configs()
+    lc = dict(lc, loss_components=['shape', 'loop', 'rotation', 'translation'],
+              quality_components=['shape', 'discrete', 'rotation', 'translation'], **loss_cfg)
+    ref_loss = cl.ComposedPatternLoss(dict(dc), dict(lc))
+    mine = ComposedPatternLoss(dict(dc), dict(lc))
+    st = dc['standardize']
+    pad = -torch.tensor(st['gt_shift']['outlines']) / torch.tensor(st['gt_scale']['outlines'])
+    for seed, epoch in ((0, 0), (1, 5), (2, 9)):
+        g = torch.Generator().manual_seed(200 + seed)
+        B = 4
+        gt = om.synthetic_ground_truth(B, seed=70 + seed)
+        gt['empty_panels_mask'] = gt['num_edges'] == 0
+        live = torch.arange(14)[None, None, :] < gt['num_edges'][..., None]
+        outl = torch.where(live[..., None], gt['outlines'], pad.expand_as(gt['outlines']).clone())
+        # predictions = GT with panels shuffled per pattern and every edge loop started at a random edge, plus noise
+        perm = torch.stack([torch.randperm(23, generator=g) for _ in range(B)])
+        pred = torch.gather(outl, 1, perm[..., None, None].expand_as(outl)).clone()
+        ne = torch.gather(gt['num_edges'], 1, perm)
+        for b in range(B):
+            for p in range(23):
+                n = int(ne[b, p])
+                if n >= 3:
+                    s0 = int(torch.randint(0, n, (1,), generator=g))
+                    pred[b, p, :n] = torch.roll(pred[b, p, :n], -s0, dims=0)
+        preds = {'outlines': pred + 0.01 * torch.randn(pred.shape, generator=g),
+                 'rotations': torch.gather(gt['rotations'], 1, perm[..., None].expand(B, 23, 4)) + 0.01 * torch.randn(B, 23, 4, generator=g),
+                 'translations': torch.gather(gt['translations'], 1, perm[..., None].expand(B, 23, 3)) + 0.01 * torch.randn(B, 23, 3, generator=g)}
+        torch.manual_seed(11)
+        t1, p1, f1 = ref_loss({k: v.clone() for k, v in preds.items()}, {k: v.clone() for k, v in gt.items()}, epoch=epoch)
+        torch.manual_seed(11)
+        t2, p2, f2 = mine(preds, {k: v.clone() for k, v in gt.items()}, epoch=epoch)
+        assert bool(f1) == bool(f2), (loss_cfg, epoch)
+        _check_loss_against(p1, t1, t2, p2)
+
+
+def test_gt_matching_matches_reference_golden():
+    """Same check as above against the committed fixture (runs everywhere, including the GPU box without the reference)."""
+    from garment_pattern_estimation_b200.losses import ComposedPatternLoss
+    gold = torch.load(os.path.join(ROOT, 'tests', 'golden', 'n1_matching.pt'))
+    dc, _, _ = _att()
+    dc['standardize'] = gold['standardize']
+    for name, case in gold['cases'].items():
+        loss_obj = ComposedPatternLoss(dc, dict(case['loss_config']))
+        total, parts, flag = loss_obj(case['preds'], {k: v.clone() for k, v in case['gt'].items()}, epoch=3)
+        assert bool(flag) == case['flag'], name
+        _check_loss_against(case['parts'], case['loss'], total, parts)
