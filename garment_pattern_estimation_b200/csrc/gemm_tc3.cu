@@ -20,15 +20,22 @@
 // The one-tile-per-CTA engine (gemm_tc.cu) remains the general path (gathered operands, unaligned rows, n_out > 224, small
 // row counts); launch_nt_tc3 returns -1 when a call is not eligible.
 #include "gemm_tc_shared.cuh"
+#include <stdlib.h>
 
 namespace nt {
 
 constexpr int P3_EPI0_WARP = 4;
 constexpr int P3_MMA_WARP = 12;
 constexpr int P3_THREADS = 13 * 32;
-constexpr int P3_STAGES = 3;
-constexpr int P3_DEPTH = 6;                        // k-blocks in flight per producer thread
-constexpr int P3_SLAB = 4 * TC_M * 16;             // raw k-block: [4 chunks][128 rows][16 B]
+// TILES = row tiles that share one weight k-block stage.  1: two TMEM accumulators are double-buffered between the MMA warp and
+// the epilogue groups (tile t+1 is multiplied while tile t drains).  2: both accumulators belong to the same pass, the two
+// tiles are multiplied against the SAME weight stage (half the L2 weight traffic per row -- the binding resource, DESIGN.md
+// section 4) and drained together by the two epilogue groups while the loaders already stage the next pass.
+template <int TILES> struct P3Cfg {
+    static constexpr int STAGES = TILES == 1 ? 3 : 2;
+    static constexpr int DEPTH = TILES == 1 ? 6 : 3;               // k-blocks in flight per producer thread
+};
+constexpr int P3_SLAB = 4 * TC_M * 16;             // raw k-block of one tile: [4 chunks][128 rows][16 B]
 constexpr int P3_TW = 32 * 36;                     // floats of one per-warp transposition tile
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
@@ -38,16 +45,20 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__host__ __device__ inline size_t tc3_smem_bytes(int n_tile) {
-    return P3_STAGES * tc_stage_bytes(n_tile) + (size_t)P3_DEPTH * P3_SLAB + 8 * P3_TW * 4 + 4 * 256 * 4 + 512 * 4 + 128;
+__host__ __device__ inline size_t tc3_stage_bytes(int n_tile, int tiles) { return (size_t)tiles * 2 * TC_A_BYTES + (size_t)n_tile * 128; }
+__host__ __device__ inline size_t tc3_smem_bytes(int n_tile, int tiles = 1) {
+    const int stages = tiles == 1 ? 3 : 2, depth = tiles == 1 ? 6 : 3;
+    return stages * tc3_stage_bytes(n_tile, tiles) + (size_t)depth * tiles * P3_SLAB + 8 * P3_TW * 4 + 4 * 256 * 4 + 512 * 4 + 128;
 }
 
-template <int EPI, bool SCAT>
+template <int EPI, bool SCAT, int TILES>
 __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, const uint8_t *__restrict__ w_split, TCGeom g) {
+    constexpr int P3_STAGES = P3Cfg<TILES>::STAGES, P3_DEPTH = P3Cfg<TILES>::DEPTH;
+    constexpr int A_STAGE = TILES * 2 * TC_A_BYTES;                                // A part of a stage: [tile][hi|lo]
     extern __shared__ __align__(128) uint8_t smem[];
-    const size_t stage_bytes = tc_stage_bytes(g.n_tile);
+    const size_t stage_bytes = tc3_stage_bytes(g.n_tile, TILES);
     uint8_t *raw = smem + P3_STAGES * stage_bytes;
-    float *tw_all = reinterpret_cast<float *>(raw + P3_DEPTH * P3_SLAB);          // 8 x [32][36]
+    float *tw_all = reinterpret_cast<float *>(raw + P3_DEPTH * TILES * P3_SLAB);  // 8 x [32][36]
     float *colv = tw_all + 8 * P3_TW;                                              // [4][256]: bias | k0 | k1 | mu
     float *red = colv + 4 * 256;                                                   // [2][256] column statistics
     uint64_t *full = reinterpret_cast<uint64_t *>(red + 512);                      // [3]
@@ -58,7 +69,8 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_row_tiles = (p.rows + p.rows_per_tile - 1) / p.rows_per_tile;
-    const int my_tiles = (int)((n_row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);      // tiles blockIdx.x, +grid, ...
+    const int64_t n_passes = (n_row_tiles + TILES - 1) / TILES;                              // a pass = TILES consecutive row tiles
+    const int my_tiles = (int)((n_passes - blockIdx.x + gridDim.x - 1) / gridDim.x);         // passes blockIdx.x, +grid, ...
 
     for (int i = tid; i < 512; i += P3_THREADS) red[i] = 0.f;
     for (int i = tid; i < 256; i += P3_THREADS) {
@@ -70,7 +82,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
     }
     if (warp == P3_MMA_WARP && lane == 0) {
         for (int s = 0; s < P3_STAGES; ++s) { mbar_init(&full[s], 128 + 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TILES == 1 ? 128 : 256); }
         mbar_fence_init();
     }
     if (warp == P3_MMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -91,23 +103,38 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
         const uint32_t raw_u32 = smem_u32(raw);
         const uint32_t slot_off = (uint32_t)(jj * (TC_M * 16));
 
-        // fetch stream position (tile, k-block) -- advanced incrementally, it runs P3_DEPTH iterations ahead of consume
-        int f_it = 0, f_kb = 0;
-        int64_t f_row0 = (int64_t)blockIdx.x * p.rows_per_tile;
+        // fetch stream position (pass, k-block) -- advanced incrementally, it runs P3_DEPTH iterations ahead of consume.  The row
+        // pointers of a pass are computed once (k-block 0); per k-block only the column offset and the K-tail size change
+        // (ncu: the converter warps, not the tensor pipe or L2, set the pace of this kernel -- keep their instruction count low).
+        int f_it = 0, f_kb = 0, f_slab = 0;
+        int64_t f_row0 = (int64_t)blockIdx.x * TILES * p.rows_per_tile;           // first row of the pass being fetched
+        const float *rowp[TILES][4];
         auto issue = [&]() {
             if (f_it < total_it) {
-                const int rows_here = (int)min((int64_t)p.rows_per_tile, p.rows - f_row0);
-                const int k = (f_kb * 4 + jj) * 4;
-                const uint32_t dst0 = raw_u32 + (uint32_t)((f_it % P3_DEPTH) * P3_SLAB) + slot_off;
+                if (f_kb == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const bool live = prow[i] < rows_here && k < p.K;
-                    const uint32_t nbytes = live ? (uint32_t)min(16, (p.K - k) * 4) : 0u;
-                    const float *src = live ? p.a + (f_row0 + prow[i]) * (int64_t)p.lda + k : p.a;
-                    cp_async16(dst0 + (uint32_t)(prow[i] * 16), src, nbytes);
+                    for (int tt = 0; tt < TILES; ++tt) {
+                        const int64_t t_row0 = f_row0 + (int64_t)tt * p.rows_per_tile;
+                        const int rows_here = (int)max((int64_t)0, min((int64_t)p.rows_per_tile, p.rows - t_row0));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            rowp[tt][i] = prow[i] < rows_here ? p.a + (t_row0 + prow[i]) * (int64_t)p.lda : nullptr;
+                    }
+                }
+                const int k = (f_kb * 4 + jj) * 4;
+                const uint32_t kbytes = k < p.K ? (uint32_t)min(16, (p.K - k) * 4) : 0u;
+#pragma unroll
+                for (int tt = 0; tt < TILES; ++tt) {
+                    const uint32_t dst0 = raw_u32 + (uint32_t)((f_slab * TILES + tt) * P3_SLAB) + slot_off;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float *rp = rowp[tt][i];
+                        cp_async16(dst0 + (uint32_t)(prow[i] * 16), rp ? rp + k : p.a, rp ? kbytes : 0u);
+                    }
                 }
                 ++f_it;
-                if (++f_kb == g.num_kb) { f_kb = 0; f_row0 += (int64_t)gridDim.x * p.rows_per_tile; }
+                if (++f_slab == P3_DEPTH) f_slab = 0;
+                if (++f_kb == g.num_kb) { f_kb = 0; f_row0 += (int64_t)gridDim.x * TILES * p.rows_per_tile; }
             }
             cp_async_commit();                       // exactly one group per call, possibly empty
         };
@@ -119,20 +146,26 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
         for (int it = 0; it < total_it; ++it) {
             cp_async_wait<P3_DEPTH - 1>();           // this thread's chunks of k-block `it` have landed
             mbar_wait(&empty[s], (use & 1) ^ 1);
-            uint8_t *a_hi = smem + s * stage_bytes, *a_lo = a_hi + TC_A_BYTES, *b_all = a_lo + TC_A_BYTES;
-            if (tid == 0) {
-                const uint32_t bytes = (uint32_t)g.n_tile * 128u;
-                mbar_arrive_expect_tx(&full[s], bytes);
-                bulk_g2s(b_all, w_split + (size_t)kb * bytes, bytes, &full[s]);
+            uint8_t *stage = smem + s * stage_bytes, *b_all = stage + A_STAGE;
+            {
+                // weight k-block: one bulk copy per producer warp (4 concurrent requests of n_tile*32 bytes; n_tile % 16 == 0 keeps
+                // them 16-byte granular).  tid 0 registers the whole transaction; the others only add their complete_tx.
+                const uint32_t bytes = (uint32_t)g.n_tile * 128u, part = bytes >> 2;
+                if (tid == 0) mbar_arrive_expect_tx(&full[s], bytes);
+                if (lane == 0) bulk_g2s(b_all + warp * part, w_split + (size_t)kb * bytes + warp * part, part, &full[s]);
             }
-            const uint8_t *rs = raw + slab * P3_SLAB + slot_off;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 x = *reinterpret_cast<const float4 *>(rs + prow[i] * 16);
-                uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-                split_tf32(x.x, h0, l0); split_tf32(x.y, h1, l1); split_tf32(x.z, h2, l2); split_tf32(x.w, h3, l3);
-                *reinterpret_cast<uint4 *>(a_hi + slot_off + prow[i] * 16) = make_uint4(h0, h1, h2, h3);
-                *reinterpret_cast<uint4 *>(a_lo + slot_off + prow[i] * 16) = make_uint4(l0, l1, l2, l3);
+            for (int tt = 0; tt < TILES; ++tt) {
+                uint8_t *a_hi = stage + tt * 2 * TC_A_BYTES, *a_lo = a_hi + TC_A_BYTES;
+                const uint8_t *rs = raw + (slab * TILES + tt) * P3_SLAB + slot_off;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 x = *reinterpret_cast<const float4 *>(rs + prow[i] * 16);
+                    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                    split_tf32(x.x, h0, l0); split_tf32(x.y, h1, l1); split_tf32(x.z, h2, l2); split_tf32(x.w, h3, l3);
+                    *reinterpret_cast<uint4 *>(a_hi + slot_off + prow[i] * 16) = make_uint4(h0, h1, h2, h3);
+                    *reinterpret_cast<uint4 *>(a_lo + slot_off + prow[i] * 16) = make_uint4(l0, l1, l2, l3);
+                }
             }
             fence_proxy_async();                     // generic-proxy smem writes -> visible to the tensor core
             mbar_arrive(&full[s]);
@@ -149,29 +182,34 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
             const uint32_t lbo_a = TC_M * 16, lbo_b = (uint32_t)g.n_tile * 16, sbo = 128;
             int s = 0, use = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
-                const int as = ti & 1, ause = ti >> 1;
-                mbar_wait(&tmem_empty[as], (ause & 1) ^ 1);         // the epilogue group has drained this accumulator
+                // TILES == 1: accumulator ti & 1, handed over per tile; TILES == 2: both accumulators, handed over per pass
+                const int bar = TILES == 1 ? (ti & 1) : 0, ause = TILES == 1 ? (ti >> 1) : ti;
+                mbar_wait(&tmem_empty[bar], (ause & 1) ^ 1);        // the epilogue group(s) have drained the accumulator(s)
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(as * 256);
                 for (int kb = 0; kb < g.num_kb; ++kb) {
                     mbar_wait(&full[s], use & 1);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + s * stage_bytes), a_lo = a_hi + TC_A_BYTES;
-                    const uint32_t b_hi = a_lo + TC_A_BYTES, b_lo = b_hi + 4 * lbo_b;
+                    const uint32_t stage = smem_u32(smem + s * stage_bytes);
+                    const uint32_t b_hi = stage + A_STAGE, b_lo = b_hi + 4 * lbo_b;
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const uint64_t dah = make_smem_desc(a_hi + kk * 2 * lbo_a, lbo_a, sbo);
-                        const uint64_t dal = make_smem_desc(a_lo + kk * 2 * lbo_a, lbo_a, sbo);
-                        const uint64_t dbh = make_smem_desc(b_hi + kk * 2 * lbo_b, lbo_b, sbo);
-                        const uint64_t dbl = make_smem_desc(b_lo + kk * 2 * lbo_b, lbo_b, sbo);
-                        umma_tf32(d, dah, dbh, idesc, (kb | kk) ? 1u : 0u);
-                        umma_tf32(d, dah, dbl, idesc, 1u);
-                        umma_tf32(d, dal, dbh, idesc, 1u);
+                    for (int tt = 0; tt < TILES; ++tt) {
+                        const uint32_t d = tmem_base + (uint32_t)((TILES == 1 ? (ti & 1) : tt) * 256);
+                        const uint32_t a_hi = stage + tt * 2 * TC_A_BYTES, a_lo = a_hi + TC_A_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint64_t dah = make_smem_desc(a_hi + kk * 2 * lbo_a, lbo_a, sbo);
+                            const uint64_t dal = make_smem_desc(a_lo + kk * 2 * lbo_a, lbo_a, sbo);
+                            const uint64_t dbh = make_smem_desc(b_hi + kk * 2 * lbo_b, lbo_b, sbo);
+                            const uint64_t dbl = make_smem_desc(b_lo + kk * 2 * lbo_b, lbo_b, sbo);
+                            umma_tf32(d, dah, dbh, idesc, (kb | kk) ? 1u : 0u);
+                            umma_tf32(d, dah, dbl, idesc, 1u);
+                            umma_tf32(d, dal, dbh, idesc, 1u);
+                        }
                     }
                     umma_commit(&empty[s]);            // stage reusable once these MMAs have read it
                     if (++s == P3_STAGES) { s = 0; ++use; }
                 }
-                umma_commit(&tmem_full[as]);           // accumulator complete -> epilogue group `as`
+                umma_commit(&tmem_full[bar]);          // accumulator(s) complete -> epilogue
             }
         }
     } else {
@@ -183,10 +221,12 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
         float *tw4 = twg + quad * P3_TW;
         const int sub = lane >> 3, q4 = (lane & 7) * 4;
         const int n_chunks = (g.n_tile + 31) / 32;
-        for (int ti = grp; ti < my_tiles; ti += 2) {
-            const int as = grp, ause = ti >> 1;
-            const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * p.rows_per_tile;
-            const int rows_here = (int)min((int64_t)p.rows_per_tile, p.rows - row0);
+        for (int ti = (TILES == 1 ? grp : 0); ti < my_tiles; ti += (TILES == 1 ? 2 : 1)) {
+            // group `grp` always drains accumulator `grp`: TILES == 1 -> every other tile; TILES == 2 -> tile `grp` of every pass
+            const int as = grp, bar = TILES == 1 ? grp : 0, ause = TILES == 1 ? (ti >> 1) : ti;
+            const int64_t pass = (int64_t)blockIdx.x + (int64_t)ti * gridDim.x;
+            const int64_t row0 = (pass * TILES + (TILES == 1 ? 0 : grp)) * p.rows_per_tile;
+            const int rows_here = (int)max((int64_t)0, min((int64_t)p.rows_per_tile, p.rows - row0));   // 0: phantom tile
             const bool valid = et < rows_here;
             const int64_t wrow0 = row0 + quad * 32;                  // first row of this warp
             const int wrows = max(0, min(32, rows_here - quad * 32));
@@ -226,7 +266,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
                     }
                 }
             }
-            mbar_wait(&tmem_full[as], ause & 1);
+            mbar_wait(&tmem_full[bar], ause & 1);
             tc_fence_after();
             for (int ch = 0; ch < n_chunks; ++ch) {
                 const int c0 = ch * 32;
@@ -370,7 +410,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
             }
             // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
             tc_fence_before();
-            mbar_arrive(&tmem_empty[as]);
+            mbar_arrive(&tmem_empty[bar]);
         }
         // flush the per-CTA column statistics once (they accumulate over all of this CTA's tiles, both groups)
         if (EPI != NT_EPI_BIAS) {
@@ -390,19 +430,40 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
     if (warp == P3_MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
-template <int EPI, bool SCAT = false>
-static int launch_tc3(const NTParams &p, const void *w_split, const TCGeom &g, int sms, cudaStream_t st) {
-    const size_t smem = tc3_smem_bytes(g.n_tile);
+template <int EPI, bool SCAT, int TILES>
+static int launch_tc3_t(const NTParams &p, const void *w_split, const TCGeom &g, int sms, cudaStream_t st) {
+    const size_t smem = tc3_smem_bytes(g.n_tile, TILES);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc3_kernel<EPI, SCAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc3_kernel<EPI, SCAT, TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail("nt_gemm_nt(tc3): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     const int64_t n_row_tiles = (p.rows + p.rows_per_tile - 1) / p.rows_per_tile;
-    const int ctas = (int)(n_row_tiles < sms ? n_row_tiles : sms);
-    gemm_nt_tc3_kernel<EPI, SCAT><<<ctas, P3_THREADS, smem, st>>>(p, reinterpret_cast<const uint8_t *>(w_split), g);
+    const int64_t n_passes = (n_row_tiles + TILES - 1) / TILES;
+    const int ctas = (int)(n_passes < sms ? n_passes : sms);
+    gemm_nt_tc3_kernel<EPI, SCAT, TILES><<<ctas, P3_THREADS, smem, st>>>(p, reinterpret_cast<const uint8_t *>(w_split), g);
     return check_launch("nt_gemm_nt(tc3)");
+}
+
+// tiles per weight stage: set by nt_set_nt_engine (3 -> 1, 4 -> 2), else the developer knob NT_TC3_TILES, else the default
+constexpr int TC3_DEFAULT_TILES = 1;
+static std::atomic<int> g_tc3_tiles{0};
+void tc3_set_tiles(int tiles) { g_tc3_tiles.store(tiles, std::memory_order_relaxed); }
+static int tc3_tiles() {
+    int tiles = g_tc3_tiles.load(std::memory_order_relaxed);
+    if (tiles == 0) {
+        const char *v = getenv("NT_TC3_TILES");
+        tiles = v ? (atoi(v) == 2 ? 2 : 1) : TC3_DEFAULT_TILES;
+        g_tc3_tiles.store(tiles, std::memory_order_relaxed);
+    }
+    return tiles;
+}
+
+template <int EPI, bool SCAT = false>
+static int launch_tc3(const NTParams &p, const void *w_split, const TCGeom &g, int sms, cudaStream_t st) {
+    if (tc3_tiles() == 2 && tc3_smem_bytes(g.n_tile, 2) <= 227 * 1024) return launch_tc3_t<EPI, SCAT, 2>(p, w_split, g, sms, st);
+    return launch_tc3_t<EPI, SCAT, 1>(p, w_split, g, sms, st);
 }
 
 bool tc3_eligible(const NTParams &p, int producer, int epilogue) {

@@ -73,5 +73,6 @@ int launch_nt_tc2(const NTParams &p, int producer, int epilogue, const void *w_s
 // streaming engine entry (gemm_tc3.cu); returns -1 when the call is not eligible (caller falls back to gemm_tc.cu)
 int launch_nt_tc3(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st);
 bool tc3_eligible(const NTParams &p, int producer, int epilogue);
+void tc3_set_tiles(int tiles);      // 0 = default (NT_TC3_TILES or built-in), 1, 2 = row tiles per weight stage
 
 }  // namespace nt

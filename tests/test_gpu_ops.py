@@ -420,13 +420,19 @@ def test_streaming_engine_matches_one_tile_engine_and_float64(ops, cuda_device, 
         aux[:, :n_out] = torch.relu(torch.randn(rows, n_out, generator=g)).to(dev)
     got = {}
     try:
-        for engine in (1, 3):
+        for engine in (1, 3, 4):
             _set_engine(engine)
             got[engine] = _run_gemm_nt(ops, epi, a, w, K, n_out, aux=aux)
             torch.cuda.synchronize()
     finally:
         _set_engine(0)
     one, stream = got[1], got[3]
+    for key in ('out', 'vmax', 'vmin', 'imax', 'imin'):       # two row tiles per weight stage: same per-tile arithmetic
+        if key in one:
+            assert torch.equal(one[key], got[4][key]), key + ' (two tiles per stage)'
+    for key in ('stats', 'colsum'):
+        if key in one:
+            assert rel_err(got[4][key], one[key]) < 1e-5, key + ' (two tiles per stage)'
     # same operand split, same MMA order: element-wise results are bit-identical; the column statistics are accumulated
     # with atomics in a different order
     for key in ('out', 'vmax', 'vmin', 'imax', 'imin'):
@@ -456,7 +462,7 @@ def test_streaming_engine_matches_one_tile_engine_and_float64(ops, cuda_device, 
     assert torch.isnan(a[:, K:]).all() and torch.isfinite(stream['out']).all()
 
 
-@pytest.mark.parametrize('engine', [0, 3])
+@pytest.mark.parametrize('engine', [0, 3, 4])
 def test_edgeconv_large_clouds_through_the_streaming_engine(ops, cuda_device, engine):
     """EdgeConv layer-2 shape (C = 150, 200-200-150, k = 5) at 4 x 4096 points: 81 920 edge rows = 640 row tiles, i.e. several
     tiles per persistent CTA, forward + backward against plain PyTorch."""
