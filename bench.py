@@ -354,9 +354,9 @@ def main():
             'traffic_source': 'profiles/dominant_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the '
                               'launches of the group in one eager step)',
             'note': 'algorithmic bytes = fp32 operand rows read once + result rows written once + weights; the same group '
-                    'reaches {:.1f} TFLOP/s of useful fp32-equivalent math (see roofline_tensor).  What caps the fraction is '
-                    'L2 throughput: every 128-row tile re-streams the TF32 hi/lo weight planes (346 KB) from L2, 3.4x the '
-                    'tile\'s own HBM bytes (DESIGN.md section 4)'.format(
+                    'reaches {:.1f} TFLOP/s of useful fp32-equivalent math (see roofline_tensor).  No unit is saturated (ncu); the '
+                    'cycle trace in DESIGN.md section 4 shows this kernel is bound by its epilogue (42 k cycles to drain a '
+                    '128-row tile per group: latency of the aux-row loads) and the forward GEMMs by their converter warps'.format(
                         gemm_flops.get(dom, 0.0) / (dom_ms * 1e-3) / 1e12),
         }
 

@@ -31,9 +31,13 @@ constexpr int P3_THREADS = 13 * 32;
 // the epilogue groups (tile t+1 is multiplied while tile t drains).  2: both accumulators belong to the same pass, the two
 // tiles are multiplied against the SAME weight stage (half the L2 weight traffic per row -- the binding resource, DESIGN.md
 // section 4) and drained together by the two epilogue groups while the loaders already stage the next pass.
-template <int TILES> struct P3Cfg {
-    static constexpr int STAGES = TILES == 1 ? 3 : 2;
-    static constexpr int DEPTH = TILES == 1 ? 6 : 3;               // k-blocks in flight per producer thread
+// CFG 1: one tile per stage, 3 stages, 6 raw k-blocks in flight (48 KB of A per SM)
+// CFG 2: two tiles per stage, 2 stages, 3 raw k-blocks (x2 tiles) in flight (48 KB)
+// CFG 3: one tile per stage, 2 stages, 12 raw k-blocks in flight (96 KB)
+template <int CFG> struct P3Cfg {
+    static constexpr int TILES = CFG == 2 ? 2 : 1;
+    static constexpr int STAGES = CFG == 1 ? 3 : 2;
+    static constexpr int DEPTH = CFG == 1 ? 6 : (CFG == 2 ? 3 : 12);   // k-blocks in flight per producer thread
 };
 constexpr int P3_SLAB = 4 * TC_M * 16;             // raw k-block of one tile: [4 chunks][128 rows][16 B]
 constexpr int P3_TW = 32 * 36;                     // floats of one per-warp transposition tile
@@ -45,15 +49,30 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- optional cycle trace (built with -DNT_TC3_TRACE; developer tool, see tools/tc3_trace.py): per CTA, cycles spent by one
+// representative thread of every role in each of its phases, accumulated over the kernel
+#ifdef NT_TC3_TRACE
+__device__ unsigned long long g_tc3_trace[256][16];
+#define TRACE_T0() long long _t0 = clock64()
+#define TRACE_ADD(slot) do { long long _t1 = clock64(); _acc[slot] += (unsigned long long)(_t1 - _t0); _t0 = _t1; } while (0)
+#define TRACE_DECL() unsigned long long _acc[16] = {0}
+#define TRACE_FLUSH(lo, hi) do { for (int _i = lo; _i < hi; ++_i) g_tc3_trace[blockIdx.x][_i] = _acc[_i]; } while (0)
+#else
+#define TRACE_T0()
+#define TRACE_ADD(slot)
+#define TRACE_DECL()
+#define TRACE_FLUSH(lo, hi)
+#endif
+
 __host__ __device__ inline size_t tc3_stage_bytes(int n_tile, int tiles) { return (size_t)tiles * 2 * TC_A_BYTES + (size_t)n_tile * 128; }
-__host__ __device__ inline size_t tc3_smem_bytes(int n_tile, int tiles = 1) {
-    const int stages = tiles == 1 ? 3 : 2, depth = tiles == 1 ? 6 : 3;
+__host__ __device__ inline size_t tc3_smem_bytes(int n_tile, int cfg = 1) {
+    const int tiles = cfg == 2 ? 2 : 1, stages = cfg == 1 ? 3 : 2, depth = cfg == 1 ? 6 : (cfg == 2 ? 3 : 12);
     return stages * tc3_stage_bytes(n_tile, tiles) + (size_t)depth * tiles * P3_SLAB + 8 * P3_TW * 4 + 4 * 256 * 4 + 512 * 4 + 128;
 }
 
-template <int EPI, bool SCAT, int TILES>
+template <int EPI, bool SCAT, int CFG>
 __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, const uint8_t *__restrict__ w_split, TCGeom g) {
-    constexpr int P3_STAGES = P3Cfg<TILES>::STAGES, P3_DEPTH = P3Cfg<TILES>::DEPTH;
+    constexpr int TILES = P3Cfg<CFG>::TILES, P3_STAGES = P3Cfg<CFG>::STAGES, P3_DEPTH = P3Cfg<CFG>::DEPTH;
     constexpr int A_STAGE = TILES * 2 * TC_A_BYTES;                                // A part of a stage: [tile][hi|lo]
     extern __shared__ __align__(128) uint8_t smem[];
     const size_t stage_bytes = tc3_stage_bytes(g.n_tile, TILES);
@@ -142,10 +161,14 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
         for (int d = 0; d < P3_DEPTH; ++d) issue();
 
         int s = 0, use = 0, kb = 0, slab = 0;
+        TRACE_DECL();
+        TRACE_T0();
 #pragma unroll 1
         for (int it = 0; it < total_it; ++it) {
             cp_async_wait<P3_DEPTH - 1>();           // this thread's chunks of k-block `it` have landed
+            TRACE_ADD(0);
             mbar_wait(&empty[s], (use & 1) ^ 1);
+            TRACE_ADD(1);
             uint8_t *stage = smem + s * stage_bytes, *b_all = stage + A_STAGE;
             {
                 // weight k-block: one bulk copy per producer warp (4 concurrent requests of n_tile*32 bytes; n_tile % 16 == 0 keeps
@@ -169,26 +192,33 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
             }
             fence_proxy_async();                     // generic-proxy smem writes -> visible to the tensor core
             mbar_arrive(&full[s]);
+            TRACE_ADD(2);
             issue();                                 // refill the raw slab this thread has just read
+            TRACE_ADD(3);
             if (++s == P3_STAGES) { s = 0; ++use; }
             if (++kb == g.num_kb) kb = 0;
             if (++slab == P3_DEPTH) slab = 0;
         }
         cp_async_wait<0>();
+        if (tid == 0) TRACE_FLUSH(0, 4);
     } else if (warp == P3_MMA_WARP) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TC_M, (uint32_t)g.n_tile, 0, 0);
             const uint32_t lbo_a = TC_M * 16, lbo_b = (uint32_t)g.n_tile * 16, sbo = 128;
             int s = 0, use = 0;
+            TRACE_DECL();
+            TRACE_T0();
             for (int ti = 0; ti < my_tiles; ++ti) {
                 // TILES == 1: accumulator ti & 1, handed over per tile; TILES == 2: both accumulators, handed over per pass
                 const int bar = TILES == 1 ? (ti & 1) : 0, ause = TILES == 1 ? (ti >> 1) : ti;
                 mbar_wait(&tmem_empty[bar], (ause & 1) ^ 1);        // the epilogue group(s) have drained the accumulator(s)
                 tc_fence_after();
+                TRACE_ADD(4);
                 for (int kb = 0; kb < g.num_kb; ++kb) {
                     mbar_wait(&full[s], use & 1);
                     tc_fence_after();
+                    TRACE_ADD(5);
                     const uint32_t stage = smem_u32(smem + s * stage_bytes);
                     const uint32_t b_hi = stage + A_STAGE, b_lo = b_hi + 4 * lbo_b;
 #pragma unroll
@@ -208,9 +238,11 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
                     }
                     umma_commit(&empty[s]);            // stage reusable once these MMAs have read it
                     if (++s == P3_STAGES) { s = 0; ++use; }
+                    TRACE_ADD(6);
                 }
                 umma_commit(&tmem_full[bar]);          // accumulator(s) complete -> epilogue
             }
+            TRACE_FLUSH(4, 7);
         }
     } else {
         // =========================== epilogue groups (thread = row of the tile, TMEM lane = row) ===========================
@@ -221,6 +253,8 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
         float *tw4 = twg + quad * P3_TW;
         const int sub = lane >> 3, q4 = (lane & 7) * 4;
         const int n_chunks = (g.n_tile + 31) / 32;
+        TRACE_DECL();
+        TRACE_T0();
         for (int ti = (TILES == 1 ? grp : 0); ti < my_tiles; ti += (TILES == 1 ? 2 : 1)) {
             // group `grp` always drains accumulator `grp`: TILES == 1 -> every other tile; TILES == 2 -> tile `grp` of every pass
             const int as = grp, bar = TILES == 1 ? grp : 0, ause = TILES == 1 ? (ti >> 1) : ti;
@@ -266,8 +300,10 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
                     }
                 }
             }
+            TRACE_ADD(9 + grp * 3);                                  // tile prologue (aux prefetch, index loads)
             mbar_wait(&tmem_full[bar], ause & 1);
             tc_fence_after();
+            TRACE_ADD(7 + grp * 3);                                  // waiting for the accumulator
             for (int ch = 0; ch < n_chunks; ++ch) {
                 const int c0 = ch * 32;
                 const int nv = min(32, p.n_out - c0);                // valid columns of this chunk (>= 1)
@@ -411,7 +447,9 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
             // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
             tc_fence_before();
             mbar_arrive(&tmem_empty[bar]);
+            TRACE_ADD(8 + grp * 3);                                  // draining
         }
+        if (et == 0) TRACE_FLUSH(7 + grp * 3, 10 + grp * 3);
         // flush the per-CTA column statistics once (they accumulate over all of this CTA's tiles, both groups)
         if (EPI != NT_EPI_BIAS) {
             asm volatile("bar.sync 3, 256;" ::: "memory");
@@ -430,19 +468,20 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
     if (warp == P3_MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
-template <int EPI, bool SCAT, int TILES>
+template <int EPI, bool SCAT, int CFG>
 static int launch_tc3_t(const NTParams &p, const void *w_split, const TCGeom &g, int sms, cudaStream_t st) {
-    const size_t smem = tc3_smem_bytes(g.n_tile, TILES);
+    constexpr int TILES = P3Cfg<CFG>::TILES;
+    const size_t smem = tc3_smem_bytes(g.n_tile, CFG);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc3_kernel<EPI, SCAT, TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc3_kernel<EPI, SCAT, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return fail("nt_gemm_nt(tc3): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     const int64_t n_row_tiles = (p.rows + p.rows_per_tile - 1) / p.rows_per_tile;
     const int64_t n_passes = (n_row_tiles + TILES - 1) / TILES;
     const int ctas = (int)(n_passes < sms ? n_passes : sms);
-    gemm_nt_tc3_kernel<EPI, SCAT, TILES><<<ctas, P3_THREADS, smem, st>>>(p, reinterpret_cast<const uint8_t *>(w_split), g);
+    gemm_nt_tc3_kernel<EPI, SCAT, CFG><<<ctas, P3_THREADS, smem, st>>>(p, reinterpret_cast<const uint8_t *>(w_split), g);
     return check_launch("nt_gemm_nt(tc3)");
 }
 
@@ -454,7 +493,7 @@ static int tc3_tiles() {
     int tiles = g_tc3_tiles.load(std::memory_order_relaxed);
     if (tiles == 0) {
         const char *v = getenv("NT_TC3_TILES");
-        tiles = v ? (atoi(v) == 2 ? 2 : 1) : TC3_DEFAULT_TILES;
+        tiles = v ? ((atoi(v) == 2 || atoi(v) == 3) ? atoi(v) : 1) : TC3_DEFAULT_TILES;
         g_tc3_tiles.store(tiles, std::memory_order_relaxed);
     }
     return tiles;
@@ -462,7 +501,9 @@ static int tc3_tiles() {
 
 template <int EPI, bool SCAT = false>
 static int launch_tc3(const NTParams &p, const void *w_split, const TCGeom &g, int sms, cudaStream_t st) {
-    if (tc3_tiles() == 2 && tc3_smem_bytes(g.n_tile, 2) <= 227 * 1024) return launch_tc3_t<EPI, SCAT, 2>(p, w_split, g, sms, st);
+    const int cfg = tc3_tiles();       // configuration index (see P3Cfg)
+    if (cfg == 2 && tc3_smem_bytes(g.n_tile, 2) <= 227 * 1024) return launch_tc3_t<EPI, SCAT, 2>(p, w_split, g, sms, st);
+    if (cfg == 3 && tc3_smem_bytes(g.n_tile, 3) <= 227 * 1024) return launch_tc3_t<EPI, SCAT, 3>(p, w_split, g, sms, st);
     return launch_tc3_t<EPI, SCAT, 1>(p, w_split, g, sms, st);
 }
 
@@ -504,3 +545,9 @@ int launch_nt_tc3(const NTParams &p, int producer, int epilogue, const void *w_s
 }
 
 }  // namespace nt
+
+#ifdef NT_TC3_TRACE
+extern "C" int nt_debug_tc3_trace(unsigned long long *host_out) {      // [256][16]
+    return cudaMemcpyFromSymbol(host_out, nt::g_tc3_trace, sizeof(nt::g_tc3_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif
