@@ -48,6 +48,12 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// Bulk prefetch of a contiguous global range into L2.  The kernel visits every operand row in 64..128-byte pieces spread over a
+// whole tile period (one piece per k-block / per 32-column chunk), which DRAM serves with poor row-buffer locality; the rows of a
+// tile are contiguous in memory, so one sequential prefetch per 32-row slab turns the piecewise visits into L2 hits.
+__device__ __forceinline__ void l2_prefetch(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 
 // ---- optional cycle trace (built with -DNT_TC3_TRACE; developer tool, see tools/tc3_trace.py): per CTA, cycles spent by one
 // representative thread of every role in each of its phases, accumulated over the kernel
@@ -138,6 +144,9 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             rowp[tt][i] = prow[i] < rows_here ? p.a + (t_row0 + prow[i]) * (int64_t)p.lda : nullptr;
+                        const int slab_rows = min(32, rows_here - warp * 32);
+                        if (lane == 0 && slab_rows > 0)
+                            l2_prefetch(p.a + (t_row0 + warp * 32) * (int64_t)p.lda, (uint32_t)slab_rows * (uint32_t)p.lda * 4u);
                     }
                 }
                 const int k = (f_kb * 4 + jj) * 4;
@@ -286,7 +295,12 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
                     ld[m] = a;
                 }
             };
-            if (EPI == NT_EPI_BNRELU_BWD) load_aux(0);               // does not depend on the accumulator
+            if (EPI == NT_EPI_BNRELU_BWD) {
+                // L2 prefetch of this warp's aux slab of the CURRENT tile (prefetching the group's next tile instead -- a whole tile
+                // period ahead -- measured slower: 1.43 vs 1.32 ms per step for the group; the lines do not survive in L2)
+                if (lane == 0 && wrows > 0) l2_prefetch(auxw, (uint32_t)wrows * (uint32_t)p.ldaux * 4u);
+                load_aux(0);                                         // does not depend on the accumulator
+            }
             // fused edge scatter: global neighbour row of each of this lane's 8 rows (4m + sub) of the warp slab
             int jrow[SCAT ? 8 : 1];
             if (SCAT) {
