@@ -13,7 +13,7 @@ EPI = {0: 'bias', 1: 'relu_stats', 2: 'relu_maxmin', 3: 'bnrelu_bwd'}
 
 
 def group_of(name):
-    m = re.search(r'gemm_nt_tc3_kernel<(?:\(int\))?(\d)>', name)
+    m = re.search(r'gemm_nt_tc3_kernel<(?:\(int\))?(\d)', name)
     if m:
         return 'nt_gemm_nt[%s,plain]' % EPI[int(m.group(1))]
     m = re.search(r'gemm_nt_tc2?_kernel<(?:\(int\))?(\d), (?:\(int\))?(\d)', name)
