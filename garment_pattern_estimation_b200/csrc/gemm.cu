@@ -328,8 +328,8 @@ extern "C" int nt_gemm_nt_scatter_supported(const nt_gemm_args *g) {
 extern "C" int nt_gemm_nt(const nt_gemm_args *g, void *stream) {
     using namespace nt;
     NTParams p;
+    if (g && g->rows == 0 && g->K >= 1 && g->n_out >= 1) return 0;       // nothing to do (operand pointers may be NULL)
     if (int rc = nt_fill_params(g, p)) return rc;
-    if (g->rows == 0) return 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool tc = g->w_split != nullptr;
     switch (g->epilogue) {
