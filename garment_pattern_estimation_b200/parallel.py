@@ -130,7 +130,9 @@ class GraphedTrainStep:
     The reference's loop (nn/trainer.py:92-103) is the eager equivalent; numerics are identical because the graph replays
     exactly the kernels the eager step launches.  Requirements of CUDA-graph capture:
       * fixed batch shape (the shape of ``example_x`` / ``example_gt``); other shapes fall back to ``eager_step``;
-      * an optimizer whose step is capturable (``torch.optim.Adam(..., capturable=True)``);
+      * an optimizer whose step is capturable (``torch.optim.Adam(..., capturable=True)``); a learning-rate schedule (the
+        reference uses OneCycleLR, nn/trainer.py:73-80) must then act on a TENSOR learning rate
+        (``lr=torch.tensor(2e-3, device=...)``), because a Python-float lr is baked into the captured kernels;
       * ``wrapper`` is a FlatDataParallel (its flat gradient buffer keeps every ``.grad`` at a static address).
     With more than one rank the NCCL all-reduce and the optimizer step stay OUTSIDE the graph (``capture_update=False`` is
     forced), i.e. the graph holds forward + loss + backward.
