@@ -7,10 +7,12 @@ Layout
   _lib.py, build.py           ctypes loader / nvcc build recipe (no CPU fallback: a missing library is an error)
   ops.py                      operator layer (autograd Functions over the C ABI)
   net_blocks.py, nets.py      drop-in mirrors of the reference's plugin surface (same names / state_dict keys)
-  losses.py                   the four loss terms active in the shipped attention config
-  parallel.py                 one-process-per-GPU data-parallel wrapper (flat-buffer NCCL allreduce)
+  losses.py, metrics.py       the reference's pattern loss (4 loss terms, GT order / origin matching, no-grad quality metrics) and
+                              the stitch-model loss, vectorised on the device
+  parallel.py                 one-process-per-GPU data-parallel wrapper (flat-buffer NCCL allreduce) and GraphedTrainStep
+                              (the whole training step as one CUDA graph)
 """
 from . import net_blocks, nets  # noqa: F401
 from .nets import GarmentFullPattern3D, GarmentSegmentPattern3D, StitchOnEdge3DPairs  # noqa: F401
 
-__all__ = ['net_blocks', 'nets', 'GarmentFullPattern3D', 'GarmentSegmentPattern3D']
+__all__ = ['net_blocks', 'nets', 'GarmentFullPattern3D', 'GarmentSegmentPattern3D', 'StitchOnEdge3DPairs']

@@ -17,6 +17,11 @@
 //               coalesced 16-byte accesses exchanged with the thread-per-row TMEM layout through a 32 x 36 transposition
 //               tile per warp, and the BNRELU_BWD aux rows of chunk c+1 are loaded while chunk c is processed.
 //
+// The rows of a tile are visited in 64..128-byte pieces over a whole tile period, so every 32-row slab of A (and of the aux
+// operand) is also prefetched into L2 with one cp.async.bulk.prefetch when the tile starts.  Build with -DNT_TC3_TRACE for a
+// per-role cycle trace (tools/tc3_trace.py; findings in DESIGN.md section 4: the forward GEMMs are bound by the converter warps,
+// BNRELU_BWD by the epilogue).
+//
 // The one-tile-per-CTA engine (gemm_tc.cu) remains the general path (gathered operands, unaligned rows, n_out > 224, small
 // row counts); launch_nt_tc3 returns -1 when a call is not eligible.
 #include "gemm_tc_shared.cuh"
