@@ -253,3 +253,29 @@ def test_stitch_loss_and_quality_metrics_match_reference_golden(golden_dir):
             assert abs(float(parts[k]) - float(want)) <= 1e-6 * max(abs(float(want)), 1e-6), (case, k)
     with pytest.raises(NotImplementedError):
         ComposedLoss({}, {'loss_components': ['shape']})
+
+
+# ------------------------------------------------------------------------------------------------------------
+# specification of the LSTM decoder as GEMMs + cell updates (oracle/lstm_decomposed.py) vs torch.nn.LSTM
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('layers,R,T,H', [(3, 23, 14, 50), (2, 5, 23, 32), (1, 7, 3, 16)])
+def test_decomposed_lstm_matches_torch_lstm_forward_and_backward(layers, R, T, H):
+    from oracle import lstm_decomposed as ld
+    torch.manual_seed(layers * 100 + R)
+    dt = torch.float64
+    lstm = torch.nn.LSTM(H, H, layers, batch_first=True).to(dt)
+    x = torch.randn(R, H, dtype=dt, requires_grad=True)
+    h0, c0 = torch.randn(layers, R, H, dtype=dt) * 0.1, torch.randn(layers, R, H, dtype=dt) * 0.1
+    out, _ = lstm(x.unsqueeze(1).repeat(1, T, 1), (h0, c0))          # the reference's decoder input (net_blocks.py:388)
+    g = torch.randn_like(out)
+    out.backward(g)
+    weights = [tuple(getattr(lstm, '{}_l{}'.format(n, l)).detach() for n in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh'))
+               for l in range(layers)]
+    mine, saved = ld.lstm_forward(x.detach(), weights, h0, c0, T)     # time-major [T, R, H]
+    assert torch.allclose(mine.transpose(0, 1), out.detach(), rtol=1e-10, atol=1e-12)
+    dx, grads = ld.lstm_backward(g.transpose(0, 1).contiguous(), x.detach(), weights, saved, T)
+    assert torch.allclose(dx, x.grad, rtol=1e-9, atol=1e-12)
+    for l in range(layers):
+        for got, name in zip(grads[l], ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh')):
+            want = getattr(lstm, '{}_l{}'.format(name, l)).grad
+            assert torch.allclose(got, want, rtol=1e-9, atol=1e-12), (l, name)
