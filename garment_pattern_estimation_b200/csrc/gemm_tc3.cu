@@ -150,8 +150,10 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
                         for (int i = 0; i < 4; ++i)
                             rowp[tt][i] = prow[i] < rows_here ? p.a + (t_row0 + prow[i]) * (int64_t)p.lda : nullptr;
                         const int slab_rows = min(32, rows_here - warp * 32);
-                        if (lane == 0 && slab_rows > 0)
-                            l2_prefetch(p.a + (t_row0 + warp * 32) * (int64_t)p.lda, (uint32_t)slab_rows * (uint32_t)p.lda * 4u);
+                        if (lane == 0 && slab_rows > 0) {    // up to the last USED column of the last row (never past the operand)
+                            const uint32_t pf = (uint32_t)(((slab_rows - 1) * p.lda + p.K) * 4) & ~15u;
+                            if (pf) l2_prefetch(p.a + (t_row0 + warp * 32) * (int64_t)p.lda, pf);
+                        }
                     }
                 }
                 const int k = (f_kb * 4 + jj) * 4;
@@ -303,7 +305,10 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
             if (EPI == NT_EPI_BNRELU_BWD) {
                 // L2 prefetch of this warp's aux slab of the CURRENT tile (prefetching the group's next tile instead -- a whole tile
                 // period ahead -- measured slower: 1.43 vs 1.32 ms per step for the group; the lines do not survive in L2)
-                if (lane == 0 && wrows > 0) l2_prefetch(auxw, (uint32_t)wrows * (uint32_t)p.ldaux * 4u);
+                if (lane == 0 && wrows > 0) {
+                    const uint32_t pf = (uint32_t)(((wrows - 1) * p.ldaux + p.n_out) * 4) & ~15u;
+                    if (pf) l2_prefetch(auxw, pf);
+                }
                 load_aux(0);                                         // does not depend on the accumulator
             }
             // fused edge scatter: global neighbour row of each of this lane's 8 rows (4m + sub) of the warp slab
