@@ -408,3 +408,16 @@ def test_gt_matching_matches_reference_golden():
         total, parts, flag = loss_obj(case['preds'], {k: v.clone() for k, v in case['gt'].items()}, epoch=3)
         assert bool(flag) == case['flag'], name
         _check_loss_against(case['parts'], case['loss'], total, parts)
+
+
+def test_bench_encoder_roofline_accounting():
+    """bench.encoder_roofline: compulsory bytes of the fused encoder over the encoder kernels' time."""
+    sys.path.insert(0, ROOT)
+    import bench
+    groups = {'nt_knn[D=3]': 0.1, 'nt_gemm_nt[relu_stats,plain]': 0.5, 'nt_edge_activation': 0.4, 'nt_attn_pool_fwd': 9.0,
+              'nt_sparsemax_fwd': 9.0}
+    r = bench.encoder_roofline(groups, 2.0, 32, 2048, 6500.0)
+    assert abs(r['ms_per_step'] - 1.0) < 1e-12                      # attention-head kernels are not part of the encoder
+    assert r['compulsory_bytes_per_step'] == 3.0 * 32 * 2048 * 1812
+    assert abs(r['achieved'] - r['compulsory_bytes_per_step'] / 1e-3 / 1e9) < 1e-6
+    assert abs(r['frac'] - r['achieved'] / 6500.0) < 1e-12 and abs(r['share_of_step'] - 0.5) < 1e-12
