@@ -60,3 +60,27 @@ def test_bad_arguments_return_error_codes_not_crashes():
     assert lib.nt_sparsemax_fwd(ctypes.cast(buf, ctypes.c_void_p), 2, 33, ctypes.cast(buf, ctypes.c_void_p), None) != 0
     with pytest.raises(RuntimeError):
         _lib.check(1, 'nt_sparsemax_fwd')
+
+
+def test_empty_inputs_are_no_ops_and_new_entry_points_validate():
+    """Zero clouds / zero rows return 0 before any CUDA call (the reference's blocks accept empty batches); the engine
+    selector and the fused-scatter query validate their arguments."""
+    from garment_pattern_estimation_b200 import _lib
+    lib = _lib.load()
+    buf = (ctypes.c_float * 64)()
+    fp = ctypes.cast(buf, ctypes.c_void_p)
+    ibuf = (ctypes.c_int32 * 64)()
+    ip = ctypes.cast(ibuf, ctypes.c_void_p)
+    assert lib.nt_knn(fp, 0, 16, 3, 3, 5, ip, None, None) == 0                      # no clouds
+    assert lib.nt_attn_pool_fwd(fp, fp, 8, 0, 4, 3, 8, 1.0, fp, None) == 0
+    assert lib.nt_global_pool_fwd(fp, 8, 0, 4, 8, 0, fp, None, None) == 0
+    assert lib.nt_sparsemax_fwd(fp, 0, 23, fp, None) == 0
+    g = _lib.GemmArgs()
+    g.rows, g.K, g.n_out = 0, 4, 4
+    g.w, g.ldw = fp, 4
+    assert lib.nt_gemm_nt(ctypes.byref(g), None) == 0                                # no rows: nothing to launch
+    assert lib.nt_global_pool_fwd(fp, 8, 1, 4, 8, 7, fp, None, None) != 0           # unknown pooling mode
+    assert b'unknown mode' in lib.nt_last_error()
+    assert lib.nt_set_nt_engine(9) != 0 and lib.nt_set_nt_engine(0) == 0
+    g.rows = 10
+    assert lib.nt_gemm_nt_scatter_supported(ctypes.byref(g)) == 0                    # no scatter target requested
