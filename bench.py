@@ -32,19 +32,32 @@ FP32_LANES_PER_SM, SMS = 128, 148
 
 
 def att_configs(k):
-    from oracle import model as om       # config VALUES only (att.yaml); the oracle code is not on the measured path
-    nc = dict(om.ATT_NN_CONFIG)
+    """(data_config, nn_config, loss_config) of the attention model: the values of models/att/att.yaml."""
+    from garment_pattern_estimation_b200.configs import ATT_DATA_CONFIG, ATT_NN_CONFIG
+    nc = dict(ATT_NN_CONFIG)
     nc['k_neighbors'] = k
     lc = {'loss_components': ['shape', 'loop', 'rotation', 'translation'], 'quality_components': [],
           'loop_loss_weight': 1., 'panel_origin_invariant_loss': False, 'panel_order_inariant_loss': False}
-    return dict(om.ATT_DATA_CONFIG), nc, lc
+    return dict(ATT_DATA_CONFIG), nc, lc
+
+
+def synthetic_ground_truth(B, seed, n_panels=23, panel_len=14):
+    """Synthetic GT of SURVEY.md section 8d / A.4: N(0,1) targets, num_edges in {0, 3..14}, zero rows past num_edges."""
+    g = torch.Generator().manual_seed(seed)
+    ne = torch.randint(2, panel_len + 1, (B, n_panels), generator=g)
+    ne = torch.where(ne < 3, torch.zeros_like(ne), ne)
+    outl = torch.randn(B, n_panels, panel_len, 4, generator=g)
+    live = torch.arange(panel_len)[None, None, :] < ne[..., None]
+    outl = outl * live[..., None]
+    return {'outlines': outl, 'rotations': torch.randn(B, n_panels, 4, generator=g),
+            'translations': torch.randn(B, n_panels, 3, generator=g), 'num_edges': ne, 'num_panels': (ne > 0).sum(-1)}
 
 
 def synthetic_batch(B, N, seed):
-    """Positions ~ N(0,1) (the reference standardises its inputs, nn/data/transforms.py:35-49) + GT of SURVEY 8d."""
-    from oracle import model as om
+    """Positions ~ N(0,1) (the reference standardises its inputs, nn/data/transforms.py:35-49) + GT of SURVEY 8d.  Generated
+    here (not by the oracle): the measured arm of this benchmark never imports oracle/."""
     g = torch.Generator().manual_seed(seed)
-    return torch.randn(B, N, 3, generator=g), om.synthetic_ground_truth(B, seed=seed + 1)
+    return torch.randn(B, N, 3, generator=g), synthetic_ground_truth(B, seed=seed + 1)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -107,7 +120,7 @@ def cpu_train_steps(steps, warmup, k, threads=None):
     tp.KNN_THREADS = cores
     dc, nc, lc = att_configs(k)
     torch.manual_seed(SEED_INIT)
-    model = om.OracleSegmentPattern3D(dc, nc, lc).train()
+    model = om.OracleSegmentPattern3D(dc, nc, lc).train()          # the CPU arm is the one place that executes oracle/
     opt = torch.optim.Adam(model.parameters(), lr=2e-3)
     x, gt = synthetic_batch(CPU_SAMPLE_CLOUDS, WORKLOAD['points'], seed=1234)
     times = []

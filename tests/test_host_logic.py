@@ -421,3 +421,22 @@ def test_bench_encoder_roofline_accounting():
     assert r['compulsory_bytes_per_step'] == 3.0 * 32 * 2048 * 1812
     assert abs(r['achieved'] - r['compulsory_bytes_per_step'] / 1e-3 / 1e9) < 1e-6
     assert abs(r['frac'] - r['achieved'] / 6500.0) < 1e-12 and abs(r['share_of_step'] - 0.5) < 1e-12
+
+
+def test_package_config_values_and_bench_inputs_equal_the_oracle_copies():
+    """bench.py's measured arm and the tools take the att.yaml values and the synthetic ground truth from the package / from
+    bench.py itself (the oracle is checker-only); both copies must stay identical to the oracle's."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from garment_pattern_estimation_b200 import configs
+    from oracle import model as om
+    assert configs.ATT_NN_CONFIG == om.ATT_NN_CONFIG and configs.ATT_DATA_CONFIG == om.ATT_DATA_CONFIG
+    a, b = bench.synthetic_ground_truth(3, seed=5), om.synthetic_ground_truth(3, seed=5)
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+    gold = torch.load(os.path.join(ROOT, 'tests', 'golden', 'n1_quality.pt'))
+    for key in ('outlines', 'rotations', 'translations'):          # att.yaml:61-73
+        assert configs.ATT_STANDARDIZE['gt_shift'][key] == gold['standardize']['gt_shift'][key]
+        assert configs.ATT_STANDARDIZE['gt_scale'][key] == gold['standardize']['gt_scale'][key]
+    src = open(os.path.join(ROOT, 'bench.py')).read()
+    measured_arm = src[src.index('def main():'):]
+    assert not [ln for ln in measured_arm.splitlines() if 'import' in ln and 'oracle' in ln], 'main() must not import oracle/'

@@ -11,7 +11,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import garment_pattern_estimation_b200 as g  # noqa: E402
 from garment_pattern_estimation_b200 import net_blocks as nb  # noqa: E402
-from oracle import model as om  # noqa: E402  (config values only)
+from garment_pattern_estimation_b200 import configs as om  # noqa: E402  (config values)
 
 dev = torch.device('cuda:0')
 

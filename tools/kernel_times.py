@@ -40,7 +40,7 @@ def main():
     pair_dims = B * N * N * 150
     res['knn_d150_Tpairdims_per_s'] = pair_dims / (res['knn_d150_ms'] * 1e-3) / 1e12
 
-    from oracle import model as om
+    from garment_pattern_estimation_b200 import configs as om
     nc = dict(om.ATT_NN_CONFIG)
     nc['k_neighbors'] = k
     lc = {'loss_components': ['shape', 'loop', 'rotation', 'translation'], 'quality_components': [],
@@ -48,7 +48,8 @@ def main():
     torch.manual_seed(0)
     model = g.GarmentSegmentPattern3D(dict(om.ATT_DATA_CONFIG), nc, lc).to(dev).train()
     pos = torch.randn(B, N, 3, device=dev)
-    gt = om.synthetic_ground_truth(B, device=dev)
+    import bench
+    gt = {kk: v.to(dev) for kk, v in bench.synthetic_ground_truth(B, seed=11).items()}
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
 
     def fwd():

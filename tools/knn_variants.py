@@ -3,7 +3,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import garment_pattern_estimation_b200 as g
 from garment_pattern_estimation_b200 import ops
-from oracle import model as om
+from garment_pattern_estimation_b200 import configs as om
 dev = torch.device('cuda:0')
 B, N = 32, 2048
 lc = {'loss_components': ['shape', 'loop', 'rotation', 'translation'], 'quality_components': [], 'panel_origin_invariant_loss': False, 'panel_order_inariant_loss': False}
