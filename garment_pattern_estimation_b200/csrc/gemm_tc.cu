@@ -553,9 +553,9 @@ int launch_nt_tc(const NTParams &p, int producer, int epilogue, int precision, c
 using namespace nt;
 
 extern "C" int nt_set_nt_engine(int engine) {
-    NT_REQUIRE(engine >= 0 && engine <= 4, "nt_set_nt_engine: engine must be 0 (auto), 1, 2, 3 or 4");
-    tc3_set_tiles(engine == 4 ? 2 : (engine == 3 ? 1 : 0));
-    g_nt_engine.store(engine == 4 ? 3 : engine, std::memory_order_relaxed);
+    NT_REQUIRE(engine >= 0 && engine <= 5, "nt_set_nt_engine: engine must be 0 (auto), 1, 2, 3, 4 or 5");
+    tc3_set_tiles(engine == 5 ? 4 : (engine == 4 ? 2 : (engine == 3 ? 1 : 0)));      // streaming-engine configuration (P3Cfg)
+    g_nt_engine.store(engine >= 4 ? 3 : engine, std::memory_order_relaxed);
     return 0;
 }
 

@@ -39,10 +39,15 @@ constexpr int P3_THREADS = 13 * 32;
 // CFG 1: one tile per stage, 3 stages, 6 raw k-blocks in flight (48 KB of A per SM)
 // CFG 2: two tiles per stage, 2 stages, 3 raw k-blocks (x2 tiles) in flight (48 KB)
 // CFG 3: one tile per stage, 2 stages, 12 raw k-blocks in flight (96 KB)
+// CFG 4: (BNRELU_BWD only; EXPERIMENTAL, written after the GPU budget of round 1 was spent -- never run yet) one tile per
+//        stage, 2 stages, 3 raw k-blocks, and the aux rows of the epilogue staged through a 3-slot cp.async shared-memory ring
+//        per warp (two 32-column chunks ahead, no registers) instead of the one-chunk-ahead register prefetch: the cycle trace
+//        shows the epilogue of this GEMM waiting on exactly those loads.  The slot of chunk c doubles as its transposition tile.
 template <int CFG> struct P3Cfg {
     static constexpr int TILES = CFG == 2 ? 2 : 1;
     static constexpr int STAGES = CFG == 1 ? 3 : 2;
-    static constexpr int DEPTH = CFG == 1 ? 6 : (CFG == 2 ? 3 : 12);   // k-blocks in flight per producer thread
+    static constexpr int DEPTH = CFG == 1 ? 6 : ((CFG == 2 || CFG == 4) ? 3 : 12);   // k-blocks in flight per producer thread
+    static constexpr int TW_SLOTS = CFG == 4 ? 3 : 1;                                 // transposition tiles per epilogue warp
 };
 constexpr int P3_SLAB = 4 * TC_M * 16;             // raw k-block of one tile: [4 chunks][128 rows][16 B]
 constexpr int P3_TW = 32 * 36;                     // floats of one per-warp transposition tile
@@ -77,19 +82,23 @@ __device__ unsigned long long g_tc3_trace[256][16];
 
 __host__ __device__ inline size_t tc3_stage_bytes(int n_tile, int tiles) { return (size_t)tiles * 2 * TC_A_BYTES + (size_t)n_tile * 128; }
 __host__ __device__ inline size_t tc3_smem_bytes(int n_tile, int cfg = 1) {
-    const int tiles = cfg == 2 ? 2 : 1, stages = cfg == 1 ? 3 : 2, depth = cfg == 1 ? 6 : (cfg == 2 ? 3 : 12);
-    return stages * tc3_stage_bytes(n_tile, tiles) + (size_t)depth * tiles * P3_SLAB + 8 * P3_TW * 4 + 4 * 256 * 4 + 512 * 4 + 128;
+    const int tiles = cfg == 2 ? 2 : 1, stages = cfg == 1 ? 3 : 2, depth = cfg == 1 ? 6 : ((cfg == 2 || cfg == 4) ? 3 : 12);
+    const int tw_slots = cfg == 4 ? 3 : 1;
+    return stages * tc3_stage_bytes(n_tile, tiles) + (size_t)depth * tiles * P3_SLAB + (size_t)8 * tw_slots * P3_TW * 4 +
+           4 * 256 * 4 + 512 * 4 + 128;
 }
 
 template <int EPI, bool SCAT, int CFG>
 __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, const uint8_t *__restrict__ w_split, TCGeom g) {
     constexpr int TILES = P3Cfg<CFG>::TILES, P3_STAGES = P3Cfg<CFG>::STAGES, P3_DEPTH = P3Cfg<CFG>::DEPTH;
+    constexpr int TW_SLOTS = P3Cfg<CFG>::TW_SLOTS;
+    constexpr bool AUXRING = (CFG == 4) && (EPI == NT_EPI_BNRELU_BWD);
     constexpr int A_STAGE = TILES * 2 * TC_A_BYTES;                                // A part of a stage: [tile][hi|lo]
     extern __shared__ __align__(128) uint8_t smem[];
     const size_t stage_bytes = tc3_stage_bytes(g.n_tile, TILES);
     uint8_t *raw = smem + P3_STAGES * stage_bytes;
     float *tw_all = reinterpret_cast<float *>(raw + P3_DEPTH * TILES * P3_SLAB);  // 8 x [32][36]
-    float *colv = tw_all + 8 * P3_TW;                                              // [4][256]: bias | k0 | k1 | mu
+    float *colv = tw_all + 8 * TW_SLOTS * P3_TW;                                   // [4][256]: bias | k0 | k1 | mu
     float *red = colv + 4 * 256;                                                   // [2][256] column statistics
     uint64_t *full = reinterpret_cast<uint64_t *>(red + 512);                      // [3]
     uint64_t *empty = full + P3_STAGES;                                            // [3]
@@ -265,7 +274,8 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
         const int grp = (warp - P3_EPI0_WARP) >> 2;                // 0: warps 4-7, 1: warps 8-11
         const int quad = warp & 3;                                  // TMEM lane quadrant this warp may read
         const int et = quad * 32 + lane;                            // 0..127 inside the group = row of the tile
-        float *twg = tw_all + grp * (4 * P3_TW);                    // the group's four tiles are contiguous: row r at r*36
+        // transposition tiles: [group][slot][quad][32 x 36]; the four tiles of a (group, slot) are contiguous: row r at r*36
+        float *twg = tw_all + (grp * TW_SLOTS) * (4 * P3_TW);
         float *tw4 = twg + quad * P3_TW;
         const int sub = lane >> 3, q4 = (lane & 7) * 4;
         const int n_chunks = (g.n_tile + 31) / 32;
@@ -302,6 +312,23 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
                     ld[m] = a;
                 }
             };
+            // AUXRING: chunk `ch` of the aux rows -> slot ch % 3 of this warp's ring (layout of the transposition tile: row 4m+sub,
+            // columns q4..q4+3), zero-filled outside the tile / the valid columns; exactly one cp.async group per call
+            auto issue_aux = [&](int ch) {
+                if (ch < n_chunks) {
+                    const int cg = ch * 32, nv = min(32, p.n_out - cg);
+                    const uint32_t dst0 = smem_u32(tw_all + ((grp * TW_SLOTS + ch % TW_SLOTS) * 4 + quad) * P3_TW);
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        const int rr = 4 * m + sub;
+                        const bool live = rr < wrows && q4 < nv;
+                        const uint32_t nbytes = live ? (uint32_t)min(16, (nv - q4) * 4) : 0u;
+                        const float *src = live ? auxw + (int64_t)rr * p.ldaux + cg + q4 : p.aux;
+                        cp_async16(dst0 + (uint32_t)((rr * 36 + q4) * 4), src, nbytes);
+                    }
+                }
+                cp_async_commit();
+            };
             if (EPI == NT_EPI_BNRELU_BWD) {
                 // L2 prefetch of this warp's aux slab of the CURRENT tile (prefetching the group's next tile instead -- a whole tile
                 // period ahead -- measured slower: 1.43 vs 1.32 ms per step for the group; the lines do not survive in L2)
@@ -309,7 +336,8 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
                     const uint32_t pf = (uint32_t)(((wrows - 1) * p.ldaux + p.n_out) * 4) & ~15u;
                     if (pf) l2_prefetch(auxw, pf);
                 }
-                load_aux(0);                                         // does not depend on the accumulator
+                if (AUXRING) { issue_aux(0); issue_aux(1); }
+                else load_aux(0);                                    // does not depend on the accumulator
             }
             // fused edge scatter: global neighbour row of each of this lane's 8 rows (4m + sub) of the warp slab
             int jrow[SCAT ? 8 : 1];
@@ -332,17 +360,25 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
                 const int c0 = ch * 32;
                 const int nv = min(32, p.n_out - c0);                // valid columns of this chunk (>= 1)
                 float auxv[32];
-                if (EPI == NT_EPI_BNRELU_BWD) {
+                if (AUXRING) {                                       // this chunk's ring slot is also its transposition tile
+                    twg = tw_all + (grp * TW_SLOTS + ch % TW_SLOTS) * (4 * P3_TW);
+                    tw4 = twg + quad * P3_TW;
+                    cp_async_wait<1>();                              // chunk ch has landed (chunk ch+1 may still be in flight)
+                    __syncwarp();
+                } else if (EPI == NT_EPI_BNRELU_BWD) {
 #pragma unroll
                     for (int m = 0; m < 8; ++m) *reinterpret_cast<float4 *>(tw4 + (4 * m + sub) * 36 + q4) = ld[m];
                     __syncwarp();
+                }
+                if (EPI == NT_EPI_BNRELU_BWD) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 a = *reinterpret_cast<const float4 *>(tw4 + lane * 36 + 4 * i);
                         auxv[4 * i] = a.x; auxv[4 * i + 1] = a.y; auxv[4 * i + 2] = a.z; auxv[4 * i + 3] = a.w;
                     }
                     __syncwarp();
-                    if (ch + 1 < n_chunks) load_aux(ch + 1);         // in flight while this chunk is processed
+                    if (AUXRING) issue_aux(ch + 2);                  // slot (ch+2) % 3 was last read in chunk ch-1
+                    else if (ch + 1 < n_chunks) load_aux(ch + 1);    // in flight while this chunk is processed
                 }
                 float acc[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + c0), acc);
@@ -517,7 +553,7 @@ static int tc3_tiles() {
     int tiles = g_tc3_tiles.load(std::memory_order_relaxed);
     if (tiles == 0) {
         const char *v = getenv("NT_TC3_TILES");
-        tiles = v ? ((atoi(v) == 2 || atoi(v) == 3) ? atoi(v) : 1) : TC3_DEFAULT_TILES;
+        tiles = v ? ((atoi(v) >= 2 && atoi(v) <= 4) ? atoi(v) : 1) : TC3_DEFAULT_TILES;
         g_tc3_tiles.store(tiles, std::memory_order_relaxed);
     }
     return tiles;
@@ -528,6 +564,9 @@ static int launch_tc3(const NTParams &p, const void *w_split, const TCGeom &g, i
     const int cfg = tc3_tiles();       // configuration index (see P3Cfg)
     if (cfg == 2 && tc3_smem_bytes(g.n_tile, 2) <= 227 * 1024) return launch_tc3_t<EPI, SCAT, 2>(p, w_split, g, sms, st);
     if (cfg == 3 && tc3_smem_bytes(g.n_tile, 3) <= 227 * 1024) return launch_tc3_t<EPI, SCAT, 3>(p, w_split, g, sms, st);
+    if constexpr (EPI == NT_EPI_BNRELU_BWD) {
+        if (cfg == 4 && tc3_smem_bytes(g.n_tile, 4) <= 227 * 1024) return launch_tc3_t<EPI, SCAT, 4>(p, w_split, g, sms, st);
+    }
     return launch_tc3_t<EPI, SCAT, 1>(p, w_split, g, sms, st);
 }
 

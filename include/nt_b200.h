@@ -102,7 +102,8 @@ int nt_gemm_nt_scatter_supported(const nt_gemm_args *args);
 
 /* Engine used for the TF32x3 row GEMMs: 0 = auto (streaming persistent engine for large aligned calls, one-tile-per-CTA
  * engine otherwise; default), 1 = one tile per CTA, 2 = persistent experiment, 3 = streaming engine whenever eligible (one row
- * tile per weight stage), 4 = streaming engine with two row tiles per weight stage.
+ * tile per weight stage), 4 = streaming engine with two row tiles per weight stage, 5 = streaming engine with the aux rows of
+ * NT_EPI_BNRELU_BWD staged through a shared-memory ring (experimental).
  * Process-wide; results are bit-identical across engines (same operand split, same accumulation order). */
 int nt_set_nt_engine(int engine);
 
