@@ -206,11 +206,16 @@ __global__ void __launch_bounds__(P3_THREADS, 1) gemm_nt_tc3_kernel(NTParams p, 
             for (int tt = 0; tt < TILES; ++tt) {
                 uint8_t *a_hi = stage + tt * 2 * TC_A_BYTES, *a_lo = a_hi + TC_A_BYTES;
                 const uint8_t *rs = raw + (slab * TILES + tt) * P3_SLAB + slot_off;
+                // all four raw chunks are read BEFORE the first store: the compiler cannot prove that the stage stores do not alias
+                // the raw slab (same shared array) and would otherwise serialise load -> split -> store four times (SASS of the first
+                // version: one LDS.128 latency exposed per chunk)
+                float4 x[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const float4 *>(rs + prow[i] * 16);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 x = *reinterpret_cast<const float4 *>(rs + prow[i] * 16);
                     uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-                    split_tf32(x.x, h0, l0); split_tf32(x.y, h1, l1); split_tf32(x.z, h2, l2); split_tf32(x.w, h3, l3);
+                    split_tf32(x[i].x, h0, l0); split_tf32(x[i].y, h1, l1); split_tf32(x[i].z, h2, l2); split_tf32(x[i].w, h3, l3);
                     *reinterpret_cast<uint4 *>(a_hi + slot_off + prow[i] * 16) = make_uint4(h0, h1, h2, h3);
                     *reinterpret_cast<uint4 *>(a_lo + slot_off + prow[i] * 16) = make_uint4(l0, l1, l2, l3);
                 }
