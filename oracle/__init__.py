@@ -3,7 +3,10 @@
 CPU restatement of the reference hot path (maria-korosteleva/Garment-Pattern-Estimation):
   * ``knn_oracle.c`` / ``knn.py``   brute-force kNN with torch_cluster's published fp32 fmaf chain
   * ``thirdparty.py``               the torch_geometric / sparsemax semantics the reference borrows
-  * ``model.py``                    nn/net_blocks.py + nn/nets.py + the 4 active loss terms, restated
+  * ``model.py``                    nn/net_blocks.py + nn/nets.py (attention, baseline and stitch models) + the 4 active loss
+                                    terms, restated
+  * ``lstm_decomposed.py``          the LSTM decoder as row GEMMs + cell updates, forward and backward (checked against
+                                    torch.nn.LSTM): the specification for replacing the cuDNN call
   * ``ref_stubs.py``                sys.modules stubs that let the UNMODIFIED reference nn/nets.py import
                                     in this container (used only to validate model.py and to generate
                                     tests/golden/* -- /root/reference does not exist on the GPU box)
