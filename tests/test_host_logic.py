@@ -136,9 +136,9 @@ def test_vectorised_loss_equals_reference_loop_form():
     g2, = torch.autograd.grad(want, preds['outlines'])
     assert torch.allclose(g1, g2, rtol=1e-5, atol=1e-8)
     assert panel_loop_loss(torch.randn(4, 14, 4)).dim() == 0          # no num_edges => no padding assumed
-    with pytest.raises(NotImplementedError):
-        ComposedPatternLoss(dc, {'loss_components': ['shape', 'stitch'], 'panel_origin_invariant_loss': False,
-                                 'panel_order_inariant_loss': False})
+    with pytest.raises(NotImplementedError):                              # accepted at construction, refused when evaluated
+        ComposedPatternLoss(dc, {'loss_components': ['shape', 'segmentation'], 'panel_origin_invariant_loss': False,
+                                 'panel_order_inariant_loss': False})(preds, gt)
     loss_obj.train(True)
     assert loss_obj.training is True
     loss_obj.eval()
@@ -307,8 +307,7 @@ def test_pattern_loss_with_quality_metrics_matches_reference_golden():
     loss_obj.with_quality_eval = False
     _, parts, _ = loss_obj(gold['cases']['mixed']['preds'], gold['cases']['mixed']['gt'])
     assert set(parts) == {'pattern_loss', 'loop_loss', 'rotation_loss', 'translation_loss'}
-    with pytest.raises(NotImplementedError):
-        ComposedPatternLoss(dc, dict(gold['loss_config'], quality_components=['stitch']))
+    ComposedPatternLoss(dc, dict(gold['loss_config'], quality_components=['stitch']))      # builds; raises when evaluated
 
 
 def test_quality_metrics_match_unmodified_reference_on_random_batches():
@@ -440,3 +439,79 @@ def test_package_config_values_and_bench_inputs_equal_the_oracle_copies():
     src = open(os.path.join(ROOT, 'bench.py')).read()
     measured_arm = src[src.index('def main():'):]
     assert not [ln for ln in measured_arm.splitlines() if 'import' in ln and 'oracle' in ln], 'main() must not import oracle/'
+
+
+# ------------------------------------------------------------------------------------------------------------
+# stitch-related loss terms of the shipped baseline config (the model must build from the shipped yaml)
+# ------------------------------------------------------------------------------------------------------------
+def test_stitch_loss_terms_match_reference_golden():
+    """nn/metrics/losses.py:PatternStitchLoss (both negative terms), the free-edge BCE, stitch_supervised and the re-numbering
+    of the stitch ground truth under panel-order / edge-origin matching, against what the unmodified reference returned
+    (tests/golden/make_golden_n1_stitch.py) -- before, at and after config['epoch_with_stitches']."""
+    from garment_pattern_estimation_b200.losses import ComposedPatternLoss
+    gold = torch.load(os.path.join(ROOT, 'tests', 'golden', 'n1_stitch_terms.pt'))
+    dc, _, _ = _att()
+    dc['standardize'] = gold['standardize']
+    for name, case in gold['cases'].items():
+        loss_obj = ComposedPatternLoss(dc, dict(case['loss_config']))
+        for epoch, want in case['runs'].items():
+            total, parts, flag = loss_obj(case['preds'], {k: v.clone() for k, v in case['gt'].items()}, epoch=epoch)
+            assert bool(flag) == want['flag'], (name, epoch)
+            _check_loss_against(want['parts'], want['loss'], total, parts)
+            assert set(parts) == set(want['parts']), (name, epoch)
+
+
+def test_models_build_from_the_shipped_yaml_loss_sections():
+    """models/baseline/lstm_stitch_tags.yaml lists `stitch, free_class`; the reference builds
+    model_class(data_config, NN, NN['loss']) (nn/experiment.py:233), so construction must not raise."""
+    import garment_pattern_estimation_b200 as g
+    dc, nc, _ = _att()
+    dc['standardize'] = torch.load(os.path.join(ROOT, 'tests', 'golden', 'n1_quality.pt'))['standardize']
+    baseline_loss = {'loss_components': ['shape', 'loop', 'rotation', 'translation', 'stitch', 'free_class'],
+                     'quality_components': ['shape', 'discrete', 'rotation', 'translation', 'stitch', 'free_class'],
+                     'panel_origin_invariant_loss': False, 'panel_order_inariant_loss': False, 'epoch_with_stitches': 40,
+                     'stitch_tags_margin': 0.3, 'stitch_hardnet_version': False, 'loop_loss_weight': 1.}
+    nc = dict(nc, pattern_decoder='LSTMDecoderModule', pattern_encoding_size=250, pattern_n_layers=2)
+    model = g.GarmentFullPattern3D(dict(dc), dict(nc), dict(baseline_loss))
+    assert model.loss.config['loss_components'] == baseline_loss['loss_components']
+    assert model.config['loss']['quality_components'] == baseline_loss['quality_components']
+    B = 2
+    gt = {'outlines': torch.randn(B, 23, 14, 4), 'rotations': torch.randn(B, 23, 4), 'translations': torch.randn(B, 23, 3),
+          'num_edges': torch.full((B, 23), 4), 'num_panels': torch.full((B,), 23)}
+    preds = {k: gt[k] + 0.1 for k in ('outlines', 'rotations', 'translations')}
+    total, parts, _ = model.loss(preds, gt, epoch=3)            # before the stitch stage: the 4 regression terms only
+    assert 'pattern_loss' in parts and 'stitch_similarity_loss' not in parts and torch.isfinite(total)
+    with pytest.raises(NotImplementedError):                    # the stitch QUALITY metric is the one piece not built
+        gt2 = dict(gt, stitches=torch.zeros(B, 2, 4, dtype=torch.long), num_stitches=torch.full((B,), 2),
+                   free_edges_mask=torch.ones(B, 23, 14))
+        preds2 = dict(preds, stitch_tags=torch.randn(B, 23, 14, 3), free_edges_mask=torch.randn(B, 23, 14))
+        model.loss(preds2, gt2, epoch=50)
+    with pytest.raises(ValueError):
+        g.GarmentFullPattern3D(dict(dc), dict(nc), dict(baseline_loss, loss_components=['shape', 'no_such_term']))
+
+
+def test_stitch_loss_terms_match_unmodified_reference_on_random_batches():
+    """Runs only where /root/reference exists: more random batches (other seeds / batch sizes than the fixture) through the
+    reference's ComposedPatternLoss and the vectorised one, all four loss-section variants of the fixture script."""
+    from oracle import ref_stubs
+    if not ref_stubs.reference_available():
+        pytest.skip('reference tree not present on this machine')
+    import importlib.util
+    from garment_pattern_estimation_b200.losses import ComposedPatternLoss
+    spec = importlib.util.spec_from_file_location('mk_n1_stitch', os.path.join(ROOT, 'tests', 'golden', 'make_golden_n1_stitch.py'))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    ref_stubs.import_reference()
+    import metrics.composed_loss as cl
+    dc, _, lc = ref_stubs.att_configs()
+    st = dc['standardize']
+    pad = -torch.tensor(st['gt_shift']['outlines']) / torch.tensor(st['gt_scale']['outlines'])
+    for i, (name, cfg) in enumerate(mk.CASES.items()):
+        cfg = dict(lc, **cfg)
+        ref_loss, mine = cl.ComposedPatternLoss(dict(dc), dict(cfg)), ComposedPatternLoss(dict(dc), dict(cfg))
+        for seed in (1, 2):
+            preds, gt = mk.stitch_batch(2 + seed, 900 + 17 * i + seed, pad, permute='order' in name, rotate='origin' in name)
+            t1, p1, f1 = ref_loss({k: v.clone() for k, v in preds.items()}, {k: v.clone() for k, v in gt.items()}, epoch=60)
+            t2, p2, f2 = mine(preds, {k: v.clone() for k, v in gt.items()}, epoch=60)
+            assert bool(f1) == bool(f2)
+            _check_loss_against(p1, t1, t2, p2)
