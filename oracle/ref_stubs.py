@@ -13,6 +13,27 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get('NT_REFERENCE_ROOT', '/root/reference')
+# The GPU box has no /root/reference.  For the one test that must execute the reference's OWN nets.py / trainer.py on a B200
+# (INTEGRATION.md swap A), __graft_entry__.build() stages those files -- verbatim, untracked (git-ignored, like
+# tests/golden/_ckpt/) -- under tests/golden/_ref_nn/, which travels with the gpurun snapshot.
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', '_ref_nn')
+_STAGED_FILES = ('nn/nets.py', 'nn/trainer.py', 'nn/metrics/composed_loss.py', 'nn/metrics/losses.py',
+                 'nn/metrics/metrics.py', 'nn/metrics/eval_utils.py', 'models/att/att.yaml')
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, 'nn', 'nets.py')) and os.path.isfile(os.path.join(STAGED_ROOT, 'nn', 'nets.py')):
+    REFERENCE_ROOT = STAGED_ROOT
+
+
+def stage_reference_sources():
+    """Copy the handful of reference files swap A executes into the untracked staging directory (build container only)."""
+    import shutil
+    src_root = os.environ.get('NT_REFERENCE_ROOT', '/root/reference')
+    if not os.path.isfile(os.path.join(src_root, 'nn', 'nets.py')):
+        return False
+    for rel in _STAGED_FILES:
+        dst = os.path.join(STAGED_ROOT, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(src_root, rel), dst)
+    return True
 
 
 def reference_available():
@@ -47,6 +68,12 @@ def install():
 
         class EmptyPanelError(Exception):
             pass
+        if 'wandb' not in sys.modules:      # nn/trainer.py:7 -- a local stand-in (no network): records what the Trainer logs
+            class _Run:
+                step, resumed = 1, False
+            wb = _module('wandb', run=_Run(), config=types.SimpleNamespace(trainer={}), logged=[],
+                         watch=lambda *a, **k: None, Image=lambda *a, **k: None)
+            wb.log = lambda d, step=None: wb.logged.append((step, dict(d)))
         _module('data', Garment3DPatternFullDataset=_DatasetPlaceholder,
                 GarmentStitchPairsDataset=_DatasetPlaceholder, DatasetWrapper=_DatasetPlaceholder,
                 InvalidPatternDefError=InvalidPatternDefError, EmptyPanelError=EmptyPanelError,

@@ -515,3 +515,19 @@ def test_stitch_loss_terms_match_unmodified_reference_on_random_batches():
             t2, p2, f2 = mine(preds, {k: v.clone() for k, v in gt.items()}, epoch=60)
             assert bool(f1) == bool(f2)
             _check_loss_against(p1, t1, t2, p2)
+
+
+def test_unmodified_reference_trainer_drives_flat_data_parallel_on_cpu():
+    """Host-side half of the swap-A/C GPU test (tests/test_gpu_baseline_shapes.py): the UNMODIFIED nn/trainer.py::Trainer.fit
+    (Adam + OneCycleLR + validation + checkpoint dict) runs against parallel.FlatDataParallel and a duck-typed experiment;
+    here with the reference's own blocks on the restated CPU operators (the B200 blocks need a GPU)."""
+    import subprocess
+    from oracle import ref_stubs
+    if not ref_stubs.reference_available():
+        pytest.skip('reference tree not present on this machine')
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import test_gpu_baseline_shapes as t
+    env = dict(os.environ, NT_SWAP_A_DRY='1')
+    out = subprocess.run([sys.executable, '-c', t._SWAP_A % {'root': ROOT}], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert 'trainer ran' in out.stdout
