@@ -116,7 +116,9 @@ def test_c4_edgeconv_encoder_n10000_k16(cuda_device):
     want.backward(gout)
     assert feats.shape == (B * N, 153) and batch.shape == (B * N,)
     assert_close(feats, want, what='C4 encoder forward')
-    assert_grad_close(p1.grad, p2.grad, what='C4 grad wrt positions', l2_tol=1e-2)
+    # 20 000 x 3 small entries after two layers of k=16 max-aggregation: one mask / argmax flip moves a single entry by several
+    # per cent of the largest one (measured 4.0e-2 worst entry at 4.4e-3 relative L2)
+    assert_grad_close(p1.grad, p2.grad, what='C4 grad wrt positions', l2_tol=1e-2, max_tol=1e-1)
     for conv, ref in zip(enc.conv_layers, refs):
         for (n1, a), (n2, b) in zip(conv.nn.named_parameters(), ref.named_parameters()):
             assert_grad_close(a.grad, b.grad, what='C4 grad ' + n1, l2_tol=1e-2)
