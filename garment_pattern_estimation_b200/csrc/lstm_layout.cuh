@@ -75,9 +75,10 @@ __host__ __device__ __forceinline__ int64_t act_flag_index(const Dims &d, int sr
 // backward: dG blocks and flags per (layer, t, row tile); dX hand-off buffers per (layer, t, row tile, slice)
 __host__ __device__ __forceinline__ int64_t dg_block_index(const Dims &d, int l, int t, int rt) { return ((int64_t)l * d.T + t) * d.RT + rt; }
 __host__ __device__ __forceinline__ int64_t dg_flag_index(const Dims &d, int l, int t, int rt, int c) { return dg_block_index(d, l, t, rt) * SLICES + c; }
-// dX[l][t][rt][c]: [row tile_rows][16] fp32 -- gradient w.r.t. the input of layer l (= h of layer l-1), units 16c..16c+15
-__host__ __device__ __forceinline__ int64_t dx_offset(const Dims &d, int l, int t, int rt, int c, int row_in_tile) {
-    return ((dg_block_index(d, l, t, rt) * SLICES + c) * d.tile_rows() + row_in_tile) * UNITS;
+// dX[l][t][rt][c]: row-inner block [u4 4][row tile_rows][4] fp32 -- gradient w.r.t. the input of layer l (= h of layer l-1),
+// units 16c..16c+15, handed from CTA (l, rt, c) to CTA (l-1, rt, c)
+__host__ __device__ __forceinline__ int64_t dx_block_offset(const Dims &d, int l, int t, int rt, int c) {
+    return (dg_block_index(d, l, t, rt) * SLICES + c) * (int64_t)(d.tile_rows() * UNITS);
 }
 
 // ---- fp32 state ------------------------------------------------------------------------------------------------------------------
@@ -223,7 +224,7 @@ __host__ __device__ __forceinline__ void load16_rowinner(const float *blk, int t
     for (int q = 0; q < 4; ++q) {
         const float *src = blk + ((int64_t)q * tile_rows + row_in_tile) * 4;
 #ifdef __CUDA_ARCH__
-        const float4 a = *reinterpret_cast<const float4 *>(src);
+        const float4 a = __ldcg(reinterpret_cast<const float4 *>(src));      // L2 only: other CTAs of this launch wrote it
         v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
 #else
         for (int e = 0; e < 4; ++e) v[4 * q + e] = src[e];

@@ -171,8 +171,10 @@ def initial_state(n_layers, rows, hidden, device, init_type='', generator=None):
 
 
 class LSTMDecoderModule(nn.Module):
-    """Encoding -> repeated out_len times -> nn.LSTM (cuDNN) -> Linear.  ``lstm_state=(h0, c0)`` or the
-    ``state_provider`` attribute inject the initial states (needed for parity: the reference's are random)."""
+    """Encoding -> repeated out_len times -> LSTM -> Linear.  ``self.lstm`` is an ``nn.LSTM`` used as the PARAMETER CONTAINER
+    (state_dict keys ``lstm.weight_ih_l*`` ... are the reference's); the recurrence itself runs in the persistent tcgen05
+    kernels of csrc/lstm.cu (``ops.lstm_decoder``), not in cuDNN.  ``lstm_state=(h0, c0)`` or the ``state_provider`` attribute
+    inject the initial states (needed for parity: the reference's are random)."""
 
     def __init__(self, encoding_size, hidden_size, out_elem_size, n_layers, dropout=0, custom_init='kaiming_normal',
                  **kwargs):
@@ -182,19 +184,28 @@ class LSTMDecoderModule(nn.Module):
         self.encoding_size = encoding_size
         self.hidden_size = hidden_size
         self.out_elem_size = out_elem_size
+        self.dropout = dropout
         self.lstm = nn.LSTM(encoding_size, hidden_size, n_layers, dropout=dropout, batch_first=True)
         self.lin = nn.Linear(hidden_size, out_elem_size)
         _init_weights(self.lstm, init_type=custom_init)
         self.state_provider = None      # callable(n_layers, rows, hidden, device) -> (h0, c0)
+        if not ops.lstm_supported(encoding_size, hidden_size, n_layers):
+            raise NotImplementedError('LSTMDecoderModule on the B200 path supports hidden_size <= {}, encoding_size <= {}, '
+                                      'n_layers <= {}'.format(ops.LSTM_MAX_HIDDEN, ops.LSTM_MAX_INPUT, ops.LSTM_MAX_LAYERS))
+
+    def _flat_params(self):
+        return [getattr(self.lstm, '{}_l{}'.format(name, l)) for l in range(self.n_layers)
+                for name in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh')]
 
     def forward(self, batch_enc, out_len, lstm_state=None):
         rows = batch_enc.size(0)
-        dec_input = batch_enc.unsqueeze(1).expand(rows, out_len, batch_enc.shape[-1]).contiguous()
+        if self.dropout and self.training:
+            raise NotImplementedError('inter-layer LSTM dropout is not part of the B200 path (every shipped config uses dropout 0)')
         if lstm_state is None and self.state_provider is not None:
             lstm_state = self.state_provider(self.n_layers, rows, self.hidden_size, batch_enc.device)
         if lstm_state is None:
             lstm_state = (initial_state(self.n_layers, rows, self.hidden_size, batch_enc.device, self.custom_init),
                           initial_state(self.n_layers, rows, self.hidden_size, batch_enc.device, self.custom_init))
-        out, _ = self.lstm(dec_input, lstm_state)
-        out = ops.linear(out.reshape(-1, self.hidden_size), self.lin.weight, self.lin.bias)
-        return out.view(rows, out_len, -1)
+        seq = ops.lstm_decoder(batch_enc, lstm_state[0], lstm_state[1], out_len, self._flat_params())      # [T, R, H] time-major
+        out = ops.linear(seq.reshape(out_len * rows, self.hidden_size), self.lin.weight, self.lin.bias)
+        return out.view(out_len, rows, -1).transpose(0, 1)                                                  # [R, T, out]

@@ -563,6 +563,115 @@ def global_pool(x, B, N, mode):
     return _GlobalPoolFunction.apply(x, int(B), int(N), _POOL_MODES[mode])
 
 
+# ----------------------------------------------------------------------------------------------------------
+# LSTM decoder (persistent tcgen05 kernels, csrc/lstm.cu)
+# ----------------------------------------------------------------------------------------------------------
+LSTM_MAX_HIDDEN, LSTM_MAX_INPUT, LSTM_MAX_LAYERS = 255, 256, 4
+_LSTM_WEIGHT_CACHE = {}
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def lstm_supported(input_size, hidden_size, num_layers):
+    return hidden_size <= LSTM_MAX_HIDDEN and input_size <= LSTM_MAX_INPUT and num_layers <= LSTM_MAX_LAYERS
+
+
+def _lstm_sizes(R, T, L, H, E):
+    z = _lib.LstmSizes()
+    _lib.check(_lib.load().nt_lstm_sizes(R, T, L, H, E, ctypes.byref(z)), 'nt_lstm_sizes')
+    return z
+
+
+def _lstm_prepared_weights(params, L, H, E, nbytes, cacheable):
+    """hi / lo split of the LSTM weights in the kernels' operand layouts.  Re-done whenever the parameters may have changed:
+    always while gradients are recorded or a CUDA graph is being captured (a replayed graph must contain the preparation of
+    the weights it runs on), cached per parameter version otherwise (inference)."""
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    if cacheable:
+        hit = _LSTM_WEIGHT_CACHE.get('w')
+        if hit is not None and hit[0] == key:
+            return hit[1]
+    buf = torch.empty(int(nbytes), dtype=torch.uint8, device=params[0].device)
+    ps = [p.detach().contiguous() for p in params]
+    _call('nt_lstm_prepare_weights', _lib.load().nt_lstm_prepare_weights, _ptr_array(ps[0::4]), _ptr_array(ps[1::4]),
+          _ptr_array(ps[2::4]), _ptr_array(ps[3::4]), L, H, E, _p(buf), _stream())
+    if cacheable:
+        _LSTM_WEIGHT_CACHE['w'] = (key, buf, ps)
+    return buf
+
+
+class _LSTMDecoderFunction(torch.autograd.Function):
+    """params = (weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, weight_ih_l1, ...)."""
+
+    @staticmethod
+    def forward(ctx, x, h0, c0, T, *params):
+        lib = _lib.load()
+        _require_cuda(x, h0, c0, *params)
+        L = len(params) // 4
+        H = params[1].shape[1]
+        x, ldx = _rows2d(x)
+        R, E = x.shape
+        if tuple(h0.shape) != (L, R, H) or tuple(c0.shape) != (L, R, H):
+            raise RuntimeError('lstm_decoder: initial states must be [{}, {}, {}]'.format(L, R, H))
+        h0, c0 = h0.contiguous().float(), c0.contiguous().float()
+        z = _lstm_sizes(R, T, L, H, E)
+        need_bwd = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        capturing = torch.cuda.is_current_stream_capturing()
+        w = _lstm_prepared_weights(params, L, H, E, z.weights_bytes, cacheable=not need_bwd and not capturing)
+        dev = x.device
+        hf = torch.empty(L, T + 1, R, z.hf_ld, dtype=torch.float32, device=dev)
+        cs = torch.empty(z.cs_bytes // 4, dtype=torch.float32, device=dev) if need_bwd else None
+        gates = torch.empty(z.gates_bytes // 4, dtype=torch.float32, device=dev) if need_bwd else None
+        ws = torch.empty(int(z.fwd_workspace_bytes), dtype=torch.uint8, device=dev)
+        _call('nt_lstm_fwd', lib.nt_lstm_fwd, _p(x), ldx, _p(h0), _p(c0), _p(w), R, T, L, H, E, _p(hf), _p(cs), _p(gates), _p(ws),
+              _stream())
+        if FLOP_SINK is not None:
+            FLOP_SINK['nt_lstm_fwd'] = FLOP_SINK.get('nt_lstm_fwd', 0.0) + 2.0 * R * T * 4 * H * sum((E if l == 0 else H) + H for l in range(L))
+        ctx.dims = (R, T, L, H, E, ldx)
+        if need_bwd:
+            ctx.save_for_backward(x, hf, cs, gates, w)
+        ctx.n_params = len(params)
+        out = hf[L - 1, 1:, :, :H]                    # [T, R, H] time-major view (row stride hf_ld)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        R, T, L, H, E, ldx = ctx.dims
+        x, hf, cs, gates, w = ctx.saved_tensors
+        gout = gout.contiguous()
+        z = _lstm_sizes(R, T, L, H, E)
+        dev = x.device
+        ws = torch.empty(int(z.bwd_workspace_bytes), dtype=torch.uint8, device=dev)
+        tn_ws = torch.empty(int(lib.nt_gemm_tn_workspace_bytes()), dtype=torch.uint8, device=dev)
+        dx = torch.empty(R, E, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        f32 = dict(dtype=torch.float32, device=dev)
+        dw_ih = [torch.empty(4 * H, E if l == 0 else H, **f32) for l in range(L)]
+        dw_hh = [torch.empty(4 * H, H, **f32) for l in range(L)]
+        db_ih = [torch.empty(4 * H, **f32) for l in range(L)]
+        db_hh = [torch.empty(4 * H, **f32) for l in range(L)]
+        _call('nt_lstm_bwd', lib.nt_lstm_bwd, _p(gout), H, _p(x), ldx, _p(hf), _p(cs), _p(gates), _p(w), R, T, L, H, E, _p(ws),
+              _p(tn_ws), _p(dx), E, _ptr_array(dw_ih), _ptr_array(dw_hh), _ptr_array(db_ih), _ptr_array(db_hh), _stream())
+        if FLOP_SINK is not None:
+            FLOP_SINK['nt_lstm_bwd'] = FLOP_SINK.get('nt_lstm_bwd', 0.0) + 4.0 * R * T * 4 * H * sum((E if l == 0 else H) + H for l in range(L))
+        flat = []
+        for l in range(L):
+            flat += [dw_ih[l], dw_hh[l], db_ih[l], db_hh[l]]
+        return (dx, None, None, None, *flat)
+
+
+def lstm_decoder(x, h0, c0, T, params):
+    """nn.LSTM(batch_first=True) on the input x [R, E] repeated T times (LSTMDecoderModule, nn/net_blocks.py:382-402).
+    params: flat list (weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, weight_ih_l1, ...); h0, c0: [L, R, H].
+    Returns the top layer's hidden states TIME-MAJOR, [T, R, H] (a strided view; row stride 256 floats)."""
+    return _LSTMDecoderFunction.apply(x, h0, c0, int(T), *params)
+
+
 class _LinearFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):

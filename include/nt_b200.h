@@ -213,6 +213,35 @@ int nt_global_pool_fwd(const float *x, int ldx, int B, int N, int F, int mode, f
 int nt_global_pool_bwd(const float *g, const int32_t *argmax, int B, int N, int F, int mode, float *gx, int ldgx,
                        void *stream);
 
+/* ---- LSTM panel decoder: nn.LSTM(batch_first=True) inside LSTMDecoderModule.forward (nn/net_blocks.py:373,382-402) ------------
+ * L layers (<= 4), hidden H (<= 255), gates in PyTorch order i, f, g, o; the layer-0 input is the SAME vector x[r, :E] (E <= 256)
+ * at each of the T steps -- the reference repeats the encoding (net_blocks.py:388).  R rows (sequences) are independent.
+ * One persistent cooperative kernel per direction (csrc/lstm.cu): weights stationary in shared memory, tcgen05 BF16x3 products,
+ * h exchanged between CTAs through L2 in the tensor-core operand layout.  Needs a device on which L*16 CTAs are co-resident.
+ *
+ * Buffers (all caller-owned device memory; sizes from nt_lstm_sizes):
+ *   weights   : prepared by nt_lstm_prepare_weights from weight_ih_l*, weight_hh_l*, bias_ih_l*, bias_hh_l* (host arrays of L
+ *               device pointers); valid until the parameters change.  128-byte aligned.
+ *   hf        : fp32 [L][T+1][R][hf_ld]; slot 0 = h0, slot t+1 = h_t.  The module output (time-major) is hf[L-1][1..T][:, :H].
+ *               In inference (cs == gates == NULL) only the top layer's slots 1..T are written.
+ *   cs, gates : saved cell states / activated gates for nt_lstm_bwd (opaque layout); NULL in inference.
+ *   workspace : scratch, 256-byte aligned; contents are not needed after the call returns (the backward has its own).
+ * nt_lstm_bwd: dy [T][R][ld_dy] = gradient w.r.t. the module output (time-major).  Writes dx [R][ld_dx] (gradient w.r.t. x, may
+ * be NULL) and, per layer, dw_ih [4H, in], dw_hh [4H, H], db_ih = db_hh [4H] (host arrays of L device pointers; entries or
+ * whole arrays may be NULL).  tn_workspace: nt_gemm_tn_workspace_bytes() bytes. */
+typedef struct nt_lstm_sizes_t {
+    int64_t weights_bytes, fwd_workspace_bytes, hf_bytes, cs_bytes, gates_bytes, bwd_workspace_bytes;
+    int hf_ld;
+} nt_lstm_sizes_t;
+int nt_lstm_sizes(int R, int T, int L, int H, int E, nt_lstm_sizes_t *out);
+int nt_lstm_prepare_weights(const float *const *w_ih, const float *const *w_hh, const float *const *b_ih,
+                            const float *const *b_hh, int L, int H, int E, void *weights, void *stream);
+int nt_lstm_fwd(const float *x, int ldx, const float *h0, const float *c0, const void *weights, int R, int T, int L, int H,
+                int E, float *hf, float *cs, float *gates, void *workspace, void *stream);
+int nt_lstm_bwd(const float *dy, int ld_dy, const float *x, int ldx, const float *hf, const float *cs, const float *gates,
+                const void *weights, int R, int T, int L, int H, int E, void *workspace, void *tn_workspace, float *dx,
+                int ld_dx, float *const *dw_ih, float *const *dw_hh, float *const *db_ih, float *const *db_hh, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
