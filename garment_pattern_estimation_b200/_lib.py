@@ -35,8 +35,8 @@ class GemmArgs(ctypes.Structure):
 
 class LstmSizes(ctypes.Structure):
     """Mirror of `struct nt_lstm_sizes_t`."""
-    _fields_ = [('weights_bytes', c_int64), ('fwd_workspace_bytes', c_int64), ('hf_bytes', c_int64), ('cs_bytes', c_int64),
-                ('gates_bytes', c_int64), ('bwd_workspace_bytes', c_int64), ('hf_ld', c_int)]
+    _fields_ = [('weights_bytes', c_int64), ('act_bytes', c_int64), ('fwd_workspace_bytes', c_int64), ('y_bytes', c_int64),
+                ('cs_bytes', c_int64), ('gates_bytes', c_int64), ('bwd_workspace_bytes', c_int64), ('y_ld', c_int)]
 
 
 _PP = ctypes.POINTER(c_void_p)      # host array of device pointers
@@ -88,9 +88,9 @@ _SIGNATURES = {
     'nt_lstm_sizes': (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(LstmSizes)]),
     'nt_lstm_prepare_weights': (c_int, [_PP, _PP, _PP, _PP, c_int, c_int, c_int, c_void_p, c_void_p]),
     'nt_lstm_fwd': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    'nt_lstm_bwd': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                            c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, _PP, _PP, _PP, _PP, c_void_p]),
+                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'nt_lstm_bwd': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                            c_void_p, c_void_p, c_int, _PP, _PP, _PP, _PP, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))

@@ -82,23 +82,51 @@ __host__ __device__ __forceinline__ int64_t dx_block_offset(const Dims &d, int l
 }
 
 // ---- fp32 state ------------------------------------------------------------------------------------------------------------------
-//   hf   [L][T+1][R][HP] row-major, rows NOT padded: slot 0 = h0, slot t+1 = h_t.  Top-layer slots 1..T are the module output;
-//        all layers are the B operand of the weight-gradient GEMMs.  Column H of every row holds 1.0 (a "ones column": the
-//        weight-gradient GEMM then yields the bias gradient as its column H); columns > H are 0.
-//   dgf  [L][T*R][4*HP] row-major: gate gradients, gate g at columns g*HP .. g*HP+H-1 (A operand of the weight-gradient GEMMs)
+//   y    [T][R][HP] row-major, rows NOT padded: the top layer's h_t = the module output (time-major); columns >= H are scratch.
 //   cs / gates: "row-inner" layout private to the kernels (thread = row writes / reads float4s that are contiguous across the
 //        rows of a warp):  cs[l][slot][rt][c][u4 4][row][4]  (slot 0 = c0),  gates[l][t][rt][c][q 4][u4 4][row][4]  (i, f, g, o)
-__host__ __device__ __forceinline__ int64_t state_offset(const Dims &d, int l, int slot, int64_t row) {
-    return (((int64_t)l * (d.T + 1) + slot) * d.R + row) * HP;
-}
-__host__ __device__ __forceinline__ int64_t dgf_offset(const Dims &d, int l, int t, int64_t row) {
-    return (((int64_t)l * d.T + t) * d.R + row) * (4 * (int64_t)HP);
-}
+// The split activation blocks double as the B operand of the weight-gradient kernel; unit H of every h block holds 1.0 (a "ones
+// column": the weight-gradient product then yields the bias gradient as its column H; the recurrence multiplies it with the
+// zero-padded weight column H, so it is inert there).
+__host__ __device__ __forceinline__ int64_t y_offset(const Dims &d, int t, int64_t row) { return ((int64_t)t * d.R + row) * HP; }
 __host__ __device__ __forceinline__ int64_t cs_offset(const Dims &d, int l, int slot, int rt, int c) {       // start of [u4][row][4]
     return ((((int64_t)l * (d.T + 1) + slot) * d.RT + rt) * SLICES + c) * (int64_t)(UNITS * d.tile_rows());
 }
 __host__ __device__ __forceinline__ int64_t gates_offset(const Dims &d, int l, int t, int rt, int c, int q) {
     return (((((int64_t)l * d.T + t) * d.RT + rt) * SLICES + c) * 4 + q) * (int64_t)(UNITS * d.tile_rows());
+}
+
+// ---- weight-gradient kernel: dW = dG^T . [X | H_prev] with the contraction over ROWS --------------------------------------------
+// Both operands are the split blocks above read "sideways": for a fixed 8-element group of gate columns / units (one 16-byte
+// chunk), the 128 rows of a sub tile are 2 KB of contiguous 16-byte rows -- exactly a column of UMMA *MN-major* no-swizzle core
+// matrices (8 k-rows x 16 B; descriptor LBO = 128 B between 8-row groups along K, SBO = distance between the 8-element groups
+// along M / N; verified on a B200 with tools/microbench/mn_major_test.cu).  Group g of a block: K-step g / 2, chunk g % 2.
+constexpr int DW_TILE = 256;                 // output tile: 256 gate columns x 256 units (two M = 128 accumulators, 512 TMEM columns)
+constexpr int DW_GROUPS = DW_TILE / 8;       // 32 eight-element groups per operand
+constexpr int DW_KB_ROWS = 32;               // rows (K) per pipeline stage
+constexpr int DW_GROUP_BYTES = DW_KB_ROWS * 16;                   // 512 B per (group, plane, stage)
+constexpr int DW_PLANE_BYTES = DW_GROUPS * DW_GROUP_BYTES;        // 16 KB
+constexpr int DW_STAGE_BYTES = 4 * DW_PLANE_BYTES;                // A hi | A lo | B hi | B lo = 64 KB
+constexpr int DW_M_TILES = 4 * HP / DW_TILE;                      // 4 tiles of gate columns (permuted order, see gate_perm_index)
+__host__ __device__ __forceinline__ int64_t group_offset(const Dims &d, int group, int sub, int plane) {
+    return (int64_t)(group >> 1) * d.stage_bytes() + (int64_t)sub * SUB_BYTES + plane * PLANE_BYTES + (group & 1) * CHUNK_BYTES;
+}
+// position of gate row g*H + unit in the K order of the dG blocks: (slice, gate, unit-in-slice)
+__host__ __device__ __forceinline__ int gate_perm_index(int unit, int g) { return ((unit >> 4) * 4 + g) * UNITS + (unit & 15); }
+struct DwKBlock { int t, rt, sub, rowblk; };
+__host__ __device__ __forceinline__ DwKBlock dw_kblock(const Dims &d, int kb) {       // kb in [0, T * RT * nsub * 4)
+    DwKBlock k;
+    k.rowblk = kb & 3;
+    const int piece = kb >> 2;
+    k.sub = piece % d.nsub;
+    const int trt = piece / d.nsub;
+    k.rt = trt % d.RT;
+    k.t = trt / d.RT;
+    return k;
+}
+// source of the B operand of (layer l, which) at step t: which = 0 -> the layer's input, which = 1 -> its own previous h
+__host__ __device__ __forceinline__ int64_t dw_b_block(const Dims &d, int l, int which, int t, int rt) {
+    return which == 0 ? act_block_index(d, l, l == 0 ? 0 : t + 1, rt) : act_block_index(d, l + 1, t, rt);
 }
 
 // ---- weights -----------------------------------------------------------------------------------------------------------------
@@ -157,7 +185,23 @@ __host__ __device__ __forceinline__ float bwd_w_value(const float *w_ih, const f
 }
 
 // ---- cell arithmetic -----------------------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// Gate non-linearities.  On the device: ex2.approx / rcp.approx based (a handful of instructions, ~1e-6 relative; the libm
+// versions cost ~10x more and made the gate math the longest phase of a step in the first cycle trace).
+// tanh(x) = 2 sigmoid(2x) - 1: absolute error ~2e-7, which is what matters for O(1) activations.
+__host__ __device__ __forceinline__ float sigmoidf_(float x) {
+#ifdef __CUDA_ARCH__
+    return __fdividef(1.f, 1.f + __expf(-x));
+#else
+    return 1.f / (1.f + expf(-x));
+#endif
+}
+__host__ __device__ __forceinline__ float tanhf_(float x) {
+#ifdef __CUDA_ARCH__
+    return fmaf(2.f, __fdividef(1.f, 1.f + __expf(-2.f * x)), -1.f);
+#else
+    return tanhf(x);
+#endif
+}
 __host__ __device__ __forceinline__ void return_h(const float (&h)[UNITS], float (&out)[UNITS]) {
 #pragma unroll
     for (int u = 0; u < UNITS; ++u) out[u] = h[u];
@@ -234,16 +278,16 @@ __host__ __device__ __forceinline__ void load16_rowinner(const float *blk, int t
 
 struct FwdOut {                 // global buffers of the forward kernel (see the offsets above)
     uint8_t *act;               // split activation blocks
-    float *hf;                  // row-major fp32 h (see above)
+    float *y;                   // row-major fp32 h of the top layer (see above)
     float *cs, *gates;          // row-inner saved state; may be null (inference)
 };
 
 // One row of cell (l, t) for unit slice c: `acc` = the 64 gate pre-activations of this row WITHOUT bias, columns g*16 + u;
-// `cst` = c_{t-1} in, c_t out (kept in registers by the kernel).  Writes h_t as split K-step c of block (l+1, t+1) and the saved
-// tensors; returns h_t in `hout` (fwd_store_hf writes the fp32 copy later).
+// `cst` = c_{t-1} in, c_t out (kept in registers by the kernel).  Writes h_t as split K-step c of block (l+1, t+1);
+// returns h_t in `hout` and the activated gates in `gsave` (fwd_store_hf / fwd_store_saved write them after the flag).
 __host__ __device__ __forceinline__ void fwd_cell_row(const Dims &d, const FwdOut &o, int l, int t, int rt, int c, int row_in_tile,
                                                       const float (&acc)[FWD_N], const float *bias64, float (&cst)[UNITS],
-                                                      float (&hout)[UNITS]) {
+                                                      float (&hout)[UNITS], float (&gsave)[4][UNITS]) {
     const int64_t grow = (int64_t)rt * d.tile_rows() + row_in_tile;
     const bool valid = grow < d.R;
     float gi[UNITS], gf[UNITS], gg[UNITS], go[UNITS], h[UNITS];
@@ -252,48 +296,45 @@ __host__ __device__ __forceinline__ void fwd_cell_row(const Dims &d, const FwdOu
         const bool live = valid && (UNITS * c + u) < d.H;
         gi[u] = sigmoidf_(acc[u] + bias64[u]);
         gf[u] = sigmoidf_(acc[16 + u] + bias64[16 + u]);
-        gg[u] = tanhf(acc[32 + u] + bias64[32 + u]);
+        gg[u] = tanhf_(acc[32 + u] + bias64[32 + u]);
         go[u] = sigmoidf_(acc[48 + u] + bias64[48 + u]);
         const float cn = gf[u] * cst[u] + gi[u] * gg[u];
         cst[u] = live ? cn : 0.f;
-        h[u] = live ? go[u] * tanhf(cn) : 0.f;
+        h[u] = live ? go[u] * tanhf_(cn) : ((UNITS * c + u == d.H) ? 1.f : 0.f);       // ones column at unit H
     }
     uint8_t *blk = o.act + act_block_index(d, l + 1, t + 1, rt) * d.act_block_bytes();
     store_split16(blk, d, c, row_in_tile, h);
     return_h(h, hout);
+#pragma unroll
+    for (int u = 0; u < UNITS; ++u) { gsave[0][u] = gi[u]; gsave[1][u] = gf[u]; gsave[2][u] = gg[u]; gsave[3][u] = go[u]; }
+}
+
+// state kept for the backward (row-inner layout); issued AFTER the flag of the step: off the critical path
+__host__ __device__ __forceinline__ void fwd_store_saved(const Dims &d, const FwdOut &o, int l, int t, int rt, int c, int row_in_tile,
+                                                        const float (&gsave)[4][UNITS], const float (&cst)[UNITS]) {
     if (o.cs) store16_rowinner(o.cs + cs_offset(d, l, t + 1, rt, c), d.tile_rows(), row_in_tile, cst);
     if (o.gates) {
-        store16_rowinner(o.gates + gates_offset(d, l, t, rt, c, 0), d.tile_rows(), row_in_tile, gi);
-        store16_rowinner(o.gates + gates_offset(d, l, t, rt, c, 1), d.tile_rows(), row_in_tile, gf);
-        store16_rowinner(o.gates + gates_offset(d, l, t, rt, c, 2), d.tile_rows(), row_in_tile, gg);
-        store16_rowinner(o.gates + gates_offset(d, l, t, rt, c, 3), d.tile_rows(), row_in_tile, go);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) store16_rowinner(o.gates + gates_offset(d, l, t, rt, c, q), d.tile_rows(), row_in_tile, gsave[q]);
     }
 }
 
-// fp32 copy of h_t for the caller / the weight-gradient GEMMs (row-major; issued AFTER the flag: off the critical path).
-// The slice that owns unit H also writes the ones column (see the hf layout above).
-__host__ __device__ __forceinline__ void fwd_store_hf(const Dims &d, float *hf, int l, int slot, int rt, int c, int row_in_tile,
-                                                     const float (&h)[UNITS]) {
+// fp32 copy of the top layer's h_t for the caller (row-major; issued AFTER the flag: off the critical path)
+__host__ __device__ __forceinline__ void fwd_store_y(const Dims &d, float *y, int t, int rt, int c, int row_in_tile, const float (&h)[UNITS]) {
     const int64_t grow = (int64_t)rt * d.tile_rows() + row_in_tile;
-    if (grow >= d.R) return;
-    float v[UNITS];
-#pragma unroll
-    for (int u = 0; u < UNITS; ++u) v[u] = (UNITS * c + u == d.H) ? 1.f : h[u];
-    store16(hf + state_offset(d, l, slot, grow) + UNITS * c, v);
+    if (grow < d.R) store16(y + y_offset(d, t, grow) + UNITS * c, h);
 }
 
 struct BwdIo {
     const float *cs, *gates;          // saved by the forward (row-inner)
     const float *dy; int64_t ld_dy;   // [T][R][ld_dy] gradient of the top layer's outputs
     uint8_t *dgs;                     // split dG blocks
-    float *dgf;                       // fp32 dG, [L][T*R][4*HP]
     float *dxbuf;                     // dX hand-off buffers (row-inner [u4][row][4] per (l, t, rt, c))
     float *dx0; int64_t ld_dx0;       // [R][ld_dx0] gradient w.r.t. the layer-0 input (sum over t), written at the end
 };
 
 // Phase 1 of backward cell (l, t): from dh (= dy or dX from the layer above, + recurrent part) and the saved state, the gate
-// gradients of this row / slice; dc carried in registers.  Writes the split K-steps 4c..4c+3; returns the four gate gradients
-// (bwd_store_dgf writes the fp32 copy later).
+// gradients of this row / slice; dc carried in registers.  Writes the split K-steps 4c..4c+3.
 __host__ __device__ __forceinline__ void bwd_cell_row(const Dims &d, const BwdIo &io, int l, int t, int rt, int c, int row_in_tile,
                                                       const float (&dh)[UNITS], float (&dc)[UNITS], float (&dgo)[4][UNITS]) {
     const int64_t grow = (int64_t)rt * d.tile_rows() + row_in_tile;
@@ -309,7 +350,7 @@ __host__ __device__ __forceinline__ void bwd_cell_row(const Dims &d, const BwdIo
 #pragma unroll
     for (int u = 0; u < UNITS; ++u) {
         const bool live = valid && (UNITS * c + u) < d.H;
-        const float tc = tanhf(ct[u]);
+        const float tc = tanhf_(ct[u]);
         const float dcu = dc[u] + dh[u] * go[u] * (1.f - tc * tc);
         dgo[3][u] = live ? dh[u] * tc * go[u] * (1.f - go[u]) : 0.f;
         dgo[0][u] = live ? dcu * gg[u] * gi[u] * (1.f - gi[u]) : 0.f;
@@ -320,15 +361,6 @@ __host__ __device__ __forceinline__ void bwd_cell_row(const Dims &d, const BwdIo
     uint8_t *blk = io.dgs + dg_block_index(d, l, t, rt) * d.dg_block_bytes();
 #pragma unroll
     for (int g = 0; g < 4; ++g) store_split16(blk, d, 4 * c + g, row_in_tile, dgo[g]);
-}
-
-__host__ __device__ __forceinline__ void bwd_store_dgf(const Dims &d, float *dgf, int l, int t, int rt, int c, int row_in_tile,
-                                                      const float (&dgo)[4][UNITS]) {
-    const int64_t grow = (int64_t)rt * d.tile_rows() + row_in_tile;
-    if (grow >= d.R) return;
-    float *dst = dgf + dgf_offset(d, l, t, grow) + UNITS * c;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) store16(dst + g * HP, dgo[g]);
 }
 
 }  // namespace lstm

@@ -567,6 +567,7 @@ def global_pool(x, B, N, mode):
 # LSTM decoder (persistent tcgen05 kernels, csrc/lstm.cu)
 # ----------------------------------------------------------------------------------------------------------
 LSTM_MAX_HIDDEN, LSTM_MAX_INPUT, LSTM_MAX_LAYERS = 255, 256, 4
+_LSTM_SKIP_DW = False          # development knob (tools/lstm_check.py): time the recurrence kernel without the dW GEMMs
 _LSTM_WEIGHT_CACHE = {}
 
 
@@ -620,43 +621,42 @@ class _LSTMDecoderFunction(torch.autograd.Function):
             raise RuntimeError('lstm_decoder: initial states must be [{}, {}, {}]'.format(L, R, H))
         h0, c0 = h0.contiguous().float(), c0.contiguous().float()
         z = _lstm_sizes(R, T, L, H, E)
-        need_bwd = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        need_bwd = any(ctx.needs_input_grad)          # (grad mode is off inside Function.forward: ask autograd instead)
         capturing = torch.cuda.is_current_stream_capturing()
         w = _lstm_prepared_weights(params, L, H, E, z.weights_bytes, cacheable=not need_bwd and not capturing)
         dev = x.device
-        hf = torch.empty(L, T + 1, R, z.hf_ld, dtype=torch.float32, device=dev)
+        y = torch.empty(T, R, z.y_ld, dtype=torch.float32, device=dev)
+        act = torch.empty(int(z.act_bytes), dtype=torch.uint8, device=dev)
         cs = torch.empty(z.cs_bytes // 4, dtype=torch.float32, device=dev) if need_bwd else None
         gates = torch.empty(z.gates_bytes // 4, dtype=torch.float32, device=dev) if need_bwd else None
         ws = torch.empty(int(z.fwd_workspace_bytes), dtype=torch.uint8, device=dev)
-        _call('nt_lstm_fwd', lib.nt_lstm_fwd, _p(x), ldx, _p(h0), _p(c0), _p(w), R, T, L, H, E, _p(hf), _p(cs), _p(gates), _p(ws),
-              _stream())
+        _call('nt_lstm_fwd', lib.nt_lstm_fwd, _p(x), ldx, _p(h0), _p(c0), _p(w), R, T, L, H, E, _p(y), _p(act), _p(cs), _p(gates),
+              _p(ws), _stream())
         if FLOP_SINK is not None:
             FLOP_SINK['nt_lstm_fwd'] = FLOP_SINK.get('nt_lstm_fwd', 0.0) + 2.0 * R * T * 4 * H * sum((E if l == 0 else H) + H for l in range(L))
-        ctx.dims = (R, T, L, H, E, ldx)
+        ctx.dims = (R, T, L, H, E)
         if need_bwd:
-            ctx.save_for_backward(x, hf, cs, gates, w)
-        ctx.n_params = len(params)
-        out = hf[L - 1, 1:, :, :H]                    # [T, R, H] time-major view (row stride hf_ld)
-        return out
+            ctx.save_for_backward(act, cs, gates, w)
+        return y[:, :, :H]                            # [T, R, H] time-major view (row stride y_ld)
 
     @staticmethod
     def backward(ctx, gout):
         lib = _lib.load()
-        R, T, L, H, E, ldx = ctx.dims
-        x, hf, cs, gates, w = ctx.saved_tensors
+        R, T, L, H, E = ctx.dims
+        act, cs, gates, w = ctx.saved_tensors
         gout = gout.contiguous()
         z = _lstm_sizes(R, T, L, H, E)
-        dev = x.device
+        dev = gout.device
         ws = torch.empty(int(z.bwd_workspace_bytes), dtype=torch.uint8, device=dev)
-        tn_ws = torch.empty(int(lib.nt_gemm_tn_workspace_bytes()), dtype=torch.uint8, device=dev)
         dx = torch.empty(R, E, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
         f32 = dict(dtype=torch.float32, device=dev)
         dw_ih = [torch.empty(4 * H, E if l == 0 else H, **f32) for l in range(L)]
         dw_hh = [torch.empty(4 * H, H, **f32) for l in range(L)]
         db_ih = [torch.empty(4 * H, **f32) for l in range(L)]
         db_hh = [torch.empty(4 * H, **f32) for l in range(L)]
-        _call('nt_lstm_bwd', lib.nt_lstm_bwd, _p(gout), H, _p(x), ldx, _p(hf), _p(cs), _p(gates), _p(w), R, T, L, H, E, _p(ws),
-              _p(tn_ws), _p(dx), E, _ptr_array(dw_ih), _ptr_array(dw_hh), _ptr_array(db_ih), _ptr_array(db_hh), _stream())
+        grads = (None,) * 4 if _LSTM_SKIP_DW else (_ptr_array(dw_ih), _ptr_array(dw_hh), _ptr_array(db_ih), _ptr_array(db_hh))
+        _call('nt_lstm_bwd', lib.nt_lstm_bwd, _p(gout), H, _p(act), _p(cs), _p(gates), _p(w), R, T, L, H, E, _p(ws), _p(dx), E,
+              *grads, _stream())
         if FLOP_SINK is not None:
             FLOP_SINK['nt_lstm_bwd'] = FLOP_SINK.get('nt_lstm_bwd', 0.0) + 4.0 * R * T * 4 * H * sum((E if l == 0 else H) + H for l in range(L))
         flat = []

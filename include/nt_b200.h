@@ -222,25 +222,25 @@ int nt_global_pool_bwd(const float *g, const int32_t *argmax, int B, int N, int 
  * Buffers (all caller-owned device memory; sizes from nt_lstm_sizes):
  *   weights   : prepared by nt_lstm_prepare_weights from weight_ih_l*, weight_hh_l*, bias_ih_l*, bias_hh_l* (host arrays of L
  *               device pointers); valid until the parameters change.  128-byte aligned.
- *   hf        : fp32 [L][T+1][R][hf_ld]; slot 0 = h0, slot t+1 = h_t.  The module output (time-major) is hf[L-1][1..T][:, :H].
- *               In inference (cs == gates == NULL) only the top layer's slots 1..T are written.
- *   cs, gates : saved cell states / activated gates for nt_lstm_bwd (opaque layout); NULL in inference.
- *   workspace : scratch, 256-byte aligned; contents are not needed after the call returns (the backward has its own).
- * nt_lstm_bwd: dy [T][R][ld_dy] = gradient w.r.t. the module output (time-major).  Writes dx [R][ld_dx] (gradient w.r.t. x, may
- * be NULL) and, per layer, dw_ih [4H, in], dw_hh [4H, H], db_ih = db_hh [4H] (host arrays of L device pointers; entries or
- * whole arrays may be NULL).  tn_workspace: nt_gemm_tn_workspace_bytes() bytes. */
+ *   y         : fp32 [T][R][y_ld] -- the module output, TIME-major (top layer's h_t); columns >= H are scratch.
+ *   act       : the hidden states of all layers / steps in the tensor-core operand layout (opaque; 256-byte aligned).  Scratch
+ *               in inference; in training it is kept for nt_lstm_bwd together with
+ *   cs, gates : saved cell states / activated gates (opaque layout); both NULL in inference.
+ *   workspace : scratch, 256-byte aligned; contents are not needed after the call returns.
+ * nt_lstm_bwd: dy [T][R][ld_dy] = gradient w.r.t. y.  Writes dx [R][ld_dx] (gradient w.r.t. x, may be NULL) and, per layer,
+ * dw_ih [4H, in], dw_hh [4H, H], db_ih = db_hh [4H] (host arrays of L device pointers; entries or whole arrays may be NULL). */
 typedef struct nt_lstm_sizes_t {
-    int64_t weights_bytes, fwd_workspace_bytes, hf_bytes, cs_bytes, gates_bytes, bwd_workspace_bytes;
-    int hf_ld;
+    int64_t weights_bytes, act_bytes, fwd_workspace_bytes, y_bytes, cs_bytes, gates_bytes, bwd_workspace_bytes;
+    int y_ld;
 } nt_lstm_sizes_t;
 int nt_lstm_sizes(int R, int T, int L, int H, int E, nt_lstm_sizes_t *out);
 int nt_lstm_prepare_weights(const float *const *w_ih, const float *const *w_hh, const float *const *b_ih,
                             const float *const *b_hh, int L, int H, int E, void *weights, void *stream);
 int nt_lstm_fwd(const float *x, int ldx, const float *h0, const float *c0, const void *weights, int R, int T, int L, int H,
-                int E, float *hf, float *cs, float *gates, void *workspace, void *stream);
-int nt_lstm_bwd(const float *dy, int ld_dy, const float *x, int ldx, const float *hf, const float *cs, const float *gates,
-                const void *weights, int R, int T, int L, int H, int E, void *workspace, void *tn_workspace, float *dx,
-                int ld_dx, float *const *dw_ih, float *const *dw_hh, float *const *db_ih, float *const *db_hh, void *stream);
+                int E, float *y, void *act, float *cs, float *gates, void *workspace, void *stream);
+int nt_lstm_bwd(const float *dy, int ld_dy, const void *act, const float *cs, const float *gates, const void *weights, int R,
+                int T, int L, int H, int E, void *workspace, float *dx, int ld_dx, float *const *dw_ih, float *const *dw_hh,
+                float *const *db_ih, float *const *db_hh, void *stream);
 
 #ifdef __cplusplus
 }

@@ -80,3 +80,9 @@ for _ in range(5):
     mine_fb()
 torch.cuda.synchronize()
 print({k: round(sum(s.elapsed_time(e) for s, e in v) / 5, 4) for k, v in ops.EVENT_SINK.items()})
+ops.EVENT_SINK = {}
+ops._LSTM_SKIP_DW = True
+for _ in range(5):
+    mine_fb()
+torch.cuda.synchronize()
+print('without the weight-gradient GEMMs:', {k: round(sum(s.elapsed_time(e) for s, e in v) / 5, 4) for k, v in ops.EVENT_SINK.items()})

@@ -174,9 +174,9 @@ int main(int argc, char **argv) {
         }
     const int TR = d.tile_rows();
     std::vector<uint8_t> actbuf((size_t)(L + 1) * (T + 1) * d.RT * d.act_block_bytes(), 0xFF);       // 0xFF: unwritten bytes show up as NaN
-    std::vector<float> hf((size_t)L * (T + 1) * R * HP, NAN), cs((size_t)L * (T + 1) * d.RT * SLICES * UNITS * TR, NAN),
+    std::vector<float> y((size_t)T * R * HP, NAN), cs((size_t)L * (T + 1) * d.RT * SLICES * UNITS * TR, NAN),
         gates((size_t)L * T * d.RT * SLICES * 4 * UNITS * TR, NAN);
-    FwdOut fo{actbuf.data(), hf.data(), cs.data(), gates.data()};
+    FwdOut fo{actbuf.data(), y.data(), cs.data(), gates.data()};
     std::vector<float> cstate((size_t)L * d.RT * SLICES * TR * UNITS);
     auto CST = [&](int l, int rt, int c, int row) { return &cstate[((((size_t)l * d.RT + rt) * SLICES + c) * TR + row) * UNITS]; };
     // step -1
@@ -190,7 +190,7 @@ int main(int argc, char **argv) {
                         const int unit = UNITS * c + u;
                         const bool live = grow < R && unit < H;
                         cst[u] = live ? fc0[((size_t)l * R + grow) * H + unit] : 0.f;
-                        h[u] = live ? fh0[((size_t)l * R + grow) * H + unit] : 0.f;
+                        h[u] = live ? fh0[((size_t)l * R + grow) * H + unit] : (unit == H ? 1.f : 0.f);
                         xv[u] = (grow < R && unit < E) ? fx[(size_t)grow * E + unit] : 0.f;
                     }
                     float (&hh)[UNITS] = *reinterpret_cast<float (*)[UNITS]>(h);
@@ -199,7 +199,6 @@ int main(int argc, char **argv) {
                     store_split16(actbuf.data() + act_block_index(d, l + 1, 0, rt) * d.act_block_bytes(), d, c, row, hh);
                     if (l == 0) store_split16(actbuf.data() + act_block_index(d, 0, 0, rt) * d.act_block_bytes(), d, c, row, xx);
                     store16_rowinner(cs.data() + cs_offset(d, l, 0, rt, c), TR, row, cc);
-                    fwd_store_hf(d, hf.data(), l, 0, rt, c, row, hh);
                 }
     std::vector<float> D((size_t)TR * FWD_N);
     for (int t = 0; t < T; ++t)
@@ -219,11 +218,12 @@ int main(int argc, char **argv) {
                         }
                     }
                     for (int row = 0; row < TR; ++row) {
-                        float h[UNITS];
+                        float h[UNITS], gsave[4][UNITS];
                         float (&acc)[FWD_N] = *reinterpret_cast<float (*)[FWD_N]>(&D[(size_t)row * FWD_N]);
                         float (&cc)[UNITS] = *reinterpret_cast<float (*)[UNITS]>(CST(l, rt, c, row));
-                        fwd_cell_row(d, fo, l, t, rt, c, row, acc, &bias[((size_t)l * SLICES + c) * FWD_N], cc, h);
-                        fwd_store_hf(d, hf.data(), l, t + 1, rt, c, row, h);
+                        fwd_cell_row(d, fo, l, t, rt, c, row, acc, &bias[((size_t)l * SLICES + c) * FWD_N], cc, h, gsave);
+                        if (l == L - 1) fwd_store_y(d, y.data(), t, rt, c, row, h);
+                        fwd_store_saved(d, fo, l, t, rt, c, row, gsave, cc);
                     }
                 }
     int bad = 0;
@@ -231,26 +231,33 @@ int main(int argc, char **argv) {
         printf("%-28s max rel err %.3e (tol %.1e) %s\n", what, err, tol, err <= tol ? "ok" : "FAIL");
         if (!(err <= tol)) ++bad;
     };
+    // h of every layer / step, read back from the split blocks (hi + lo), and the fp32 output of the top layer
+    auto act_h = [&](int src, int slot, int64_t r, int unit) {
+        const int rt = (int)(r / TR), row = (int)(r % TR);
+        const uint8_t *blk = actbuf.data() + act_block_index(d, src, slot, rt) * d.act_block_bytes();
+        return bf(blk + split_offset(d, unit / 16, row, unit % 16, 0)) + bf(blk + split_offset(d, unit / 16, row, unit % 16, 1));
+    };
     {
-        double err = 0, scale = 0, ones_bad = 0;
+        double err = 0, scale = 0, ones_bad = 0, erry = 0;
         for (int l = 0; l < L; ++l)
-            for (int s = 0; s <= T; ++s)
+            for (int sl = 0; sl <= T; ++sl)
                 for (int r = 0; r < R; ++r) {
                     for (int u = 0; u < H; ++u) {
-                        const double want = HS(l, s, r, u), got = hf[state_offset(d, l, s, r) + u];
-                        err = fmax(err, fabs(want - got)); scale = fmax(scale, fabs(want));
-                        if (std::isnan(got)) err = 1e30;
+                        const double want = HS(l, sl, r, u), got = act_h(l + 1, sl, r, u);
+                        err = fmax(err, std::isnan(got) ? 1e30 : fabs(want - got)); scale = fmax(scale, fabs(want));
+                        if (l == L - 1 && sl > 0) { const double gy = y[y_offset(d, sl - 1, r) + u]; erry = fmax(erry, std::isnan(gy) ? 1e30 : fabs(want - gy)); }
                     }
-                    if (hf[state_offset(d, l, s, r) + H] != 1.f) ones_bad = 1;
+                    if (act_h(l + 1, sl, r, H) != 1.f) ones_bad = 1;
                 }
         report("forward h (all layers)", err / scale, 5e-5);
+        report("forward y (top layer)", erry / scale, 5e-5);
         report("ones column", ones_bad, 0.0);
     }
 
     // ---- backward
     std::vector<uint8_t> dgs((size_t)L * T * d.RT * d.dg_block_bytes(), 0xFF);
-    std::vector<float> dgf((size_t)L * T * R * 4 * HP, NAN), dxbuf((size_t)L * T * d.RT * SLICES * TR * UNITS, NAN), dx0((size_t)R * E, NAN);
-    BwdIo io{cs.data(), gates.data(), fdy.data(), H, dgs.data(), dgf.data(), dxbuf.data(), dx0.data(), E};
+    std::vector<float> dxbuf((size_t)L * T * d.RT * SLICES * TR * UNITS, NAN), dx0((size_t)R * E, NAN);
+    BwdIo io{cs.data(), gates.data(), fdy.data(), H, dgs.data(), dxbuf.data(), dx0.data(), E};
     std::vector<float> dcst((size_t)L * d.RT * SLICES * TR * UNITS, 0.f), dhrec(dcst.size(), 0.f), dxsum(dcst.size(), 0.f);
     auto ST = [&](std::vector<float> &v, int l, int rt, int c, int row) { return &v[((((size_t)l * d.RT + rt) * SLICES + c) * TR + row) * UNITS]; };
     std::vector<float> D2((size_t)TR * BWD_N);
@@ -273,7 +280,6 @@ int main(int argc, char **argv) {
                         for (int u = 0; u < UNITS; ++u) dh[u] += rec[u];
                         float (&dcr)[UNITS] = *reinterpret_cast<float (*)[UNITS]>(ST(dcst, l, rt, c, row));
                         bwd_cell_row(d, io, l, t, rt, c, row, dh, dcr, dgo);
-                        bwd_store_dgf(d, dgf.data(), l, t, rt, c, row, dgo);
                     }
             for (int rt = 0; rt < d.RT; ++rt)
                 for (int c = 0; c < SLICES; ++c) {
@@ -317,27 +323,61 @@ int main(int argc, char **argv) {
         for (size_t i = 0; i < rdx.size(); ++i) { err = fmax(err, std::isnan(dx0[i]) ? 1e30 : fabs(rdx[i] - dx0[i])); scale = fmax(scale, fabs(rdx[i])); }
         report("backward dx", err / scale, 5e-5);
     }
-    // weight gradients the way nt_lstm_bwd assembles them: raw = dG^T . [X | H_prev | 1], un-padded by lstm_finish_grads_kernel
-    for (int l = 0; l < L; ++l) {
-        const int in = l == 0 ? E : H;
-        double e_ih = 0, s_ih = 0, e_hh = 0, s_hh = 0, e_b = 0, s_b = 0;
-        for (int row = 0; row < 4 * H; ++row) {
-            const int gate = row / H, u = row % H, col_a = gate * HP + u;
-            std::vector<double> acc_ih(in, 0.0), acc_hh(H + 1, 0.0);
-            for (int t = 0; t < T; ++t)
-                for (int r = 0; r < R; ++r) {
-                    const double g = dgf[dgf_offset(d, l, t, r) + col_a];
-                    for (int k = 0; k < in; ++k) acc_ih[k] += g * (l == 0 ? (double)fx[(size_t)r * E + k] : (double)hf[state_offset(d, l - 1, t + 1, r) + k]);
-                    for (int k = 0; k <= H; ++k) acc_hh[k] += g * hf[state_offset(d, l, t, r) + k];
-                }
-            for (int k = 0; k < in; ++k) { e_ih = fmax(e_ih, fabs(acc_ih[k] - rdw_ih[l][(size_t)row * in + k])); s_ih = fmax(s_ih, fabs(rdw_ih[l][(size_t)row * in + k])); }
-            for (int k = 0; k < H; ++k) { e_hh = fmax(e_hh, fabs(acc_hh[k] - rdw_hh[l][(size_t)row * H + k])); s_hh = fmax(s_hh, fabs(rdw_hh[l][(size_t)row * H + k])); }
-            e_b = fmax(e_b, fabs(acc_hh[H] - rdb[l][row])); s_b = fmax(s_b, fabs(rdb[l][row]));
+    // weight gradients the way lstm_dw_kernel + lstm_finish_grads_kernel compute them: per (layer, which, m-tile) a 256 x 256
+    // tile, K-blocks of 32 rows copied group by group into the stage image, operands read through MN-major descriptors
+    // (element (m, k): start + (m/8)*SBO + (k/8)*LBO + (k%8)*16 + (m%8)*2 with LBO = 128, SBO = DW_GROUP_BYTES)
+    {
+        const int tiles = L * 2 * DW_M_TILES, n_kb = T * d.RT * d.nsub * 4;
+        std::vector<float> partial((size_t)tiles * DW_TILE * DW_TILE, 0.f);
+        std::vector<uint8_t> stage(DW_STAGE_BYTES);
+        auto mn_elem = [&](const uint8_t *plane, int m, int k) { return bf(plane + (m / 8) * DW_GROUP_BYTES + (k / 8) * 128 + (k % 8) * 16 + (m % 8) * 2); };
+        for (int tile = 0; tile < tiles; ++tile) {
+            const int l = tile / (2 * DW_M_TILES), which = (tile / DW_M_TILES) & 1, mt = tile % DW_M_TILES;
+            float *D = &partial[(size_t)tile * DW_TILE * DW_TILE];
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const DwKBlock k = dw_kblock(d, kb);
+                const uint8_t *a_blk = dgs.data() + dg_block_index(d, l, k.t, k.rt) * d.dg_block_bytes();
+                const uint8_t *b_blk = actbuf.data() + dw_b_block(d, l, which, k.t, k.rt) * d.act_block_bytes();
+                for (int lane = 0; lane < 32; ++lane)
+                    for (int plane = 0; plane < 2; ++plane) {
+                        memcpy(&stage[plane * DW_PLANE_BYTES + lane * DW_GROUP_BYTES],
+                               a_blk + group_offset(d, mt * DW_GROUPS + lane, k.sub, plane) + k.rowblk * DW_GROUP_BYTES, DW_GROUP_BYTES);
+                        memcpy(&stage[(2 + plane) * DW_PLANE_BYTES + lane * DW_GROUP_BYTES],
+                               b_blk + group_offset(d, lane, k.sub, plane) + k.rowblk * DW_GROUP_BYTES, DW_GROUP_BYTES);
+                    }
+                for (int m = 0; m < DW_TILE; ++m)
+                    for (int nn = 0; nn < DW_TILE; ++nn) {
+                        float acc = 0.f;
+                        for (int kk = 0; kk < DW_KB_ROWS; ++kk) {
+                            const float ah = mn_elem(&stage[0], m, kk), al = mn_elem(&stage[DW_PLANE_BYTES], m, kk);
+                            const float bh = mn_elem(&stage[2 * DW_PLANE_BYTES], nn, kk), bl = mn_elem(&stage[3 * DW_PLANE_BYTES], nn, kk);
+                            acc += ah * bh + ah * bl + al * bh;
+                        }
+                        D[(size_t)m * DW_TILE + nn] += acc;
+                    }
+            }
         }
-        char name[64];
-        snprintf(name, sizeof(name), "backward dW_ih[%d]", l); report(name, e_ih / s_ih, 5e-5);
-        snprintf(name, sizeof(name), "backward dW_hh[%d]", l); report(name, e_hh / s_hh, 5e-5);
-        snprintf(name, sizeof(name), "backward db[%d]", l); report(name, e_b / s_b, 5e-5);
+        for (int l = 0; l < L; ++l) {
+            const int in = l == 0 ? E : H;
+            double e_ih = 0, s_ih = 0, e_hh = 0, s_hh = 0, e_b = 0, s_b = 0;
+            for (int row = 0; row < 4 * H; ++row) {
+                const int gate = row / H, unit = row % H, m = gate_perm_index(unit, gate);
+                for (int which = 0; which < 2; ++which) {
+                    const int tile = (l * 2 + which) * DW_M_TILES + m / DW_TILE;
+                    const float *src = &partial[((size_t)tile * DW_TILE + (m % DW_TILE)) * DW_TILE];
+                    if (which == 0)
+                        for (int k = 0; k < in; ++k) { e_ih = fmax(e_ih, fabs(src[k] - rdw_ih[l][(size_t)row * in + k])); s_ih = fmax(s_ih, fabs(rdw_ih[l][(size_t)row * in + k])); }
+                    else {
+                        for (int k = 0; k < H; ++k) { e_hh = fmax(e_hh, fabs(src[k] - rdw_hh[l][(size_t)row * H + k])); s_hh = fmax(s_hh, fabs(rdw_hh[l][(size_t)row * H + k])); }
+                        e_b = fmax(e_b, fabs(src[H] - rdb[l][row])); s_b = fmax(s_b, fabs(rdb[l][row]));
+                    }
+                }
+            }
+            char name[64];
+            snprintf(name, sizeof(name), "backward dW_ih[%d]", l); report(name, e_ih / s_ih, 5e-5);
+            snprintf(name, sizeof(name), "backward dW_hh[%d]", l); report(name, e_hh / s_hh, 5e-5);
+            snprintf(name, sizeof(name), "backward db[%d]", l); report(name, e_b / s_b, 5e-5);
+        }
     }
     printf(bad ? "EMULATION FAILED (%d)\n" : "emulation ok\n", bad);
     return bad ? 1 : 0;
