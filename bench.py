@@ -226,14 +226,14 @@ def main():
 
     import garment_pattern_estimation_b200 as g
     from garment_pattern_estimation_b200 import _lib, ops
-    from garment_pattern_estimation_b200.parallel import FlatDataParallel, GraphedTrainStep
+    from garment_pattern_estimation_b200.parallel import FlatAdam, FlatDataParallel, GraphedTrainStep
 
     B, N, k = WORKLOAD['batch_per_gpu'], WORKLOAD['points'], WORKLOAD['k']
     dc, nc, lc = att_configs(k)
     torch.manual_seed(SEED_INIT)
     model = g.GarmentSegmentPattern3D(dc, nc, lc).to(dev).train()
     wrapper = FlatDataParallel(model, device_ids=[dev], auto_reduce=False)
-    opt = torch.optim.Adam(model.parameters(), lr=2e-3, capturable=True)
+    opt = FlatAdam(wrapper, lr=2e-3)            # torch.optim.Adam semantics, one kernel on the flat buffers (csrc/train_step.cu)
 
     # 4 distinct synthetic batches per rank, in pinned host memory (e2e) and resident copies (value)
     host, resident = [], []
@@ -249,9 +249,8 @@ def main():
         out = wrapper(x)
         loss, _, _ = model.loss(out, gt)
         loss.backward()
-        wrapper.reduce_gradients()
-        opt.step()
-        wrapper.zero_grad()
+        wrapper.sum_gradients()                  # one NCCL all-reduce of the flat gradient buffer (no-op on one GPU)
+        opt.step(zero_grad=True)                 # the 1 / world_size average and zero_grad are folded into the Adam kernel
         return loss
 
     # The product's training-step API: the whole step captured once into a CUDA graph (parallel.GraphedTrainStep) and

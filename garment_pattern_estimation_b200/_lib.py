@@ -39,6 +39,17 @@ class LstmSizes(ctypes.Structure):
                 ('cs_bytes', c_int64), ('gates_bytes', c_int64), ('bwd_workspace_bytes', c_int64), ('y_ld', c_int)]
 
 
+class PatternLossArgs(ctypes.Structure):
+    """Mirror of `struct nt_pattern_loss_args`."""
+    _fields_ = [('outlines', c_void_p), ('outl_stride_b', c_int64), ('outl_stride_p', c_int64), ('outl_stride_e', c_int64),
+                ('rotations', c_void_p), ('rot_stride_b', c_int64), ('rot_stride_p', c_int64),
+                ('translations', c_void_p), ('tr_stride_b', c_int64), ('tr_stride_p', c_int64),
+                ('gt_outlines', c_void_p), ('gt_rotations', c_void_p), ('gt_translations', c_void_p), ('num_edges', c_void_p),
+                ('B', c_int), ('P', c_int), ('Lp', c_int), ('D', c_int), ('Dr', c_int), ('Dt', c_int),
+                ('pad_x', c_float), ('pad_y', c_float), ('loop_weight', c_float),
+                ('use_shape', c_int), ('use_loop', c_int), ('use_rotation', c_int), ('use_translation', c_int)]
+
+
 _PP = ctypes.POINTER(c_void_p)      # host array of device pointers
 
 _SIGNATURES = {
@@ -85,6 +96,10 @@ _SIGNATURES = {
                                  c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'nt_global_pool_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'nt_global_pool_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    'nt_pattern_loss_fwd': (c_int, [ctypes.POINTER(PatternLossArgs), c_void_p, c_void_p, c_void_p]),
+    'nt_pattern_loss_bwd': (c_int, [ctypes.POINTER(PatternLossArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'nt_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_float,
+                             c_float, c_int, c_void_p, c_void_p]),
     'nt_lstm_sizes': (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(LstmSizes)]),
     'nt_lstm_prepare_weights': (c_int, [_PP, _PP, _PP, _PP, c_int, c_int, c_int, c_void_p, c_void_p]),
     'nt_lstm_fwd': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -19,6 +19,7 @@ NotImplementedError only when a call would actually evaluate them.
 import torch
 import torch.nn.functional as F
 
+from . import ops
 from .metrics import PatternQuality
 
 _MAIN = ('shape', 'loop', 'rotation', 'translation')
@@ -244,18 +245,31 @@ class ComposedPatternLoss:
                         gt['stitch_tags'] = shift_panel_rows(gt['stitch_tags'], lead, ne)
         loss_dict = {}
         full = 0.
-        if 'shape' in self.l_components:
-            loss_dict['pattern_loss'] = F.mse_loss(preds['outlines'], gt['outlines'])
-            full = full + loss_dict['pattern_loss']
-        if 'loop' in self.l_components:
-            loss_dict['loop_loss'] = panel_loop_loss(preds['outlines'], gt['num_edges'].int().view(-1), self.pad_xy)
-            full = full + self.config['loop_loss_weight'] * loss_dict['loop_loss']
-        if 'rotation' in self.l_components:
-            loss_dict['rotation_loss'] = F.mse_loss(preds['rotations'], gt['rotations'])
-            full = full + loss_dict['rotation_loss']
-        if 'translation' in self.l_components:
-            loss_dict['translation_loss'] = F.mse_loss(preds['translations'], gt['translations'])
-            full = full + loss_dict['translation_loss']
+        fused = (preds['outlines'].is_cuda and preds['outlines'].dim() == 4 and 'rotations' in preds and 'translations' in preds
+                 and all(preds[k].dtype == torch.float32 and preds[k].stride(-1) == 1 for k in ('outlines', 'rotations', 'translations')))
+        if fused:
+            # one kernel for the four terms and one for their gradients (csrc/train_step.cu) instead of ~50 element-wise launches
+            pad = (0., 0.) if self.pad_xy is None else (float(self.pad_xy[0]), float(self.pad_xy[1]))
+            parts = ops.pattern_loss(preds['outlines'], preds['rotations'], preds['translations'], gt['outlines'], gt['rotations'],
+                                     gt['translations'], gt['num_edges'], self.l_components, self.config['loop_loss_weight'], pad)
+            full = parts[0]
+            for i, (name, key) in enumerate((('shape', 'pattern_loss'), ('loop', 'loop_loss'), ('rotation', 'rotation_loss'),
+                                             ('translation', 'translation_loss'))):
+                if name in self.l_components:
+                    loss_dict[key] = parts[i + 1]
+        else:
+            if 'shape' in self.l_components:
+                loss_dict['pattern_loss'] = F.mse_loss(preds['outlines'], gt['outlines'])
+                full = full + loss_dict['pattern_loss']
+            if 'loop' in self.l_components:
+                loss_dict['loop_loss'] = panel_loop_loss(preds['outlines'], gt['num_edges'].int().view(-1), self.pad_xy)
+                full = full + self.config['loop_loss_weight'] * loss_dict['loop_loss']
+            if 'rotation' in self.l_components:
+                loss_dict['rotation_loss'] = F.mse_loss(preds['rotations'], gt['rotations'])
+                full = full + loss_dict['rotation_loss']
+            if 'translation' in self.l_components:
+                loss_dict['translation_loss'] = F.mse_loss(preds['translations'], gt['translations'])
+                full = full + loss_dict['translation_loss']
         if stitch_stage:                                             # composed_loss.py:336-363
             if 'stitch' in self.l_components:
                 st_loss, parts = pattern_stitch_loss(preds['stitch_tags'], gt['stitches'], gt['num_stitches'],

@@ -672,6 +672,66 @@ def lstm_decoder(x, h0, c0, T, params):
     return _LSTMDecoderFunction.apply(x, h0, c0, int(T), *params)
 
 
+# ----------------------------------------------------------------------------------------------------------
+# pattern loss (shape / loop / rotation / translation) and Adam on a flat buffer (csrc/train_step.cu)
+# ----------------------------------------------------------------------------------------------------------
+class _PatternLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, outl, rot, tr, gt_outl, gt_rot, gt_tr, num_edges, cfg):
+        _require_cuda(outl, rot, tr, gt_outl, gt_rot, gt_tr, num_edges)
+        for t in (outl, rot, tr):
+            if t.dtype != torch.float32 or t.stride(-1) != 1:
+                raise RuntimeError('pattern_loss: predictions must be fp32 with a dense last dimension')
+        B, P, Lp, D = outl.shape
+        a = _lib.PatternLossArgs()
+        a.outlines, a.outl_stride_b, a.outl_stride_p, a.outl_stride_e = outl.data_ptr(), outl.stride(0), outl.stride(1), outl.stride(2)
+        a.rotations, a.rot_stride_b, a.rot_stride_p = rot.data_ptr(), rot.stride(0), rot.stride(1)
+        a.translations, a.tr_stride_b, a.tr_stride_p = tr.data_ptr(), tr.stride(0), tr.stride(1)
+        gt_outl, gt_rot, gt_tr = gt_outl.contiguous().float(), gt_rot.contiguous().float(), gt_tr.contiguous().float()
+        num_edges = num_edges.contiguous().long()
+        a.gt_outlines, a.gt_rotations, a.gt_translations, a.num_edges = (gt_outl.data_ptr(), gt_rot.data_ptr(), gt_tr.data_ptr(),
+                                                                           num_edges.data_ptr())
+        a.B, a.P, a.Lp, a.D, a.Dr, a.Dt = B, P, Lp, D, rot.shape[-1], tr.shape[-1]
+        a.pad_x, a.pad_y, a.loop_weight = cfg['pad_x'], cfg['pad_y'], cfg['loop_weight']
+        a.use_shape, a.use_loop, a.use_rotation, a.use_translation = (int(cfg[k]) for k in ('shape', 'loop', 'rotation', 'translation'))
+        acc = torch.empty(5, dtype=torch.float64, device=outl.device)
+        out = torch.empty(5, dtype=torch.float32, device=outl.device)
+        _call('nt_pattern_loss_fwd', _lib.load().nt_pattern_loss_fwd, ctypes.byref(a), _p(acc), _p(out), _stream())
+        ctx.args = a
+        ctx.save_for_backward(outl, rot, tr, gt_outl, gt_rot, gt_tr, num_edges)          # keeps the pointers in `a` alive
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        outl, rot, tr = ctx.saved_tensors[:3]
+        # only the total (element 0) carries gradient in the training step; the parts are reported values
+        gscale = g[0:1].contiguous()
+        g_outl = torch.empty(outl.shape, dtype=torch.float32, device=outl.device)
+        g_rot = torch.empty(rot.shape, dtype=torch.float32, device=outl.device)
+        g_tr = torch.empty(tr.shape, dtype=torch.float32, device=outl.device)
+        _call('nt_pattern_loss_bwd', _lib.load().nt_pattern_loss_bwd, ctypes.byref(ctx.args), _p(gscale), _p(g_outl), _p(g_rot),
+              _p(g_tr), _stream())
+        return g_outl, g_rot, g_tr, None, None, None, None, None
+
+
+def pattern_loss(outlines, rotations, translations, gt_outlines, gt_rotations, gt_translations, num_edges, components,
+                 loop_weight=1.0, pad_xy=(0.0, 0.0)):
+    """The main loss terms of ComposedPatternLoss (composed_loss.py:294-321) in one kernel.  Returns a [5] tensor:
+    (total, pattern_loss, loop_loss, rotation_loss, translation_loss); gradients flow from element 0 only."""
+    cfg = dict(shape='shape' in components, loop='loop' in components, rotation='rotation' in components,
+               translation='translation' in components, loop_weight=float(loop_weight), pad_x=float(pad_xy[0]), pad_y=float(pad_xy[1]))
+    return _PatternLossFunction.apply(outlines, rotations, translations, gt_outlines, gt_rotations, gt_translations, num_edges, cfg)
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, state, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0,
+              zero_grad=True):
+    """torch.optim.Adam on flat fp32 buffers; `lr` is a 1-element device tensor, `state` a 2-element device tensor (zeros at start)."""
+    _require_cuda(params, grads, exp_avg, exp_avg_sq, lr, state)
+    _call('nt_adam_step', _lib.load().nt_adam_step, _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), params.numel(), _p(lr),
+          float(betas[0]), float(betas[1]), float(eps), float(weight_decay), float(grad_scale), int(bool(zero_grad)), _p(state),
+          _stream())
+
+
 class _LinearFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):

@@ -242,6 +242,34 @@ int nt_lstm_bwd(const float *dy, int ld_dy, const void *act, const float *cs, co
                 int T, int L, int H, int E, void *workspace, float *dx, int ld_dx, float *const *dw_ih, float *const *dw_hh,
                 float *const *db_ih, float *const *db_hh, void *stream);
 
+/* ---- training step: loss and optimizer (nn/trainer.py:96-101) ---------------------------------------------------------------------
+ * The four loss terms of the shipped attention config (models/att/att.yaml:124) -- nn.MSELoss on outlines / rotations /
+ * translations (nn/metrics/composed_loss.py:301-321) and PanelLoopLoss (nn/metrics/losses.py:19-51: for every panel with
+ * num_edges >= 3, the squared sum of its first num_edges edge vectors minus the padding vector, averaged over ALL panels x 2) --
+ * in one pass.  Predictions may be strided views (element strides; the last dimension must be dense), ground truth is contiguous.
+ * fwd: acc5 = 5 doubles of scratch, out5 = {total, pattern_loss, loop_loss, rotation_loss, translation_loss} (device floats).
+ * bwd: gradients w.r.t. the three predictions (contiguous), multiplied by the device scalar *grad_scale. */
+typedef struct nt_pattern_loss_args {
+    const float *outlines; int64_t outl_stride_b, outl_stride_p, outl_stride_e;     /* [B, P, Lp, D] */
+    const float *rotations; int64_t rot_stride_b, rot_stride_p;                      /* [B, P, Dr] */
+    const float *translations; int64_t tr_stride_b, tr_stride_p;                     /* [B, P, Dt] */
+    const float *gt_outlines, *gt_rotations, *gt_translations;
+    const int64_t *num_edges;                                                        /* [B, P] */
+    int B, P, Lp, D, Dr, Dt;
+    float pad_x, pad_y, loop_weight;
+    int use_shape, use_loop, use_rotation, use_translation;
+} nt_pattern_loss_args;
+int nt_pattern_loss_fwd(const nt_pattern_loss_args *args, double *acc5, float *out5, void *stream);
+int nt_pattern_loss_bwd(const nt_pattern_loss_args *args, const float *grad_scale, float *g_outlines, float *g_rotations,
+                        float *g_translations, void *stream);
+
+/* torch.optim.Adam (nn/trainer.py:64,98-99; amsgrad off) on one flat buffer of n parameters: g = grads * grad_scale
+ * (+ weight_decay * p), moment updates, bias-corrected update, and -- if zero_grad -- grads = 0 (optimizer.zero_grad).
+ * lr: device scalar (a stepping scheduler only rewrites it).  state2: two device floats, zero-initialised by the caller once:
+ * [0] = number of steps taken (advanced by the kernel), [1] = internal.  CUDA-graph safe. */
+int nt_adam_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, const float *lr, float beta1,
+                 float beta2, float eps, float weight_decay, float grad_scale, int zero_grad, float *state2, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
