@@ -4,12 +4,19 @@ gradient all-reduce -> Adam) of the attention model on synthetic clouds (BASELIN
 models/att architecture, N = 2048 points, batch 32 per GPU, k = 5), plus the roofline of the dominant kernel and the
 oracle's CPU timing on the same box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config C2|C3|C4|C5] [--no-extras]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One JSON line on stdout (rank 0).  `value` = clouds/s with the inputs already resident in HBM, device-timed with CUDA events,
 max over ranks; `e2e` = the same step through the public module API with inputs in pinned HOST memory (H2D every step, loss
-read back every step).  Weak scaling: every rank keeps 32 clouds.
+read back every step).  The headline line is C2 under weak scaling (every rank keeps 32 clouds).
+
+The other BASELINE.json configurations ride along in the same line under `extras` (skip with --no-extras) or become the headline
+with --config:
+  C3  training step at a FIXED global batch of 64 clouds split over the ranks (strong scaling; 8 clouds per GPU at 8 ranks)
+  C4  EdgeConv encoder forward + backward, B=16, N=10 000, k=16 (kNN stress; one GPU)
+  C5  full-model inference (eval mode, shipped checkpoint when tests/golden/_ckpt/att_state.pt exists), B=128 split over the
+      ranks, N in {1024, 2048, 4096, 8192}
 """
 import argparse
 import json
@@ -26,7 +33,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(points=2048, batch_per_gpu=32, k=5)           # BASELINE.json configs[1] (C2)
-CPU_SAMPLE_CLOUDS = 4                                          # bounded CPU sample (cpu_baseline / --impl reference)
+CPU_SAMPLE_CLOUDS = 8                                          # cpu_baseline sample inside the b200 arm (B reduced to 8)
+C3_GLOBAL_BATCH = 64
 SEED_INIT = 916143406                                          # models/att/att.yaml:147
 FP32_LANES_PER_SM, SMS = 128, 148
 
@@ -112,7 +120,10 @@ class ClockSampler:
 # CPU arm: the oracle (pure-PyTorch restatement of the reference path; the reference itself cannot be imported on the
 # GPU box -- torch_geometric / torch_cluster / sparsemax are not installable and /root/reference is absent there)
 # ------------------------------------------------------------------------------------------------------------
-def cpu_train_steps(steps, warmup, k, threads=None):
+def cpu_train_steps(steps, warmup, k, clouds, threads=None, budget_s=None):
+    """The oracle (restatement of nn/nets.py + nn/net_blocks.py + the 4 active loss terms, stock Python loops) training on the host
+    cores: `clouds` per step.  With `budget_s` the number of timed steps is cut so that the run stays inside the budget (the cut is
+    reported).  Returns (clouds/s, seconds per step, threads, timed steps)."""
     from oracle import model as om
     from oracle import thirdparty as tp
     cores = threads or (os.cpu_count() or 1)
@@ -122,46 +133,52 @@ def cpu_train_steps(steps, warmup, k, threads=None):
     torch.manual_seed(SEED_INIT)
     model = om.OracleSegmentPattern3D(dc, nc, lc).train()          # the CPU arm is the one place that executes oracle/
     opt = torch.optim.Adam(model.parameters(), lr=2e-3)
-    x, gt = synthetic_batch(CPU_SAMPLE_CLOUDS, WORKLOAD['points'], seed=1234)
-    times = []
+    x, gt = synthetic_batch(clouds, WORKLOAD['points'], seed=1234)
+    times, t_start = [], time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        out = model(x, fast=True)
-        loss, _ = om.main_losses(out, gt, fast=True)
+        out = model(x)
+        loss, _ = om.main_losses(out, gt)
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
+        dt = time.perf_counter() - t0
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(dt)
+        if budget_s is not None and i >= warmup + 2 and (time.perf_counter() - t_start) + dt > budget_s:
+            break
     sec = sum(times) / len(times)
-    return CPU_SAMPLE_CLOUDS / sec, sec, cores
+    return clouds / sec, sec, cores, len(times)
 
 
-def cpu_best(steps, warmup, k):
-    """All host threads is not always the fastest setting for these small per-cloud GEMMs: try the full core count and
-    two smaller pools (one quick step each) and time the reported baseline with the best of them."""
+def cpu_best_threads(k):
+    """All host threads is not always the fastest setting for these small per-cloud GEMMs: probe the full core count and two
+    smaller pools with one quick 2-cloud step each."""
     total = os.cpu_count() or 1
     cands = sorted({total, max(1, total // 2), min(total, 32)}, reverse=True)
-    if len(cands) > 1:
-        probe = {t: cpu_train_steps(1, 1, k, threads=t)[0] for t in cands}
-        best = max(probe, key=probe.get)
-    else:
-        best = cands[0]
-    return cpu_train_steps(steps, warmup, k, threads=best)
+    if len(cands) == 1:
+        return cands[0]
+    probe = {t: cpu_train_steps(1, 1, k, clouds=2, threads=t)[0] for t in cands}
+    return max(probe, key=probe.get)
 
 
 def run_reference_arm(args, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path (the oracle port -- the reference is Python and its
+    third-party operators cannot be installed) at the SAME batch as the b200 arm (32 clouds x 2048 points per
+    step), the requested number of steps unless that would exceed ~2.5 minutes of host time (then fewer, stated in `sample`)."""
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    cps, sec, cores = cpu_best(steps, warmup, WORKLOAD['k'])
-    sample = '{} clouds x {} pts per step, {} timed steps (oracle port of nn/nets.py + nn/net_blocks.py, torch CPU ' \
-             'fp32, {} threads)'.format(CPU_SAMPLE_CLOUDS, WORKLOAD['points'], steps, cores)
+    k, clouds = WORKLOAD['k'], WORKLOAD['batch_per_gpu']
+    threads = cpu_best_threads(k)
+    cps, sec, cores, timed = cpu_train_steps(args.steps, max(1, min(args.warmup, 3)), k, clouds=clouds, threads=threads, budget_s=150.0)
+    sample = '{} clouds x {} pts per step (the full C2 batch), {} timed steps of {} requested after warm-up, {:.2f} s/step; oracle ' \
+             'port of nn/nets.py + nn/net_blocks.py + the 4 loss terms with the reference\'s own Python loops, torch CPU fp32, {} ' \
+             'threads'.format(clouds, WORKLOAD['points'], timed, args.steps, sec, cores)
     line = {
         'impl': 'reference', 'metric': 'point-clouds/sec (fwd+bwd+optimizer, training step)', 'value': cps,
-        'unit': 'clouds/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3,
+        'unit': 'clouds/s', 'n_gpus': args.gpus, 'steps': timed, 'warmup': max(1, min(args.warmup, 3)), 'ms_per_step': sec * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(args.gpus),
+        'config': workload_config(1),
         'cpu_baseline': {'value': cps, 'unit': 'clouds/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': cps, 'unit': 'clouds/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,

@@ -283,8 +283,15 @@ class _FusedMLPFunction(torch.autograd.Function):
                                       _p(wn), _p(bn_), n_next, _p(w_f), _p(w_ft), _p(b_f), _stream())
             return vec, w_f, w_ft, b_f
 
+        # one zero-fill for the BatchNorm statistics of every layer of this call (was one fill kernel per layer)
+        stats_all = torch.zeros(2 * sum(widths), dtype=torch.float64, device=dev) if training else None
+        stats_off = [2 * sum(widths[:l]) for l in range(L)]
+
+        def stats_of(layer):
+            return stats_all[stats_off[layer]:stats_off[layer] + 2 * widths[layer]] if training else None
+
         # ---- BN_1 statistics of a_1 = relu(P + Q) (no GEMM at row level); edge mode also materialises a_1
-        stats = torch.zeros(2 * H1, dtype=torch.float64, device=dev) if training else None
+        stats = stats_of(0)
         a1 = None
         if EDGE_MATERIALIZE:           # both row modes: every consumer then streams a plain, 16-byte aligned operand
             a1 = _rowbuf(R, H1, dev)
@@ -302,7 +309,7 @@ class _FusedMLPFunction(torch.autograd.Function):
         acts = [None] * (L + 1)       # acts[l] = a_l for l >= 2 (a_1 is recomputed from pq)
         for l in range(1, L - 1):
             Hn = widths[l]
-            stats = torch.zeros(2 * Hn, dtype=torch.float64, device=dev) if training else None
+            stats = stats_of(l)
             out = _rowbuf(R, Hn, dev)
             if l == 1:
                 gemm_nt(R, widths[0], Hn, w_f, widths[0], NT_EPI_RELU_STATS, bias=b_f, out=out,
@@ -315,7 +322,7 @@ class _FusedMLPFunction(torch.autograd.Function):
 
         # ---- last layer
         HL, Kin = widths[L - 1], widths[L - 2]
-        stats = torch.zeros(2 * HL, dtype=torch.float64, device=dev) if training else None
+        stats = stats_of(L - 1)
         last_in = first_in if L == 2 else dict(a=acts[L - 1], lda=acts[L - 1].stride(0))
         need_bwd = training and any(ctx.needs_input_grad)
         if mode == 'edge':
@@ -379,14 +386,24 @@ class _FusedMLPFunction(torch.autograd.Function):
         grads_W, grads_b, grads_g, grads_beta = [None] * L, [None] * L, [None] * L, [None] * L
 
         # ---- trailing BN (after the aggregation in edge mode): column sums, then dz_L for every row
+        # one zero-fill for every double accumulator of the backward: [sums 2HL | csum_l (l = L-1 .. 0) | raw_l (l = L-1 .. 1)]
+        n_acc = 2 * HL + sum(widths) + sum(widths[l] * widths[l - 1] for l in range(1, L))
+        acc_all = torch.zeros(n_acc, **f64)
+        acc_pos = [0]
+
+        def take(n):
+            out = acc_all[acc_pos[0]:acc_pos[0] + n]
+            acc_pos[0] += n
+            return out
+
         mean, rstd, s, t = bn_vec[L - 1]
-        sums = torch.zeros(2 * HL, **f64)
+        sums = take(2 * HL)
         v_ref = vsel if mode == 'edge' else acts[L]
         _call('nt_bn_bwd_reduce', _lib.load().nt_bn_bwd_reduce, _p(gout), ldg, _p(v_ref), v_ref.stride(0), _p(mean), _p(rstd), M, HL, _p(sums), _stream())
         grads_beta[L - 1] = sums[:HL].float()
         grads_g[L - 1] = sums[HL:].float()
         dz = _rowbuf(R, HL, dev)
-        csum = torch.zeros(HL, **f64)
+        csum = take(HL)
         _call('nt_bn_relu_bwd_last', _lib.load().nt_bn_relu_bwd_last, _p(acts[L]), acts[L].stride(0), _p(gout), ldg, _p(sel), k, _p(s), _p(mean), _p(rstd),
                                            _p(sums), R, R, HL, _p(dz), dz.stride(0), _p(csum), _stream())
 
@@ -395,7 +412,7 @@ class _FusedMLPFunction(torch.autograd.Function):
         for l in range(L - 1, 0, -1):
             Hout, Hin = widths[l], widths[l - 1]
             pmean, prstd, ps, pt = bn_vec[l - 1]
-            raw = torch.zeros(Hout, Hin, **f64)            # dz^T . (a_l - mean_l), accumulated in double
+            raw = take(Hout * Hin).view(Hout, Hin)         # dz^T . (a_l - mean_l), accumulated in double
             if l == 1 and a1 is None:
                 gemm_tn(dz, dz.stride(0), Hout, R, raw, n=Hin, edge=src, mu=pmean)
             else:
@@ -408,7 +425,7 @@ class _FusedMLPFunction(torch.autograd.Function):
                                             _p(vecs[1]), _p(vecs[2]), _p(vecs[3]), _stream())
             grads_W[l], grads_b[l] = dW, db
             grads_g[l - 1], grads_beta[l - 1] = vecs[0], vecs[1]
-            csum_prev = torch.zeros(Hin, **f64)
+            csum_prev = take(Hin)
             if l == 1 and mode == 'edge' and a1 is not None and FUSED_SCATTER:
                 dpq = torch.zeros(M, 2 * H1, **f32)
                 if gemm_nt(R, Hout, Hin, w_fts[l], Hout, NT_EPI_BNRELU_BWD, a=dz, lda=dz.stride(0), edge=src, aux=acts[l],

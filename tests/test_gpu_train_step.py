@@ -42,6 +42,9 @@ def test_pattern_loss_kernel_matches_torch(cuda_device, components):
     (got[0] * 1.5).backward()
     (total * 1.5).backward()
     for a, b, name in ((dec.grad, dec2.grad, 'decoder output'), (place.grad, place2.grad, 'placement')):
+        if b is None:                                      # term not requested: the kernel returns exact zeros
+            assert float(a.abs().max()) == 0.0, name
+            continue
         assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-12, name
 
 
@@ -120,7 +123,8 @@ def test_graphed_step_with_flat_adam_follows_the_scheduler(cuda_device):
         torch.cuda.synchronize()
         if graphed:
             assert float(wrapper.flat_grad.abs().max()) == 0.0 and opt.steps_taken == 4
-        return losses, lrs, {k: v.detach().clone() for k, v in model.state_dict().items()}
+        # parameters only: the BatchNorm running statistics of the graphed arm also saw the warm-up passes of the capture
+        return losses, lrs, {k: v.detach().clone() for k, v in model.named_parameters()}
 
     l_ref, lr_ref, sd_ref = run(False)
     l_g, lr_g, sd_g = run(True)
