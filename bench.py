@@ -203,12 +203,129 @@ def encoder_roofline(groups, ms_per_step, B, N, hbm_peak):
                     'construction (SURVEY F9: the fused path is compute-bound), reported because BASELINE.json asks for it'}
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, strong=False):
+    if strong:
+        return {'workload': 'C3: attention model (models/att NN config) training step, N=2048 pts/cloud, k=5, FIXED global batch {} '
+                            '({} clouds per GPU), Adam lr 2e-3, random init seed 916143406'.format(C3_GLOBAL_BATCH, C3_GLOBAL_BATCH // n_gpus),
+                'global_batch': C3_GLOBAL_BATCH, 'points': WORKLOAD['points'], 'parallelism': 'dp{}'.format(n_gpus),
+                'l2': 'per-step activations exceed the 126 MB L2 and 4 distinct input batches rotate; no flush'}
     return {'workload': 'C2: attention model (models/att NN config) training step, N=2048 pts/cloud, k=5, '
                         'batch 32 clouds per GPU, Adam lr 2e-3, random init seed 916143406',
             'global_batch': WORKLOAD['batch_per_gpu'] * n_gpus, 'points': WORKLOAD['points'],
             'parallelism': 'dp{}'.format(n_gpus),
             'l2': 'per-step activations (~1.9 GB) exceed the 126 MB L2 and 4 distinct input batches rotate; no flush'}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# C4 / C5
+# ------------------------------------------------------------------------------------------------------------
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
+def run_c4(dev, timed, args, as_extra=False):
+    """BASELINE.json configs[3]: EdgeConv encoder (models/att NN config with k = 16) forward + backward on 16 clouds of 10 000
+    points, one GPU.  Reports clouds/s, the per-kernel-group device times and the two rooflines that matter at this shape: the
+    150-d kNN (direct-form-equivalent FP32 work) and the dominant row-GEMM group (algorithmic HBM bytes)."""
+    from garment_pattern_estimation_b200 import net_blocks as nb, ops
+    from garment_pattern_estimation_b200.configs import ATT_NN_CONFIG
+    B, N, k = 16, 10000, 16
+    cfg = dict(ATT_NN_CONFIG)
+    cfg['k_neighbors'] = k
+    torch.manual_seed(SEED_INIT)
+    enc = nb.EdgeConvFeatures(250, cfg).to(dev).train()
+    pos = [torch.randn(B, N, 3, generator=torch.Generator().manual_seed(77 + i)).to(dev) for i in range(2)]
+    gout = torch.randn(B * N, 153, generator=torch.Generator().manual_seed(5)).to(dev)
+
+    def step(i):
+        for p in enc.parameters():
+            p.grad = None
+        _, feats, _ = enc(pos[i % 2], False)
+        feats.backward(gout)
+
+    steps = max(3, min(args.steps, 10))
+    for i in range(3):
+        step(i)
+    torch.cuda.reset_peak_memory_stats()
+    ms_total, launches = timed(step, steps)
+    ms = ms_total / steps
+    ops.EVENT_SINK, ops.FLOP_SINK, ops.BYTES_SINK = {}, {}, {}
+    for i in range(2):
+        step(i)
+    torch.cuda.synchronize()
+    groups = {n: sum(s.elapsed_time(e) for s, e in evs) / 2.0 for n, evs in ops.EVENT_SINK.items()}
+    counts = {n: len(evs) / 2.0 for n, evs in ops.EVENT_SINK.items()}
+    gbytes = {n: v / 2.0 for n, v in ops.BYTES_SINK.items()}
+    ops.EVENT_SINK = ops.FLOP_SINK = ops.BYTES_SINK = None
+    peaks = _peaks()
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    dom = max(gbytes, key=lambda n: groups.get(n, 0.0)) if gbytes else None
+    roofline = None
+    if dom:
+        gbs = gbytes[dom] / (groups[dom] * 1e-3) / 1e9
+        roofline = {'group': dom, 'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+                    'traffic': None, 'launches_per_step': counts[dom], 'ms_per_step': groups[dom],
+                    'peak_source': 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'}
+    knn_ms = groups.get('nt_knn[D=150]', 0.0)
+    fp32_peak = SMS * FP32_LANES_PER_SM * 2 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12
+    knn = {'launch_ms': knn_ms, 'direct_form_tflops': B * N * N * (3 * 150 - 1) / (knn_ms * 1e-3) / 1e12 if knn_ms else None,
+           'fp32_alu_peak_tflops': fp32_peak, 'pair_dims_per_s': B * N * N * 150 / (knn_ms * 1e-3) if knn_ms else None}
+    res = {'workload': 'C4: EdgeConv encoder (2 x DynamicEdgeConv 200-200-150, k=16, skip connection) forward + backward, '
+                       'B=16 clouds x N=10000 points, 1 GPU; 2.56 M edge rows per GEMM',
+           'value': B / (ms * 1e-3), 'unit': 'clouds/s', 'ms_per_step': ms, 'steps': steps,
+           'peak_memory_GB': torch.cuda.max_memory_allocated() / 1e9, 'roofline': roofline, 'roofline_knn': knn,
+           'kernel_ms_per_step': {n: round(v, 4) for n, v in sorted(groups.items(), key=lambda kv: -kv[1])[:12]}}
+    if as_extra:
+        return res
+    return {'metric': 'point-clouds/sec (EdgeConv encoder fwd+bwd)', 'value': res['value'], 'unit': 'clouds/s', 'n_gpus': 1,
+            'steps': steps, 'warmup': 3, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': res['workload']}, 'gpu_launches': launches,
+            'roofline': roofline, 'roofline_knn': knn, 'kernel_ms_per_step': res['kernel_ms_per_step'],
+            'peak_memory_GB': res['peak_memory_GB']}
+
+
+def run_c5(dev, rank, world, timed, args, as_extra=False):
+    """BASELINE.json configs[4]: full-model inference (eval mode: BatchNorm running statistics folded into the GEMMs), B = 128
+    clouds split over the ranks, N in {1024, 2048, 4096, 8192}; shipped checkpoint when its extracted copy is present."""
+    import garment_pattern_estimation_b200 as g
+    dc, nc, lc = att_configs(WORKLOAD['k'])
+    torch.manual_seed(SEED_INIT)
+    model = g.GarmentSegmentPattern3D(dc, nc, lc)
+    ck = os.path.join(ROOT, 'tests', 'golden', '_ckpt', 'att_state.pt')
+    weights = 'random init (seed 916143406)'
+    if os.path.exists(ck):
+        model.load_state_dict(torch.load(ck))
+        weights = 'shipped models/att/neural_tailor_panels.pth'
+    model.to(dev).eval()
+    B_global = 128
+    b = B_global // world
+    sweep = {}
+    steps = max(3, min(args.steps, 10))
+    for N in (1024, 2048, 4096, 8192):
+        pos = [torch.randn(b, N, 3, generator=torch.Generator().manual_seed(900 + 10 * rank + i)).to(dev) for i in range(2)]
+
+        def step(i):
+            with torch.no_grad():
+                model(pos[i % 2])
+
+        for i in range(3):
+            step(i)
+        ms_total, _ = timed(step, steps)
+        ms = ms_total / steps
+        sweep[str(N)] = {'ms_per_batch': ms, 'clouds_per_s': b * world / (ms * 1e-3)}
+        del pos
+    res = {'workload': 'C5: attention model inference (eval mode), B=128 clouds split over {} GPU(s), {}'.format(world, weights),
+           'unit': 'clouds/s', 'steps': steps, 'sweep': sweep}
+    if as_extra:
+        return res
+    return {'metric': 'point-clouds/sec (inference forward)', 'value': sweep['2048']['clouds_per_s'], 'unit': 'clouds/s',
+            'n_gpus': world, 'steps': steps, 'warmup': 3, 'ms_per_step': sweep['2048']['ms_per_batch'], 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': res['workload'], 'points': 2048, 'global_batch': B_global}, 'sweep': sweep}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -220,6 +337,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of parallel.GraphedTrainStep')
+    ap.add_argument('--config', default='C2', choices=['C2', 'C3', 'C4', 'C5'], help='BASELINE.json configuration of the headline line')
+    ap.add_argument('--no-extras', action='store_true', help='skip the C3 / C4 / C5 measurements that ride along with the C2 line')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -245,49 +364,12 @@ def main():
     from garment_pattern_estimation_b200 import _lib, ops
     from garment_pattern_estimation_b200.parallel import FlatAdam, FlatDataParallel, GraphedTrainStep
 
-    B, N, k = WORKLOAD['batch_per_gpu'], WORKLOAD['points'], WORKLOAD['k']
+    N, k = WORKLOAD['points'], WORKLOAD['k']
+    strong = args.config == 'C3'
+    if strong and C3_GLOBAL_BATCH % world != 0:
+        raise RuntimeError('C3: the global batch of {} clouds is not divisible by {} ranks'.format(C3_GLOBAL_BATCH, world))
+    B = C3_GLOBAL_BATCH // world if strong else WORKLOAD['batch_per_gpu']
     dc, nc, lc = att_configs(k)
-    torch.manual_seed(SEED_INIT)
-    model = g.GarmentSegmentPattern3D(dc, nc, lc).to(dev).train()
-    wrapper = FlatDataParallel(model, device_ids=[dev], auto_reduce=False)
-    opt = FlatAdam(wrapper, lr=2e-3)            # torch.optim.Adam semantics, one kernel on the flat buffers (csrc/train_step.cu)
-
-    # 4 distinct synthetic batches per rank, in pinned host memory (e2e) and resident copies (value)
-    host, resident = [], []
-    for i in range(4):
-        x, gt = synthetic_batch(B, N, seed=1234 + 100 * rank + i)
-        hx = x.pin_memory()
-        hgt = {kk: v.pin_memory() for kk, v in gt.items()}
-        host.append((hx, hgt))
-        resident.append((hx.to(dev), {kk: v.to(dev) for kk, v in hgt.items()}))
-    h2d_bytes = host[0][0].numel() * 4 + sum(v.numel() * v.element_size() for v in host[0][1].values())
-
-    def eager_step(x, gt):
-        out = wrapper(x)
-        loss, _, _ = model.loss(out, gt)
-        loss.backward()
-        wrapper.sum_gradients()                  # one NCCL all-reduce of the flat gradient buffer (no-op on one GPU)
-        opt.step(zero_grad=True)                 # the 1 / world_size average and zero_grad are folded into the Adam kernel
-        return loss
-
-    # The product's training-step API: the whole step captured once into a CUDA graph (parallel.GraphedTrainStep) and
-    # replayed per batch; with more than one rank the all-reduce + optimizer step stay outside the graph.
-    graphed, graph_note = None, 'eager launches (--no-graph)'
-    launches_per_eager_step = None
-    if not args.no_graph:
-        l0 = _lib.launch_count()
-        eager_step(*resident[0])
-        launches_per_eager_step = _lib.launch_count() - l0
-        try:
-            graphed = GraphedTrainStep(wrapper, opt, resident[0][0], resident[0][1], warmup=3)
-            graph_note = ('parallel.GraphedTrainStep: forward + loss + backward{} replayed as one CUDA graph'
-                          .format(' + Adam' if graphed.capture_update else ' (all-reduce + Adam eager)'))
-        except Exception as e:  # noqa: BLE001 -- capture problems must not hide the eager number
-            graphed, graph_note = None, 'eager launches (graph capture failed: {})'.format(str(e)[:120])
-            torch.cuda.synchronize()
-
-    def train_step(x, gt):
-        return graphed(x, gt) if graphed is not None else eager_step(x, gt)
 
     def barrier():
         if world > 1:
@@ -310,35 +392,95 @@ def main():
         barrier()
         return float(ms.item()), launches
 
-    # ---- warm-up
-    for i in range(args.warmup):
-        train_step(*resident[i % 4])
+    if args.config in ('C4', 'C5'):
+        res = run_c4(dev, timed, args) if args.config == 'C4' else run_c5(dev, rank, world, timed, args)
+        if rank == 0:
+            print(json.dumps(res))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
-    # ---- value: inputs resident in HBM
+    class Training:
+        """The training step of the attention model at `b` clouds per rank: model, flat data-parallel wrapper, FlatAdam, four
+        synthetic batches (pinned host + resident copies) and the CUDA-graph step."""
+
+        def __init__(self, b):
+            self.b = b
+            torch.manual_seed(SEED_INIT)
+            self.model = g.GarmentSegmentPattern3D(dict(dc), dict(nc), dict(lc)).to(dev).train()
+            self.wrapper = FlatDataParallel(self.model, device_ids=[dev], auto_reduce=False)
+            self.opt = FlatAdam(self.wrapper, lr=2e-3)      # torch.optim.Adam semantics, one kernel on the flat buffers (csrc/train_step.cu)
+            self.host, self.resident = [], []
+            for i in range(4):      # 4 distinct synthetic batches per rank, in pinned host memory (e2e) and resident copies (value)
+                x, gt = synthetic_batch(b, N, seed=1234 + 100 * rank + i)
+                hx = x.pin_memory()
+                hgt = {kk: v.pin_memory() for kk, v in gt.items()}
+                self.host.append((hx, hgt))
+                self.resident.append((hx.to(dev), {kk: v.to(dev) for kk, v in hgt.items()}))
+            self.h2d_bytes = self.host[0][0].numel() * 4 + sum(v.numel() * v.element_size() for v in self.host[0][1].values())
+            # The product's training-step API: the whole step (forward, loss, backward, NCCL all-reduce of the flat gradient
+            # buffer, Adam) captured once into a CUDA graph (parallel.GraphedTrainStep) and replayed per batch.
+            self.graphed, self.graph_note, self.launches_per_eager_step = None, 'eager launches (--no-graph)', None
+            if not args.no_graph:
+                l0 = _lib.launch_count()
+                self.eager_step(*self.resident[0])
+                self.launches_per_eager_step = _lib.launch_count() - l0
+                try:
+                    self.graphed = GraphedTrainStep(self.wrapper, self.opt, self.resident[0][0], self.resident[0][1], warmup=3)
+                    self.graph_note = ('parallel.GraphedTrainStep: forward + loss + backward{} replayed as one CUDA graph'.format(
+                        (' + all-reduce + Adam' if world > 1 else ' + Adam') if self.graphed.capture_update else ' (all-reduce + Adam eager)'))
+                except Exception as e:  # noqa: BLE001 -- capture problems must not hide the eager number
+                    self.graphed, self.graph_note = None, 'eager launches (graph capture failed: {})'.format(str(e)[:120])
+                    torch.cuda.synchronize()
+
+        def eager_step(self, x, gt):
+            out = self.wrapper(x)
+            loss, _, _ = self.model.loss(out, gt)
+            loss.backward()
+            self.wrapper.sum_gradients()             # one NCCL all-reduce of the flat gradient buffer (no-op on one GPU)
+            self.opt.step(zero_grad=True)            # the 1 / world_size average and zero_grad are folded into the Adam kernel
+            return loss
+
+        def step(self, x, gt):
+            return self.graphed(x, gt) if self.graphed is not None else self.eager_step(x, gt)
+
+        def e2e_step(self, i):
+            """host buffers: H2D of the inputs and D2H of the loss every step"""
+            hx, hgt = self.host[i % 4]
+            if self.graphed is not None:                 # H2D straight into the graph's static input buffers
+                loss = self.graphed(hx, hgt)
+            else:
+                x = hx.to(dev, non_blocking=True)
+                gt = {kk: v.to(dev, non_blocking=True) for kk, v in hgt.items()}
+                loss = self.eager_step(x, gt)
+            return float(loss.item())                    # device -> host read of the step's result
+
+        def measure(self, steps, warmup, e2e=True):
+            for i in range(warmup):
+                self.step(*self.resident[i % 4])
+            ms_total, launches = timed(lambda i: self.step(*self.resident[i % 4]), steps)
+            if self.graphed is not None:   # replayed kernel nodes do not pass through the library's host entry points: count =
+                launches = self.launches_per_eager_step * steps     # the libnt_b200 launches of one eager step (captured 1:1) x steps
+            out = {'ms_per_step': ms_total / steps, 'launches': launches}
+            if e2e:
+                for i in range(2):
+                    self.e2e_step(i)
+                e2e_ms, _ = timed(self.e2e_step, steps)
+                out['e2e_ms_per_step'] = e2e_ms / steps
+            return out
+
+    tr = Training(B)
+    model, wrapper, opt, graphed, graph_note = tr.model, tr.wrapper, tr.opt, tr.graphed, tr.graph_note
+    resident, eager_step, h2d_bytes = tr.resident, tr.eager_step, tr.h2d_bytes
+
+    # ---- value (inputs resident in HBM) and e2e (host buffers), clocks sampled across both timed regions
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_total, launches = timed(lambda i: train_step(*resident[i % 4]), args.steps)
-    if graphed is not None:      # replayed kernel nodes do not pass through the library's host entry points: count = the
-        launches = launches_per_eager_step * args.steps      # libnt_b200 launches of one eager step (captured 1:1) x steps
-    ms_per_step = ms_total / args.steps
+    m = tr.measure(args.steps, args.warmup)
+    ms_per_step, launches, e2e_ms = m['ms_per_step'], m['launches'], m['e2e_ms_per_step'] * args.steps
     value = world * B / (ms_per_step * 1e-3)
-
-    # ---- e2e: host buffers, H2D of inputs and D2H of the loss every step
-    def e2e_step(i):
-        hx, hgt = host[i % 4]
-        if graphed is not None:                      # H2D straight into the graph's static input buffers
-            loss = graphed(hx, hgt)
-        else:
-            x = hx.to(dev, non_blocking=True)
-            gt = {kk: v.to(dev, non_blocking=True) for kk, v in hgt.items()}
-            loss = eager_step(x, gt)
-        return float(loss.item())                    # device -> host read of the step's result
-
-    for i in range(2):
-        e2e_step(i)
-    e2e_ms, _ = timed(e2e_step, args.steps)
-    e2e_value = world * B / (e2e_ms / args.steps * 1e-3)
+    e2e_value = world * B / (m['e2e_ms_per_step'] * 1e-3)
     clocks = sampler.stop() if rank == 0 else None          # sampled (100 ms period) across both timed regions
 
     # ---- per-kernel-group device times (CUDA events on the launching stream) for the roofline of the dominant kernel
@@ -355,6 +497,37 @@ def main():
     groups = {name: sum(s.elapsed_time(e) for s, e in evs) / 3.0 for name, evs in ops.EVENT_SINK.items()}
     counts = {name: len(evs) / 3.0 for name, evs in ops.EVENT_SINK.items()}
     ops.EVENT_SINK = None
+
+    # ---- the other BASELINE.json configurations, measured by every rank (collective timing) before rank 0 assembles the line
+    extras = None
+    if args.config == 'C2' and not args.no_extras:
+        extras = {}
+        del tr, graphed
+        torch.cuda.empty_cache()
+        x_steps, x_warm = max(5, min(args.steps, 20)), 3
+        if C3_GLOBAL_BATCH % world == 0:
+            try:
+                t3 = Training(C3_GLOBAL_BATCH // world)
+                m3 = t3.measure(x_steps, x_warm)
+                extras['C3_strong'] = {
+                    'workload': 'C3: attention model training step, N=2048, FIXED global batch {} = {} clouds per GPU x {} GPUs '
+                                '(strong scaling)'.format(C3_GLOBAL_BATCH, C3_GLOBAL_BATCH // world, world),
+                    'value': C3_GLOBAL_BATCH / (m3['ms_per_step'] * 1e-3), 'unit': 'clouds/s', 'ms_per_step': m3['ms_per_step'],
+                    'e2e': C3_GLOBAL_BATCH / (m3['e2e_ms_per_step'] * 1e-3), 'scaling': 'strong', 'steps': x_steps, 'launch_mode': t3.graph_note}
+                del t3
+            except Exception as e:  # noqa: BLE001
+                extras['C3_strong'] = {'error': str(e)[:200]}
+            torch.cuda.empty_cache()
+        if world == 1:
+            try:
+                extras['C4'] = run_c4(dev, timed, args, as_extra=True)
+            except Exception as e:  # noqa: BLE001
+                extras['C4'] = {'error': str(e)[:200]}
+            torch.cuda.empty_cache()
+        try:
+            extras['C5'] = run_c5(dev, rank, world, timed, args, as_extra=True)
+        except Exception as e:  # noqa: BLE001
+            extras['C5'] = {'error': str(e)[:200]}
 
     if rank != 0:
         if world > 1:
@@ -447,16 +620,18 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        cps, sec, cores = cpu_best(steps=2, warmup=1, k=k)
+        cps, sec, cores, timed_steps = cpu_train_steps(3, 1, k, clouds=CPU_SAMPLE_CLOUDS, threads=cpu_best_threads(k), budget_s=60.0)
         cpu_baseline = {'value': cps, 'unit': 'clouds/s', 'cores': cores, 'kind': 'port',
-                        'sample': '{} clouds x {} pts per step, 2 timed steps after 1 warm-up ({:.1f} s/step); oracle '
-                                  'port of the reference path, torch CPU fp32'.format(CPU_SAMPLE_CLOUDS, N, sec)}
+                        'sample': '{} clouds x {} pts per step (BASELINE.md section 3: C2 with B reduced to 8), {} timed steps after 1 '
+                                  'warm-up ({:.2f} s/step); oracle port of the reference path with its stock Python loops, torch CPU '
+                                  'fp32; `bench.py --impl reference` times the full 32-cloud batch'.format(CPU_SAMPLE_CLOUDS, N,
+                                                                                                          timed_steps, sec)}
 
     line = {
         'metric': 'point-clouds/sec (fwd+bwd+optimizer, training step)', 'value': value, 'unit': 'clouds/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(world),
+        'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(world, strong),
         'e2e': {'value': e2e_value, 'unit': 'clouds/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
                 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': launches, 'gpu_launches_per_step': launches / args.steps, 'launch_mode': graph_note,
@@ -464,6 +639,7 @@ def main():
         'roofline_encoder': roofline_encoder,
         'cpu_baseline': cpu_baseline,
         'kernel_ms_per_step': {kk: round(v, 4) for kk, v in sorted(groups.items(), key=lambda kv: -kv[1])},
+        'extras': extras,
     }
     print(json.dumps(line))
     if world > 1:
