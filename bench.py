@@ -329,6 +329,17 @@ def run_c5(dev, rank, world, timed, args, as_extra=False):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def finish(world):
+    """End of a rank.  With more than one rank the process leaves through os._exit after a device synchronize: tearing the NCCL
+    communicator down while CUDA graphs that captured its all-reduce are still alive hung the interpreter at exit (measured: the
+    JSON line was printed, then the ranks sat in destroy_process_group until the launcher's timeout)."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -396,8 +407,7 @@ def main():
         res = run_c4(dev, timed, args) if args.config == 'C4' else run_c5(dev, rank, world, timed, args)
         if rank == 0:
             print(json.dumps(res))
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
 
     class Training:
@@ -530,8 +540,7 @@ def main():
             extras['C5'] = {'error': str(e)[:200]}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
 
     peaks = {}
@@ -642,8 +651,7 @@ def main():
         'extras': extras,
     }
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world)
 
 
 if __name__ == '__main__':
