@@ -96,6 +96,13 @@ _SIGNATURES = {
                                  c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'nt_global_pool_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'nt_global_pool_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    'nt_fps': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'nt_radius': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    'nt_point_edges_count': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'nt_point_edges_fill': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                    c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    'nt_scatter_max_fwd': (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'nt_scatter_max_bwd': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
     'nt_pattern_loss_fwd': (c_int, [ctypes.POINTER(PatternLossArgs), c_void_p, c_void_p, c_void_p]),
     'nt_pattern_loss_bwd': (c_int, [ctypes.POINTER(PatternLossArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'nt_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_float,

@@ -5,8 +5,8 @@ The reference resolves these classes BY NAME (``getattr(blocks, config['feature_
 ``getattr(blocks, config['panel_decoder'])`` nn/nets.py:106-115, ``blocks.MLP(...)`` nn/nets.py:224), so installing this
 module as ``net_blocks`` swaps the hot path under the unmodified ``nets.py`` / ``trainer.py``.
 
-In scope: ``MLP``, ``EdgeConvFeatures`` (+ ``DynamicEdgeConv``), ``LSTMDecoderModule``.
-Out of scope and therefore absent: PointNet++ blocks, graph-pooling variants, GRU / MLP / double-reverse decoders.
+In scope: ``MLP``, ``EdgeConvFeatures`` (+ ``DynamicEdgeConv``), ``LSTMDecoderModule``, ``PointNetPlusPlus``.
+Out of scope and therefore absent: graph-pooling variants, GRU / MLP / double-reverse decoders.
 """
 import math
 
@@ -143,6 +143,88 @@ class EdgeConvFeatures(nn.Module):
             pooled = self.global_pool(out, batch, B)
             return ops.linear(pooled, self.lin.weight, self.lin.bias), out, batch
         return None, out, batch
+
+
+# ----------------------------------------------------------------------------------------------------------
+# PointNet++  (reference nn/net_blocks.py:10-88)
+# ----------------------------------------------------------------------------------------------------------
+class PointConv(nn.Module):
+    """torch_geometric.nn.PointConv as the reference calls it (nn/net_blocks.py:16,22): bipartite (points -> sampled centres),
+    message = local_nn(pos_j - pos_i), max aggregation, the library's index-based self-loop handling (include/nt_b200.h).  The
+    attribute name ``local_nn`` is part of the state_dict contract (``sa1_module.conv.local_nn.L.{0,2}.*``)."""
+
+    def __init__(self, local_nn=None, global_nn=None, add_self_loops=True, **kwargs):
+        super().__init__()
+        if global_nn is not None or not add_self_loops:
+            raise NotImplementedError('only PointConv(local_nn) with the default self loops (the reference call) runs on the B200 path')
+        self.local_nn = local_nn
+        self.global_nn = None
+        self.last_edges = None        # (src, dst) of the last forward -- for parity tests
+
+    def forward(self, pos_flat, cloud_shape, centres, nbr, cnt):
+        B, N = cloud_shape
+        src, dst, msg = ops.point_edges(pos_flat, B, N, centres, nbr, cnt)
+        self.last_edges = (src, dst)
+        out = self.local_nn(msg)                                               # [E, F] fused Linear/ReLU/BN stack on the edge rows
+        return ops.scatter_max(out, dst, B * centres.shape[1])
+
+
+class _SetAbstractionModule(nn.Module):
+    """fps -> radius(max 25 neighbours) -> PointConv (nn/net_blocks.py:10-26) on the dense equal-size layout."""
+
+    def __init__(self, ratio, conv_radius, per_point_nn):
+        super().__init__()
+        self.ratio = ratio
+        self.radius = conv_radius
+        self.conv = PointConv(per_point_nn)
+
+    def forward(self, features, pos, cloud_shape):
+        if features is not None:
+            raise NotImplementedError('set abstraction on point FEATURES (a second sa module) is commented out in the reference '
+                                      '(nn/net_blocks.py:66-68) and not built here')
+        B, N = cloud_shape
+        idx = ops.fps(pos, B, N, self.ratio)                                   # [B, M] local
+        nbr, cnt = ops.radius(pos, B, N, idx, self.radius, 25)
+        features = self.conv(pos, cloud_shape, idx, nbr, cnt)
+        M = idx.shape[1]
+        gidx = (idx.long() + (torch.arange(B, device=pos.device) * N).view(B, 1)).reshape(-1)
+        return features, pos[gidx], (B, M)
+
+
+class _GlobalSetAbstractionModule(nn.Module):
+    """cat[features, pos] -> per-point MLP -> global max pool (nn/net_blocks.py:29-40)."""
+
+    def __init__(self, per_point_net):
+        super().__init__()
+        self.nn = per_point_net
+
+    def forward(self, features, pos, cloud_shape):
+        B, M = cloud_shape
+        features = torch.cat([features, pos], dim=1) if features is not None else pos
+        features = self.nn(features)
+        features = ops.global_pool(features, B, M, 'max')
+        return features, pos.new_zeros((B, 3)), (B, 1)
+
+
+class PointNetPlusPlus(nn.Module):
+    """The reference's alternative extractor (nn/net_blocks.py:50-88): one set-abstraction level + a global one + Linear.
+    Like the reference it returns the bare encoding tensor [B, out_size]."""
+
+    def __init__(self, out_size, config={}):
+        super().__init__()
+        self.config = {'r1': 0.3, 'r2': 0.4, 'r3': 5, 'r4': 7}
+        self.config.update(config)
+        hid, feat = self.config['EConv_hidden'], self.config['EConv_feature']
+        self.sa1_module = _SetAbstractionModule(0.2, self.config['r1'], MLP([3, hid, hid, feat]))
+        self.sa_last_module = _GlobalSetAbstractionModule(MLP([3 + feat, hid, hid, feat]))
+        self.lin = nn.Linear(feat, out_size)
+
+    def forward(self, positions):
+        B, N = positions.shape[0], positions.shape[1]
+        pos_flat = positions.reshape(B * N, positions.shape[-1])
+        sa_out = self.sa1_module(None, pos_flat, (B, N))
+        out, _, _ = self.sa_last_module(*sa_out)
+        return ops.linear(out, self.lin.weight, self.lin.bias)
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -690,6 +690,82 @@ def lstm_decoder(x, h0, c0, T, params):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# PointNet++ set abstraction (csrc/pointnet.cu)
+# ----------------------------------------------------------------------------------------------------------
+def fps(pos, B, N, ratio):
+    """torch_geometric.nn.fps on the dense equal-size layout with a deterministic start (nn/net_blocks.py:19): ceil(ratio * N)
+    farthest points per cloud.  Returns LOCAL indices [B, n] int32."""
+    import math
+    _require_cuda(pos)
+    pos, ld = _rows2d(pos)
+    n = int(math.ceil(ratio * N))
+    idx = torch.empty(B, n, dtype=torch.int32, device=pos.device)
+    _call('nt_fps', _lib.load().nt_fps, _p(pos), ld, B, N, pos.shape[1], n, _p(idx), _stream())
+    return idx
+
+
+def radius(pos, B, N, centres, r, max_num_neighbors):
+    """torch_geometric.nn.radius(pos, pos[idx], r, batch, batch[idx], max_num_neighbors) (nn/net_blocks.py:20-21) for centres
+    given as LOCAL point indices [B, M].  Returns (nbr [B*M, max] int32 local, -1 padded; count [B*M] int32)."""
+    _require_cuda(pos, centres)
+    pos, ld = _rows2d(pos)
+    M = centres.shape[1]
+    nbr = torch.empty(B * M, max_num_neighbors, dtype=torch.int32, device=pos.device)
+    cnt = torch.empty(B * M, dtype=torch.int32, device=pos.device)
+    _call('nt_radius', _lib.load().nt_radius, _p(pos), ld, B, N, pos.shape[1], _p(centres.contiguous()), M, float(r),
+          int(max_num_neighbors), _p(nbr), _p(cnt), _stream())
+    return nbr, cnt
+
+
+def point_edges(pos, B, N, centres, nbr, cnt):
+    """Edge list + message input of PointConv in the reference's bipartite call (see include/nt_b200.h).  One host read (the
+    edge count decides the size of the result, as in the library).  Returns (src [E], dst [E] int64 global rows, msg [E, D])."""
+    pos, ld = _rows2d(pos)
+    D, M, max_nbr = pos.shape[1], centres.shape[1], nbr.shape[1]
+    lib = _lib.load()
+    keep = torch.empty(B * M, dtype=torch.int32, device=pos.device)
+    _call('nt_point_edges_count', lib.nt_point_edges_count, _p(nbr), _p(cnt), B, N, M, max_nbr, _p(keep), _stream())
+    ends = torch.cumsum(keep.long(), 0)
+    offsets = (ends - keep.long()).contiguous()
+    n_radius = int(ends[-1].item())
+    E = n_radius + min(B * N, B * M)
+    src = torch.empty(E, dtype=torch.int64, device=pos.device)
+    dst = torch.empty(E, dtype=torch.int64, device=pos.device)
+    msg = torch.empty(E, D, dtype=torch.float32, device=pos.device)
+    _call('nt_point_edges_fill', lib.nt_point_edges_fill, _p(pos), ld, D, _p(centres.contiguous()), _p(nbr), _p(cnt), _p(offsets), B, N, M,
+          max_nbr, n_radius, _p(src), _p(dst), _p(msg), D, _stream())
+    return src, dst, msg
+
+
+class _ScatterMaxFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, dst, T):
+        _require_cuda(v, dst)
+        v, ldv = _rows2d(v)
+        E, F = v.shape
+        out = torch.empty(T, F, dtype=torch.float32, device=v.device)
+        arg = torch.empty(T, F, dtype=torch.int64, device=v.device)
+        key = torch.empty(T, F, dtype=torch.int32, device=v.device)
+        _call('nt_scatter_max_fwd', _lib.load().nt_scatter_max_fwd, _p(v), ldv, _p(dst), E, F, T, _p(out), _p(arg), _p(key), _stream())
+        ctx.save_for_backward(arg)
+        ctx.dims = (E, F, T)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        arg, = ctx.saved_tensors
+        E, F, T = ctx.dims
+        gv = torch.zeros(E, F, dtype=torch.float32, device=g.device)
+        _call('nt_scatter_max_bwd', _lib.load().nt_scatter_max_bwd, _p(g.contiguous()), _p(arg), T, F, _p(gv), F, _stream())
+        return gv, None, None
+
+
+def scatter_max(values, dst, n_targets):
+    """max aggregation of per-edge rows `values` [E, F] into n_targets rows by the int64 target index `dst` (PyG aggr='max')."""
+    return _ScatterMaxFunction.apply(values, dst.contiguous(), int(n_targets))
+
+
+# ----------------------------------------------------------------------------------------------------------
 # pattern loss (shape / loop / rotation / translation) and Adam on a flat buffer (csrc/train_step.cu)
 # ----------------------------------------------------------------------------------------------------------
 class _PatternLossFunction(torch.autograd.Function):

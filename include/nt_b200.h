@@ -242,6 +242,31 @@ int nt_lstm_bwd(const float *dy, int ld_dy, const void *act, const float *cs, co
                 int T, int L, int H, int E, void *workspace, float *dx, int ld_dx, float *const *dw_ih, float *const *dw_hh,
                 float *const *db_ih, float *const *db_hh, void *stream);
 
+/* ---- PointNet++ set abstraction (nn/net_blocks.py:10-88: torch_geometric.nn.fps / radius / PointConv) --------------------------
+ * pos: [B*N, >=D] fp32, row stride ld, B equal-size clouds, D <= 8 coordinates.  Index outputs are LOCAL to the cloud.
+ * nt_fps: farthest point sampling, n_samples = ceil(ratio * N) per cloud, starting from point 0 of every cloud (torch_cluster's
+ *   random_start=False; the library default, a random first point, cannot be pinned); ties -> lowest index.  idx: [B, n_samples].
+ * nt_radius: for every centre (centres: [B, M] local point indices) the first max_nbr points of its cloud, ascending index, with
+ *   squared distance < r*r.  nbr: [B*M, max_nbr] (-1 padded), count: [B*M].
+ * nt_point_edges_count / _fill: the edge list PointConv builds in the reference's bipartite call (radius edges whose global source
+ *   index equals their target index removed, then one edge i -> i appended per centre i < min(B*N, B*M) -- the library's
+ *   index-based self-loop handling), with the message input msg[e, :D] = pos[src] - pos[centre(dst)].  keep_count: [B*M] kept
+ *   radius edges per centre; offsets: their exclusive prefix sum (caller); n_radius_edges = their total; E = n_radius_edges +
+ *   min(B*N, B*M).  src / dst: [E] int64 GLOBAL rows.
+ * nt_scatter_max_fwd: out[t, f] = max over edges with dst == t of v[e, f] (0 for targets without edges), arg[t, f] = lowest such
+ *   edge (INT64_MAX if none); key_scratch: T*F int32.  nt_scatter_max_bwd: gv[arg[t, f], f] = g[t, f] (gv zeroed by the caller). */
+int nt_fps(const float *pos, int ld, int B, int N, int D, int n_samples, int32_t *idx, void *stream);
+int nt_radius(const float *pos, int ld, int B, int N, int D, const int32_t *centres, int M, float r, int max_nbr, int32_t *nbr,
+              int32_t *count, void *stream);
+int nt_point_edges_count(const int32_t *nbr, const int32_t *count, int B, int N, int M, int max_nbr, int32_t *keep_count,
+                         void *stream);
+int nt_point_edges_fill(const float *pos, int ld, int D, const int32_t *centres, const int32_t *nbr, const int32_t *count,
+                        const int64_t *offsets, int B, int N, int M, int max_nbr, int64_t n_radius_edges, int64_t *src,
+                        int64_t *dst, float *msg, int ldm, void *stream);
+int nt_scatter_max_fwd(const float *v, int ldv, const int64_t *dst, int64_t E, int F, int64_t T, float *out, int64_t *arg,
+                       int32_t *key_scratch, void *stream);
+int nt_scatter_max_bwd(const float *g, const int64_t *arg, int64_t T, int F, float *gv, int ldg, void *stream);
+
 /* ---- training step: loss and optimizer (nn/trainer.py:96-101) ---------------------------------------------------------------------
  * The four loss terms of the shipped attention config (models/att/att.yaml:124) -- nn.MSELoss on outlines / rotations /
  * translations (nn/metrics/composed_loss.py:301-321) and PanelLoopLoss (nn/metrics/losses.py:19-51: for every panel with

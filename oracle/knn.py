@@ -31,6 +31,11 @@ def _load():
         lib.nt_oracle_knn.restype = ctypes.c_int
         lib.nt_oracle_knn.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        lib.nt_oracle_fps.restype = ctypes.c_int
+        lib.nt_oracle_fps.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
+        lib.nt_oracle_radius.restype = ctypes.c_int
+        lib.nt_oracle_radius.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                         ctypes.c_int64, ctypes.c_float, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
         lib.nt_oracle_sqdist.restype = ctypes.c_float
         lib.nt_oracle_sqdist.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
         _lib = lib
@@ -61,3 +66,30 @@ def sqdist(a, b):
     a = np.ascontiguousarray(a, dtype=np.float32)
     b = np.ascontiguousarray(b, dtype=np.float32)
     return float(lib.nt_oracle_sqdist(a.ctypes.data, b.ctypes.data, a.shape[0]))
+
+
+def fps_indices(pos, n_samples):
+    """pos: [B, N, D] fp32.  Returns [B, n_samples] int32 local indices (farthest point sampling from point 0, see knn_oracle.c)."""
+    lib = _load()
+    xn = np.ascontiguousarray(pos.detach().cpu().numpy() if isinstance(pos, torch.Tensor) else pos, dtype=np.float32)
+    B, N, D = xn.shape
+    idx = np.empty((B, n_samples), dtype=np.int32)
+    rc = lib.nt_oracle_fps(xn.ctypes.data, B, N, D, n_samples, idx.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("nt_oracle_fps failed with status %d" % rc)
+    return torch.from_numpy(idx)
+
+
+def radius_neighbours(pos, centres, r, max_nbr):
+    """pos: [B, N, D] fp32, centres: [B, M] int32 local indices.  Returns (nbr [B, M, max_nbr] int32 local, -1 padded; count [B, M])."""
+    lib = _load()
+    xn = np.ascontiguousarray(pos.detach().cpu().numpy() if isinstance(pos, torch.Tensor) else pos, dtype=np.float32)
+    cn = np.ascontiguousarray(centres.detach().cpu().numpy() if isinstance(centres, torch.Tensor) else centres, dtype=np.int32)
+    B, N, D = xn.shape
+    M = cn.shape[1]
+    nbr = np.empty((B, M, max_nbr), dtype=np.int32)
+    cnt = np.empty((B, M), dtype=np.int32)
+    rc = lib.nt_oracle_radius(xn.ctypes.data, B, N, D, cn.ctypes.data, M, float(r), max_nbr, nbr.ctypes.data, cnt.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("nt_oracle_radius failed with status %d" % rc)
+    return torch.from_numpy(nbr), torch.from_numpy(cnt)

@@ -102,3 +102,66 @@ float nt_oracle_sqdist(const float *a, const float *b, int64_t D)
     for (int64_t d = 0; d < D; ++d) { float diff = a[d] - b[d]; acc = fmaf(diff, diff, acc); }
     return acc;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * PointNet++ sampling / grouping (nn/net_blocks.py:19-21 -> torch_geometric.nn.fps / radius -> torch_cluster).
+ * Restated from the published CUDA algorithms of torch-cluster (fps_cuda.cu, radius_cuda.cu); UNPINNED like the kNN above.
+ *
+ * fps: iterative farthest point sampling inside every cloud.  torch_cluster starts from a RANDOM point by default
+ * (random_start=True), which cannot be pinned; this restatement (and the B200 kernel) start from point 0 of the cloud, the
+ * library's random_start=False behaviour.  Each step keeps, per point, the squared distance to the nearest selected point
+ * (fp32, the same fmaf chain as above) and selects the point with the largest one; ties -> lowest index.
+ * n_samples = ceil(ratio * N) is computed by the caller.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int nt_oracle_fps(const float *pos, int64_t B, int64_t N, int64_t D, int64_t n_samples, int32_t *idx_out)
+{
+    if (!pos || !idx_out || B < 0 || N < 1 || D < 1 || n_samples < 1 || n_samples > N) return 1;
+    float *mind = (float *)malloc((size_t)N * sizeof(float));
+    if (!mind) return 2;
+    for (int64_t b = 0; b < B; ++b) {
+        const float *cloud = pos + b * N * D;
+        for (int64_t i = 0; i < N; ++i) mind[i] = INFINITY;
+        int64_t cur = 0;
+        for (int64_t s = 0; s < n_samples; ++s) {
+            idx_out[b * n_samples + s] = (int32_t)cur;
+            const float *pc = cloud + cur * D;
+            float best = -1.0f;
+            int64_t best_i = 0;
+            for (int64_t i = 0; i < N; ++i) {
+                float acc = 0.0f;
+                for (int64_t d = 0; d < D; ++d) { float diff = cloud[i * D + d] - pc[d]; acc = fmaf(diff, diff, acc); }
+                if (acc < mind[i]) mind[i] = acc;
+                if (mind[i] > best) { best = mind[i]; best_i = i; }
+            }
+            cur = best_i;
+        }
+    }
+    free(mind);
+    return 0;
+}
+
+/* radius: for every centre (given as local point indices [B, M]) the first `max_nbr` points of ITS cloud, in ascending index
+ * order, whose squared distance is STRICTLY below r*r (radius_cuda.cu: `if (dist < r)` with r squared by the caller).
+ * nbr_out: [B, M, max_nbr] local indices, -1 past count_out[b, m]. */
+int nt_oracle_radius(const float *pos, int64_t B, int64_t N, int64_t D, const int32_t *centres, int64_t M, float r,
+                     int64_t max_nbr, int32_t *nbr_out, int32_t *count_out)
+{
+    if (!pos || !centres || !nbr_out || !count_out || B < 0 || N < 1 || D < 1 || M < 1 || max_nbr < 1) return 1;
+    const float r2 = r * r;
+    for (int64_t b = 0; b < B; ++b) {
+        const float *cloud = pos + b * N * D;
+        for (int64_t m = 0; m < M; ++m) {
+            const float *pc = cloud + (int64_t)centres[b * M + m] * D;
+            int32_t *out = nbr_out + (b * M + m) * max_nbr;
+            int64_t cnt = 0;
+            for (int64_t i = 0; i < N && cnt < max_nbr; ++i) {
+                float acc = 0.0f;
+                for (int64_t d = 0; d < D; ++d) { float diff = cloud[i * D + d] - pc[d]; acc = fmaf(diff, diff, acc); }
+                if (acc < r2) out[cnt++] = (int32_t)i;
+            }
+            count_out[b * M + m] = (int32_t)cnt;
+            for (; cnt < max_nbr; ++cnt) out[cnt] = -1;
+        }
+    }
+    return 0;
+}

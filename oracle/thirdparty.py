@@ -147,17 +147,79 @@ def _out_of_scope(name):
     return fn
 
 
-fps = _out_of_scope('torch_geometric.nn.fps')
-radius = _out_of_scope('torch_geometric.nn.radius')
 knn = _out_of_scope('torch_geometric.nn.knn')
 
 
-class PointConv(nn.Module):
-    def __init__(self, *a, **kw):
-        super().__init__()
+# ----------------------------------------------------------------------------------------------------
+# PointNet++ operators (call sites: nn/net_blocks.py:16,19-21 -- fps, radius, PointConv)
+# ----------------------------------------------------------------------------------------------------
+def fps(pos, batch, ratio=0.5, random_start=False):
+    """torch_geometric.nn.fps / torch_cluster.fps restated (oracle/knn_oracle.c::nt_oracle_fps): ceil(ratio * N) farthest
+    points per cloud, returned as GLOBAL row indices in selection order, cloud after cloud.  The library's default is a random
+    first point; parity needs the deterministic variant (first point of every cloud), so random_start must stay False."""
+    if random_start:
+        raise NotImplementedError('oracle fps: a random start cannot be pinned; the restatement starts from the first point')
+    import math
+    B, N = _equal_cloud_layout(pos, batch)
+    n = int(math.ceil(ratio * N))
+    idx = _knn.fps_indices(pos.detach().float().cpu().reshape(B, N, -1), n)                # [B, n] local
+    return (idx.long() + (torch.arange(B) * N).view(B, 1)).reshape(-1).to(pos.device)
 
-    def forward(self, *a, **kw):
-        raise NotImplementedError('PointConv is outside the hot path')
+
+def radius(x, y, r, batch_x=None, batch_y=None, max_num_neighbors=32):
+    """torch_geometric.nn.radius(x, y, r, batch_x, batch_y, max_num_neighbors) restated (nt_oracle_radius): for every row of
+    y, the first max_num_neighbors rows of x of the same cloud (ascending index) with squared distance < r^2.  Returns
+    [2, E] = (row: index into y, col: index into x), grouped by y row.  y must be x[idx] for this restatement (as at the only
+    call site); it is matched back to its source row by equality."""
+    B, N = _equal_cloud_layout(x, batch_x)
+    My = y.shape[0] // B
+    xc, yc = x.detach().float().cpu().reshape(B, N, -1), y.detach().float().cpu().reshape(B, My, -1)
+    centres = torch.empty(B, My, dtype=torch.int32)
+    for b in range(B):          # recover the (first) source index of every centre
+        eq = (yc[b].unsqueeze(1) == xc[b].unsqueeze(0)).all(-1)
+        centres[b] = eq.float().argmax(dim=1).int()
+    nbr, cnt = _knn.radius_neighbours(xc, centres, float(r), int(max_num_neighbors))     # [B, My, max], [B, My]
+    rows, cols = [], []
+    for b in range(B):
+        for m in range(My):
+            c = int(cnt[b, m])
+            rows.append(torch.full((c,), b * My + m, dtype=torch.long))
+            cols.append(nbr[b, m, :c].long() + b * N)
+    return torch.stack([torch.cat(rows), torch.cat(cols)], dim=0).to(x.device)
+
+
+class PointConv(nn.Module):
+    """torch_geometric.nn.PointConv (= PointNetConv) as published: message = local_nn(cat[x_j, pos_j - pos_i]), max
+    aggregation, add_self_loops=True.  In the bipartite call of the reference (pos = (points, centres)) the self-loop handling
+    is index-based exactly as in the library: edges whose source INDEX equals their target INDEX are removed, then an edge
+    (i -> i) is appended for every i < min(#points, #centres) -- i.e. centre i additionally receives point i, whatever cloud it
+    belongs to.  Restated as is."""
+
+    def __init__(self, local_nn=None, global_nn=None, add_self_loops=True, **kw):
+        super().__init__()
+        self.local_nn, self.global_nn, self.add_self_loops = local_nn, global_nn, add_self_loops
+
+    def forward(self, x, pos, edge_index):
+        x_src = x[0] if isinstance(x, tuple) else x
+        pos_src, pos_dst = pos if isinstance(pos, tuple) else (pos, pos)
+        src, dst = edge_index[0], edge_index[1]
+        if self.add_self_loops:
+            keep = src != dst
+            src, dst = src[keep], dst[keep]
+            loops = torch.arange(min(pos_src.shape[0], pos_dst.shape[0]), device=src.device)
+            src, dst = torch.cat([src, loops]), torch.cat([dst, loops])
+        msg = pos_src[src] - pos_dst[dst]
+        if x_src is not None:
+            msg = torch.cat([x_src[src], msg], dim=1)
+        if self.local_nn is not None:
+            msg = self.local_nn(msg)
+        M = pos_dst.shape[0]
+        out = torch.full((M, msg.shape[1]), float('-inf'), dtype=msg.dtype, device=msg.device)
+        out = out.scatter_reduce(0, dst.view(-1, 1).expand_as(msg), msg, reduce='amax', include_self=True)
+        out = torch.where(torch.isinf(out), torch.zeros_like(out), out)
+        if self.global_nn is not None:
+            out = self.global_nn(out)
+        return out
 
 
 class ASAPooling(nn.Module):

@@ -279,3 +279,46 @@ def test_decomposed_lstm_matches_torch_lstm_forward_and_backward(layers, R, T, H
         for got, name in zip(grads[l], ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh')):
             want = getattr(lstm, '{}_l{}'.format(name, l)).grad
             assert torch.allclose(got, want, rtol=1e-9, atol=1e-12), (l, name)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# PointNet++ operators (fps / radius / PointConv restated in oracle/)
+# ------------------------------------------------------------------------------------------------------------
+def test_pointnet_oracle_known_answers_and_reference_golden(golden_dir):
+    from oracle import knn as oknn
+    from oracle import thirdparty as tp
+    gold = torch.load(os.path.join(golden_dir, 'pointnet.pt'))
+    # farthest point sampling on 12 collinear equispaced points from point 0: the far end, then the ties resolve to the lower index
+    line = torch.arange(12, dtype=torch.float32).view(1, 12, 1) * torch.tensor([1., 0., 0.]).view(1, 1, 3)
+    assert oknn.fps_indices(line, 5).tolist() == [[0, 11, 5, 8, 2]] == gold['kat_fps_line'].tolist()
+    # radius: more than max_num_neighbors points inside the ball -> the first 25 in index order, strict '<' on the squared distance
+    kd = gold['kat_dense']
+    nbr, cnt = oknn.radius_neighbours(kd['pos'], torch.tensor([[0, 7]], dtype=torch.int32), 0.3, 25)
+    assert torch.equal(nbr, kd['nbr']) and cnt.tolist() == [[25, 25]] and nbr[0, 0].tolist() == list(range(25))
+    two = torch.tensor([[[0., 0., 0.], [0.3, 0., 0.], [0.29, 0., 0.]]])
+    nbr, cnt = oknn.radius_neighbours(two, torch.tensor([[0]], dtype=torch.int32), 0.3, 4)
+    assert cnt.tolist() == [[2]] and nbr[0, 0].tolist() == [0, 2, -1, -1]            # the point AT distance r is excluded
+    # the integer results stored with the reference golden
+    x = gold['x']
+    B, N = x.shape[0], x.shape[1]
+    flat, batch = x.view(-1, 3), torch.arange(B).repeat_interleave(N)
+    idx = tp.fps(flat, batch, ratio=0.2)
+    assert torch.equal(idx, gold['fps_idx']) and idx.numel() == B * 80
+    row, col = tp.radius(flat, flat[idx], 0.3, batch, batch[idx], max_num_neighbors=25)
+    assert torch.equal(torch.stack([row, col]), gold['radius_row_col'])
+    with pytest.raises(NotImplementedError):
+        tp.fps(flat, batch, ratio=0.2, random_start=True)
+
+
+def test_unmodified_reference_pointnet_reproduces_its_golden_when_available(golden_dir):
+    from oracle import ref_stubs
+    if not ref_stubs.reference_available() or not os.path.isfile(os.path.join(ref_stubs.REFERENCE_ROOT, 'nn', 'net_blocks.py')):
+        pytest.skip('reference tree not present on this machine')
+    _, nb = ref_stubs.import_reference()
+    gold = torch.load(os.path.join(golden_dir, 'pointnet.pt'))
+    model = nb.PointNetPlusPlus(gold['out_size'], dict(gold['config']))
+    model.load_state_dict(gold['state'])
+    model.eval()
+    with torch.no_grad():
+        y = model(gold['x'])
+    assert torch.allclose(y, gold['eval_y'], rtol=1e-5, atol=1e-6)
