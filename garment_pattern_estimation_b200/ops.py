@@ -102,6 +102,9 @@ EDGE_MATERIALIZE = os.environ.get('NT_EDGE_MATERIALIZE', '1') != '0'
 # never written) instead of a separate nt_edge_scatter pass.  Correct (tests) but OFF by default: measured at C2 the 16-byte
 # reductions in the epilogue cost the GEMM +0.13 ms per launch while the separate pass costs 0.10 ms (8.89 vs 8.83 ms/step).
 FUSED_SCATTER = os.environ.get('NT_FUSED_SCATTER', '0') != '0'
+# Inference EdgeConv: one kernel per layer (gather -> GEMM -> GEMM -> max -> BN, csrc/edgeconv_eval.cu) instead of the layer-by-layer
+# path; '0' keeps the latter (A/B measurements, and the reference point of the parity test).
+EDGE_EVAL_FUSED = os.environ.get('NT_EDGE_EVAL_FUSED', '1') != '0'
 GEMM_ENGINE = 'tc'    # 'tc' = tcgen05 tensor-core engine (product path); 'simt' = fp32 CUDA-core engine (validation only)
 
 
@@ -282,6 +285,23 @@ class _FusedMLPFunction(torch.autograd.Function):
                                       int(training), _p(vec[0]), _p(vec[1]), _p(vec[2]), _p(vec[3]),
                                       _p(wn), _p(bn_), n_next, _p(w_f), _p(w_ft), _p(b_f), _stream())
             return vec, w_f, w_ft, b_f
+
+        # ---- inference, EdgeConv with three Linear layers: everything after PQ is ONE kernel; no edge-sized tensor touches HBM
+        if (mode == 'edge' and not training and L == 3 and EDGE_EVAL_FUSED and GEMM_ENGINE == 'tc'
+                and lib.nt_edgeconv_eval_supported(H1, widths[1], widths[2], k, pq.stride(0))):
+            _, w2f, _, b2f = fold(0, None, 1)
+            _, w3f, _, b3f = fold(1, None, 2)
+            vec3, _, _, _ = fold(2, None, None)
+            w2s = prepare_weights(w2f, H1, widths[1], H1, _lib.NT_PREC_BF16X3)
+            w3s = prepare_weights(w3f, widths[1], widths[2], widths[1], _lib.NT_PREC_BF16X3)
+            tail = 0 if tail_src is None else tail_src.shape[1]
+            ts, tld = (None, 0) if not tail else _rows2d(tail_src)
+            out = torch.empty(M, widths[2] + tail, **f32)
+            _call('nt_edgeconv_eval_fwd', lib.nt_edgeconv_eval_fwd, _p(pq), pq.stride(0), H1, _p(idx), k, N, M, _p(w2s), _p(b2f),
+                  widths[1], _p(w3s), _p(b3f), widths[2], _p(vec3[2]), _p(vec3[3]), _p(ts), tld, tail, _p(out), widths[2] + tail,
+                  _stream())
+            ctx.meta = None
+            return out
 
         # one zero-fill for the BatchNorm statistics of every layer of this call (was one fill kernel per layer)
         stats_all = torch.zeros(2 * sum(widths), dtype=torch.float64, device=dev) if training else None

@@ -567,3 +567,50 @@ def test_fused_edge_scatter_matches_separate_scatter_pass(ops, cuda_device):
 def _launches():
     from garment_pattern_estimation_b200 import _lib
     return _lib.launch_count()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fused inference EdgeConv (csrc/edgeconv_eval.cu, BASELINE.json north_star "single kernel" EdgeConv)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('C,widths,k,B,N,tail', [(150, [200, 200, 150], 5, 4, 2048, 3), (3, [200, 200, 150], 5, 3, 1000, 0),
+                                                 (150, [200, 200, 150], 16, 2, 1500, 3), (8, [64, 48, 40], 7, 2, 333, 0)])
+def test_fused_eval_edgeconv_matches_layerwise_path_and_torch(ops, cuda_device, C, widths, k, B, N, tail):
+    """Eval-mode DynamicEdgeConv through the single fused kernel (gather -> GEMM -> GEMM -> max -> BN) against (a) the layer-by-layer
+    kernels on the same kNN graph and (b) plain PyTorch with running-statistics BatchNorm (incl. negative gammas: max vs min)."""
+    from garment_pattern_estimation_b200 import net_blocks as nb
+    dev = cuda_device
+    torch.manual_seed(5)
+    ref_mlp = torch_mlp([2 * C] + widths).to(dev)
+    with torch.no_grad():
+        for blk in ref_mlp:
+            blk[2].weight.copy_(torch.randn_like(blk[2].weight))
+            blk[2].bias.copy_(torch.randn_like(blk[2].bias) * 0.3)
+            blk[2].running_mean.copy_(torch.rand_like(blk[2].running_mean))
+            blk[2].running_var.copy_(torch.rand_like(blk[2].running_var) + 0.5)
+    conv = nb.DynamicEdgeConv(nb.MLP([2 * C] + widths), k=k).to(dev).eval()
+    _copy_mlp(conv.nn, ref_mlp)
+    ref_mlp.eval()
+    x = torch.randn(B * N, C, device=dev)
+    pos = torch.randn(B * N, 3, device=dev) if tail else None
+    before = _launches()
+    with torch.no_grad():
+        assert ops.EDGE_EVAL_FUSED
+        fused = conv(x, cloud_shape=(B, N), tail_src=pos)
+        n_fused = _launches() - before
+        ops.EDGE_EVAL_FUSED = False
+        try:
+            layerwise = conv(x, cloud_shape=(B, N), tail_src=pos)
+        finally:
+            ops.EDGE_EVAL_FUSED = True
+        want = ref_edgeconv(x, global_index(conv.last_index, N), ref_mlp)
+    if tail:
+        want = torch.cat([want, pos], dim=-1)
+    assert fused.shape == want.shape
+    assert rel_err(fused, layerwise) <= 1e-4, 'fused vs layer-by-layer {:.2e}'.format(rel_err(fused, layerwise))
+    assert_close(fused, want, what='fused eval edgeconv vs torch')
+    assert n_fused <= 12, 'the fused path should be kNN + PQ GEMM + 3 folds + 2 weight preps + 1 fused kernel, got {} launches'.format(n_fused)
+
+
+def _launches():
+    from garment_pattern_estimation_b200 import _lib
+    return _lib.launch_count()
