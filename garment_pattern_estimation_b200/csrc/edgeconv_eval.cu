@@ -21,8 +21,10 @@
 
 namespace nt {
 
-constexpr int EE_WORKERS = 128;                 // warps 0-3: gather / bridge / finish (thread = row)
-constexpr int EE_THREADS = EE_WORKERS + 64;     // warp 4: MMA issuer, warp 5: weight loader + TMEM
+constexpr int EE_WORKERS = 256;                 // warps 0-7: gather / bridge / finish; two threads per edge row (TMEM lane = row), each
+                                                // owning one half (16 columns) of every 32-column K block
+constexpr int EE_WORKER_WARPS = EE_WORKERS / 32;
+constexpr int EE_THREADS = EE_WORKERS + 64;     // warp 8: MMA issuer, warp 9: weight loader + TMEM
 constexpr int EE_NST = 3;
 constexpr int EE_KB = 32;                       // bf16 elements per K block (4 chunks of 8)
 constexpr int EE_A_PLANE = 4 * TC_M * 16;       // 8 KB: [chunk 4][row 128][16 B]
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p
     uint64_t *d1_full = empty + EE_NST, *d2_full = d1_full + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_full + 1);
     float *vec = reinterpret_cast<float *>(tail_s + 128);            // b2 [224] | b3 [160] | s [160] | t [160]
-    float *vt = vec + 224 + 3 * 160;                                 // [128][33] transposition tile
+    float *vt_all = vec + 224 + 3 * 160;                             // 2 x [128][33] transposition tiles (one per worker half)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kb1 = (p.H1 + EE_KB - 1) / EE_KB, kb2 = (p.H2 + EE_KB - 1) / EE_KB;
     const uint32_t d2_col = 224;                                     // D1: TMEM columns [0, 224), D2: [224, 224 + n3)
@@ -59,21 +61,22 @@ __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p
         vec[384 + i] = i < p.C ? p.s_out[i] : 0.f;
         vec[544 + i] = i < p.C ? p.t_out[i] : 0.f;
     }
-    if (warp == 4 && lane == 0) {
+    if (warp == EE_WORKER_WARPS && lane == 0) {
         for (int s = 0; s < EE_NST; ++s) { mbar_init(&full[s], EE_WORKERS + 1); mbar_init(&empty[s], 1); }
         mbar_init(d1_full, 1);
         mbar_init(d2_full, 1);
         mbar_fence_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    if (warp == EE_WORKER_WARPS + 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
-        // =========================== workers: thread = edge row of the tile ===========================
-        const int r = tid;
+    if (warp < EE_WORKER_WARPS) {
+        // =========================== workers: (row r, half) -- 16 of the 32 columns of every K block ===========================
+        const int r = tid & (TC_M - 1), half = tid >> 7, quad = warp & 3;
+        float *vt = vt_all + half * (TC_M * 33);
         uint32_t it = 0;                                             // ring position (shared numbering with the other roles)
         uint32_t tile_i = 0;
         for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_i) {
@@ -87,32 +90,40 @@ __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p
                 pp = p.pq + centre * p.ldpq;
                 qq = p.pq + (base + p.idx[e]) * p.ldpq + p.H1;
             }
-            // ---- gather -> A operand of GEMM 1
-            for (int kb = 0; kb < kb1; ++kb, ++it) {
-                float v[EE_KB];
+            // ---- gather -> A operand of GEMM 1 (the loads of K block kb + 1 are in flight while block kb is converted)
+            float4 pa[4], pb[4];
+            auto fetch = [&](int kb) {
 #pragma unroll
-                for (int j = 0; j < EE_KB / 4; ++j) {
-                    const int c = kb * EE_KB + 4 * j;
-                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-                    if (live && c < p.H1) {                          // H1 % 4 == 0 and 16-byte aligned rows (checked by the launcher)
-                        a = __ldg(reinterpret_cast<const float4 *>(pp + c));
-                        b = __ldg(reinterpret_cast<const float4 *>(qq + c));
+                for (int j = 0; j < 4; ++j) {
+                    const int c = kb * EE_KB + half * 16 + 4 * j;
+                    pa[j] = pb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live && kb < kb1 && c < p.H1) {              // H1 % 4 == 0 and 16-byte aligned rows (checked by the launcher)
+                        pa[j] = __ldg(reinterpret_cast<const float4 *>(pp + c));
+                        pb[j] = __ldg(reinterpret_cast<const float4 *>(qq + c));
                     }
-                    v[4 * j] = fmaxf(a.x + b.x, 0.f); v[4 * j + 1] = fmaxf(a.y + b.y, 0.f);
-                    v[4 * j + 2] = fmaxf(a.z + b.z, 0.f); v[4 * j + 3] = fmaxf(a.w + b.w, 0.f);
                 }
+            };
+            fetch(0);
+            for (int kb = 0; kb < kb1; ++kb, ++it) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[4 * j] = fmaxf(pa[j].x + pb[j].x, 0.f); v[4 * j + 1] = fmaxf(pa[j].y + pb[j].y, 0.f);
+                    v[4 * j + 2] = fmaxf(pa[j].z + pb[j].z, 0.f); v[4 * j + 3] = fmaxf(pa[j].w + pb[j].w, 0.f);
+                }
+                fetch(kb + 1);
                 const uint32_t st = it % EE_NST;
                 mbar_wait(&empty[st], ((it / EE_NST) & 1u) ^ 1u);
                 uint8_t *a_hi = smem + (size_t)st * EE_STAGE_BYTES, *a_lo = a_hi + EE_A_PLANE;
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
+                for (int ch = 0; ch < 2; ++ch) {
                     float t8[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) t8[e] = v[8 * ch + e];
                     uint4 h, l;
                     pack_chunk(t8, false, h, l);
-                    *reinterpret_cast<uint4 *>(a_hi + ch * (TC_M * 16) + r * 16) = h;
-                    *reinterpret_cast<uint4 *>(a_lo + ch * (TC_M * 16) + r * 16) = l;
+                    *reinterpret_cast<uint4 *>(a_hi + (2 * half + ch) * (TC_M * 16) + r * 16) = h;
+                    *reinterpret_cast<uint4 *>(a_lo + (2 * half + ch) * (TC_M * 16) + r * 16) = l;
                 }
                 fence_proxy_async();
                 mbar_arrive(&full[st]);
@@ -121,40 +132,41 @@ __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p
             mbar_wait(d1_full, tile_i & 1u);
             tc_fence_after();
             for (int kb = 0; kb < kb2; ++kb, ++it) {
-                float acc[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kb * EE_KB), acc);
+                float acc[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kb * EE_KB + half * 16), acc);
                 const uint32_t st = it % EE_NST;
                 mbar_wait(&empty[st], ((it / EE_NST) & 1u) ^ 1u);
                 uint8_t *a_hi = smem + (size_t)st * EE_STAGE_BYTES, *a_lo = a_hi + EE_A_PLANE;
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
+                for (int ch = 0; ch < 2; ++ch) {
                     float t8[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const int c = kb * EE_KB + 8 * ch + e;
+                        const int c = kb * EE_KB + half * 16 + 8 * ch + e;
                         t8[e] = (live && c < p.H2) ? fmaxf(acc[8 * ch + e] + vec[c], 0.f) : 0.f;
                     }
                     uint4 h, l;
                     pack_chunk(t8, false, h, l);
-                    *reinterpret_cast<uint4 *>(a_hi + ch * (TC_M * 16) + r * 16) = h;
-                    *reinterpret_cast<uint4 *>(a_lo + ch * (TC_M * 16) + r * 16) = l;
+                    *reinterpret_cast<uint4 *>(a_hi + (2 * half + ch) * (TC_M * 16) + r * 16) = h;
+                    *reinterpret_cast<uint4 *>(a_lo + (2 * half + ch) * (TC_M * 16) + r * 16) = l;
                 }
                 fence_proxy_async();
                 tc_fence_before();               // the TMEM reads of this K block precede the arrive the MMA thread waits on
                 mbar_arrive(&full[st]);
             }
-            // ---- finish: D2 -> relu(+ b3') -> max / min over the k rows of a point -> BN3 -> out
+            // ---- finish: D2 -> relu(+ b3') -> max / min over the k rows of a point -> BN3 -> out; the two halves take alternate
+            //      32-column chunks, each with its own transposition tile and named barrier
             mbar_wait(d2_full, tile_i & 1u);
             tc_fence_after();
             const int nodes_here = (int)min((int64_t)(p.rows_per_tile / p.k), p.M - row0 / p.k);
             const int64_t node0 = row0 / p.k;
-            for (int c0 = 0; c0 < p.C; c0 += 32) {
+            for (int c0 = half * 32; c0 < p.C; c0 += 64) {
                 float acc[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + d2_col + (uint32_t)c0, acc);
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + d2_col + (uint32_t)c0, acc);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) vt[r * 33 + i] = fmaxf(acc[i] + vec[224 + ((c0 + i) < 160 ? c0 + i : 159)], 0.f);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int t = tid; t < nodes_here * 32; t += EE_WORKERS) {
+                if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                for (int t = r; t < nodes_here * 32; t += TC_M) {
                     const int nd = t >> 5, cc = t & 31, c = c0 + cc;
                     if (c >= p.C) continue;
                     float mx = vt[(nd * p.k) * 33 + cc], mn = mx;
@@ -166,7 +178,7 @@ __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p
                     const float s = vec[384 + c];
                     p.out[(node0 + nd) * (int64_t)p.ldo + c] = fmaf(s, s >= 0.f ? mx : mn, vec[544 + c]);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
             }
             if (p.tail)
                 for (int t = tid; t < nodes_here * p.tail; t += EE_WORKERS) {
@@ -174,9 +186,9 @@ __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p
                     p.out[(node0 + nd) * (int64_t)p.ldo + p.C + cc] = p.tail_src[(node0 + nd) * (int64_t)p.tail_ld + cc];
                 }
             tc_fence_before();
-            asm volatile("bar.sync 1, 128;" ::: "memory");          // every worker is done with D1 / D2 before the next tile's MMAs
+            asm volatile("bar.sync 3, 256;" ::: "memory");          // every worker is done with D1 / D2 before the next tile's MMAs
         }
-    } else if (warp == 4) {
+    } else if (warp == EE_WORKER_WARPS) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             const uint32_t idesc1 = make_idesc_bf16(TC_M, (uint32_t)p.n2, 0, 0), idesc2 = make_idesc_bf16(TC_M, (uint32_t)p.n3, 0, 0);
@@ -229,7 +241,7 @@ __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, 512);
+    if (warp == EE_WORKER_WARPS + 1) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace nt
@@ -258,7 +270,7 @@ extern "C" int nt_edgeconv_eval_fwd(const float *pq, int ldpq, int H1, const int
     const int64_t nodes_per_tile = p.rows_per_tile / k;
     p.n_tiles = (M + nodes_per_tile - 1) / nodes_per_tile;
     static int sms = 0;
-    const size_t smem = (size_t)EE_NST * EE_STAGE_BYTES + 128 + (224 + 3 * 160) * sizeof(float) + 128 * 33 * sizeof(float);
+    const size_t smem = (size_t)EE_NST * EE_STAGE_BYTES + 128 + (224 + 3 * 160) * sizeof(float) + 2 * 128 * 33 * sizeof(float);
     if (sms == 0) {
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
