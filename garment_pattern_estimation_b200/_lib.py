@@ -29,7 +29,7 @@ class GemmArgs(ctypes.Structure):
         ('aux', c_void_p), ('ldaux', c_int), ('aux_edge', c_int),
         ('k0', c_void_p), ('k1', c_void_p), ('mu', c_void_p),
         ('colsum', c_void_p),
-        ('scatter_dpq', c_void_p), ('ldscatter', c_int),
+        ('scatter_dpq', c_void_p), ('ldscatter', c_int), ('engine', c_int),
     ]
 
 
@@ -57,11 +57,11 @@ _SIGNATURES = {
     'nt_version': (c_int, []),
     'nt_built_arch': (c_int, []),
     'nt_launch_count': (c_int64, []),
+    'nt_sizeof': (c_int, [ctypes.c_char_p]),
     'nt_knn_workspace_bytes': (c_int64, [c_int, c_int, c_int]),
     'nt_knn': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'nt_gemm_nt': (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
     'nt_gemm_nt_scatter_supported': (c_int, [ctypes.POINTER(GemmArgs)]),
-    'nt_set_nt_engine': (c_int, [c_int]),
     'nt_gemm_weights_bytes': (c_int64, [c_int, c_int, c_int]),
     'nt_gemm_prepare_weights': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'nt_gemm_tn_workspace_bytes': (c_int64, []),
@@ -132,12 +132,14 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if not os.path.exists(path):
+    if not _build.is_current():
+        # missing, or STALE (sources / header / flags changed since it was linked: a stale library with a drifted argument
+        # struct would read garbage instead of failing) -> rebuild, or refuse to load what does not match the sources
         try:
             _build.build()
         except Exception as e:  # noqa: BLE001 -- turn every build problem into the documented error type
-            raise RuntimeError('libnt_b200.so is missing and could not be built ({}); the B200 hot path has no '
-                               'CPU or library fallback'.format(e))
+            raise RuntimeError('libnt_b200.so is missing or older than its sources and could not be rebuilt ({}); the B200 hot '
+                               'path has no CPU or library fallback'.format(e))
     try:
         lib = ctypes.CDLL(path)
     except OSError as e:
@@ -149,6 +151,11 @@ def load():
             raise RuntimeError('{} does not export {} (stale build? run garment_pattern_estimation_b200/build.py '
                                '--force)'.format(path, name))
         fn.restype, fn.argtypes = restype, argtypes
+    for name, struct in (('nt_gemm_args', GemmArgs), ('nt_pattern_loss_args', PatternLossArgs), ('nt_lstm_sizes_t', LstmSizes)):
+        lib.nt_sizeof.restype, lib.nt_sizeof.argtypes = c_int, [ctypes.c_char_p]
+        if lib.nt_sizeof(name.encode()) != ctypes.sizeof(struct):
+            raise RuntimeError('{}: struct {} is {} bytes in the library but {} in the ctypes mirror (layout drift)'.format(
+                path, name, lib.nt_sizeof(name.encode()), ctypes.sizeof(struct)))
     _lib = lib
     return lib
 

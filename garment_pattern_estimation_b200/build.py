@@ -30,7 +30,7 @@ def _fingerprint():
     for path in sources() + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith('.cuh')] + \
             [os.path.join(INCLUDE, 'nt_b200.h')]:
         with open(path, 'rb') as f:
-            h.update(path.encode() + b'\0' + f.read())
+            h.update(os.path.basename(path).encode() + b'\0' + f.read())      # path-independent: the tree is copied to the GPU box
     h.update(' '.join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
@@ -47,6 +47,12 @@ def _compile_one(nvcc, src, obj, flags, verbose):
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd)
+
+
+def is_current():
+    """True if lib/libnt_b200.so exists and its stamp matches the sources (csrc/*.cu, *.cuh, include/nt_b200.h, flags)."""
+    stamp = os.path.join(LIB_DIR, 'libnt_b200.stamp')
+    return os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == _fingerprint()
 
 
 def build(force=False, verbose=False, extra_flags=()):

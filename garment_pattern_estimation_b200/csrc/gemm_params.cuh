@@ -33,6 +33,7 @@ struct NTParams {
     const float *aux; int ldaux; int aux_edge; EdgeSrc ae;
     const float *k0, *k1, *mu; double *colsum;
     float *scatter; int ldscatter;               // fused edge scatter (BNRELU_BWD on the streaming engine only)
+    int engine;                                  // nt_gemm_args.engine: 0 = auto, 1 = one tile per CTA, 3 / 4 / 5 = streaming configurations
 };
 
 

@@ -15,7 +15,6 @@
 //   warp 5    : TMEM alloc / dealloc.
 //   W tiles   : pre-split bf16 in the same core-matrix layout (nt_gemm_prepare_weights), one cp.async.bulk per stage.
 #include "gemm_tc_shared.cuh"
-#include <stdlib.h>
 
 namespace nt {
 
@@ -510,38 +509,22 @@ static int dispatch_tc(const NTParams &p, int producer, int epilogue, const void
     }
 }
 
-// Engine choice for the TF32x3 row GEMMs.  0 = auto (default): the streaming engine (gemm_tc3.cu) for eligible calls with at
-// least TC3_MIN_ROWS rows, the one-tile-per-CTA engine (this file) otherwise; 1 = always this file; 2 = persistent engine
-// of gemm_tc2.cu (experiment); 3 = streaming engine whenever eligible, whatever the row count (tests).
-// Set by nt_set_nt_engine() or, before the first call, by the developer knob NT_NT_ENGINE.
-static std::atomic<int> g_nt_engine{-1};
+// Engine choice for the TF32x3 row GEMMs, PER CALL (nt_gemm_args.engine; the library keeps no mutable state): 0 = auto -- the
+// streaming engine (gemm_tc3.cu) for eligible calls with at least TC3_MIN_ROWS rows, the one-tile-per-CTA engine (this file)
+// otherwise; 1 = always this file; 3 / 4 / 5 = streaming engine whenever eligible, whatever the row count, with one / two row
+// tiles per weight stage / the aux-row ring for BNRELU_BWD (tests compare them; results are bit-identical across engines).
 constexpr int64_t TC3_MIN_ROWS = 32768;
 
-static int nt_engine() {
-    int engine = g_nt_engine.load(std::memory_order_relaxed);
-    if (engine < 0) {
-        const char *v = getenv("NT_NT_ENGINE");
-        engine = v ? atoi(v) : 0;
-        g_nt_engine.store(engine, std::memory_order_relaxed);
-    }
-    return engine;
-}
-
 bool nt_tc_would_stream(const NTParams &p, int producer, int epilogue, int precision) {
-    const int engine = nt_engine();
     if (precision != NT_PREC_TF32X3) return false;
-    if (!(engine == 3 || (engine == 0 && p.rows >= TC3_MIN_ROWS))) return false;
+    if (!(p.engine >= 3 || (p.engine == 0 && p.rows >= TC3_MIN_ROWS))) return false;
     return tc3_eligible(p, producer, epilogue);
 }
 
 int launch_nt_tc(const NTParams &p, int producer, int epilogue, int precision, const void *w_split, cudaStream_t st) {
-    const int engine = nt_engine();
-    if (precision == NT_PREC_TF32X3) {
-        if (engine == 2 && !p.scatter) return launch_nt_tc2(p, producer, epilogue, w_split, st);
-        if (engine == 3 || (engine == 0 && p.rows >= TC3_MIN_ROWS)) {
-            const int rc = launch_nt_tc3(p, producer, epilogue, w_split, st);
-            if (rc >= 0) return rc;
-        }
+    if (precision == NT_PREC_TF32X3 && (p.engine >= 3 || (p.engine == 0 && p.rows >= TC3_MIN_ROWS))) {
+        const int rc = launch_nt_tc3(p, producer, epilogue, w_split, st);
+        if (rc >= 0) return rc;
     }
     if (p.scatter) return fail("nt_gemm_nt: the fused scatter epilogue needs the streaming engine (see nt_gemm_nt_scatter_supported)%s", "");
     return precision == NT_PREC_TF32X3 ? dispatch_tc<true>(p, producer, epilogue, w_split, st)
@@ -551,13 +534,6 @@ int launch_nt_tc(const NTParams &p, int producer, int epilogue, int precision, c
 }  // namespace nt
 
 using namespace nt;
-
-extern "C" int nt_set_nt_engine(int engine) {
-    NT_REQUIRE(engine >= 0 && engine <= 5, "nt_set_nt_engine: engine must be 0 (auto), 1, 2, 3, 4 or 5");
-    tc3_set_tiles(engine == 5 ? 4 : (engine == 4 ? 2 : (engine == 3 ? 1 : 0)));      // streaming-engine configuration (P3Cfg)
-    g_nt_engine.store(engine >= 4 ? 3 : engine, std::memory_order_relaxed);
-    return 0;
-}
 
 extern "C" int64_t nt_gemm_weights_bytes(int n_out, int K, int precision) {
     if (n_out < 1 || K < 1) return 0;

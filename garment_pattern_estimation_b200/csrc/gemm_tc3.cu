@@ -550,23 +550,13 @@ static int launch_tc3_t(const NTParams &p, const void *w_split, const TCGeom &g,
     return check_launch("nt_gemm_nt(tc3)");
 }
 
-// tiles per weight stage: set by nt_set_nt_engine (3 -> 1, 4 -> 2), else the developer knob NT_TC3_TILES, else the default
-constexpr int TC3_DEFAULT_TILES = 4;      // cfg 4 = aux-row ring for NT_EPI_BNRELU_BWD (measured r2: 1.33 -> 1.09 ms per step at C2); other epilogues run cfg 1
-static std::atomic<int> g_tc3_tiles{0};
-void tc3_set_tiles(int tiles) { g_tc3_tiles.store(tiles, std::memory_order_relaxed); }
-static int tc3_tiles() {
-    int tiles = g_tc3_tiles.load(std::memory_order_relaxed);
-    if (tiles == 0) {
-        const char *v = getenv("NT_TC3_TILES");
-        tiles = v ? ((atoi(v) >= 2 && atoi(v) <= 4) ? atoi(v) : 1) : TC3_DEFAULT_TILES;
-        g_tc3_tiles.store(tiles, std::memory_order_relaxed);
-    }
-    return tiles;
-}
+// configuration (P3Cfg) from the call's engine: 3 -> one row tile per weight stage, 4 -> two, 5 or auto -> the aux-row ring for
+// BNRELU_BWD (cfg 4; measured r2: 1.33 -> 1.09 ms per C2 step) and one tile per stage for the other epilogues
+static int tc3_cfg(int engine) { return engine == 3 ? 1 : (engine == 4 ? 2 : 4); }
 
 template <int EPI, bool SCAT = false>
 static int launch_tc3(const NTParams &p, const void *w_split, const TCGeom &g, int sms, cudaStream_t st) {
-    const int cfg = tc3_tiles();       // configuration index (see P3Cfg)
+    const int cfg = tc3_cfg(p.engine);       // configuration index (see P3Cfg)
     if (cfg == 2 && tc3_smem_bytes(g.n_tile, 2) <= 227 * 1024) return launch_tc3_t<EPI, SCAT, 2>(p, w_split, g, sms, st);
     if (cfg == 3 && tc3_smem_bytes(g.n_tile, 3) <= 227 * 1024) return launch_tc3_t<EPI, SCAT, 3>(p, w_split, g, sms, st);
     if constexpr (EPI == NT_EPI_BNRELU_BWD) {

@@ -1,4 +1,4 @@
-// Helpers shared by the tensor-core row-GEMM kernels (gemm_tc.cu: one tile per CTA; gemm_tc2.cu: persistent, warp-specialised).
+// Helpers shared by the tensor-core row-GEMM kernels (gemm_tc.cu: one tile per CTA; gemm_tc3.cu: persistent streaming engine).
 #pragma once
 #include "gemm_params.cuh"
 #include "tc_common.cuh"
@@ -68,11 +68,8 @@ __device__ __forceinline__ void load_chunk(const float *src, int k, int K, bool 
 }
 
 
-// persistent engine entry (gemm_tc2.cu)
-int launch_nt_tc2(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st);
 // streaming engine entry (gemm_tc3.cu); returns -1 when the call is not eligible (caller falls back to gemm_tc.cu)
 int launch_nt_tc3(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st);
 bool tc3_eligible(const NTParams &p, int producer, int epilogue);
-void tc3_set_tiles(int tiles);      // 0 = default (NT_TC3_TILES or built-in), 1, 2 = row tiles per weight stage
 
 }  // namespace nt

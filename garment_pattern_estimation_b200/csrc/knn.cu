@@ -204,387 +204,6 @@ __global__ void knn_merge_kernel(const float *__restrict__ part_d, const int32_t
         if (e < k) idx[q * k + e] = li[e];
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// High-occupancy variant: 16 candidates per tile so the thread fits in 64 registers and 32 warps are resident per SM.
-// ------------------------------------------------------------------------------------------------------------------
-template <int K, int DT>
-__global__ void __launch_bounds__(256, 4)
-knn_kernel_occ(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int32_t *__restrict__ idx) {
-    constexpr int TC = 16;
-    extern __shared__ __align__(16) float tile[];   // [TC][Dp]
-    const int D = DT ? DT : D_rt;
-    const int Dp = (D + 3) & ~3;
-    const int b = blockIdx.y;
-    const int q = blockIdx.x * 256 + threadIdx.x;
-    const bool q_ok = q < N;
-    const float *cloud = x + (size_t)b * N * ldx;
-    const float *xq = cloud + (size_t)(q_ok ? q : 0) * ldx;
-    const bool qvec = DT ? true : (((ldx & 3) == 0) && aligned16(x));
-    const bool q_ld = DT ? true : q_ok;
-    float ld[K];
-    int li[K];
-#pragma unroll
-    for (int e = 0; e < K; ++e) { ld[e] = 1e10f; li[e] = -1; }
-    const int n_groups = Dp >> 2;
-    for (int c0 = 0; c0 < N; c0 += TC) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < TC * Dp; i += 256) {
-            int c = i / Dp, d = i - c * Dp;
-            float v = 0.f;
-            if (c0 + c < N && d < D) v = __ldg(cloud + (size_t)(c0 + c) * ldx + d);
-            tile[i] = v;
-        }
-        __syncthreads();
-        float acc[TC];
-#pragma unroll
-        for (int c = 0; c < TC; ++c) acc[c] = 0.f;
-#pragma unroll 2
-        for (int g = 0; g < n_groups; ++g) {
-            float qv4[KNN_DC];
-            // one float4 of the query per step (4 dims), 16 chains advance by 4 dims each
-            {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int d = 4 * g;
-                if (q_ld) {
-                    if (qvec && d + 3 < D) v = __ldg(reinterpret_cast<const float4 *>(xq + d));
-                    else if (qvec && d + 2 == D) { const float2 t = __ldg(reinterpret_cast<const float2 *>(xq + d)); v.x = t.x; v.y = t.y; }
-                    else {
-                        if (d + 0 < D) v.x = __ldg(xq + d + 0);
-                        if (d + 1 < D) v.y = __ldg(xq + d + 1);
-                        if (d + 2 < D) v.z = __ldg(xq + d + 2);
-                        if (d + 3 < D) v.w = __ldg(xq + d + 3);
-                    }
-                }
-                qv4[0] = v.x; qv4[1] = v.y; qv4[2] = v.z; qv4[3] = v.w;
-            }
-#pragma unroll
-            for (int c = 0; c < TC; ++c) {
-                const float4 cv = *reinterpret_cast<const float4 *>(tile + c * Dp + 4 * g);
-                float a = acc[c], t;
-                t = __fsub_rn(cv.x, qv4[0]); a = __fmaf_rn(t, t, a);
-                t = __fsub_rn(cv.y, qv4[1]); a = __fmaf_rn(t, t, a);
-                t = __fsub_rn(cv.z, qv4[2]); a = __fmaf_rn(t, t, a);
-                t = __fsub_rn(cv.w, qv4[3]); a = __fmaf_rn(t, t, a);
-                acc[c] = a;
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < TC; ++c)
-            if (c0 + c < N && acc[c] < ld[K - 1]) topk_insert<K>(ld, li, acc[c], c0 + c);
-    }
-    if (q_ok) {
-        int32_t *o = idx + ((size_t)b * N + q) * k;
-#pragma unroll
-        for (int e = 0; e < K; ++e)
-            if (e < k) o[e] = li[e];
-    }
-}
-
-template <int K>
-static int launch_knn_occ(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
-    const int Dp = (D + 3) & ~3;
-    size_t smem = (size_t)16 * Dp * sizeof(float);
-    if (smem > 48 * 1024) return fail("nt_knn: feature dimension %s too large (D=%ld)", "", D);
-    const bool aligned = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
-    dim3 grid((N + 255) / 256, B);
-    if (D == 150 && aligned) knn_kernel_occ<K, 150><<<grid, 256, smem, st>>>(x, N, D, ldx, k, idx);
-    else knn_kernel_occ<K, 0><<<grid, 256, smem, st>>>(x, N, D, ldx, k, idx);
-    return check_launch("nt_knn");
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Packed-FP32x2 variant (Blackwell FADD2 / FFMA2: add.rn.f32x2, fma.rn.f32x2).  Two candidates share one instruction, so
-// a pair-dimension costs 1 issue slot instead of 2; every half is an independent IEEE fma.rn, i.e. the same bits as the
-// scalar chain.  The candidate tile is stored TRANSPOSED ([dim][candidate], row stride 36 floats) so that one broadcast
-// LDS.128 delivers the same dimension of four consecutive candidates = two packed operands.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int KNN_TS = 36;     // transposed tile row stride (floats): 16-byte aligned rows, 4-way instead of 32-way store conflicts
-
-__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float &lo, float &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-
-template <int K, int KNN_THREADS>
-__global__ void __launch_bounds__(KNN_THREADS, (K <= 16) ? 512 / KNN_THREADS : 256 / KNN_THREADS)
-knn_kernel_x2(const float *__restrict__ x, int N, int D, int ldx, int k, int32_t *__restrict__ idx) {
-    extern __shared__ __align__(16) float tile[];   // [Dp][KNN_TS]
-    const int Dp = (D + 3) & ~3;
-    const int b = blockIdx.y;
-    const int q = blockIdx.x * KNN_THREADS + threadIdx.x;
-    const bool q_ok = q < N;
-    const float *cloud = x + (size_t)b * N * ldx;
-    const float *xq = cloud + (size_t)(q_ok ? q : 0) * ldx;
-    const bool qvec = ((ldx & 3) == 0) && aligned16(x);
-
-    float ld[K];
-    int li[K];
-#pragma unroll
-    for (int e = 0; e < K; ++e) { ld[e] = 1e10f; li[e] = -1; }
-
-    const int full_chunks = Dp / KNN_DC;
-    const int tail_groups = (Dp - full_chunks * KNN_DC) >> 2;
-    const int n_chunks = full_chunks + (tail_groups ? 1 : 0);
-
-    for (int c0 = 0; c0 < N; c0 += KNN_TC) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < KNN_TC * Dp; i += KNN_THREADS) {
-            int c = i / Dp, d = i - c * Dp;
-            float v = 0.f;
-            if (c0 + c < N && d < D) v = __ldg(cloud + (size_t)(c0 + c) * ldx + d);
-            tile[d * KNN_TS + c] = v;
-        }
-        __syncthreads();
-
-        unsigned long long acc2[KNN_TC / 2];
-#pragma unroll
-        for (int c = 0; c < KNN_TC / 2; ++c) acc2[c] = 0ull;       // {0.f, 0.f}
-
-        for (int ch = 0; ch < n_chunks; ++ch) {
-            const int d0 = ch * KNN_DC;
-            const int groups = (ch < full_chunks) ? (KNN_DC / 4) : tail_groups;
-            float qv[KNN_DC];
-            if (ch < full_chunks && qvec && q_ok) {                  // straight-line fast path: 4 x LDG.128
-#pragma unroll
-                for (int g = 0; g < KNN_DC / 4; ++g) {
-                    const float4 v = __ldg(reinterpret_cast<const float4 *>(xq + d0 + 4 * g));
-                    qv[4 * g + 0] = v.x; qv[4 * g + 1] = v.y; qv[4 * g + 2] = v.z; qv[4 * g + 3] = v.w;
-                }
-            } else {
-                load_query_chunk(xq, d0, groups, D, q_ok, qvec, qv);
-            }
-            const int dims = groups * 4;
-#pragma unroll
-            for (int dd = 0; dd < KNN_DC; ++dd) {
-                if (dd < dims) {
-                    const unsigned long long nq2 = pack_f32x2(-qv[dd], -qv[dd]);
-                    const float4 *row = reinterpret_cast<const float4 *>(tile + (d0 + dd) * KNN_TS);
-#pragma unroll
-                    for (int c4 = 0; c4 < KNN_TC / 4; ++c4) {
-                        const float4 cv = row[c4];
-                        const unsigned long long da = add_f32x2(pack_f32x2(cv.x, cv.y), nq2);
-                        const unsigned long long db = add_f32x2(pack_f32x2(cv.z, cv.w), nq2);
-                        acc2[2 * c4] = fma_f32x2(da, da, acc2[2 * c4]);
-                        acc2[2 * c4 + 1] = fma_f32x2(db, db, acc2[2 * c4 + 1]);
-                    }
-                }
-            }
-        }
-
-#pragma unroll
-        for (int c2 = 0; c2 < KNN_TC / 2; ++c2) {
-            float a0, a1;
-            unpack_f32x2(acc2[c2], a0, a1);
-            if (c0 + 2 * c2 < N && a0 < ld[K - 1]) topk_insert<K>(ld, li, a0, c0 + 2 * c2);
-            if (c0 + 2 * c2 + 1 < N && a1 < ld[K - 1]) topk_insert<K>(ld, li, a1, c0 + 2 * c2 + 1);
-        }
-    }
-
-    if (q_ok) {
-        int32_t *o = idx + ((size_t)b * N + q) * k;
-#pragma unroll
-        for (int e = 0; e < K; ++e)
-            if (e < k) o[e] = li[e];
-    }
-}
-
-template <int K, int THREADS>
-static int launch_knn_x2(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, cudaStream_t st) {
-    const int Dp = (D + 3) & ~3;
-    size_t smem = (size_t)KNN_TS * Dp * sizeof(float);
-    if (smem > 200 * 1024) return fail("nt_knn: feature dimension %s too large for the staging tile (D=%ld)", "", D);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(knn_kernel_x2<K, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail("nt_knn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    }
-    dim3 grid((N + THREADS - 1) / THREADS, B);
-    knn_kernel_x2<K, THREADS><<<grid, THREADS, smem, st>>>(x, N, D, ldx, k, idx);
-    return check_launch("nt_knn");
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Two queries per thread (default).  ncu on the one-query kernel: FP32 pipe 43 % busy and identical run time for the
-// scalar, the packed-FP32x2 and the guard-free variants -> the limiter is the shared-memory -> register return path
-// (128 B/clk/SM): a broadcast LDS.128 still writes 512 B of registers per warp, i.e. 4 cycles per 8 FP instructions.
-// Reusing every candidate word for TWO queries halves that traffic (16 FP instructions per LDS.128) and puts the bound
-// back on the FP32 pipe.  Candidates are processed 16 at a time so the 2 x 16 fma chains still fit in registers.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int KNN_HC = 16;     // candidates per half tile
-
-template <int NG>
-__device__ __forceinline__ void chain_chunk_q2(float (&a0)[KNN_HC], float (&a1)[KNN_HC], const float *__restrict__ tile, int Dp,
-                                               int d0, const float (&q0)[KNN_DC], const float (&q1)[KNN_DC]) {
-#pragma unroll
-    for (int c = 0; c < KNN_HC; ++c) {
-        const float4 *row = reinterpret_cast<const float4 *>(tile + c * Dp + d0);
-        float x = a0[c], y = a1[c];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const float4 cv = row[g];
-            float d, e;
-            d = __fsub_rn(cv.x, q0[4 * g + 0]); e = __fsub_rn(cv.x, q1[4 * g + 0]); x = __fmaf_rn(d, d, x); y = __fmaf_rn(e, e, y);
-            d = __fsub_rn(cv.y, q0[4 * g + 1]); e = __fsub_rn(cv.y, q1[4 * g + 1]); x = __fmaf_rn(d, d, x); y = __fmaf_rn(e, e, y);
-            d = __fsub_rn(cv.z, q0[4 * g + 2]); e = __fsub_rn(cv.z, q1[4 * g + 2]); x = __fmaf_rn(d, d, x); y = __fmaf_rn(e, e, y);
-            d = __fsub_rn(cv.w, q0[4 * g + 3]); e = __fsub_rn(cv.w, q1[4 * g + 3]); x = __fmaf_rn(d, d, x); y = __fmaf_rn(e, e, y);
-        }
-        a0[c] = x; a1[c] = y;
-    }
-}
-
-// blockIdx.z selects a slice of the CANDIDATE range (split S = gridDim.z): with one thread per query pair the grid would
-// only hold B*N/64 warps (1024 at C2, 7 per SM), so the scan of every query is split over S CTAs that each write a partial
-// sorted list; knn_merge_kernel then takes the k lexicographically smallest (distance, index) pairs -- still exact.
-template <int K, int KNN_THREADS, int DT>
-__global__ void __launch_bounds__(KNN_THREADS, (K <= 8) ? 512 / KNN_THREADS : 256 / KNN_THREADS)
-knn_kernel_q2(const float *__restrict__ x, int N, int D_rt, int ldx, int k, int32_t *__restrict__ idx,
-              float *__restrict__ part_d, int32_t *__restrict__ part_i, int cand_per_split) {
-    extern __shared__ __align__(16) float tile[];   // [KNN_TC][Dp]
-    const int D = DT ? DT : D_rt;
-    const int Dp = (D + 3) & ~3;
-    const int b = blockIdx.y;
-    const int qa = blockIdx.x * (2 * KNN_THREADS) + threadIdx.x;
-    const int qb = qa + KNN_THREADS;
-    const bool a_ok = qa < N, b_ok = qb < N;
-    const float *cloud = x + (size_t)b * N * ldx;
-    const float *xa = cloud + (size_t)(a_ok ? qa : 0) * ldx;
-    const float *xb = cloud + (size_t)(b_ok ? qb : 0) * ldx;
-    const bool qvec = DT ? true : (((ldx & 3) == 0) && aligned16(x));
-    const bool la = DT ? true : a_ok, lb = DT ? true : b_ok;
-
-    float lda_[K], ldb_[K];
-    int lia[K], lib[K];
-#pragma unroll
-    for (int e = 0; e < K; ++e) { lda_[e] = 1e10f; lia[e] = -1; ldb_[e] = 1e10f; lib[e] = -1; }
-
-    const int full_chunks = Dp / KNN_DC;
-    const int tail_groups = (Dp - full_chunks * KNN_DC) >> 2;
-    const int n_chunks = full_chunks + (tail_groups ? 1 : 0);
-
-    const int c_begin = blockIdx.z * cand_per_split;
-    const int c_end = min(N, c_begin + cand_per_split);
-    for (int c0 = c_begin; c0 < c_end; c0 += KNN_TC) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < KNN_TC * Dp; i += KNN_THREADS) {
-            int c = i / Dp, d = i - c * Dp;
-            float v = 0.f;
-            if (c0 + c < c_end && d < D) v = __ldg(cloud + (size_t)(c0 + c) * ldx + d);
-            tile[i] = v;
-        }
-        __syncthreads();
-
-#pragma unroll 1
-        for (int h = 0; h < KNN_TC / KNN_HC; ++h) {
-            const float *half_tile = tile + h * KNN_HC * Dp;
-            const int cbase = c0 + h * KNN_HC;
-            if (cbase >= c_end) break;
-            float a0[KNN_HC], a1[KNN_HC];
-#pragma unroll
-            for (int c = 0; c < KNN_HC; ++c) { a0[c] = 0.f; a1[c] = 0.f; }
-            for (int ch = 0; ch < n_chunks; ++ch) {
-                const int d0 = ch * KNN_DC;
-                const int groups = (ch < full_chunks) ? (KNN_DC / 4) : tail_groups;
-                float q0[KNN_DC], q1[KNN_DC];
-                load_query_chunk(xa, d0, groups, D, la, qvec, q0);
-                load_query_chunk(xb, d0, groups, D, lb, qvec, q1);
-                switch (groups) {
-                    case 4: chain_chunk_q2<4>(a0, a1, half_tile, Dp, d0, q0, q1); break;
-                    case 3: chain_chunk_q2<3>(a0, a1, half_tile, Dp, d0, q0, q1); break;
-                    case 2: chain_chunk_q2<2>(a0, a1, half_tile, Dp, d0, q0, q1); break;
-                    default: chain_chunk_q2<1>(a0, a1, half_tile, Dp, d0, q0, q1); break;
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < KNN_HC; ++c) {
-                if (cbase + c < c_end) {
-                    if (a0[c] < lda_[K - 1]) topk_insert<K>(lda_, lia, a0[c], cbase + c);
-                    if (a1[c] < ldb_[K - 1]) topk_insert<K>(ldb_, lib, a1[c], cbase + c);
-                }
-            }
-        }
-    }
-
-    if (gridDim.z == 1) {
-        if (a_ok) {
-            int32_t *o = idx + ((size_t)b * N + qa) * k;
-#pragma unroll
-            for (int e = 0; e < K; ++e)
-                if (e < k) o[e] = lia[e];
-        }
-        if (b_ok) {
-            int32_t *o = idx + ((size_t)b * N + qb) * k;
-#pragma unroll
-            for (int e = 0; e < K; ++e)
-                if (e < k) o[e] = lib[e];
-        }
-    } else {      // partial lists: [query][split][K]
-        if (a_ok) {
-            const size_t o = (((size_t)b * N + qa) * gridDim.z + blockIdx.z) * K;
-#pragma unroll
-            for (int e = 0; e < K; ++e) { part_d[o + e] = lda_[e]; part_i[o + e] = lia[e]; }
-        }
-        if (b_ok) {
-            const size_t o = (((size_t)b * N + qb) * gridDim.z + blockIdx.z) * K;
-#pragma unroll
-            for (int e = 0; e < K; ++e) { part_d[o + e] = ldb_[e]; part_i[o + e] = lib[e]; }
-        }
-    }
-}
-
-static int knn_split_for(int B, int N, int threads) {
-    // enough CTAs for ~2 resident waves of warps; every slice a multiple of the 32-candidate tile
-    const long ctas = (long)B * ((N + 2 * threads - 1) / (2 * threads));
-    int S = 1;
-    while (S < 8 && ctas * S * (threads / 32) < 2 * 148 * 8 && (N / (2 * S)) >= 2 * KNN_TC) S *= 2;
-    return S;
-}
-
-template <int K, int THREADS, int DT>
-static int launch_knn_q2(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *workspace, int S,
-                         cudaStream_t st) {
-    const int Dp = (D + 3) & ~3;
-    size_t smem = (size_t)KNN_TC * Dp * sizeof(float);
-    if (smem > 200 * 1024) return fail("nt_knn: feature dimension %s too large for the staging tile (D=%ld)", "", D);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(knn_kernel_q2<K, THREADS, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail("nt_knn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    }
-    if (!workspace) S = 1;
-    const int per = ((N + S - 1) / S + KNN_TC - 1) / KNN_TC * KNN_TC;
-    S = (N + per - 1) / per;
-    const int64_t M = (int64_t)B * N;
-    float *part_d = reinterpret_cast<float *>(workspace);
-    int32_t *part_i = reinterpret_cast<int32_t *>(part_d + (size_t)M * S * K);
-    dim3 grid((N + 2 * THREADS - 1) / (2 * THREADS), B, S);
-    knn_kernel_q2<K, THREADS, DT><<<grid, THREADS, smem, st>>>(x, N, D, ldx, k, idx, part_d, part_i, per);
-    int rc = check_launch("nt_knn");
-    if (rc || S == 1) return rc;
-    knn_merge_kernel<K><<<(unsigned)((M + 255) / 256), 256, 0, st>>>(part_d, part_i, M, S, k, idx);
-    return check_launch("nt_knn(merge)");
-}
-
-template <int K, int THREADS>
-static int launch_knn_q2_any(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *workspace, int S,
-                             cudaStream_t st) {
-    const bool aligned = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
-    if (S <= 0) S = knn_split_for(B, N, THREADS);
-    if (D == 150 && aligned) return launch_knn_q2<K, THREADS, 150>(x, B, N, D, ldx, k, idx, workspace, S, st);
-    return launch_knn_q2<K, THREADS, 0>(x, B, N, D, ldx, k, idx, workspace, S, st);
-}
-
 template <int K, int THREADS, bool PRUNE, bool PREFETCH, int DT>
 static int launch_knn_dt(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *workspace, int S,
                          cudaStream_t st) {
@@ -632,24 +251,9 @@ static int launch_knn_cfg(const float *x, int B, int N, int D, int ldx, int k, i
     return launch_knn_dt<K, THREADS, PRUNE, PREFETCH, 0>(x, B, N, D, ldx, k, idx, workspace, S, st);
 }
 
-static int g_knn_variant = -1;      // developer knob (NT_KNN_VARIANT), read once
-
 template <int K>
 static int launch_knn(const float *x, int B, int N, int D, int ldx, int k, int32_t *idx, void *ws, cudaStream_t st) {
-    if (g_knn_variant < 0) {
-        const char *v = getenv("NT_KNN_VARIANT");
-        g_knn_variant = v ? atoi(v) : 0;
-    }
-    switch (g_knn_variant) {
-        // experiments kept for the record; all bit-exact, none faster than the default
-        case 4: return launch_knn_cfg<K, 256, true, false>(x, B, N, D, ldx, k, idx, ws, 1, st);     // warp-level pruning
-        case 7: return launch_knn_x2<K, 256>(x, B, N, D, ldx, k, idx, st);                           // packed FP32x2
-        case 9: return launch_knn_cfg<K, 256, false, false>(x, B, N, D, ldx, k, idx, ws, 1, st);    // no candidate split
-        case 13: return launch_knn_q2_any<K, 128>(x, B, N, D, ldx, k, idx, ws, 4, st);              // two queries per thread
-        case 15: return launch_knn_occ<K>(x, B, N, D, ldx, k, idx, st);                              // 64 registers, 32 warps/SM
-        case 16: return launch_knn_cfg<K, 256, false, false>(x, B, N, D, ldx, k, idx, ws, 4, st);
-        default: return launch_knn_cfg<K, 256, false, false>(x, B, N, D, ldx, k, idx, ws, 0, st);   // auto split (8 at C2)
-    }
+    return launch_knn_cfg<K, 256, false, false>(x, B, N, D, ldx, k, idx, ws, 0, st);      // auto candidate split
 }
 
 // tensor-core filter + exact re-rank path (knn_tc.cu)
@@ -680,9 +284,9 @@ extern "C" int nt_knn(const float *x, int B, int N, int D, int ldx, int k, int32
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // feature-space graphs (D >= 8): bf16 tcgen05 filter + exact fp32 re-rank, bit-identical to the direct form below
     if (knn_tc_eligible(N, D, workspace)) return knn_tc_run(x, B, N, D, ldx, k, idx, workspace, st);
-    // coordinate-space graphs (D = 3): register top-k over a shared-memory copy of the cloud (knn3.cu); NT_KNN_VARIANT keeps
-    // the generic kernels reachable for comparison
-    if (D == 3 && getenv("NT_KNN_VARIANT") == nullptr) return knn3_run(x, B, N, ldx, k, idx, st);
+    // coordinate-space graphs (D = 3): register top-k over a shared-memory copy of the cloud (knn3.cu)
+    if (D == 3) return knn3_run(x, B, N, ldx, k, idx, st);
+    // everything else (4 <= D < 8, or no workspace): the generic direct-form kernel of this file
     if (k <= 5) return launch_knn<5>(x, B, N, D, ldx, k, idx, workspace, st);
     if (k <= 8) return launch_knn<8>(x, B, N, D, ldx, k, idx, workspace, st);
     if (k <= 16) return launch_knn<16>(x, B, N, D, ldx, k, idx, workspace, st);

@@ -54,10 +54,20 @@ def _call(name, fn, *args, group=None):
 
 
 def _require_cuda(*tensors):
+    """Every operand on a CUDA device -- and on the CURRENT one: the kernels are enqueued on torch.cuda.current_stream(), so a
+    tensor living on another GPU would be addressed from the wrong device."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError('garment_pattern_estimation_b200: tensors must be on a CUDA device '
                                '(the B200 hot path has no CPU fallback)')
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError('garment_pattern_estimation_b200: tensor on cuda:{} but the current device is cuda:{} -- call '
+                               'torch.cuda.set_device() / use torch.cuda.device() around the model'.format(t.device.index, cur))
 
 
 def _pad4(c):
@@ -92,8 +102,6 @@ class EdgeSrc:
 
 
 GRAD_PRECISION = _lib.NT_PREC_BF16X3 if os.environ.get('NT_GRAD_PRECISION', 'tf32x3') == 'bf16x3' else _lib.NT_PREC_TF32X3
-TN_ENGINE = os.environ.get('NT_TN_ENGINE', 'tc')      # weight-gradient GEMM: 'tc' = tcgen05 + deterministic split reduction (0.6 ms per
-                      # launch at C2), 'simt' = fp32 CUDA-core kernel with atomics (1.0 ms; validation only)
 # EdgeConv: materialise the first edge activation a1 = relu(P[i] + Q[j]) once ([E, H] fp32) instead of re-gathering two
 # random PQ rows per edge in every consumer (next GEMM, weight-gradient GEMM, BN/ReLU backward epilogue).  '0' keeps the
 # gather fused into those kernels (smaller footprint, ~2x slower consumers).
@@ -105,7 +113,7 @@ FUSED_SCATTER = os.environ.get('NT_FUSED_SCATTER', '0') != '0'
 # Inference EdgeConv: one kernel per layer (gather -> GEMM -> GEMM -> max -> BN, csrc/edgeconv_eval.cu) instead of the layer-by-layer
 # path; '0' keeps the latter (A/B measurements, and the reference point of the parity test).
 EDGE_EVAL_FUSED = os.environ.get('NT_EDGE_EVAL_FUSED', '1') != '0'
-GEMM_ENGINE = 'tc'    # 'tc' = tcgen05 tensor-core engine (product path); 'simt' = fp32 CUDA-core engine (validation only)
+NT_ENGINE = 0         # nt_gemm_args.engine of every row GEMM launched from here: 0 = auto (product); tests set 1 / 3 / 4 / 5
 
 
 def prepare_weights(w, ldw, n_out, K, precision):
@@ -127,9 +135,9 @@ def gemm_nt(rows, K, n_out, w, ldw, epilogue, a=None, lda=0, edge=None, bias=Non
     # and BatchNorm's backward is cancellation-heavy (sum_r da = 0), which amplifies BF16x3's 1e-5 to ~5e-3 on bias
     # gradients.  GRAD_PRECISION can be switched to NT_PREC_BF16X3 for the data-gradient GEMMs.
     precision = GRAD_PRECISION if (epilogue == NT_EPI_BNRELU_BWD or grad_gemm) else _lib.NT_PREC_TF32X3
-    w_split = prepare_weights(w, ldw, n_out, K, precision) if GEMM_ENGINE == 'tc' else None
+    w_split = prepare_weights(w, ldw, n_out, K, precision)
     g = GemmArgs()
-    g.w_split, g.precision = _p(w_split), precision
+    g.w_split, g.precision, g.engine = _p(w_split), precision, int(NT_ENGINE)
     g.rows, g.K, g.n_out = int(rows), int(K), int(n_out)
     g.producer = NT_PROD_PLAIN if edge is None or a is not None else NT_PROD_EDGE
     g.epilogue = epilogue
@@ -164,9 +172,7 @@ def gemm_nt(rows, K, n_out, w, ldw, epilogue, a=None, lda=0, edge=None, bias=Non
 def gemm_tn(a, lda, m, rows, out, b=None, ldb=0, n=0, edge=None, mu=None):
     """out[m, n] += sum_r a[r, m] * Bop[r, n].  With `mu` the B operand is centred and `out` must be float64."""
     lib = _lib.load()
-    ws = None
-    if GEMM_ENGINE == 'tc' and TN_ENGINE == 'tc':
-        ws = torch.empty(int(lib.nt_gemm_tn_workspace_bytes()), dtype=torch.uint8, device=a.device)
+    ws = torch.empty(int(lib.nt_gemm_tn_workspace_bytes()), dtype=torch.uint8, device=a.device)
     if edge is not None:
         bop = (None, 0, n, rows, _p(edge.pq), edge.ldpq, edge.qoff, _p(edge.idx), edge.k, edge.n_per_cloud)
     else:
@@ -221,7 +227,10 @@ class _BNBuffers:
 
     def __init__(self, running_mean, running_var, num_batches_tracked, momentum, eps):
         self.running_mean, self.running_var, self.nbt = running_mean, running_var, num_batches_tracked
-        self.momentum = 0.1 if momentum is None else float(momentum)
+        if momentum is None:
+            raise NotImplementedError('BatchNorm1d(momentum=None) (cumulative moving average) is not built on the B200 path; the '
+                                      'reference uses the default momentum 0.1 (nn/net_blocks.py:46)')
+        self.momentum = float(momentum)
         self.eps = float(eps)
 
 
@@ -287,7 +296,7 @@ class _FusedMLPFunction(torch.autograd.Function):
             return vec, w_f, w_ft, b_f
 
         # ---- inference, EdgeConv with three Linear layers: everything after PQ is ONE kernel; no edge-sized tensor touches HBM
-        if (mode == 'edge' and not training and L == 3 and EDGE_EVAL_FUSED and GEMM_ENGINE == 'tc'
+        if (mode == 'edge' and not training and L == 3 and EDGE_EVAL_FUSED
                 and lib.nt_edgeconv_eval_supported(H1, widths[1], widths[2], k, pq.stride(0))):
             _, w2f, _, b2f = fold(0, None, 1)
             _, w3f, _, b3f = fold(1, None, 2)

@@ -9,7 +9,7 @@
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated; fp32 row-major;
  *     `ld*` arguments are row strides in elements.
  *   - the caller owns every buffer (PyTorch tensors in the shipped host code); the library never allocates or
- *     frees user-visible memory and keeps no global mutable state.
+ *     frees user-visible memory and keeps no global mutable state (nt_launch_count's counter and the debug hooks aside).
  *   - every function only ENQUEUES work on `stream` (a cudaStream_t passed as void*); no hidden synchronisation.
  *   - return value: 0 = ok, non-zero = error (message via nt_last_error(), thread-local).  No exceptions cross
  *     the ABI.  The Python host maps non-zero to RuntimeError (reference convention: nn/trainer.py:60).
@@ -31,6 +31,9 @@ int nt_version(void);                          /* ABI version, bumped on incompa
 int nt_built_arch(void);                       /* 100 for sm_100a */
 /* number of kernels launched by this library in the calling process since load (bench.py's gpu_launches) */
 int64_t nt_launch_count(void);
+/* sizeof() of an argument struct of this header by name ("nt_gemm_args", "nt_pattern_loss_args", "nt_lstm_sizes_t"; 0 = unknown), so
+ * that a foreign-language binding can verify its mirror of the layout when it loads the library */
+int nt_sizeof(const char *struct_name);
 
 /* ---- kNN graph: torch_cluster.knn via DynamicEdgeConv.forward (nn/net_blocks.py:127-135,174) ------------
  * For every point of every cloud: the k nearest points of the SAME cloud by squared L2 over D features, self
@@ -77,8 +80,8 @@ typedef struct nt_gemm_args {
     /* NT_PROD_EDGE (also used by the aux operand of NT_EPI_BNRELU_BWD when aux_edge != 0) */
     const float *pq; int ldpq; int qoff;
     const int32_t *idx; int k; int n_per_cloud;
-    /* weights: w is always required; w_split (from nt_gemm_prepare_weights) selects the tcgen05 tensor-core engine,
-     * w_split == NULL runs the fp32 CUDA-core engine (kept for validation, not used by the shipped host code) */
+    /* weights: w (fp32, [n_out, K]) and w_split (its hi / lo planes from nt_gemm_prepare_weights) are both required: the GEMMs run
+     * on the tcgen05 tensor cores only (no CUDA-core or CPU fallback) */
     const float *w; int ldw; const float *bias; const void *w_split; int precision;
     /* outputs */
     float *out; int ldo;
@@ -94,18 +97,16 @@ typedef struct nt_gemm_args {
      * that half).  Uses idx / k / n_per_cloud; `out` may then be NULL (dz is never written).  Only for calls for which
      * nt_gemm_nt_scatter_supported() returns 1; otherwise nt_gemm_nt fails. */
     float *scatter_dpq; int ldscatter;
+    /* kernel engine for THIS call (TF32X3 only): 0 = auto (streaming persistent engine for large aligned calls, one tile per CTA
+     * otherwise), 1 = one tile per CTA, 3 / 4 = streaming engine with one / two row tiles per weight stage, 5 = streaming engine with
+     * the aux rows of NT_EPI_BNRELU_BWD staged through a shared-memory ring (what auto picks).  Results are bit-identical across
+     * engines (same operand split, same accumulation order); the field exists for tests and measurements. */
+    int engine;
 } nt_gemm_args;
 
 int nt_gemm_nt(const nt_gemm_args *args, void *stream);
 /* 1 if nt_gemm_nt(args) would run the fused-scatter epilogue (streaming engine, aligned operands), 0 otherwise. */
 int nt_gemm_nt_scatter_supported(const nt_gemm_args *args);
-
-/* Engine used for the TF32x3 row GEMMs: 0 = auto (streaming persistent engine for large aligned calls, one-tile-per-CTA
- * engine otherwise; default), 1 = one tile per CTA, 2 = persistent experiment, 3 = streaming engine whenever eligible (one row
- * tile per weight stage), 4 = streaming engine with two row tiles per weight stage, 5 = streaming engine with the aux rows of
- * NT_EPI_BNRELU_BWD staged through a shared-memory ring (experimental).
- * Process-wide; results are bit-identical across engines (same operand split, same accumulation order). */
-int nt_set_nt_engine(int engine);
 
 /* Tensor-core operand preparation: splits W [n_out, K] (fp32) into bf16 hi/lo planes laid out as UMMA core matrices per
  * (column tile, K block of 32 bf16 / 16 tf32 elements).  w_split must hold nt_gemm_weights_bytes(n_out, K) bytes, 16-byte aligned. */
@@ -114,8 +115,8 @@ int nt_gemm_prepare_weights(const float *w, int ldw, int n_out, int K, int preci
 
 /* Weight-gradient GEMM: out[m, n] += sum_r A[r, m] * Bop[r, n]  (out must be zeroed / initialised by the caller).
  * Bop is a plain matrix (b, ldb) or, when pq != NULL, the EDGE producer above.  Backward of nn.Linear.
- * workspace: nt_gemm_tn_workspace_bytes() bytes of device memory -> tcgen05 tensor-core engine (TF32x3, per-CTA partial
- * products reduced deterministically in double); workspace == NULL -> fp32 CUDA-core engine with atomics (validation). */
+ * workspace: nt_gemm_tn_workspace_bytes() bytes of device memory (required): tcgen05 tensor-core engine, TF32x3, per-CTA partial
+ * products reduced deterministically in double. */
 int64_t nt_gemm_tn_workspace_bytes(void);
 int nt_gemm_tn(const float *a, int lda, int m, const float *b, int ldb, int n, int64_t rows,
                const float *pq, int ldpq, int qoff, const int32_t *idx, int k, int n_per_cloud,
