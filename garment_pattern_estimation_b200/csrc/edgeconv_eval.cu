@@ -9,7 +9,9 @@
 //
 //   gather  : thread = edge row; relu(P[centre] + Q[nbr]) in 32-column K blocks, split into bf16 hi / lo planes, written to the
 //             shared-memory ring directly in the UMMA K-major core-matrix layout
-//   GEMM 1  : tcgen05 BF16x3 (hi.hi + hi.lo + lo.hi), D1[128, H2] in TMEM; W2' K blocks arrive by cp.async.bulk
+//   GEMM 1  : tcgen05, error-compensated 3-product split (hi.hi + hi.lo + lo.hi; TF32x3 by default -- the forward path keeps fp32-class
+//             accuracy so that the kNN graph of the NEXT layer matches the reference's, see DESIGN.md -- or BF16x3), D1[128, H2] in
+//             TMEM; W2' K blocks arrive by cp.async.bulk
 //   bridge  : D1 is read back 32 columns at a time (thread = row = TMEM lane), + b2', relu, split, and becomes -- through the same
 //             ring -- the A operand of
 //   GEMM 2  : D2[128, C] in TMEM; W3' K blocks by cp.async.bulk
@@ -26,7 +28,6 @@ constexpr int EE_WORKERS = 256;                 // warps 0-7: gather / bridge / 
 constexpr int EE_WORKER_WARPS = EE_WORKERS / 32;
 constexpr int EE_THREADS = EE_WORKERS + 64;     // warp 8: MMA issuer, warp 9: weight loader + TMEM
 constexpr int EE_NST = 3;
-constexpr int EE_KB = 32;                       // bf16 elements per K block (4 chunks of 8)
 constexpr int EE_A_PLANE = 4 * TC_M * 16;       // 8 KB: [chunk 4][row 128][16 B]
 constexpr int EE_MAX_N = 224;
 constexpr int EE_STAGE_BYTES = 2 * EE_A_PLANE + EE_MAX_N * 128;         // A hi | A lo | B (hi | lo planes of n_tile rows) = 45056
@@ -42,7 +43,11 @@ struct EEParams {
     int rows_per_tile; int64_t n_tiles;
 };
 
+template <bool TF32>
 __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p) {
+    constexpr int EPC = TF32 ? 4 : 8;               // elements per 16-byte chunk
+    constexpr int EE_KB = 4 * EPC;                  // elements per K block (4 chunks): 16 tf32 or 32 bf16
+    constexpr int HC = 2 * EPC;                     // columns of a K block owned by one worker half
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *tail_s = smem + (size_t)EE_NST * EE_STAGE_BYTES;
     uint64_t *full = reinterpret_cast<uint64_t *>(tail_s);           // [NST]
@@ -91,11 +96,11 @@ __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p
                 qq = p.pq + (base + p.idx[e]) * p.ldpq + p.H1;
             }
             // ---- gather -> A operand of GEMM 1 (the loads of K block kb + 1 are in flight while block kb is converted)
-            float4 pa[4], pb[4];
+            float4 pa[HC / 4], pb[HC / 4];
             auto fetch = [&](int kb) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = kb * EE_KB + half * 16 + 4 * j;
+                for (int j = 0; j < HC / 4; ++j) {
+                    const int c = kb * EE_KB + half * HC + 4 * j;
                     pa[j] = pb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (live && kb < kb1 && c < p.H1) {              // H1 % 4 == 0 and 16-byte aligned rows (checked by the launcher)
                         pa[j] = __ldg(reinterpret_cast<const float4 *>(pp + c));
@@ -105,9 +110,9 @@ __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p
             };
             fetch(0);
             for (int kb = 0; kb < kb1; ++kb, ++it) {
-                float v[16];
+                float v[HC];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < HC / 4; ++j) {
                     v[4 * j] = fmaxf(pa[j].x + pb[j].x, 0.f); v[4 * j + 1] = fmaxf(pa[j].y + pb[j].y, 0.f);
                     v[4 * j + 2] = fmaxf(pa[j].z + pb[j].z, 0.f); v[4 * j + 3] = fmaxf(pa[j].w + pb[j].w, 0.f);
                 }
@@ -119,9 +124,9 @@ __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p
                 for (int ch = 0; ch < 2; ++ch) {
                     float t8[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) t8[e] = v[8 * ch + e];
+                    for (int e = 0; e < 8; ++e) t8[e] = e < EPC ? v[EPC * ch + e] : 0.f;
                     uint4 h, l;
-                    pack_chunk(t8, false, h, l);
+                    pack_chunk(t8, TF32, h, l);
                     *reinterpret_cast<uint4 *>(a_hi + (2 * half + ch) * (TC_M * 16) + r * 16) = h;
                     *reinterpret_cast<uint4 *>(a_lo + (2 * half + ch) * (TC_M * 16) + r * 16) = l;
                 }
@@ -132,8 +137,9 @@ __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p
             mbar_wait(d1_full, tile_i & 1u);
             tc_fence_after();
             for (int kb = 0; kb < kb2; ++kb, ++it) {
-                float acc[16];
-                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kb * EE_KB + half * 16), acc);
+                float acc[HC];
+                if constexpr (TF32) tmem_ld8(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kb * EE_KB + half * HC), acc);
+                else tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kb * EE_KB + half * HC), acc);
                 const uint32_t st = it % EE_NST;
                 mbar_wait(&empty[st], ((it / EE_NST) & 1u) ^ 1u);
                 uint8_t *a_hi = smem + (size_t)st * EE_STAGE_BYTES, *a_lo = a_hi + EE_A_PLANE;
@@ -142,11 +148,11 @@ __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p
                     float t8[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const int c = kb * EE_KB + half * 16 + 8 * ch + e;
-                        t8[e] = (live && c < p.H2) ? fmaxf(acc[8 * ch + e] + vec[c], 0.f) : 0.f;
+                        const int c = kb * EE_KB + half * HC + EPC * ch + e;
+                        t8[e] = (e < EPC && live && c < p.H2) ? fmaxf(acc[(EPC * ch + e) % HC] + vec[c < 224 ? c : 223], 0.f) : 0.f;
                     }
                     uint4 h, l;
-                    pack_chunk(t8, false, h, l);
+                    pack_chunk(t8, TF32, h, l);
                     *reinterpret_cast<uint4 *>(a_hi + (2 * half + ch) * (TC_M * 16) + r * 16) = h;
                     *reinterpret_cast<uint4 *>(a_lo + (2 * half + ch) * (TC_M * 16) + r * 16) = l;
                 }
@@ -191,7 +197,8 @@ __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p
     } else if (warp == EE_WORKER_WARPS) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
-            const uint32_t idesc1 = make_idesc_bf16(TC_M, (uint32_t)p.n2, 0, 0), idesc2 = make_idesc_bf16(TC_M, (uint32_t)p.n3, 0, 0);
+            const uint32_t idesc1 = TF32 ? make_idesc_tf32(TC_M, (uint32_t)p.n2, 0, 0) : make_idesc_bf16(TC_M, (uint32_t)p.n2, 0, 0);
+            const uint32_t idesc2 = TF32 ? make_idesc_tf32(TC_M, (uint32_t)p.n3, 0, 0) : make_idesc_bf16(TC_M, (uint32_t)p.n3, 0, 0);
             const uint32_t lbo_a = TC_M * 16, sbo = 128;
             uint32_t it = 0;
             for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -210,9 +217,15 @@ __global__ void __launch_bounds__(EE_THREADS, 1) edgeconv_eval_kernel(EEParams p
                         for (int kk = 0; kk < 2; ++kk) {
                             const uint64_t dah = make_smem_desc(a_hi + kk * 2 * lbo_a, lbo_a, sbo), dal = make_smem_desc(a_lo + kk * 2 * lbo_a, lbo_a, sbo);
                             const uint64_t dbh = make_smem_desc(b_hi + kk * 2 * lbo_b, lbo_b, sbo), dbl = make_smem_desc(b_lo + kk * 2 * lbo_b, lbo_b, sbo);
-                            umma_bf16(dst, dah, dbh, idesc, (kb | kk) ? 1u : 0u);
-                            umma_bf16(dst, dah, dbl, idesc, 1u);
-                            umma_bf16(dst, dal, dbh, idesc, 1u);
+                            if constexpr (TF32) {
+                                umma_tf32(dst, dah, dbh, idesc, (kb | kk) ? 1u : 0u);
+                                umma_tf32(dst, dah, dbl, idesc, 1u);
+                                umma_tf32(dst, dal, dbh, idesc, 1u);
+                            } else {
+                                umma_bf16(dst, dah, dbh, idesc, (kb | kk) ? 1u : 0u);
+                                umma_bf16(dst, dah, dbl, idesc, 1u);
+                                umma_bf16(dst, dal, dbh, idesc, 1u);
+                            }
                         }
                         umma_commit(&empty[st]);
                     }
@@ -256,15 +269,16 @@ extern "C" int nt_edgeconv_eval_supported(int H1, int H2, int C, int k, int ldpq
 
 extern "C" int nt_edgeconv_eval_fwd(const float *pq, int ldpq, int H1, const int32_t *idx, int k, int n_per_cloud, int64_t M,
                                     const void *w2_split, const float *b2, int H2, const void *w3_split, const float *b3, int C,
-                                    const float *s_out, const float *t_out, const float *tail_src, int tail_ld, int tail, float *out,
-                                    int ldo, void *stream) {
+                                    int precision, const float *s_out, const float *t_out, const float *tail_src, int tail_ld, int tail,
+                                    float *out, int ldo, void *stream) {
+    NT_REQUIRE(precision == NT_PREC_BF16X3 || precision == NT_PREC_TF32X3, "nt_edgeconv_eval_fwd: bad precision");
     NT_REQUIRE(pq && idx && w2_split && b2 && w3_split && b3 && s_out && t_out && out, "nt_edgeconv_eval_fwd: null argument");
     NT_REQUIRE(nt_edgeconv_eval_supported(H1, H2, C, k, ldpq), "nt_edgeconv_eval_fwd: unsupported sizes (see nt_edgeconv_eval_supported)");
     NT_REQUIRE(aligned16(pq) && M >= 1 && n_per_cloud >= 1 && ldo >= C + tail && (tail == 0 || tail_src), "nt_edgeconv_eval_fwd: bad arguments");
     EEParams p{};
     p.pq = pq; p.ldpq = ldpq; p.H1 = H1; p.idx = idx; p.k = k; p.n_per_cloud = n_per_cloud; p.M = M;
-    p.w2 = reinterpret_cast<const uint8_t *>(w2_split); p.b2 = b2; p.H2 = H2; p.n2 = tc_geometry(H2, H1, NT_PREC_BF16X3).n_tile;
-    p.w3 = reinterpret_cast<const uint8_t *>(w3_split); p.b3 = b3; p.C = C; p.n3 = tc_geometry(C, H2, NT_PREC_BF16X3).n_tile;
+    p.w2 = reinterpret_cast<const uint8_t *>(w2_split); p.b2 = b2; p.H2 = H2; p.n2 = tc_geometry(H2, H1, precision).n_tile;
+    p.w3 = reinterpret_cast<const uint8_t *>(w3_split); p.b3 = b3; p.C = C; p.n3 = tc_geometry(C, H2, precision).n_tile;
     p.s_out = s_out; p.t_out = t_out; p.tail_src = tail_src; p.tail_ld = tail_ld; p.tail = tail; p.out = out; p.ldo = ldo;
     p.rows_per_tile = (TC_M / k) * k;
     const int64_t nodes_per_tile = p.rows_per_tile / k;
@@ -275,11 +289,13 @@ extern "C" int nt_edgeconv_eval_fwd(const float *pq, int ldpq, int H1, const int
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
             return fail("nt_edgeconv_eval_fwd: cannot query the SM count%s", "");
-        if (cudaFuncSetAttribute(edgeconv_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(edgeconv_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(edgeconv_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return fail("nt_edgeconv_eval_fwd: cudaFuncSetAttribute failed%s", "");
         sms = n;
     }
     const int ctas = (int)(p.n_tiles < sms ? p.n_tiles : sms);
-    edgeconv_eval_kernel<<<ctas, EE_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    if (precision == NT_PREC_TF32X3) edgeconv_eval_kernel<true><<<ctas, EE_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    else edgeconv_eval_kernel<false><<<ctas, EE_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return check_launch("nt_edgeconv_eval_fwd");
 }

@@ -113,6 +113,7 @@ FUSED_SCATTER = os.environ.get('NT_FUSED_SCATTER', '0') != '0'
 # Inference EdgeConv: one kernel per layer (gather -> GEMM -> GEMM -> max -> BN, csrc/edgeconv_eval.cu) instead of the layer-by-layer
 # path; '0' keeps the latter (A/B measurements, and the reference point of the parity test).
 EDGE_EVAL_FUSED = os.environ.get('NT_EDGE_EVAL_FUSED', '1') != '0'
+EDGE_EVAL_PRECISION = _lib.NT_PREC_BF16X3 if os.environ.get('NT_EDGE_EVAL_PREC', 'tf32x3') == 'bf16x3' else _lib.NT_PREC_TF32X3
 NT_ENGINE = 0         # nt_gemm_args.engine of every row GEMM launched from here: 0 = auto (product); tests set 1 / 3 / 4 / 5
 
 
@@ -301,13 +302,14 @@ class _FusedMLPFunction(torch.autograd.Function):
             _, w2f, _, b2f = fold(0, None, 1)
             _, w3f, _, b3f = fold(1, None, 2)
             vec3, _, _, _ = fold(2, None, None)
-            w2s = prepare_weights(w2f, H1, widths[1], H1, _lib.NT_PREC_BF16X3)
-            w3s = prepare_weights(w3f, widths[1], widths[2], widths[1], _lib.NT_PREC_BF16X3)
+            w2s = prepare_weights(w2f, H1, widths[1], H1, EDGE_EVAL_PRECISION)
+            w3s = prepare_weights(w3f, widths[1], widths[2], widths[1], EDGE_EVAL_PRECISION)
             tail = 0 if tail_src is None else tail_src.shape[1]
             ts, tld = (None, 0) if not tail else _rows2d(tail_src)
             out = torch.empty(M, widths[2] + tail, **f32)
             _call('nt_edgeconv_eval_fwd', lib.nt_edgeconv_eval_fwd, _p(pq), pq.stride(0), H1, _p(idx), k, N, M, _p(w2s), _p(b2f),
-                  widths[1], _p(w3s), _p(b3f), widths[2], _p(vec3[2]), _p(vec3[3]), _p(ts), tld, tail, _p(out), widths[2] + tail,
+                  widths[1], _p(w3s), _p(b3f), widths[2], EDGE_EVAL_PRECISION, _p(vec3[2]), _p(vec3[3]), _p(ts), tld, tail, _p(out),
+                  widths[2] + tail,
                   _stream())
             ctx.meta = None
             return out

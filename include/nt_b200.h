@@ -247,14 +247,15 @@ int nt_lstm_bwd(const float *dy, int ld_dy, const void *act, const float *cs, co
  * out[i, 0:C] = s*max|min_{j in kNN(i)} relu(W3' relu(W2' relu(P[i] + Q[j]) + b2') + b3') + t  in ONE kernel (gather, two chained
  * tcgen05 GEMMs with the intermediate kept in TMEM / shared memory, max over the k rows of a point, trailing BatchNorm affine,
  * optional skip-connection columns out[i, C:C+tail] = tail_src[i]).  pq = [P | Q] per point (row stride ldpq, Q at column H1) from
- * the split first Linear; w2_split / w3_split = nt_gemm_prepare_weights(NT_PREC_BF16X3) of the BatchNorm-folded weights W2' [H2, H1],
- * W3' [C, H2] (nt_bn_fold with training = 0); s_out / t_out = the folded affine of the last BatchNorm.
+ * the split first Linear; w2_split / w3_split = nt_gemm_prepare_weights(precision) of the BatchNorm-folded weights W2' [H2, H1],
+ * W3' [C, H2] (nt_bn_fold with training = 0); precision = NT_PREC_TF32X3 (fp32-class, what the shipped host code uses) or
+ * NT_PREC_BF16X3; s_out / t_out = the folded affine of the last BatchNorm.
  * Sizes: nt_edgeconv_eval_supported(H1, H2, C, k, ldpq) must return 1. */
 int nt_edgeconv_eval_supported(int H1, int H2, int C, int k, int ldpq);
 int nt_edgeconv_eval_fwd(const float *pq, int ldpq, int H1, const int32_t *idx, int k, int n_per_cloud, int64_t M,
                          const void *w2_split, const float *b2, int H2, const void *w3_split, const float *b3, int C,
-                         const float *s_out, const float *t_out, const float *tail_src, int tail_ld, int tail, float *out,
-                         int ldo, void *stream);
+                         int precision, const float *s_out, const float *t_out, const float *tail_src, int tail_ld, int tail,
+                         float *out, int ldo, void *stream);
 
 /* ---- PointNet++ set abstraction (nn/net_blocks.py:10-88: torch_geometric.nn.fps / radius / PointConv) --------------------------
  * pos: [B*N, >=D] fp32, row stride ld, B equal-size clouds, D <= 8 coordinates.  Index outputs are LOCAL to the cloud.
