@@ -99,6 +99,7 @@ _SIGNATURES = {
     'nt_edgeconv_eval_supported': (c_int, [c_int, c_int, c_int, c_int, c_int]),
     'nt_edgeconv_eval_fwd': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p,
                                      c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    'nt_edge_pairs': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     'nt_fps': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'nt_radius': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p]),
     'nt_point_edges_count': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

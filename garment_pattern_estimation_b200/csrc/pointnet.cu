@@ -173,9 +173,40 @@ __global__ void scatter_max_bwd_kernel(const float *__restrict__ g, const int64_
     if (e != INT64_MAX) gv[e * ldg + (i % F)] = g[i];          // one writer per (edge, feature): arg is unique per target
 }
 
+// ---- stage-2 input: all pairs of 3D edges from different panels (NNSewingPattern.all_edge_pairs, nn/data/pattern_converter.py:458) ----
+// block b = panel pair (i < j) in the reference's loop order; pair p of the block = (row r of panel i, row c of panel j), r-major.
+__global__ void edge_pairs_kernel(const float *__restrict__ edges, int Lmax, int F, const int32_t *__restrict__ blk_i,
+                                  const int32_t *__restrict__ blk_j, const int32_t *__restrict__ blk_cols,
+                                  const int64_t *__restrict__ blk_off, int n_blocks, int64_t n_pairs, float *__restrict__ pairs,
+                                  int32_t *__restrict__ mapping) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_pairs) return;
+    int lo = 0, hi = n_blocks - 1;                       // last block with blk_off <= q
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (blk_off[mid] <= q) lo = mid; else hi = mid - 1;
+    }
+    const int i = blk_i[lo], j = blk_j[lo], cols = blk_cols[lo];
+    const int64_t within = q - blk_off[lo];
+    const int r = (int)(within / cols), c = (int)(within % cols);
+    const float *ei = edges + ((int64_t)i * Lmax + r) * F, *ej = edges + ((int64_t)j * Lmax + c) * F;
+    float *o = pairs + q * 2 * F;
+    for (int f = 0; f < F; ++f) { o[f] = ei[f]; o[F + f] = ej[f]; }
+    if (mapping) { mapping[q * 4] = i; mapping[q * 4 + 1] = r; mapping[q * 4 + 2] = j; mapping[q * 4 + 3] = c; }
+}
+
 }  // namespace nt
 
 using namespace nt;
+
+extern "C" int nt_edge_pairs(const float *edges, int Lmax, int F, const int32_t *blk_i, const int32_t *blk_j, const int32_t *blk_cols,
+                             const int64_t *blk_off, int n_blocks, int64_t n_pairs, float *pairs, int32_t *mapping, void *stream) {
+    NT_REQUIRE(edges && blk_i && blk_j && blk_cols && blk_off && pairs && Lmax >= 1 && F >= 1 && n_blocks >= 1 && n_pairs >= 1,
+               "nt_edge_pairs: bad arguments");
+    edge_pairs_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        edges, Lmax, F, blk_i, blk_j, blk_cols, blk_off, n_blocks, n_pairs, pairs, mapping);
+    return check_launch("nt_edge_pairs");
+}
 
 extern "C" int nt_fps(const float *pos, int ld, int B, int N, int D, int n_samples, int32_t *idx, void *stream) {
     NT_REQUIRE(pos && idx && B >= 1 && N >= 1 && D >= 1 && D <= 8 && ld >= D, "nt_fps: bad arguments");

@@ -796,6 +796,34 @@ def scatter_max(values, dst, n_targets):
     return _ScatterMaxFunction.apply(values, dst.contiguous(), int(n_targets))
 
 
+def all_edge_pairs(edges, num_edges):
+    """Device batching of ``NNSewingPattern.all_edge_pairs`` (nn/data/pattern_converter.py:458-499): every pair of 3D edges that
+    belong to DIFFERENT panels, in the reference's order (panel i, panel j > i, edges of i x edges of j row-major).
+    edges: [P, Lmax, F] fp32 on the device; num_edges: the per-panel edge counts (host list / tensor).  Returns (pairs
+    [n_pairs, 2F], mapping [n_pairs, 4] int32 = (panel i, edge, panel j, edge)) -- the input of StitchOnEdge3DPairs and the table
+    ``stitches_from_pair_classifier`` indexes."""
+    _require_cuda(edges)
+    edges = edges.contiguous().float()
+    P, Lmax, F = edges.shape
+    counts = [int(c) for c in (num_edges.tolist() if torch.is_tensor(num_edges) else num_edges)]
+    bi, bj, bc, off, total = [], [], [], [], 0
+    for i in range(P):
+        for j in range(i + 1, P):
+            if counts[i] > 0 and counts[j] > 0:
+                bi.append(i); bj.append(j); bc.append(counts[j]); off.append(total)
+                total += counts[i] * counts[j]
+    if total == 0:
+        raise ValueError('No edges to construct')            # InvalidPatternDefError in the reference (pattern_converter.py:494)
+    dev = edges.device
+    t = lambda v, dt: torch.tensor(v, dtype=dt, device=dev)
+    bi_t, bj_t, bc_t, off_t = t(bi, torch.int32), t(bj, torch.int32), t(bc, torch.int32), t(off, torch.int64)
+    pairs = torch.empty(total, 2 * F, dtype=torch.float32, device=dev)
+    mapping = torch.empty(total, 4, dtype=torch.int32, device=dev)
+    _call('nt_edge_pairs', _lib.load().nt_edge_pairs, _p(edges), Lmax, F, _p(bi_t), _p(bj_t), _p(bc_t), _p(off_t), len(bi), total,
+          _p(pairs), _p(mapping), _stream())
+    return pairs, mapping
+
+
 # ----------------------------------------------------------------------------------------------------------
 # pattern loss (shape / loop / rotation / translation) and Adam on a flat buffer (csrc/train_step.cu)
 # ----------------------------------------------------------------------------------------------------------

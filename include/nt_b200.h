@@ -282,6 +282,14 @@ int nt_scatter_max_fwd(const float *v, int ldv, const int64_t *dst, int64_t E, i
                        int32_t *key_scratch, void *stream);
 int nt_scatter_max_bwd(const float *g, const int64_t *arg, int64_t T, int F, float *gv, int ldg, void *stream);
 
+/* ---- stage-2 input batching: NNSewingPattern.all_edge_pairs (nn/data/pattern_converter.py:458-499) -----------------------------
+ * edges: [P, Lmax, F] 3D edge features per panel (device).  Block b enumerates, in the reference's loop order, the panel pairs
+ * (blk_i[b] < blk_j[b]) that both have edges; the block holds rows(i) x blk_cols[b] pairs, row-major, starting at pair blk_off[b]
+ * (device arrays built by the host from the per-panel edge counts).  pairs: [n_pairs, 2F] = cat(edge of panel i, edge of panel j);
+ * mapping (optional): [n_pairs, 4] = (panel i, edge, panel j, edge). */
+int nt_edge_pairs(const float *edges, int Lmax, int F, const int32_t *blk_i, const int32_t *blk_j, const int32_t *blk_cols,
+                  const int64_t *blk_off, int n_blocks, int64_t n_pairs, float *pairs, int32_t *mapping, void *stream);
+
 /* ---- training step: loss and optimizer (nn/trainer.py:96-101) ---------------------------------------------------------------------
  * The four loss terms of the shipped attention config (models/att/att.yaml:124) -- nn.MSELoss on outlines / rotations /
  * translations (nn/metrics/composed_loss.py:301-321) and PanelLoopLoss (nn/metrics/losses.py:19-51: for every panel with

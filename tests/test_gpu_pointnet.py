@@ -106,3 +106,34 @@ def test_pointnet_plus_plus_matches_reference_golden(cuda_device, golden_dir):
         assert_close(model(x), gold['eval_y'], what='PointNet++ eval forward')
     src, dst = model.sa1_module.conv.last_edges
     assert src.numel() == gold['radius_row_col'].shape[1] - int((gold['radius_row_col'][0] == gold['radius_row_col'][1]).sum()) + 240
+
+
+def test_all_edge_pairs_matches_the_reference_loop(cuda_device):
+    """the edge-pair batching in front of StitchOnEdge3DPairs.  The reference builds the pairs panel pair
+    by panel pair with numpy (nn/data/pattern_converter.py:458-499); restated here as that loop on the same per-panel edge arrays."""
+    import numpy as np
+    from garment_pattern_estimation_b200 import ops
+    dev = cuda_device
+    rng = np.random.default_rng(3)
+    counts = [4, 0, 7, 3, 0, 14, 5]
+    P, Lmax, F = len(counts), 14, 8
+    edges = np.zeros((P, Lmax, F), dtype=np.float32)
+    for p_, n in enumerate(counts):
+        edges[p_, :n] = rng.standard_normal((n, F)).astype(np.float32)
+    want_pairs, want_map = [], []
+    for i in range(P):                                   # pattern_converter.py:471-490 (panels without edges contribute nothing)
+        ei = edges[i, :counts[i]]
+        for j in range(i + 1, P):
+            ej = edges[j, :counts[j]]
+            if len(ei) == 0 or len(ej) == 0:
+                continue
+            rows, cols = np.indices((len(ei), len(ej)))
+            want_pairs.append(np.concatenate([ei[rows], ej[cols]], axis=-1).reshape(-1, 2 * F))
+            want_map += [(i, r, j, c) for r in range(len(ei)) for c in range(len(ej))]
+    want_pairs = np.concatenate(want_pairs)
+    pairs, mapping = ops.all_edge_pairs(torch.from_numpy(edges).to(dev), counts)
+    assert pairs.shape == want_pairs.shape == (len(want_map), 2 * F)
+    assert np.array_equal(pairs.cpu().numpy(), want_pairs)
+    assert mapping.cpu().tolist() == [list(m) for m in want_map]
+    with pytest.raises(ValueError):
+        ops.all_edge_pairs(torch.zeros(3, Lmax, F, device=dev), [0, 5, 0])
