@@ -28,13 +28,25 @@ elif what == 'model':
     import garment_pattern_estimation_b200 as g
     dc, nc, lc = bench.att_configs(k)
     torch.manual_seed(bench.SEED_INIT)
+    from garment_pattern_estimation_b200.parallel import FlatAdam, FlatDataParallel
     model = g.GarmentSegmentPattern3D(dc, nc, lc).to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=2e-3)
+    wrapper = FlatDataParallel(model, device_ids=[dev], auto_reduce=False)
+    opt = FlatAdam(wrapper, lr=2e-3)
     x, gt = bench.synthetic_batch(B, N, seed=1234)
     x, gt = x.to(dev), {kk: v.to(dev) for kk, v in gt.items()}
-    for _ in range(2):
-        loss, _, _ = model.loss(model(x), gt)
+    for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 2):
+        loss, _, _ = model.loss(wrapper(x), gt)
         loss.backward()
-        opt.step()
-        opt.zero_grad()
+        opt.step(zero_grad=True)
+elif what == 'infer':
+    # one C5 inference batch (B=128, N=2048, eval mode): the fused EdgeConv kernel, the kNN kernels, the LSTM forward
+    import bench
+    import garment_pattern_estimation_b200 as g
+    dc, nc, lc = bench.att_configs(k)
+    torch.manual_seed(bench.SEED_INIT)
+    model = g.GarmentSegmentPattern3D(dc, nc, lc).to(dev).eval()
+    x = torch.randn(128, N, 3, device=dev)
+    with torch.no_grad():
+        for _ in range(2):
+            model(x)
 torch.cuda.synchronize()
