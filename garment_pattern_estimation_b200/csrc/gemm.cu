@@ -10,6 +10,8 @@
 // the max/min aggregation over the k neighbours, and the BN+ReLU backward.
 // (Round 1 also shipped an fp32 CUDA-core engine for validation; the float64 comparisons in tests/ replaced it.)
 #include "common.cuh"
+#include <cstdlib>
+#include <cstring>
 #include "gemm_params.cuh"
 
 namespace nt {
@@ -94,6 +96,11 @@ static int gemm_tn_impl(const float *a, int lda, int m, const float *b, int ldb,
     if (rows == 0) return 0;
     NT_REQUIRE(workspace != nullptr, "nt_gemm_tn: workspace missing (nt_gemm_tn_workspace_bytes() bytes; there is no CUDA-core fallback)");
     const EdgeSrc e{pq, ldpq, qoff, idx, k > 0 ? k : 1, n_per_cloud > 0 ? n_per_cloud : 1};
+    // plain operands: MN-major BF16x3 engine (rows are read as they lie); NT_TN_PRECISION=tf32x3 keeps the transposing TF32x3 engine
+    static const bool force_tf32 = [] { const char *v = getenv("NT_TN_PRECISION"); return v && strcmp(v, "tf32x3") == 0; }();
+    if (!pq && !force_tf32)
+        return gemm_tn_mn(a, lda, m, b, ldb, n, rows, mu, out, out_double, ldo, reinterpret_cast<float *>(workspace),
+                          reinterpret_cast<cudaStream_t>(stream));
     return gemm_tn_tc(a, lda, m, b, ldb, n, rows, e, pq != nullptr, mu, out, out_double, ldo, reinterpret_cast<float *>(workspace),
                       reinterpret_cast<cudaStream_t>(stream));
 }

@@ -45,5 +45,8 @@ bool nt_tc_would_stream(const NTParams &p, int producer, int epilogue, int preci
 // tensor-core weight-gradient engine (gemm_tn_tc.cu)
 int gemm_tn_tc(const float *a, int lda, int m, const float *b, int ldb, int n, int64_t rows, const EdgeSrc &e, int b_edge,
                const float *mu, void *out, int out_double, int ldo, float *workspace, cudaStream_t st);
+// the same product for plain (not gathered) operands through MN-major BF16x3 tensor-core operands (gemm_tn_mn.cu)
+int gemm_tn_mn(const float *a, int lda, int m, const float *b, int ldb, int n, int64_t rows, const float *mu, void *out, int out_double,
+               int ldo, float *workspace, cudaStream_t st);
 
 }  // namespace nt

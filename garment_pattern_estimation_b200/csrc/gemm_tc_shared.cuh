@@ -43,11 +43,11 @@ __device__ __forceinline__ void pack_chunk(const float (&v)[8], bool tf32, uint4
         h = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         l = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     } else {
-        __nv_bfloat16 hi[8], lo[8];
+        uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) split_bf16(v[e], hi[e], lo[e]);
-        h = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
-        l = make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
+        for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+        h = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        l = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 

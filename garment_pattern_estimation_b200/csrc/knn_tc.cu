@@ -104,10 +104,13 @@ __device__ __forceinline__ float chain_dist(const float *__restrict__ xc, const 
     return acc;
 }
 
-__device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+
+__device__ __forceinline__ uint32_t bf16x2_bits(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
 __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
-    return make_uint4(bf16_bits(v[0]) | (bf16_bits(v[1]) << 16), bf16_bits(v[2]) | (bf16_bits(v[3]) << 16),
-                      bf16_bits(v[4]) | (bf16_bits(v[5]) << 16), bf16_bits(v[6]) | (bf16_bits(v[7]) << 16));
+    return make_uint4(bf16x2_bits(v[0], v[1]), bf16x2_bits(v[2], v[3]), bf16x2_bits(v[4], v[5]), bf16x2_bits(v[6], v[7]));
 }
 
 // ------------------------------------------------------------------------------------------------------------------

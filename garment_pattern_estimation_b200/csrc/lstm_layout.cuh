@@ -19,6 +19,9 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#ifdef __CUDACC__
+#include <cuda_bf16.h>
+#endif
 
 #ifndef __CUDACC__
 #define __host__
@@ -209,16 +212,27 @@ __host__ __device__ __forceinline__ void return_h(const float (&h)[UNITS], float
 
 // write 16 values of one row into a split block (two 16-byte chunks per plane)
 __host__ __device__ __forceinline__ void store_split16(uint8_t *block, const Dims &d, int kstep, int row_in_tile, const float (&v)[UNITS]) {
+#ifndef __CUDA_ARCH__
     uint16_t hi[UNITS], lo[UNITS];
 #pragma unroll
     for (int u = 0; u < UNITS; ++u) split_hi_lo(v[u], hi[u], lo[u]);
+#endif
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
         uint32_t ph[4], pl[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
+#ifdef __CUDA_ARCH__
+            // packed conversion (one F2FP per pair and term); same round-to-nearest-even bits as split_hi_lo for finite values
+            const float a = v[8 * ch + 2 * e], b = v[8 * ch + 2 * e + 1];
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+            ph[e] = *reinterpret_cast<uint32_t *>(&h2);
+            __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(ph[e] << 16), b - __uint_as_float(ph[e] & 0xFFFF0000u));
+            pl[e] = *reinterpret_cast<uint32_t *>(&l2);
+#else
             ph[e] = (uint32_t)hi[8 * ch + 2 * e] | ((uint32_t)hi[8 * ch + 2 * e + 1] << 16);
             pl[e] = (uint32_t)lo[8 * ch + 2 * e] | ((uint32_t)lo[8 * ch + 2 * e + 1] << 16);
+#endif
         }
         uint32_t *dh = reinterpret_cast<uint32_t *>(block + split_offset(d, kstep, row_in_tile, 8 * ch, 0));
         uint32_t *dl = reinterpret_cast<uint32_t *>(block + split_offset(d, kstep, row_in_tile, 8 * ch, 1));

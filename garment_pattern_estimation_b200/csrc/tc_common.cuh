@@ -156,6 +156,14 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bflo
     hi = __float2bfloat16_rn(x);
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+// two values at once, bit-identical to split_bf16 + pack2(a, b): one F2FP.BF16.F32.PACK_AB (ALU pipe) per pair and term instead of
+// two F2F.BF16.F32 (conversion pipe, a quarter of the rate) plus a PRMT -- every operand producer / converter goes through this
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                 // .x (low half) = a, .y (high half) = b
+    hi = *reinterpret_cast<uint32_t *>(&h);
+    __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
+    lo = *reinterpret_cast<uint32_t *>(&l);
+}
 // error-compensated tf32 split: hi and lo are fp32 words whose low 13 mantissa bits are zero (exact tf32 values),
 // x = hi + lo + O(2^-21 |x|); round-to-nearest on both terms so the residuals have no sign bias.
 __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {

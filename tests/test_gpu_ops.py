@@ -323,9 +323,10 @@ def test_tc_engine_linear_matches_float64(ops, cuda_device, rows, K, n_out):
 
 
 @pytest.mark.parametrize('rows,m,n', [(5000, 150, 200), (777, 200, 200), (300, 400, 3), (100000, 23, 153), (64, 8, 250),
-                                      (4096, 400, 150)])
+                                      (4096, 400, 150), (500, 64, 10), (33, 300, 260), (1, 5, 5)])
 def test_tc_weight_gradient_gemm_matches_float64(ops, cuda_device, rows, m, n):
-    """out = A^T . B on the tensor cores (TF32x3, deterministic split reduction) vs a float64 reference, plain and centred."""
+    """out = A^T . B on the tensor cores (plain operands: MN-major BF16x3 engine of gemm_tn_mn.cu; deterministic split reduction) vs a
+    float64 reference, plain and centred."""
     dev = cuda_device
     g = torch.Generator().manual_seed(rows + m)
     a = torch.randn(rows, m, generator=g).to(dev)
@@ -333,6 +334,27 @@ def test_tc_weight_gradient_gemm_matches_float64(ops, cuda_device, rows, m, n):
     mu = b.mean(0)
     want = a.double().t() @ b.double()
     want_c = a.double().t() @ (b.double() - mu.double())
+    out = torch.zeros(m, n, device=dev)
+    ops.gemm_tn(a, a.stride(0), m, rows, out, b=b, ldb=b.stride(0), n=n)
+    out_c = torch.zeros(m, n, dtype=torch.float64, device=dev)
+    ops.gemm_tn(a, a.stride(0), m, rows, out_c, b=b, ldb=b.stride(0), n=n, mu=mu)
+    assert rel_err(out, want) < 2e-5
+    assert rel_err(out_c, want_c) < 2e-5
+
+
+@pytest.mark.parametrize('rows,m,n', [(3000, 150, 200), (40000, 200, 150), (2049, 6, 3)])
+def test_tc_weight_gradient_gemm_padded_rows(ops, cuda_device, rows, m, n):
+    """The same product on operands that sit in padded row buffers (stride = columns rounded up to 4 floats, the layout every
+    intermediate of the EdgeConv has): rows go through the bulk-copy path, a partial last quad carries NaN padding that must not leak."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(rows)
+    a = ops._rowbuf(rows, m, dev).fill_(float('nan'))
+    b = ops._rowbuf(rows, n, dev).fill_(float('nan'))
+    a[:, :m] = torch.randn(rows, m, generator=g).to(dev)
+    b[:, :n] = (torch.randn(rows, n, generator=g) + 0.5).to(dev)
+    mu = b[:, :n].mean(0)
+    want = a[:, :m].double().t() @ b[:, :n].double()
+    want_c = a[:, :m].double().t() @ (b[:, :n].double() - mu.double())
     out = torch.zeros(m, n, device=dev)
     ops.gemm_tn(a, a.stride(0), m, rows, out, b=b, ldb=b.stride(0), n=n)
     out_c = torch.zeros(m, n, dtype=torch.float64, device=dev)

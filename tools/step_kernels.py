@@ -46,3 +46,11 @@ print('total device time %.3f ms over %d launches; nt:: kernels %.3f ms (%.1f %%
     tot / 1e3, sum(r[1] for r in rows), ours / 1e3, 100 * ours / tot, (tot - ours) / 1e3, sum(r[1] for r in rows if 'nt::' not in r[2])))
 for t, c, k in rows[:60]:
     print('%9.1f us %5d  %s' % (t, c, k[:150]))
+
+each = os.environ.get('NT_CENSUS_EACH')
+if each:
+    print('---- every launch matching %r, in launch order' % each)
+    evs = [e for e in prof.events() if e.device_type.name == 'CUDA' and each in e.name]
+    evs.sort(key=lambda e: e.time_range.start)
+    for e in evs:
+        print('%9.1f us  %s' % (e.time_range.elapsed_us(), e.name[:90]))
