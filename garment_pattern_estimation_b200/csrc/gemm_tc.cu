@@ -523,6 +523,10 @@ bool nt_tc_would_stream(const NTParams &p, int producer, int epilogue, int preci
 
 int launch_nt_tc(const NTParams &p, int producer, int epilogue, int precision, const void *w_split, cudaStream_t st) {
     if (precision == NT_PREC_TF32X3 && (p.engine >= 3 || (p.engine == 0 && p.rows >= TC3_MIN_ROWS))) {
+        if (p.engine >= 6) {                  // second-generation streaming engine (gemm_tc4.cu: eight converter warps, TMA epilogue)
+            const int rc4 = launch_nt_tc4(p, producer, epilogue, w_split, st);
+            if (rc4 >= 0) return rc4;
+        }
         const int rc = launch_nt_tc3(p, producer, epilogue, w_split, st);
         if (rc >= 0) return rc;
     }

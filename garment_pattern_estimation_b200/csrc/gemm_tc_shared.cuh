@@ -71,5 +71,8 @@ __device__ __forceinline__ void load_chunk(const float *src, int k, int K, bool 
 // streaming engine entry (gemm_tc3.cu); returns -1 when the call is not eligible (caller falls back to gemm_tc.cu)
 int launch_nt_tc3(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st);
 bool tc3_eligible(const NTParams &p, int producer, int epilogue);
+// second-generation streaming engine (gemm_tc4.cu); -1 when the call is not eligible
+int launch_nt_tc4(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st);
+bool tc4_eligible(const NTParams &p, int producer, int epilogue);
 
 }  // namespace nt

@@ -431,7 +431,7 @@ def test_streaming_engine_matches_one_tile_engine_and_float64(ops, cuda_device, 
     got = {}
     try:
         # engine 5 (aux rows of BNRELU_BWD through a shared-memory ring) is what engine 0 (auto) picks for large calls since round 2
-        for engine in (1, 3, 4, 5):
+        for engine in (1, 3, 4, 5, 6):
             _set_engine(engine)
             got[engine] = _run_gemm_nt(ops, epi, a, w, K, n_out, aux=aux)
             torch.cuda.synchronize()
@@ -451,6 +451,13 @@ def test_streaming_engine_matches_one_tile_engine_and_float64(ops, cuda_device, 
         for key in ('stats', 'colsum'):
             if key in one:
                 assert rel_err(got[5][key], one[key]) < 1e-5, key + ' (aux ring)'
+    # second-generation streaming engine (gemm_tc4.cu: eight converter warps, TMA tensor-map epilogue)
+    for key in ('out', 'vmax', 'vmin', 'imax', 'imin'):
+        if key in one:
+            assert torch.equal(one[key], got[6][key]), key + ' (TMA epilogue)'
+    for key in ('stats', 'colsum'):
+        if key in one:
+            assert rel_err(got[6][key], one[key]) < 1e-5, key + ' (TMA epilogue)'
     # same operand split, same MMA order: element-wise results are bit-identical; the column statistics are accumulated
     # with atomics in a different order
     for key in ('out', 'vmax', 'vmin', 'imax', 'imin'):

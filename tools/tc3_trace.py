@@ -3,7 +3,7 @@
 role, the share of the kernel time one representative thread spends in each phase (mean over CTAs).
 
     python tools/tc3_trace.py --build          # CPU box
-    python tools/tc3_trace.py [cfg]            # GPU box; cfg = NT_TC3_TILES configuration (1, 2, 3)
+    python tools/tc3_trace.py [engine]         # GPU box; engine = nt_gemm_args.engine (0 auto, 3/4/5 gemm_tc3.cu, 6 gemm_tc4.cu)
 """
 import ctypes
 import os
@@ -30,14 +30,15 @@ if '--build' in sys.argv:
 
 import torch  # noqa: E402
 
-if len(sys.argv) > 1:
-    os.environ['NT_TC3_TILES'] = sys.argv[1]
+ENGINE = int(sys.argv[1]) if len(sys.argv) > 1 else 0      # nt_gemm_args.engine: 0 / 3 / 4 / 5 = gemm_tc3.cu, 6 = gemm_tc4.cu
 nt_build.LIB_PATH = TRACE_LIB
 from garment_pattern_estimation_b200 import _lib, ops  # noqa: E402
 
 lib = _lib.load()
-lib.nt_debug_tc3_trace.restype = ctypes.c_int
-lib.nt_debug_tc3_trace.argtypes = [ctypes.c_void_p]
+read_trace = lib.nt_debug_tc4_trace if ENGINE == 6 else lib.nt_debug_tc3_trace
+read_trace.restype = ctypes.c_int
+read_trace.argtypes = [ctypes.c_void_p]
+ops.NT_ENGINE = ENGINE
 dev = torch.device('cuda:0')
 rows = 32 * 2048 * 5
 NAMES = ['prod: wait cp.async', 'prod: wait empty stage', 'prod: convert+fence+arrive', 'prod: issue cp.async',
@@ -75,10 +76,10 @@ def run(name, epi, K, n_out):
     e.record()
     torch.cuda.synchronize()
     buf = torch.zeros(256, 16, dtype=torch.int64)
-    assert lib.nt_debug_tc3_trace(buf.data_ptr()) == 0
+    assert read_trace(buf.data_ptr()) == 0
     t = buf[:148].double()
     ms = s.elapsed_time(e)
-    print('== {} K={} n_out={}: {:.3f} ms (cfg {})'.format(name, K, n_out, ms, os.environ.get('NT_TC3_TILES', '1')))
+    print('== {} K={} n_out={}: {:.3f} ms (engine {})'.format(name, K, n_out, ms, ENGINE))
     total = [t[:, 0:4].sum(1).mean(), t[:, 4:7].sum(1).mean(), t[:, 7:10].sum(1).mean(), t[:, 10:13].sum(1).mean()]
     for i, nm in enumerate(NAMES):
         role = 0 if i < 4 else (1 if i < 7 else (2 if i < 10 else 3))
