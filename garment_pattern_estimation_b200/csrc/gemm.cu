@@ -34,7 +34,7 @@ static int nt_fill_params(const nt_gemm_args *g, nt::NTParams &p) {
     p.k0 = g->k0; p.k1 = g->k1; p.mu = g->mu; p.colsum = g->colsum;
     p.scatter = g->scatter_dpq; p.ldscatter = g->ldscatter;
     p.engine = g->engine;
-    NT_REQUIRE(g->engine == 0 || g->engine == 1 || (g->engine >= 3 && g->engine <= 7), "nt_gemm_nt: engine must be 0 (auto), 1, 3, 4, 5 or 6");
+    NT_REQUIRE(g->engine == 0 || g->engine == 1 || (g->engine >= 3 && g->engine <= 6), "nt_gemm_nt: engine must be 0 (auto), 1, 3, 4, 5 or 6");
     if (g->producer == NT_PROD_PLAIN) NT_REQUIRE(g->a && g->lda >= g->K, "nt_gemm_nt: bad plain operand");
     else if (g->producer == NT_PROD_EDGE) {
         NT_REQUIRE(g->pq && g->ldpq >= g->K, "nt_gemm_nt: bad edge operand");

@@ -511,8 +511,9 @@ static int dispatch_tc(const NTParams &p, int producer, int epilogue, const void
 
 // Engine choice for the TF32x3 row GEMMs, PER CALL (nt_gemm_args.engine; the library keeps no mutable state): 0 = auto -- the
 // streaming engine (gemm_tc3.cu) for eligible calls with at least TC3_MIN_ROWS rows, the one-tile-per-CTA engine (this file)
-// otherwise; 1 = always this file; 3 / 4 / 5 = streaming engine whenever eligible, whatever the row count, with one / two row
-// tiles per weight stage / the aux-row ring for BNRELU_BWD (tests compare them; results are bit-identical across engines).
+// otherwise; 1 = always this file; 3 / 4 / 5 = first-generation streaming engine whenever eligible, whatever the row count, with
+// one / two row tiles per weight stage / the aux-row ring for BNRELU_BWD; 6 = second-generation streaming engine (gemm_tc4.cu),
+// which is also what auto picks first (tests compare them; results are bit-identical across engines).
 constexpr int64_t TC3_MIN_ROWS = 32768;
 
 bool nt_tc_would_stream(const NTParams &p, int producer, int epilogue, int precision) {
@@ -523,7 +524,7 @@ bool nt_tc_would_stream(const NTParams &p, int producer, int epilogue, int preci
 
 int launch_nt_tc(const NTParams &p, int producer, int epilogue, int precision, const void *w_split, cudaStream_t st) {
     if (precision == NT_PREC_TF32X3 && (p.engine >= 3 || (p.engine == 0 && p.rows >= TC3_MIN_ROWS))) {
-        if (p.engine >= 6) {                  // second-generation streaming engine (gemm_tc4.cu: eight converter warps, TMA epilogue)
+        if (p.engine == 0 || p.engine == 6) {  // second-generation streaming engine (gemm_tc4.cu: A operand in TMEM, TMA epilogue)
             const int rc4 = launch_nt_tc4(p, producer, epilogue, w_split, st);
             if (rc4 >= 0) return rc4;
         }

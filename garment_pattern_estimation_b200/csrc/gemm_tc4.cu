@@ -1,4 +1,4 @@
-// Streaming engine, second generation (nt_gemm_args.engine = 6, and the default for eligible calls): the persistent tcgen05 row
+// Streaming engine, second generation (nt_gemm_args.engine = 6, and what engine 0 = auto picks for eligible calls): the persistent tcgen05 row
 // GEMM of gemm_tc3.cu with the two measured bottlenecks of that kernel taken out (cycle trace):
 //
 //   * the forward GEMMs were bound by their four converter warps (one warp per scheduler: LDS -> TF32 split -> 2 x STS ->
@@ -12,6 +12,14 @@
 //     no tail code).  A thread touches only ITS row of the tile (TMEM lane = row): it reads the aux values and writes the result
 //     in place, 16-byte accesses whose chunk index is XOR-ed with (row & 7) -- the SWIZZLE_128B pattern -- so they are
 //     conflict-free without padding.  Column statistics go to per-warp accumulators (no shared-memory atomics).
+//   * shared-memory bandwidth was the next wall (per 128-row tile of the 200 -> 200 GEMM: 1.86 MB through the 128 B/cycle port =
+//     14.5 k of the measured 19 k cycles): the split A operand was written to shared memory by the converters (205 KB) and read
+//     back three times by the tensor core (307 KB).  Here the A operand lives in TENSOR MEMORY: a converter thread owns one row
+//     (= one TMEM lane), splits its 16 fp32 values of the k-block and writes hi | lo with two tcgen05.st (one 32-bit column per
+//     K element -- tools/microbench/ts_mode_test.cu: bit-identical to the shared-memory operand, second K = 8 step at +8
+//     columns), and the MMAs read it from there (`tcgen05.mma [d], [a], b-desc`).  No generic-proxy store, no
+//     fence.proxy.async on the operand path; the 32 KB of A stages become a third weight stage.  TMEM: two accumulators of
+//     n_tile columns + three A stages of 32 columns (n_tile <= 208).
 //
 // Results are bit-identical to the other engines (same operand split, same MMA order, same epilogue arithmetic); the tests
 // compare them.  Calls this file does not take (fused scatter, operands that are not 16-byte aligned) stay on gemm_tc3.cu.
@@ -23,7 +31,7 @@ namespace nt {
 template <int EPI, int SETS_> struct P4Cfg {
     static constexpr bool BWD = EPI == NT_EPI_BNRELU_BWD;
     static constexpr int SETS = SETS_;                     // converter warp sets (4 warps each)
-    static constexpr int STAGES = 2;
+    static constexpr int STAGES = 3;                       // weight k-blocks in shared memory + A k-blocks (hi | lo) in tensor memory
     static constexpr int DEPTH = BWD ? 4 : 6;              // raw k-blocks in flight per CTA (multiple of SETS)
     static constexpr int SLOTS = BWD ? 3 : 2;              // swizzled [32][32] tiles per epilogue warp
     static constexpr int EPI0_WARP = 4 * SETS;
@@ -58,6 +66,25 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand is read from tensor memory (lane = row, one 32-bit column per K element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// registers -> TMEM: 16 consecutive columns of this thread's lane (warp w writes lanes 32 (w % 4) .. +31); no wait inside
+__device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 #ifdef NT_TC3_TRACE
 __device__ unsigned long long g_tc4_trace[256][16];
 #define TRACE_T0() long long _t0 = clock64()
@@ -71,13 +98,56 @@ __device__ unsigned long long g_tc4_trace[256][16];
 #define TRACE_FLUSH(lo, hi)
 #endif
 
-__host__ __device__ inline size_t tc4_stage_bytes(int n_tile) { return (size_t)2 * TC_A_BYTES + (size_t)n_tile * 128; }
+constexpr int P4_MAX_NTILE = 208;                          // 2 accumulators x n_tile + 3 A stages x 32 columns <= 512 TMEM columns
+__host__ __device__ inline size_t tc4_stage_bytes(int n_tile) { return (size_t)n_tile * 128; }      // weight k-block: hi | lo planes
 // 1 KB alignment slack | epilogue tiles | operand stages | raw slabs | column constants [4][256] | per-warp statistics [8][512] |
 // barriers
 __host__ __device__ inline size_t tc4_smem_bytes(int n_tile, bool bwd) {
-    const int stages = 2, depth = bwd ? 4 : 6, slots = bwd ? 3 : 2;
+    const int stages = 3, depth = bwd ? 4 : 6, slots = bwd ? 3 : 2;
     return 1024 + (size_t)8 * slots * P4_TILE + stages * tc4_stage_bytes(n_tile) + (size_t)depth * P4_SLAB + 4 * 256 * 4 +
            (size_t)8 * (bwd ? 256 : 512) * 4 + 512;
+}
+
+// RELU_MAXMIN: thread (row slot et, column) scans the k edge rows of the centre points et / 32, et / 32 + 4, ... of one 128-row
+// group tile (element (R, c) at float index R*32 + (((c >> 2) ^ (R & 7)) << 2) + (c & 3)): max / min / their slots + column sums.
+// KC > 0: compile-time k (all loads of a point issued before the compare chain).
+template <int KC>
+__device__ __forceinline__ void maxmin_scan(const float *gt, int kk_rt, int et, int cq, int cr, int nodes_here, int64_t node0,
+                                            const NTParams &p, int col, float &t1, float &t2) {
+    const int kk = KC ? KC : kk_rt;
+    for (int t = et; t < nodes_here * 32; t += 128) {
+        const int nd = t >> 5;
+        const int R0 = nd * kk;
+        float mx, mn;
+        int ix = 0, in = 0;
+        if (KC) {
+            float xs[KC ? KC : 1];
+#pragma unroll
+            for (int sl = 0; sl < (KC ? KC : 1); ++sl) { const int R = R0 + sl; xs[sl] = gt[R * 32 + ((cq ^ (R & 7)) << 2) + cr]; }
+            mx = mn = xs[0];
+            t1 += xs[0]; t2 = fmaf(xs[0], xs[0], t2);
+#pragma unroll
+            for (int sl = 1; sl < (KC ? KC : 1); ++sl) {
+                const float x = xs[sl];
+                if (x > mx) { mx = x; ix = sl; }
+                if (x < mn) { mn = x; in = sl; }
+                t1 += x; t2 = fmaf(x, x, t2);
+            }
+        } else {
+            float x = gt[R0 * 32 + ((cq ^ (R0 & 7)) << 2) + cr];
+            mx = mn = x;
+            t1 += x; t2 = fmaf(x, x, t2);
+            for (int sl = 1; sl < kk; ++sl) {
+                const int R = R0 + sl;
+                x = gt[R * 32 + ((cq ^ (R & 7)) << 2) + cr];
+                if (x > mx) { mx = x; ix = sl; }
+                if (x < mn) { mn = x; in = sl; }
+                t1 += x; t2 = fmaf(x, x, t2);
+            }
+        }
+        const int64_t o = (node0 + nd) * (int64_t)p.n_out + col;
+        p.vmax[o] = mx; p.vmin[o] = mn; p.imax[o] = (uint8_t)ix; p.imin[o] = (uint8_t)in;
+    }
 }
 
 template <int EPI, int SETS_>
@@ -130,9 +200,10 @@ gemm_nt_tc4_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_cons
 
     if (warp < C::EPI0_WARP) {
         // =========================== A loaders / converters ===========================
-        // set q = warp >> 2 handles the k-block stream positions q, q + SETS, ...; inside a set, warp cw owns rows 32 cw .. 32 cw + 31:
-        // lane -> 16-byte chunk jj = lane >> 3 of the rows cw*32 + 8*i + (lane & 7).  A thread only ever converts what it fetched
-        // itself (cp.async groups are per thread), so no barrier is needed between fetch and conversion.
+        // set q = warp >> 2 handles the k-block stream positions q, q + SETS, ...; inside a set, warp cw owns rows 32 cw .. 32 cw + 31.
+        // FETCH mapping (coalesced): lane -> 16-byte chunk jj = lane >> 3 of the rows cw*32 + 8*i + (lane & 7).  CONVERT mapping:
+        // lane -> row cw*32 + lane (= the TMEM lane this warp may write), all four chunks.  The 32 rows of a warp's slab are
+        // fetched and converted by the same warp, so a __syncwarp() on either side of the conversion is all the ordering needed.
         const int set = warp >> 2, cw = warp & 3;
         const int jj = lane >> 3;
         int prow[4];
@@ -141,6 +212,7 @@ gemm_nt_tc4_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_cons
         const uint32_t raw_u32 = smem_u32(raw);
         const uint32_t slot_off = (uint32_t)(jj * (TC_M * 16));
         const bool set_leader = cw == 0 && lane == 0;
+        const uint32_t my_a = tmem_base + ((uint32_t)(cw * 32) << 16) + (uint32_t)(2 * g.n_tile);     // A stages of this warp's lanes
 
         // fetch position: runs DEPTH / SETS of this set's iterations ahead of the conversion
         int f_it = set, f_kb = set, f_slab = set, f_tile = 0;
@@ -185,34 +257,40 @@ gemm_nt_tc4_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_cons
 #pragma unroll 1
         for (int it = set; it < total_it; it += SETS) {
             while (kb >= g.num_kb) kb -= g.num_kb;
-            cp_async_wait_4<DEPTH / SETS - 1>();     // this thread's chunks of k-block `it` have landed
+            cp_async_wait_4<DEPTH / SETS - 1>();     // this thread's chunks of k-block `it` have landed ...
+            __syncwarp();                            // ... and so have the other lanes' (the warp's 32 rows are complete)
             TRACE_ADD(0);
-            mbar_wait(&empty[s], (use & 1) ^ 1);
+            mbar_wait(&empty[s], (use & 1) ^ 1);     // the MMAs that read this stage (weights in smem, A in TMEM) are complete
+            tc_fence_after();
             TRACE_ADD(1);
-            uint8_t *stage = stages + s * stage_bytes, *b_all = stage + 2 * TC_A_BYTES;
             {
+                // weight k-block: one bulk copy per converter warp of the set (4 concurrent requests of n_tile*32 bytes)
+                uint8_t *b_all = stages + s * stage_bytes;
                 const uint32_t bytes = (uint32_t)g.n_tile * 128u, part = bytes >> 2;
                 if (set_leader) mbar_arrive_expect_tx(&full[s], bytes);
                 if (lane == 0) bulk_g2s(b_all + cw * part, w_split + (size_t)kb * bytes + cw * part, part, &full[s]);
             }
             {
-                uint8_t *a_hi = stage, *a_lo = a_hi + TC_A_BYTES;
-                const uint8_t *rs = raw + slab * P4_SLAB + slot_off;
+                const uint8_t *rs = raw + slab * P4_SLAB + (cw * 32 + lane) * 16;
                 float4 x[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const float4 *>(rs + prow[i] * 16);
+                for (int j = 0; j < 4; ++j) x[j] = *reinterpret_cast<const float4 *>(rs + j * (TC_M * 16));
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-                    split_tf32(x[i].x, h0, l0); split_tf32(x[i].y, h1, l1); split_tf32(x[i].z, h2, l2); split_tf32(x[i].w, h3, l3);
-                    *reinterpret_cast<uint4 *>(a_hi + slot_off + prow[i] * 16) = make_uint4(h0, h1, h2, h3);
-                    *reinterpret_cast<uint4 *>(a_lo + slot_off + prow[i] * 16) = make_uint4(l0, l1, l2, l3);
+                for (int j = 0; j < 4; ++j) {
+                    split_tf32(x[j].x, hi[4 * j], lo[4 * j]); split_tf32(x[j].y, hi[4 * j + 1], lo[4 * j + 1]);
+                    split_tf32(x[j].z, hi[4 * j + 2], lo[4 * j + 2]); split_tf32(x[j].w, hi[4 * j + 3], lo[4 * j + 3]);
                 }
+                const uint32_t ta = my_a + (uint32_t)(s * 32);
+                tmem_st16_nowait(ta, hi);
+                tmem_st16_nowait(ta + 16, lo);
+                tmem_st_wait();
             }
-            fence_proxy_async();                     // generic-proxy smem writes -> visible to the tensor core
+            tc_fence_before();                       // the TMEM writes are ordered before the arrive the MMA thread waits for
             mbar_arrive(&full[s]);
+            __syncwarp();                            // every lane has read its row before any lane refills the slab
             TRACE_ADD(2);
-            issue();                                 // refill the raw slab this thread has just read
+            issue();                                 // refill the raw slab this warp has just read
             TRACE_ADD(3);
             s += SETS;
             while (s >= STAGES) { s -= STAGES; ++use; }
@@ -226,7 +304,7 @@ gemm_nt_tc4_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_cons
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TC_M, (uint32_t)g.n_tile, 0, 0);
-            const uint32_t lbo_a = TC_M * 16, lbo_b = (uint32_t)g.n_tile * 16, sbo = 128;
+            const uint32_t lbo_b = (uint32_t)g.n_tile * 16, sbo = 128;
             int s = 0, use = 0;
             TRACE_DECL();
             TRACE_T0();
@@ -239,19 +317,16 @@ gemm_nt_tc4_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_cons
                     mbar_wait(&full[s], use & 1);
                     tc_fence_after();
                     TRACE_ADD(5);
-                    const uint32_t stage = smem_u32(stages + s * stage_bytes);
-                    const uint32_t a_hi = stage, a_lo = a_hi + TC_A_BYTES;
-                    const uint32_t b_hi = stage + 2 * TC_A_BYTES, b_lo = b_hi + 4 * lbo_b;
-                    const uint32_t d = tmem_base + (uint32_t)(bar * 256);
+                    const uint32_t b_hi = smem_u32(stages + s * stage_bytes), b_lo = b_hi + 4 * lbo_b;
+                    const uint32_t a_hi = tmem_base + (uint32_t)(2 * g.n_tile + s * 32), a_lo = a_hi + 16;
+                    const uint32_t d = tmem_base + (uint32_t)(bar * g.n_tile);
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk) {
-                        const uint64_t dah = make_smem_desc(a_hi + kk * 2 * lbo_a, lbo_a, sbo);
-                        const uint64_t dal = make_smem_desc(a_lo + kk * 2 * lbo_a, lbo_a, sbo);
                         const uint64_t dbh = make_smem_desc(b_hi + kk * 2 * lbo_b, lbo_b, sbo);
                         const uint64_t dbl = make_smem_desc(b_lo + kk * 2 * lbo_b, lbo_b, sbo);
-                        umma_tf32(d, dah, dbh, idesc, (kb | kk) ? 1u : 0u);
-                        umma_tf32(d, dah, dbl, idesc, 1u);
-                        umma_tf32(d, dal, dbh, idesc, 1u);
+                        umma_tf32_ts(d, a_hi + kk * 8, dbh, idesc, (kb | kk) ? 1u : 0u);
+                        umma_tf32_ts(d, a_hi + kk * 8, dbl, idesc, 1u);
+                        umma_tf32_ts(d, a_lo + kk * 8, dbh, idesc, 1u);
                     }
                     umma_commit(&empty[s]);            // stage reusable once these MMAs have read it
                     if (++s == STAGES) { s = 0; ++use; }
@@ -316,7 +391,7 @@ gemm_nt_tc4_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_cons
                     __syncwarp();
                 }
                 float acc[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * 256 + c0), acc);
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(grp * g.n_tile + c0), acc);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     float4 *cell = reinterpret_cast<float4 *>(myrow + ((i ^ r7) << 4));      // logical chunk i of this row
@@ -368,23 +443,8 @@ gemm_nt_tc4_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_cons
                     const int cq = lane >> 2, cr = lane & 3;
                     float t1 = 0.f, t2 = 0.f;
                     if (lane < nv) {
-                        for (int t = et; t < nodes_here * 32; t += 128) {
-                            const int nd = t >> 5;
-                            int R = nd * kk;
-                            float x = gt[R * 32 + ((cq ^ (R & 7)) << 2) + cr];
-                            float mx = x, mn = x;
-                            int ix = 0, in = 0;
-                            t1 += x; t2 = fmaf(x, x, t2);
-                            for (int sl2 = 1; sl2 < kk; ++sl2) {
-                                ++R;
-                                x = gt[R * 32 + ((cq ^ (R & 7)) << 2) + cr];
-                                if (x > mx) { mx = x; ix = sl2; }
-                                if (x < mn) { mn = x; in = sl2; }
-                                t1 += x; t2 = fmaf(x, x, t2);
-                            }
-                            const int64_t o = (node0 + nd) * (int64_t)p.n_out + c0 + lane;
-                            p.vmax[o] = mx; p.vmin[o] = mn; p.imax[o] = (uint8_t)ix; p.imin[o] = (uint8_t)in;
-                        }
+                        if (kk == 5) maxmin_scan<5>(gt, kk, et, cq, cr, nodes_here, node0, p, c0 + lane, t1, t2);
+                        else maxmin_scan<0>(gt, kk, et, cq, cr, nodes_here, node0, p, c0 + lane, t1, t2);
                         if (p.stats) { mystat[c0 + lane] += t1; mystat[256 + c0 + lane] += t2; }
                     }
                     // no trailing barrier: the next chunk writes the OTHER slot, and a thread reaches the barrier of chunk n + 1 only
@@ -473,7 +533,7 @@ bool tc4_eligible(const NTParams &p, int producer, int epilogue) {
     if (bwd && !p.out) return false;
     if (p.rows >= ((int64_t)1 << 31) - 256) return false;
     const TCGeom g = tc_geometry(p.n_out, p.K, NT_PREC_TF32X3);
-    return tc4_smem_bytes(g.n_tile, bwd) <= 227 * 1024;
+    return g.n_tile <= P4_MAX_NTILE && tc4_smem_bytes(g.n_tile, bwd) <= 227 * 1024;
 }
 
 template <int EPI, int SETS>
@@ -518,9 +578,7 @@ int launch_nt_tc4(const NTParams &p, int producer, int epilogue, const void *w_s
         case NT_EPI_BIAS: return launch_tc4_t<NT_EPI_BIAS, 2>(p, w_split, g, sms, st);
         case NT_EPI_RELU_STATS: return launch_tc4_t<NT_EPI_RELU_STATS, 2>(p, w_split, g, sms, st);
         case NT_EPI_RELU_MAXMIN: return launch_tc4_t<NT_EPI_RELU_MAXMIN, 2>(p, w_split, g, sms, st);
-        default:           // engine 7 (measurement only): eight converter warps for the data-gradient GEMM too
-            return p.engine == 7 ? launch_tc4_t<NT_EPI_BNRELU_BWD, 2>(p, w_split, g, sms, st)
-                                 : launch_tc4_t<NT_EPI_BNRELU_BWD, 1>(p, w_split, g, sms, st);
+        default: return launch_tc4_t<NT_EPI_BNRELU_BWD, 2>(p, w_split, g, sms, st);      // (one converter set: 0.212 vs 0.206 ms)
     }
 }
 

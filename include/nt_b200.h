@@ -99,7 +99,8 @@ typedef struct nt_gemm_args {
     float *scatter_dpq; int ldscatter;
     /* kernel engine for THIS call (TF32X3 only): 0 = auto (streaming persistent engine for large aligned calls, one tile per CTA
      * otherwise), 1 = one tile per CTA, 3 / 4 = streaming engine with one / two row tiles per weight stage, 5 = streaming engine with
-     * the aux rows of NT_EPI_BNRELU_BWD staged through a shared-memory ring (what auto picks).  Results are bit-identical across
+     * the aux rows of NT_EPI_BNRELU_BWD staged through a shared-memory ring, 6 = second-generation streaming engine (A operand in
+     * tensor memory, TMA tensor-map epilogue; what auto picks when the call is eligible).  Results are bit-identical across
      * engines (same operand split, same accumulation order); the field exists for tests and measurements. */
     int engine;
 } nt_gemm_args;
