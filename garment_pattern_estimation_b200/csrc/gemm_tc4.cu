@@ -3,7 +3,9 @@
 //
 //   * the forward GEMMs were bound by their four converter warps (one warp per scheduler: LDS -> TF32 split -> 2 x STS ->
 //     fence.proxy.async -> arrive is a serial latency chain).  Here EIGHT converter warps work on alternating k-blocks (two
-//     independent chains per scheduler); a set owns its raw slabs and its stage, the barrier protocol is unchanged.
+//     independent chains per scheduler), and they no longer fetch: a loader thread brings every raw k-block in with ONE TMA
+//     tensor-map load ([128 rows x 16 columns] box, 64B-swizzled, K tail and rows past the end zero-filled by the hardware) --
+//     the 4 x 32-lane cp.async per k-block and thread cost the converters a third of their time (LSU back-pressure).
 //   * the epilogues spent their time on per-thread global traffic: 8 cp.async (aux rows) + 8 LDS.128 + 8 STG.128 per thread and
 //     32-column chunk, with the address / tail predicates around them.  Here every global access of the epilogue is a TMA
 //     tensor-map copy issued by one lane per warp: `cp.async.bulk.tensor.2d` loads the [32 rows x 32 columns] aux box into a
@@ -36,17 +38,12 @@ template <int EPI, int SETS_> struct P4Cfg {
     static constexpr int SLOTS = BWD ? 3 : 2;              // swizzled [32][32] tiles per epilogue warp
     static constexpr int EPI0_WARP = 4 * SETS;
     static constexpr int MMA_WARP = EPI0_WARP + 8;
-    static constexpr int THREADS = (MMA_WARP + 1) * 32;
+    static constexpr int LOAD_WARP = MMA_WARP + 1;         // one thread: TMA loads of the raw A k-blocks
+    static constexpr int THREADS = (LOAD_WARP + 1) * 32;
 };
-constexpr int P4_SLAB = 4 * TC_M * 16;                     // raw k-block: [4 chunks][128 rows][16 B]
+constexpr int P4_SLAB = TC_M * 64;                         // raw k-block: [128 rows][16 fp32], 64B-swizzled TMA box
 constexpr int P4_TILE = 32 * 32 * 4;                       // one epilogue tile (4 KB, 1024-byte aligned)
 
-__device__ __forceinline__ void cp_async16_4(uint32_t dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_4() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_4() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void l2_prefetch_4(const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
@@ -152,8 +149,8 @@ __device__ __forceinline__ void maxmin_scan(const float *gt, int kk_rt, int et, 
 
 template <int EPI, int SETS_>
 __global__ void __launch_bounds__(P4Cfg<EPI, SETS_>::THREADS, 1)
-gemm_nt_tc4_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out_tail,
-                   const __grid_constant__ CUtensorMap tm_aux, NTParams p, const uint8_t *__restrict__ w_split, TCGeom g) {
+gemm_nt_tc4_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_out,
+                   const __grid_constant__ CUtensorMap tm_out_tail, const __grid_constant__ CUtensorMap tm_aux, NTParams p, const uint8_t *__restrict__ w_split, TCGeom g) {
     using C = P4Cfg<EPI, SETS_>;
     constexpr bool BWD = C::BWD;
     constexpr int SETS = C::SETS, STAGES = C::STAGES, DEPTH = C::DEPTH, SLOTS = C::SLOTS;
@@ -161,17 +158,19 @@ gemm_nt_tc4_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_cons
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B tiles need 1 KB alignment
     uint8_t *tiles = smem;                                                       // [group][slot][quad][32 x 128 B]
-    uint8_t *stages = tiles + 8 * SLOTS * P4_TILE;
+    uint8_t *raw = tiles + 8 * SLOTS * P4_TILE;                                  // [DEPTH][128 rows x 64 B] (8 KB aligned)
+    uint8_t *stages = raw + DEPTH * P4_SLAB;
     const size_t stage_bytes = tc4_stage_bytes(g.n_tile);
-    uint8_t *raw = stages + STAGES * stage_bytes;
-    float *colv = reinterpret_cast<float *>(raw + DEPTH * P4_SLAB);              // [4][256]: bias | k0 | k1 | mu
+    float *colv = reinterpret_cast<float *>(stages + STAGES * stage_bytes);      // [4][256]: bias | k0 | k1 | mu
     float *wstat = colv + 4 * 256;                                               // [8 epilogue warps][STATW]
     uint64_t *full = reinterpret_cast<uint64_t *>(wstat + 8 * STATW);            // [STAGES]
     uint64_t *empty = full + STAGES;                                             // [STAGES]
     uint64_t *tmem_full = empty + STAGES;                                        // [2]
     uint64_t *tmem_empty = tmem_full + 2;                                        // [2]
     uint64_t *aux_bar = tmem_empty + 2;                                          // [8 epilogue warps][SLOTS]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(aux_bar + 8 * 3);
+    uint64_t *raw_full = aux_bar + 8 * 3;                                        // [DEPTH]
+    uint64_t *raw_empty = raw_full + DEPTH;                                      // [DEPTH]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + DEPTH);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_row_tiles = (p.rows + p.rows_per_tile - 1) / p.rows_per_tile;
@@ -189,6 +188,7 @@ gemm_nt_tc4_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_cons
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 128 + 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
         for (int i = 0; i < 8 * 3; ++i) mbar_init(&aux_bar[i], 1);
+        for (int i = 0; i < DEPTH; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 128); }
         mbar_fence_init();
     }
     if (warp == C::MMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -200,65 +200,23 @@ gemm_nt_tc4_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_cons
 
     if (warp < C::EPI0_WARP) {
         // =========================== A loaders / converters ===========================
-        // set q = warp >> 2 handles the k-block stream positions q, q + SETS, ...; inside a set, warp cw owns rows 32 cw .. 32 cw + 31.
-        // FETCH mapping (coalesced): lane -> 16-byte chunk jj = lane >> 3 of the rows cw*32 + 8*i + (lane & 7).  CONVERT mapping:
-        // lane -> row cw*32 + lane (= the TMEM lane this warp may write), all four chunks.  The 32 rows of a warp's slab are
-        // fetched and converted by the same warp, so a __syncwarp() on either side of the conversion is all the ordering needed.
+        // set q = warp >> 2 handles the k-block stream positions q, q + SETS, ...; inside a set, warp cw owns rows 32 cw .. 32 cw + 31
+        // and lane -> row cw*32 + lane (= the TMEM lane this warp may write).  The raw k-block arrives by TMA (loader warp) as
+        // [128 rows][64 B] with the 16-byte chunks of a row XOR-ed with (row >> 1) & 3 (SWIZZLE_64B): the four LDS.128 of a
+        // thread are conflict-free.  Columns >= K and rows >= rows arrive as zeros (tensor-map bounds).
         const int set = warp >> 2, cw = warp & 3;
-        const int jj = lane >> 3;
-        int prow[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) prow[i] = cw * 32 + 8 * i + (lane & 7);
-        const uint32_t raw_u32 = smem_u32(raw);
-        const uint32_t slot_off = (uint32_t)(jj * (TC_M * 16));
         const bool set_leader = cw == 0 && lane == 0;
+        const int myrow = cw * 32 + lane;
         const uint32_t my_a = tmem_base + ((uint32_t)(cw * 32) << 16) + (uint32_t)(2 * g.n_tile);     // A stages of this warp's lanes
+        const int sw = (myrow >> 1) & 3;
 
-        // fetch position: runs DEPTH / SETS of this set's iterations ahead of the conversion
-        int f_it = set, f_kb = set, f_slab = set, f_tile = 0;
-        int f_loaded_tile = -1;
-        const float *rowp[4];
-        auto issue = [&]() {
-            if (f_it < total_it) {
-                while (f_kb >= g.num_kb) { f_kb -= g.num_kb; ++f_tile; }
-                if (f_tile != f_loaded_tile) {
-                    f_loaded_tile = f_tile;
-                    const int64_t t_row0 = ((int64_t)blockIdx.x + (int64_t)f_tile * gridDim.x) * p.rows_per_tile;
-                    const int rows_here = (int)max((int64_t)0, min((int64_t)p.rows_per_tile, p.rows - t_row0));
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) rowp[i] = prow[i] < rows_here ? p.a + (t_row0 + prow[i]) * (int64_t)p.lda : nullptr;
-                    const int slab_rows = min(32, rows_here - cw * 32);
-                    if (lane == 0 && slab_rows > 0 && f_kb == 0) {       // the set that fetches the tile's first k-block prefetches it
-                        const uint32_t pf = (uint32_t)(((slab_rows - 1) * p.lda + p.K) * 4) & ~15u;
-                        if (pf) l2_prefetch_4(p.a + (t_row0 + cw * 32) * (int64_t)p.lda, pf);
-                    }
-                }
-                const int k = (f_kb * 4 + jj) * 4;
-                const uint32_t kbytes = k < p.K ? (uint32_t)min(16, (p.K - k) * 4) : 0u;
-                const uint32_t dst0 = raw_u32 + (uint32_t)(f_slab * P4_SLAB) + slot_off;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float *rp = rowp[i];
-                    cp_async16_4(dst0 + (uint32_t)(prow[i] * 16), rp ? rp + k : p.a, rp ? kbytes : 0u);
-                }
-                f_it += SETS;
-                f_kb += SETS;
-                f_slab += SETS;
-                if (f_slab >= DEPTH) f_slab -= DEPTH;
-            }
-            cp_async_commit_4();                     // exactly one group per call, possibly empty
-        };
-#pragma unroll 1
-        for (int d = 0; d < DEPTH / SETS; ++d) issue();
-
-        int s = set % STAGES, use = set / STAGES, kb = set, slab = set;
+        int s = set % STAGES, use = set / STAGES, kb = set, slab = set % DEPTH, suse = set / DEPTH;
         TRACE_DECL();
         TRACE_T0();
 #pragma unroll 1
         for (int it = set; it < total_it; it += SETS) {
             while (kb >= g.num_kb) kb -= g.num_kb;
-            cp_async_wait_4<DEPTH / SETS - 1>();     // this thread's chunks of k-block `it` have landed ...
-            __syncwarp();                            // ... and so have the other lanes' (the warp's 32 rows are complete)
+            mbar_wait(&raw_full[slab], suse & 1);    // the raw k-block has landed (async proxy -> mbarrier -> visible)
             TRACE_ADD(0);
             mbar_wait(&empty[s], (use & 1) ^ 1);     // the MMAs that read this stage (weights in smem, A in TMEM) are complete
             tc_fence_after();
@@ -271,10 +229,10 @@ gemm_nt_tc4_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_cons
                 if (lane == 0) bulk_g2s(b_all + cw * part, w_split + (size_t)kb * bytes + cw * part, part, &full[s]);
             }
             {
-                const uint8_t *rs = raw + slab * P4_SLAB + (cw * 32 + lane) * 16;
+                const uint8_t *rs = raw + slab * P4_SLAB + myrow * 64;
                 float4 x[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) x[j] = *reinterpret_cast<const float4 *>(rs + j * (TC_M * 16));
+                for (int j = 0; j < 4; ++j) x[j] = *reinterpret_cast<const float4 *>(rs + ((j ^ sw) << 4));
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -288,18 +246,39 @@ gemm_nt_tc4_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_cons
             }
             tc_fence_before();                       // the TMEM writes are ordered before the arrive the MMA thread waits for
             mbar_arrive(&full[s]);
-            __syncwarp();                            // every lane has read its row before any lane refills the slab
+            mbar_arrive(&raw_empty[slab]);           // this row of the raw k-block is in registers / TMEM: the slab may be refilled
             TRACE_ADD(2);
-            issue();                                 // refill the raw slab this warp has just read
-            TRACE_ADD(3);
             s += SETS;
             while (s >= STAGES) { s -= STAGES; ++use; }
             kb += SETS;
             slab += SETS;
-            if (slab >= DEPTH) slab -= DEPTH;
+            while (slab >= DEPTH) { slab -= DEPTH; ++suse; }
         }
-        cp_async_wait_4<0>();
         if (tid == 0) TRACE_FLUSH(0, 4);
+    } else if (warp == C::LOAD_WARP) {
+        // =========================== raw A loader: one TMA box [128 rows x 16 columns] per k-block, DEPTH k-blocks ahead ===========
+        if (lane == 0) {
+            int slab = 0, suse = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)ti * gridDim.x) * p.rows_per_tile;
+                const int rows_here = (int)max((int64_t)0, min((int64_t)p.rows_per_tile, p.rows - row0));
+                // the k-blocks visit every row of the tile in 64-byte pieces over a tile period: pull the tile's rows (contiguous in
+                // memory) into L2 with four sequential bulk prefetches first (DRAM row-buffer locality; measured in round 1)
+                for (int q = 0; q < 4; ++q) {
+                    const int slab_rows = min(32, rows_here - q * 32);
+                    if (slab_rows > 0) {
+                        const uint32_t pf = (uint32_t)(((slab_rows - 1) * p.lda + p.K) * 4) & ~15u;
+                        if (pf) l2_prefetch_4(p.a + (row0 + q * 32) * (int64_t)p.lda, pf);
+                    }
+                }
+                for (int kb = 0; kb < g.num_kb; ++kb) {
+                    mbar_wait(&raw_empty[slab], (suse & 1) ^ 1);     // the converters have read the k-block that was here
+                    mbar_arrive_expect_tx(&raw_full[slab], P4_SLAB);
+                    tma_load_2d(smem_u32(raw + slab * P4_SLAB), &tm_a, kb * 16, (int)row0, &raw_full[slab]);
+                    if (++slab == DEPTH) { slab = 0; ++suse; }
+                }
+            }
+        }
     } else if (warp == C::MMA_WARP) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
@@ -515,16 +494,16 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// fp32 matrix [rows, cols] with row stride ld (floats), boxes of box_rows x 32 columns, 128-byte swizzle
-static bool make_map(CUtensorMap *m, const float *base, int64_t rows, int cols, int ld, int box_rows) {
+// fp32 matrix [rows, cols] with row stride ld (floats), boxes of box_rows x box_cols (32: 128-byte swizzle, 16: 64-byte swizzle)
+static bool make_map(CUtensorMap *m, const float *base, int64_t rows, int cols, int ld, int box_rows, int box_cols = 32) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1u, 1u};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool tc4_eligible(const NTParams &p, int producer, int epilogue) {
@@ -548,7 +527,8 @@ static int launch_tc4_t(const NTParams &p, const void *w_split, const TCGeom &g,
     }
     // tensor maps: the result (32-row boxes, and the box of a tile's last quadrant when tiles are not a multiple of 32 rows high)
     // and the aux operand of BNRELU_BWD.  Unused maps alias a valid one (the kernel never dereferences them).
-    CUtensorMap tm_out, tm_tail, tm_aux;
+    CUtensorMap tm_a, tm_out, tm_tail, tm_aux;
+    if (!make_map(&tm_a, p.a, p.rows, p.K, p.lda, TC_M, 16)) return fail("nt_gemm_nt(tc4): cuTensorMapEncodeTiled failed%s", "");
     const float *some = p.out ? p.out : p.a;
     const int some_cols = p.out ? p.n_out : p.K, some_ld = p.out ? p.ldo : p.lda;
     if (!make_map(&tm_out, some, p.rows, some_cols, some_ld, 32)) return fail("nt_gemm_nt(tc4): cuTensorMapEncodeTiled failed%s", "");
@@ -559,7 +539,7 @@ static int launch_tc4_t(const NTParams &p, const void *w_split, const TCGeom &g,
     if (BWD && !make_map(&tm_aux, p.aux, p.rows, p.n_out, p.ldaux, 32)) return fail("nt_gemm_nt(tc4): cuTensorMapEncodeTiled failed%s", "");
     const int64_t n_row_tiles = (p.rows + p.rows_per_tile - 1) / p.rows_per_tile;
     const int ctas = (int)(n_row_tiles < sms ? n_row_tiles : sms);
-    gemm_nt_tc4_kernel<EPI, SETS><<<ctas, P4Cfg<EPI, SETS>::THREADS, smem, st>>>(tm_out, tm_tail, tm_aux, p, reinterpret_cast<const uint8_t *>(w_split), g);
+    gemm_nt_tc4_kernel<EPI, SETS><<<ctas, P4Cfg<EPI, SETS>::THREADS, smem, st>>>(tm_a, tm_out, tm_tail, tm_aux, p, reinterpret_cast<const uint8_t *>(w_split), g);
     return check_launch("nt_gemm_nt(tc4)");
 }
 
