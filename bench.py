@@ -566,10 +566,15 @@ def main():
             traffic = tj.get(dom, {}).get('dram_bytes_per_launch') if isinstance(tj.get(dom), dict) else None
     except (OSError, ValueError):
         pass
-    kernel_names = {'nt_gemm_nt[bnrelu_bwd,plain]': 'nt::gemm_nt_tc3_kernel<BNRELU_BWD> (streaming tcgen05 TF32x3 data-gradient GEMM '
-                                                    'fused with the BatchNorm/ReLU backward; the two per-point launches of the '
-                                                    'group run nt::gemm_nt_tc_kernel)',
-                    'nt_gemm_tn_centered': 'nt::gemm_tn_tc_kernel (weight-gradient GEMM with centred operand)'}
+    kernel_names = {'nt_gemm_nt[bnrelu_bwd,plain]': 'nt::gemm_nt_tc4_kernel<BNRELU_BWD> (persistent streaming tcgen05 TF32x3 data-gradient GEMM '
+                                                    'fused with the BatchNorm/ReLU backward: raw A k-blocks and aux boxes by TMA tensor-map '
+                                                    'loads, A operand split into tensor memory, result boxes by TMA stores; the two '
+                                                    'per-point launches of the group run nt::gemm_nt_tc_kernel)',
+                    'nt_gemm_nt[relu_stats,plain]': 'nt::gemm_nt_tc4_kernel<RELU_STATS> (same engine, forward Linear + ReLU + BatchNorm statistics)',
+                    'nt_gemm_nt[relu_maxmin,plain]': 'nt::gemm_nt_tc4_kernel<RELU_MAXMIN> (same engine, forward Linear + ReLU + max/min over the k edges)',
+                    'nt_gemm_tn_centered': 'nt::gemm_tn_mn_kernel + mn_reduce_kernel (weight-gradient GEMM with centred operand: rows consumed as '
+                                           'MN-major BF16x3 tcgen05 operands, whole-row bulk copies)',
+                    'nt_gemm_tn': 'nt::gemm_tn_mn_kernel + mn_reduce_kernel (weight-gradient GEMM, MN-major BF16x3 tcgen05 operands)'}
     roofline = None
     if dom:
         dom_ms, dom_n = groups[dom], max(counts.get(dom, 1.0), 1.0)
@@ -582,9 +587,8 @@ def main():
             'traffic_source': 'profiles/dominant_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the '
                               'launches of the group in one eager step)',
             'note': 'algorithmic bytes = fp32 operand rows read once + result rows written once + weights; the same group '
-                    'reaches {:.1f} TFLOP/s of useful fp32-equivalent math (see roofline_tensor).  No unit is saturated (ncu); the '
-                    'cycle trace in DESIGN.md section 4 shows this kernel is bound by its epilogue (42 k cycles to drain a '
-                    '128-row tile per group: latency of the aux-row loads) and the forward GEMMs by their converter warps'.format(
+                    'reaches {:.1f} TFLOP/s of useful fp32-equivalent math (see roofline_tensor).  What bounds the group is in DESIGN.md '
+                    'section 4 (cycle traces profiles/r02_tc4_cycle_trace.txt, ncu summaries under profiles/)'.format(
                         gemm_flops.get(dom, 0.0) / (dom_ms * 1e-3) / 1e12),
         }
 
@@ -613,13 +617,13 @@ def main():
     tc_flops = sum(gemm_flops.get(n, 0.0) for n in tc_names)
     tensor_peak = peaks.get('bf16_tflops_sustained', 1414.4)
     roofline_tensor = {
-        'kernels': 'nt::gemm_nt_tc_kernel<*> + nt::gemm_tn_tc_kernel (all fused row / weight-gradient GEMMs of the step)',
+        'kernels': 'nt::gemm_nt_tc4_kernel<*> + nt::gemm_nt_tc_kernel<*> + nt::gemm_tn_mn_kernel (all fused row / weight-gradient GEMMs of the step)',
         'bound': 'tensor', 'achieved': tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else None, 'peak': tensor_peak,
         'unit': 'TFLOP/s', 'frac': (tc_flops / (tc_ms * 1e-3) / 1e12 / tensor_peak) if tc_ms else None,
         'ms_per_step': tc_ms, 'useful_gflop_per_step': tc_flops / 1e9,
         'note': 'peak = measured sustained bf16 cuBLAS GEMM (MEASURED_PEAKS.json); these kernels run kind::tf32 (half the '
                 'bf16 rate) with a 3-product error-compensated split, so 1/6 of that peak is the precision-imposed ceiling; '
-                'they are bound by HBM streaming and instruction issue of the operand split, not by the tensor pipe (profiles/)',
+                'they are streaming kernels (K, n_out <= 200) bound by HBM and shared-memory bandwidth, not by the tensor pipe (profiles/)',
     }
 
     try:

@@ -50,6 +50,18 @@ class PatternLossArgs(ctypes.Structure):
                 ('use_shape', c_int), ('use_loop', c_int), ('use_rotation', c_int), ('use_translation', c_int)]
 
 
+class EdgeConvArgs(ctypes.Structure):
+    """Mirror of `struct nt_edgeconv_args`."""
+    _fields_ = [('M', c_int64), ('C', c_int), ('H1', c_int), ('H2', c_int), ('H3', c_int), ('k', c_int), ('n_per_cloud', c_int),
+                ('x', c_void_p), ('ldx', c_int), ('idx', c_void_p), ('tail_src', c_void_p), ('tail_ld', c_int), ('tail', c_int),
+                ('W', c_void_p * 3), ('b', c_void_p * 3), ('gamma', c_void_p * 3), ('beta', c_void_p * 3),
+                ('running_mean', c_void_p * 3), ('running_var', c_void_p * 3), ('num_batches_tracked', c_void_p * 3),
+                ('momentum', c_float), ('eps', c_float),
+                ('out', c_void_p), ('ldo', c_int), ('saved', c_void_p), ('scratch', c_void_p),
+                ('gout', c_void_p), ('ldg', c_int), ('gx', c_void_p), ('ldgx', c_int),
+                ('gW', c_void_p * 3), ('gb', c_void_p * 3), ('ggamma', c_void_p * 3), ('gbeta', c_void_p * 3)]
+
+
 _PP = ctypes.POINTER(c_void_p)      # host array of device pointers
 
 _SIGNATURES = {
@@ -99,6 +111,10 @@ _SIGNATURES = {
     'nt_edgeconv_eval_supported': (c_int, [c_int, c_int, c_int, c_int, c_int]),
     'nt_edgeconv_eval_fwd': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p,
                                      c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    'nt_edgeconv_saved_bytes': (c_int64, [ctypes.POINTER(EdgeConvArgs)]),
+    'nt_edgeconv_scratch_bytes': (c_int64, [ctypes.POINTER(EdgeConvArgs), c_int]),
+    'nt_edgeconv_train_fwd': (c_int, [ctypes.POINTER(EdgeConvArgs), c_void_p]),
+    'nt_edgeconv_train_bwd': (c_int, [ctypes.POINTER(EdgeConvArgs), c_void_p]),
     'nt_edge_pairs': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     'nt_fps': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'nt_radius': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p]),
@@ -152,7 +168,8 @@ def load():
             raise RuntimeError('{} does not export {} (stale build? run garment_pattern_estimation_b200/build.py '
                                '--force)'.format(path, name))
         fn.restype, fn.argtypes = restype, argtypes
-    for name, struct in (('nt_gemm_args', GemmArgs), ('nt_pattern_loss_args', PatternLossArgs), ('nt_lstm_sizes_t', LstmSizes)):
+    for name, struct in (('nt_gemm_args', GemmArgs), ('nt_pattern_loss_args', PatternLossArgs), ('nt_lstm_sizes_t', LstmSizes),
+                         ('nt_edgeconv_args', EdgeConvArgs)):
         lib.nt_sizeof.restype, lib.nt_sizeof.argtypes = c_int, [ctypes.c_char_p]
         if lib.nt_sizeof(name.encode()) != ctypes.sizeof(struct):
             raise RuntimeError('{}: struct {} is {} bytes in the library but {} in the ctypes mirror (layout drift)'.format(

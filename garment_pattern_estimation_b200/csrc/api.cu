@@ -7,7 +7,7 @@ std::atomic<int64_t> g_launches{0};
 }  // namespace nt
 
 extern "C" const char *nt_last_error(void) { return nt::g_err; }
-extern "C" int nt_version(void) { return 2; }       // 2: per-call engine in nt_gemm_args, LSTM / PointNet++ / train-step entry points
+extern "C" int nt_version(void) { return 3; }       // 3: composite nt_edgeconv_train_fwd / _bwd, engine 6; 2: per-call engine, LSTM / PointNet++ / train-step
 extern "C" int nt_built_arch(void) {
 #ifdef NT_BUILT_ARCH
     return NT_BUILT_ARCH;
@@ -24,5 +24,6 @@ extern "C" int nt_sizeof(const char *struct_name) {
     if (!strcmp(struct_name, "nt_gemm_args")) return (int)sizeof(nt_gemm_args);
     if (!strcmp(struct_name, "nt_pattern_loss_args")) return (int)sizeof(nt_pattern_loss_args);
     if (!strcmp(struct_name, "nt_lstm_sizes_t")) return (int)sizeof(nt_lstm_sizes_t);
+    if (!strcmp(struct_name, "nt_edgeconv_args")) return (int)sizeof(nt_edgeconv_args);
     return 0;
 }

@@ -22,6 +22,9 @@
 //     columns), and the MMAs read it from there (`tcgen05.mma [d], [a], b-desc`).  No generic-proxy store, no
 //     fence.proxy.async on the operand path; the 32 KB of A stages become a third weight stage.  TMEM: two accumulators of
 //     n_tile columns + three A stages of 32 columns (n_tile <= 208).
+//   (Tried and dropped: independent rings for the A stages and FOUR weight stages filled by their own loader thread -- the MMA
+//   thread waits 35-45 % of its time for full stages either way, 0.151 vs 0.142 ms: what it waits for is the weight stream itself,
+//   n_tile*128 bytes per k-block and CTA from L2 = 3.2x the A bytes)
 //
 // Results are bit-identical to the other engines (same operand split, same MMA order, same epilogue arithmetic); the tests
 // compare them.  Calls this file does not take (fused scatter, operands that are not 16-byte aligned) stay on gemm_tc3.cu.
@@ -545,7 +548,7 @@ static int launch_tc4_t(const NTParams &p, const void *w_split, const TCGeom &g,
 
 // -1: not eligible (the caller tries the first-generation streaming engine, then the one-tile-per-CTA engine)
 int launch_nt_tc4(const NTParams &p, int producer, int epilogue, const void *w_split, cudaStream_t st) {
-    if (!tc4_eligible(p, producer, epilogue) || encode_fn() == nullptr) return -1;
+    if (encode_fn() == nullptr) return -1;
     const TCGeom g = tc_geometry(p.n_out, p.K, NT_PREC_TF32X3);
     static int sms = 0;
     if (sms == 0) {
@@ -554,6 +557,28 @@ int launch_nt_tc4(const NTParams &p, int producer, int epilogue, const void *w_s
             return fail("nt_gemm_nt(tc4): cannot query the SM count%s", "");
         sms = n;
     }
+    if (g.n_tiles > 1) {
+        // NT_EPI_BIAS with several column tiles (the split first EdgeConv Linear: n_out = 2 H1 = 400): one launch per column tile of the
+        // prepared weights -- the rows are read once per tile (K is small for these calls), every tile streams
+        if (epilogue != NT_EPI_BIAS || g.n_tile > P4_MAX_NTILE || g.n_tiles > 4 || tc4_smem_bytes(g.n_tile, false) > 227 * 1024) return -1;
+        TCGeom g1 = g;
+        g1.n_tiles = 1;
+        NTParams q[4];
+        for (int t = 0; t < g.n_tiles; ++t) {
+            q[t] = p;
+            q[t].n_out = p.n_out - t * g.n_tile < g.n_tile ? p.n_out - t * g.n_tile : g.n_tile;
+            q[t].out = p.out + t * g.n_tile;
+            q[t].bias = p.bias ? p.bias + t * g.n_tile : nullptr;
+            if (!tc4_eligible(q[t], producer, epilogue)) return -1;
+        }
+        for (int t = 0; t < g.n_tiles; ++t) {
+            const uint8_t *ws = reinterpret_cast<const uint8_t *>(w_split) + (size_t)t * g.num_kb * g.n_tile * 128;
+            const int rc = launch_tc4_t<NT_EPI_BIAS, 2>(q[t], ws, g1, sms, st);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    if (!tc4_eligible(p, producer, epilogue)) return -1;
     switch (epilogue) {
         case NT_EPI_BIAS: return launch_tc4_t<NT_EPI_BIAS, 2>(p, w_split, g, sms, st);
         case NT_EPI_RELU_STATS: return launch_tc4_t<NT_EPI_RELU_STATS, 2>(p, w_split, g, sms, st);

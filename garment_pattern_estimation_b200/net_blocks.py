@@ -58,7 +58,7 @@ class DynamicEdgeConv(nn.Module):
         self.aggr = aggr
         self.last_index = None      # kNN indices of the last forward (int32 [M, k], local) -- for parity tests
 
-    def forward(self, x, batch=None, cloud_shape=None, tail_src=None):
+    def forward(self, x, batch=None, cloud_shape=None, tail_src=None, pad_out=False):
         if cloud_shape is None:
             if batch is None:
                 cloud_shape = (1, x.shape[0])
@@ -69,7 +69,7 @@ class DynamicEdgeConv(nn.Module):
         idx = ops.knn_graph(x.detach(), B, N, self.k)
         self.last_index = idx
         return ops.fused_mlp(x, self.nn.layer_pairs(), self.nn.training, mode='edge', idx=idx, k=self.k,
-                             n_per_cloud=N, tail_src=tail_src)
+                             n_per_cloud=N, tail_src=tail_src, pad_out=pad_out)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -138,7 +138,7 @@ class EdgeConvFeatures(nn.Module):
         for i, conv in enumerate(self.conv_layers):
             # the skip connection (cat[out, pos], nn/net_blocks.py:178-180) is written by the last layer's epilogue
             tail = pos_flat if (i == last and self.config['skip_connections']) else None
-            out = conv(out, cloud_shape=(B, N), tail_src=tail)
+            out = conv(out, cloud_shape=(B, N), tail_src=tail, pad_out=(i != last))       # inner layers: 16-byte aligned rows
         if global_pool:
             pooled = self.global_pool(out, batch, B)
             return ops.linear(pooled, self.lin.weight, self.lin.bias), out, batch

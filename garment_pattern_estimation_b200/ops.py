@@ -80,6 +80,13 @@ def _rowbuf(rows, cols, device):
     return torch.empty(rows, _pad4(cols), dtype=torch.float32, device=device)
 
 
+def _out_rows(rows, cols, device, padded):
+    """Result tensor [rows, cols]: contiguous, or (padded) a view of a buffer with 16-byte aligned rows."""
+    if padded:
+        return _rowbuf(rows, cols, device)[:, :cols]
+    return torch.empty(rows, cols, dtype=torch.float32, device=device)
+
+
 def _rows2d(t):
     """(tensor, row stride) for a 2-D fp32 tensor whose last dim is dense."""
     assert t.dim() == 2 and t.dtype == torch.float32
@@ -114,6 +121,10 @@ FUSED_SCATTER = os.environ.get('NT_FUSED_SCATTER', '0') != '0'
 # path; '0' keeps the latter (A/B measurements, and the reference point of the parity test).
 EDGE_EVAL_FUSED = os.environ.get('NT_EDGE_EVAL_FUSED', '1') != '0'
 EDGE_EVAL_PRECISION = _lib.NT_PREC_BF16X3 if os.environ.get('NT_EDGE_EVAL_PREC', 'tf32x3') == 'bf16x3' else _lib.NT_PREC_TF32X3
+# Training-mode EdgeConv layers with three Linear stages run through the library's composite entry points (nt_edgeconv_train_fwd /
+# _bwd: the whole layer per call, orchestrated in C++).  '0' keeps the kernel-by-kernel orchestration below (same kernels, same
+# order; also what runs while bench.py brackets the individual kernels with CUDA events, and for other depths / the plain MLP).
+EDGECONV_COMPOSITE = os.environ.get('NT_EDGECONV_COMPOSITE', '1') != '0'
 NT_ENGINE = 0         # nt_gemm_args.engine of every row GEMM launched from here: 0 = auto (product); tests set 1 / 3 / 4 / 5
 
 
@@ -235,6 +246,31 @@ class _BNBuffers:
         self.eps = float(eps)
 
 
+def _ptr3(ts):
+    arr = (ctypes.c_void_p * 3)()
+    for i, t in enumerate(ts):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def _edgeconv_args(x, ldx, idx, tail_src, k, n_per_cloud, Ws, bs, gammas, betas, bn_bufs=None):
+    """nt_edgeconv_args for one EdgeConv layer (three stages); the caller fills out / saved / scratch / gradient pointers."""
+    g = _lib.EdgeConvArgs()
+    g.M, g.C = int(x.shape[0]), int(x.shape[1])
+    g.H1, g.H2, g.H3 = (int(W.shape[0]) for W in Ws)
+    g.k, g.n_per_cloud = int(k), int(n_per_cloud)
+    g.x, g.ldx, g.idx = _p(x), int(ldx), _p(idx)
+    if tail_src is not None:
+        ts, tld = _rows2d(tail_src)
+        g.tail_src, g.tail_ld, g.tail = _p(ts), int(tld), int(ts.shape[1])
+    g.W, g.b, g.gamma, g.beta = _ptr3(Ws), _ptr3(bs), _ptr3(gammas), _ptr3(betas)
+    if bn_bufs is not None:
+        g.running_mean, g.running_var = _ptr3([b.running_mean for b in bn_bufs]), _ptr3([b.running_var for b in bn_bufs])
+        g.num_batches_tracked = _ptr3([b.nbt for b in bn_bufs])
+        g.momentum, g.eps = bn_bufs[0].momentum, bn_bufs[0].eps
+    return g
+
+
 class _FusedMLPFunction(torch.autograd.Function):
     """params = (W_0, b_0, gamma_1, beta_1, W_1, b_1, gamma_2, beta_2, ...): 4 tensors per layer."""
 
@@ -255,6 +291,28 @@ class _FusedMLPFunction(torch.autograd.Function):
         M, C = x.shape
         widths = [W.shape[0] for W in Ws]           # H_1 .. H_L
         f32 = dict(dtype=torch.float32, device=dev)
+
+        # ---- training, EdgeConv with three Linear layers: the whole layer is ONE library call (csrc/edgeconv_train.cu)
+        if (mode == 'edge' and training and L == 3 and EDGECONV_COMPOSITE and EDGE_MATERIALIZE and not FUSED_SCATTER
+                and EVENT_SINK is None and all(b is not None for b in bs)
+                and all(b.momentum == bn_bufs[0].momentum and b.eps == bn_bufs[0].eps for b in bn_bufs)):
+            cWs, cbs = [W.contiguous() for W in Ws], [b.contiguous() for b in bs]
+            cgs, cbetas = [t.contiguous() for t in gammas], [t.contiguous() for t in betas]
+            if Ws[0].shape[1] != 2 * C:
+                raise RuntimeError('edge MLP expects first Linear with {} inputs, got {}'.format(2 * C, Ws[0].shape[1]))
+            k, N = meta['k'], meta['n_per_cloud']
+            g = _edgeconv_args(x, ldx, idx, tail_src, k, N, cWs, cbs, cgs, cbetas, bn_bufs)
+            tail = int(g.tail)
+            out = _out_rows(M, widths[2] + tail, dev, meta.get('pad_out'))
+            saved = torch.empty(int(lib.nt_edgeconv_saved_bytes(ctypes.byref(g))), dtype=torch.uint8, device=dev)
+            scratch = torch.empty(int(lib.nt_edgeconv_scratch_bytes(ctypes.byref(g), 0)), dtype=torch.uint8, device=dev)
+            g.out, g.ldo, g.saved, g.scratch = _p(out), out.stride(0), _p(saved), _p(scratch)
+            _call('nt_edgeconv_train_fwd', lib.nt_edgeconv_train_fwd, ctypes.byref(g), _stream())
+            ctx.meta = None
+            if any(ctx.needs_input_grad):
+                ctx.meta = dict(composite=True, k=k, N=N, tail=tail, ldx=ldx)
+                ctx.save_for_backward(x, idx, saved, *cWs, *cbs, *cgs, *cbetas)
+            return out
 
         # ---- first Linear, evaluated per POINT (edge mode: split W_0 = [W_a | W_b] on [x_i, x_j - x_i])
         H1 = widths[0]
@@ -306,10 +364,10 @@ class _FusedMLPFunction(torch.autograd.Function):
             w3s = prepare_weights(w3f, widths[1], widths[2], widths[1], EDGE_EVAL_PRECISION)
             tail = 0 if tail_src is None else tail_src.shape[1]
             ts, tld = (None, 0) if not tail else _rows2d(tail_src)
-            out = torch.empty(M, widths[2] + tail, **f32)
+            out = _out_rows(M, widths[2] + tail, dev, meta.get('pad_out'))
             _call('nt_edgeconv_eval_fwd', lib.nt_edgeconv_eval_fwd, _p(pq), pq.stride(0), H1, _p(idx), k, N, M, _p(w2s), _p(b2f),
                   widths[1], _p(w3s), _p(b3f), widths[2], EDGE_EVAL_PRECISION, _p(vec3[2]), _p(vec3[3]), _p(ts), tld, tail, _p(out),
-                  widths[2] + tail,
+                  out.stride(0),
                   _stream())
             ctx.meta = None
             return out
@@ -365,14 +423,14 @@ class _FusedMLPFunction(torch.autograd.Function):
             gemm_nt(R, Kin, HL, w_f, Kin, NT_EPI_RELU_MAXMIN, bias=b_f, out=a_last, ldo=ld_last, stats=stats, agg=agg,
                     k_agg=k, **last_in)
             bn_vec[L - 1], _, _, _ = fold(L - 1, stats, None)
-            out = torch.empty(M, HL + tail, **f32)
+            out = _out_rows(M, HL + tail, dev, meta.get('pad_out'))
             sel = torch.empty(M, HL, dtype=torch.uint8, device=dev) if need_bwd else None
             vsel = torch.empty(M, HL, **f32) if need_bwd else None
             ts, tld = (None, 0)
             if tail:
                 ts, tld = _rows2d(tail_src)
             _call('nt_maxmin_finish', _lib.load().nt_maxmin_finish, _p(agg[0]), _p(agg[1]), _p(agg[2]), _p(agg[3]), _p(bn_vec[L - 1][2]),
-                                            _p(bn_vec[L - 1][3]), M, HL, _p(out), HL + tail, _p(sel), _p(vsel),
+                                            _p(bn_vec[L - 1][3]), M, HL, _p(out), out.stride(0), _p(sel), _p(vsel),
                                             _p(ts), tld, tail, _stream())
         else:
             a_last = _rowbuf(R, HL, dev)
@@ -398,6 +456,31 @@ class _FusedMLPFunction(torch.autograd.Function):
         m = ctx.meta
         if m is None:
             raise RuntimeError('fused_mlp: backward through an eval-mode (running-statistics) forward is not supported')
+        if m.get('composite'):
+            sv = ctx.saved_tensors
+            x, idx, saved = sv[:3]
+            Ws, bs, gammas, betas = sv[3:6], sv[6:9], sv[9:12], sv[12:15]
+            dev = x.device
+            g = _edgeconv_args(x, m['ldx'], idx, None, m['k'], m['N'], Ws, bs, gammas, betas)
+            gout, ldg = _rows2d(gout)
+            scratch = torch.empty(int(lib.nt_edgeconv_scratch_bytes(ctypes.byref(g), 1)), dtype=torch.uint8, device=dev)
+            gW = [torch.empty_like(W) for W in Ws]
+            gb = [torch.empty_like(b) for b in bs]
+            gg = [torch.empty_like(t) for t in gammas]
+            gbeta = [torch.empty_like(t) for t in betas]
+            gx = _rowbuf(x.shape[0], x.shape[1], dev)[:, :x.shape[1]] if ctx.needs_input_grad[0] else None
+            g.saved, g.scratch, g.gout, g.ldg = _p(saved), _p(scratch), _p(gout), int(ldg)
+            g.gx, g.ldgx = _p(gx), int(gx.stride(0)) if gx is not None else 0
+            g.gW, g.gb, g.ggamma, g.gbeta = _ptr3(gW), _ptr3(gb), _ptr3(gg), _ptr3(gbeta)
+            _call('nt_edgeconv_train_bwd', lib.nt_edgeconv_train_bwd, ctypes.byref(g), _stream())
+            g_tail = None
+            H3 = Ws[2].shape[0]
+            if m['tail'] and ctx.needs_input_grad[2]:
+                g_tail = gout[:, H3:H3 + m['tail']].contiguous()
+            flat = []
+            for l in range(3):
+                flat += [gW[l], gb[l], gg[l], gbeta[l]]
+            return (gx, None, g_tail, None, *flat)
         mode, k, N, L, widths, M, C, R, tail = (m[key] for key in ('mode', 'k', 'N', 'L', 'widths', 'M', 'C', 'R', 'tail'))
         sv = ctx.saved_tensors
         x, idx, pq, Wc, sel, vsel, a1 = sv[:7]
@@ -485,9 +568,9 @@ class _FusedMLPFunction(torch.autograd.Function):
             gemm_tn(dpq, 2 * H1, 2 * H1, M, dWc, b=x, ldb=m['ldx'], n=C)
             grads_W[0] = torch.cat([dWc[:H1], dWc[H1:] - dWc[:H1]], dim=1)
             if ctx.needs_input_grad[0]:
-                gx = torch.empty(M, C, **f32)
+                gx = _rowbuf(M, C, dev)[:, :C]         # 16-byte aligned rows: the call streams (TMA result boxes)
                 WcT = Wc.t().contiguous()              # [C, 2*H1]
-                gemm_nt(M, 2 * H1, C, WcT, 2 * H1, NT_EPI_BIAS, a=dpq, lda=2 * H1, out=gx, ldo=C, grad_gemm=True)
+                gemm_nt(M, 2 * H1, C, WcT, 2 * H1, NT_EPI_BIAS, a=dpq, lda=2 * H1, out=gx, ldo=gx.stride(0), grad_gemm=True)
         else:
             dW0 = torch.zeros(H1, C, **f32)
             gemm_tn(dz, dz.stride(0), H1, M, dW0, b=x, ldb=m['ldx'], n=C)
@@ -506,13 +589,15 @@ class _FusedMLPFunction(torch.autograd.Function):
         return (gx, None, g_tail, None, *flat)
 
 
-def fused_mlp(x, layers, training, mode='plain', idx=None, k=1, n_per_cloud=1, tail_src=None):
-    """layers: list of (nn.Linear, nn.BatchNorm1d) pairs (the reference's Sequential(Linear, ReLU, BatchNorm1d))."""
+def fused_mlp(x, layers, training, mode='plain', idx=None, k=1, n_per_cloud=1, tail_src=None, pad_out=False):
+    """layers: list of (nn.Linear, nn.BatchNorm1d) pairs (the reference's Sequential(Linear, ReLU, BatchNorm1d)).
+    pad_out (edge mode): return a [M, C] view of a buffer whose rows are padded to a multiple of 4 floats, so that the NEXT
+    EdgeConv layer streams 16-byte aligned rows (set for the layers whose output only feeds the next layer)."""
     params, bufs = [], []
     for lin, bn in layers:
         params += [lin.weight, lin.bias, bn.weight, bn.bias]
         bufs.append(_BNBuffers(bn.running_mean, bn.running_var, bn.num_batches_tracked, bn.momentum, bn.eps))
-    meta = dict(mode=mode, training=bool(training), bn=bufs, k=int(k), n_per_cloud=int(n_per_cloud))
+    meta = dict(mode=mode, training=bool(training), bn=bufs, k=int(k), n_per_cloud=int(n_per_cloud), pad_out=bool(pad_out))
     return _FusedMLPFunction.apply(x, idx, tail_src, meta, *params)
 
 

@@ -244,6 +244,37 @@ int nt_lstm_bwd(const float *dy, int ld_dy, const void *act, const float *cs, co
                 int T, int L, int H, int E, void *workspace, float *dx, int ld_dx, float *const *dw_ih, float *const *dw_hh,
                 float *const *db_ih, float *const *db_hh, void *stream);
 
+/* ---- composite EdgeConv layer, TRAINING mode (DynamicEdgeConv over MLP([2C, H1, H2, H3]) with batch-statistics BatchNorm;
+ * nn/net_blocks.py:126-135,172-180; SURVEY 8b "nt_edgeconv_fwd/bwd ... training variants with BN stat buffers") --------------------
+ * One call per direction runs the whole layer on `stream` with this library's kernels (forward: split first Linear per point ->
+ * nt_edge_activation -> nt_bn_fold -> nt_gemm_nt(RELU_STATS) -> nt_bn_fold -> nt_gemm_nt(RELU_MAXMIN) -> nt_bn_fold ->
+ * nt_maxmin_finish; backward: the mirror image, down to the gradients of x and of every parameter).  The caller allocates
+ * `saved` (nt_edgeconv_saved_bytes(): written by the forward, read by the backward -- activations a1..a3, PQ, BatchNorm vectors,
+ * folded transposed weights) and `scratch` (nt_edgeconv_scratch_bytes(args, backward): temporaries, reusable once the stream has
+ * passed the call); both 256-byte aligned device memory.  Row layouts: x [M, C] (row stride ldx), idx [M, k] int32 LOCAL to the
+ * cloud (nt_knn), out / gout [M, H3 + tail], W[l] contiguous [H_l, in_l] (in_0 = 2C), gradients contiguous and OVERWRITTEN.
+ * The running BatchNorm buffers are updated in place like nn.BatchNorm1d (momentum; num_batches_tracked += 1).  TF32x3 products. */
+typedef struct nt_edgeconv_args {
+    int64_t M;                                   /* points = clouds * n_per_cloud */
+    int C, H1, H2, H3, k, n_per_cloud;
+    const float *x; int ldx;
+    const int32_t *idx;
+    const float *tail_src; int tail_ld, tail;    /* skip-connection columns copied to out[:, H3:H3+tail] (tail = 0: none) */
+    const float *W[3], *b[3], *gamma[3], *beta[3];
+    float *running_mean[3], *running_var[3]; int64_t *num_batches_tracked[3];
+    float momentum, eps;
+    float *out; int ldo;                         /* forward result */
+    void *saved, *scratch;
+    /* backward only */
+    const float *gout; int ldg;
+    float *gx; int ldgx;                         /* [M, C] or NULL */
+    float *gW[3], *gb[3], *ggamma[3], *gbeta[3];
+} nt_edgeconv_args;
+int64_t nt_edgeconv_saved_bytes(const nt_edgeconv_args *args);                  /* -1: bad shape */
+int64_t nt_edgeconv_scratch_bytes(const nt_edgeconv_args *args, int backward);
+int nt_edgeconv_train_fwd(const nt_edgeconv_args *args, void *stream);
+int nt_edgeconv_train_bwd(const nt_edgeconv_args *args, void *stream);
+
 /* ---- fused inference EdgeConv layer (DynamicEdgeConv in eval mode; nn/net_blocks.py:126-135,172-180) ------------------------------
  * out[i, 0:C] = s*max|min_{j in kNN(i)} relu(W3' relu(W2' relu(P[i] + Q[j]) + b2') + b3') + t  in ONE kernel (gather, two chained
  * tcgen05 GEMMs with the intermediate kept in TMEM / shared memory, max over the k rows of a point, trailing BatchNorm affine,

@@ -204,6 +204,50 @@ def test_edgeconv_matches_torch(ops, cuda_device, C, widths, k, B, N, tail, trai
             assert torch.equal(b1, b2), n1
 
 
+@pytest.mark.parametrize('C,widths,k,B,N,tail', [(3, [200, 200, 150], 5, 2, 300, 0), (150, [200, 200, 150], 5, 3, 257, 3),
+                                                 (7, [24, 40, 18], 16, 2, 130, 0)])
+def test_edgeconv_composite_entry_points_match_the_kernel_by_kernel_path(ops, cuda_device, C, widths, k, B, N, tail):
+    """nt_edgeconv_train_fwd / _bwd (the whole training-mode EdgeConv layer per call, orchestrated in C++: csrc/edgeconv_train.cu)
+    against the kernel-by-kernel orchestration of the same kernels in ops.py: outputs, every gradient, BatchNorm buffers."""
+    from garment_pattern_estimation_b200 import net_blocks as nb
+    dev = cuda_device
+    res = {}
+    for composite in (True, False):
+        torch.manual_seed(5)
+        conv = nb.DynamicEdgeConv(nb.MLP([2 * C] + widths), k=k).to(dev).train()
+        with torch.no_grad():
+            for blk in conv.nn:
+                blk[2].weight.copy_(torch.randn_like(blk[2].weight))
+                blk[2].bias.copy_(torch.randn_like(blk[2].bias) * 0.3)
+        g = torch.Generator().manual_seed(9)
+        x = torch.randn(B * N, C, generator=g).to(dev).requires_grad_(True)
+        pos = torch.randn(B * N, 3, generator=g).to(dev).requires_grad_(True) if tail else None
+        gout = torch.randn(B * N, widths[-1] + tail, generator=g).to(dev)
+        ops.EDGECONV_COMPOSITE = composite
+        before = ops._lib.launch_count()
+        try:
+            out = conv(x, cloud_shape=(B, N), tail_src=pos)
+            out.backward(gout)
+        finally:
+            ops.EDGECONV_COMPOSITE = True
+        torch.cuda.synchronize()
+        res[composite] = dict(out=out.detach(), gx=x.grad, gpos=None if pos is None else pos.grad, launches=ops._lib.launch_count() - before,
+                              grads={n: p.grad for n, p in conv.nn.named_parameters()}, bufs=dict(conv.nn.named_buffers()))
+    a, b = res[True], res[False]
+    assert a['launches'] > 0 and abs(a['launches'] - b['launches']) <= 4      # same kernels (+ the three small glue kernels)
+    assert rel_err(a['out'], b['out']) < 1e-6
+    assert rel_err(a['gx'], b['gx']) < 1e-5
+    if tail:
+        assert torch.equal(a['gpos'], b['gpos'])
+    for n in a['grads']:
+        assert rel_err(a['grads'][n], b['grads'][n]) < 1e-5, n
+    for n in a['bufs']:
+        if a['bufs'][n].dtype.is_floating_point:
+            assert rel_err(a['bufs'][n], b['bufs'][n]) < 1e-6, n
+        else:
+            assert torch.equal(a['bufs'][n], b['bufs'][n]), n
+
+
 @pytest.mark.parametrize('widths,rows', [([153, 153, 153, 23], 1000), ([16, 200, 200, 200, 1], 333), ([7, 9, 5], 64)])
 @pytest.mark.parametrize('training', [True, False])
 def test_plain_mlp_matches_torch(ops, cuda_device, widths, rows, training):
@@ -562,6 +606,7 @@ def test_fused_edge_scatter_matches_separate_scatter_pass(ops, cuda_device):
     results = {}
     try:
         _set_engine(3)
+        ops.EDGECONV_COMPOSITE = False        # both passes through the kernel-by-kernel orchestration (the launch counts are compared)
         for fused in (True, False):
             ops.FUSED_SCATTER = fused
             conv.zero_grad()
@@ -572,6 +617,7 @@ def test_fused_edge_scatter_matches_separate_scatter_pass(ops, cuda_device):
             results[fused] = (xi.grad.clone(), {n: p.grad.clone() for n, p in conv.named_parameters()}, _launches() - before)
     finally:
         ops.FUSED_SCATTER = False
+        ops.EDGECONV_COMPOSITE = True
         _set_engine(0)
     assert results[True][2] == results[False][2] - 1, 'the fused path must save exactly the nt_edge_scatter launch'
     assert rel_err(results[True][0], results[False][0]) < 1e-5
