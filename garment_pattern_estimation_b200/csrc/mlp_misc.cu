@@ -355,21 +355,23 @@ __global__ void edge_scatter_kernel(const float *dz, int lddz, const int32_t *id
 // A thread owns 4 consecutive columns of one centre point and walks its k edge rows with up to 4 independent 16-byte
 // loads in flight; per-node operands (centre row of PQ, upstream gradient, selected slots) are read once instead of k
 // times and no 64-bit division is left in the loops.  Block = (32 column quads, 8 node lanes).
-constexpr int NV_NODES = 32;   // nodes per block
+// Block = (column quads of a row, node lanes): when a row has at most 64 quads the block's x extent IS the number of quads (every lane
+// live: H = 200 -> 50 x 5 threads, C = 150 -> 38 x 6), otherwise 32 quads per block and blockIdx.y walks the row (the first
+// version always did: 22 % / 41 % of the lanes idle at H = 200 / C = 150).  npb = nodes per block.
 
 __device__ __forceinline__ float4 ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
 __global__ void __launch_bounds__(256) edge_activation_v4_kernel(const float *__restrict__ pq, int ldpq, int qoff,
                                                                  const int32_t *__restrict__ idx, int k, int n_per_cloud,
                                                                  int64_t nodes, int H, float *__restrict__ out, int ldo,
-                                                                 double *__restrict__ stats) {
-    __shared__ float red[8][32][8];
-    const int c0 = (blockIdx.y * 32 + threadIdx.x) * 4;
-    const int64_t nbeg = (int64_t)blockIdx.x * NV_NODES;
-    const int64_t nend = min(nodes, nbeg + NV_NODES);
+                                                                 double *__restrict__ stats, int npb) {
+    __shared__ float red[8][64][8];
+    const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    const int64_t nbeg = (int64_t)blockIdx.x * npb;
+    const int64_t nend = min(nodes, nbeg + npb);
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     if (c0 < H) {
-        for (int64_t node = nbeg + threadIdx.y; node < nend; node += 8) {
+        for (int64_t node = nbeg + threadIdx.y; node < nend; node += blockDim.y) {
             const float4 pc = ld4(pq + node * ldpq + c0);
             const int64_t base = (node / n_per_cloud) * (int64_t)n_per_cloud;
             const int32_t *ip = idx + node * k;
@@ -402,8 +404,7 @@ __global__ void __launch_bounds__(256) edge_activation_v4_kernel(const float *__
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { t1 += red[i][threadIdx.x][e]; t2 += red[i][threadIdx.x][4 + e]; }
+            for (int i = 0; i < (int)blockDim.y; ++i) { t1 += red[i][threadIdx.x][e]; t2 += red[i][threadIdx.x][4 + e]; }
             atomicAdd(stats + c0 + e, (double)t1);
             atomicAdd(stats + H + c0 + e, (double)t2);
         }
@@ -415,11 +416,11 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_last_v4_kernel(const float *_
                                                                   const float *__restrict__ s, const float *__restrict__ mu,
                                                                   const float *__restrict__ rstd, const double *__restrict__ sums,
                                                                   int64_t count, int64_t nodes, int C, float *__restrict__ dz,
-                                                                  int lddz, double *__restrict__ colsum) {
-    __shared__ float red[8][32][4];
-    const int c0 = (blockIdx.y * 32 + threadIdx.x) * 4;     // C % 4 == 0 is NOT required: the tail quad is masked per column
-    const int64_t nbeg = (int64_t)blockIdx.x * NV_NODES;
-    const int64_t nend = min(nodes, nbeg + NV_NODES);
+                                                                  int lddz, double *__restrict__ colsum, int npb) {
+    __shared__ float red[8][64][4];
+    const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;     // C % 4 == 0 is NOT required: the tail quad is masked per column
+    const int64_t nbeg = (int64_t)blockIdx.x * npb;
+    const int64_t nend = min(nodes, nbeg + npb);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (c0 < C) {
         const float inv = 1.0f / (float)count;
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_last_v4_kernel(const float *_
             k0[j] = (float)sums[c] * inv;                        // dbeta / count
             k1[j] = rstd[c] * ((float)sums[C + c] * inv);        // rstd * dgamma / count
         }
-        for (int64_t node = nbeg + threadIdx.y; node < nend; node += 8) {
+        for (int64_t node = nbeg + threadIdx.y; node < nend; node += blockDim.y) {
             float gv[4];                                         // upstream gradient rows may have any stride: scalar loads
 #pragma unroll
             for (int j = 0; j < 4; ++j) gv[j] = ok[j] ? __ldg(g + node * ldg + c0 + j) : 0.f;
@@ -475,8 +476,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_last_v4_kernel(const float *_
         for (int j = 0; j < 4; ++j) {
             if (c0 + j >= C) continue;
             float t = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x][j];
+            for (int i = 0; i < (int)blockDim.y; ++i) t += red[i][threadIdx.x][j];
             atomicAdd(colsum + c0 + j, (double)t);
         }
     }
@@ -491,15 +491,15 @@ template <int NX_K>
 __global__ void __launch_bounds__(256, 2) edge_activation_x2_kernel(const float *__restrict__ pq, int ldpq, int qoff,
                                                                  const int32_t *__restrict__ idx, int k, int n_per_cloud,
                                                                  int64_t nodes, int H, float *__restrict__ out, int ldo,
-                                                                 double *__restrict__ stats) {
-    __shared__ float red[8][32][8];
-    const int c0 = (blockIdx.y * 32 + threadIdx.x) * 4;
-    const int64_t nbeg = (int64_t)blockIdx.x * NV_NODES;
-    const int64_t nend = min(nodes, nbeg + NV_NODES);
+                                                                 double *__restrict__ stats, int npb) {
+    __shared__ float red[8][64][8];
+    const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    const int64_t nbeg = (int64_t)blockIdx.x * npb;
+    const int64_t nend = min(nodes, nbeg + npb);
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     if (c0 < H) {
-        for (int64_t nodeA = nbeg + threadIdx.y; nodeA < nend; nodeA += 16) {
-            const int64_t nodeB = nodeA + 8;
+        for (int64_t nodeA = nbeg + threadIdx.y; nodeA < nend; nodeA += 2 * blockDim.y) {
+            const int64_t nodeB = nodeA + blockDim.y;
             const bool hasB = nodeB < nend;
             const int32_t *ipA = idx + nodeA * k, *ipB = idx + (hasB ? nodeB : nodeA) * k;
             int jA[NX_K], jB[NX_K];
@@ -548,8 +548,7 @@ __global__ void __launch_bounds__(256, 2) edge_activation_x2_kernel(const float 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { t1 += red[i][threadIdx.x][e]; t2 += red[i][threadIdx.x][4 + e]; }
+            for (int i = 0; i < (int)blockDim.y; ++i) { t1 += red[i][threadIdx.x][e]; t2 += red[i][threadIdx.x][4 + e]; }
             atomicAdd(stats + c0 + e, (double)t1);
             atomicAdd(stats + H + c0 + e, (double)t2);
         }
@@ -562,11 +561,11 @@ __global__ void __launch_bounds__(256, 2) bn_relu_bwd_last_x2_kernel(const float
                                                                   const float *__restrict__ s, const float *__restrict__ mu,
                                                                   const float *__restrict__ rstd, const double *__restrict__ sums,
                                                                   int64_t count, int64_t nodes, int C, float *__restrict__ dz,
-                                                                  int lddz, double *__restrict__ colsum) {
-    __shared__ float red[8][32][4];
-    const int c0 = (blockIdx.y * 32 + threadIdx.x) * 4;
-    const int64_t nbeg = (int64_t)blockIdx.x * NV_NODES;
-    const int64_t nend = min(nodes, nbeg + NV_NODES);
+                                                                  int lddz, double *__restrict__ colsum, int npb) {
+    __shared__ float red[8][64][4];
+    const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    const int64_t nbeg = (int64_t)blockIdx.x * npb;
+    const int64_t nend = min(nodes, nbeg + npb);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (c0 < C) {
         const float inv = 1.0f / (float)count;
@@ -580,9 +579,9 @@ __global__ void __launch_bounds__(256, 2) bn_relu_bwd_last_x2_kernel(const float
             k0[j] = (float)sums[c] * inv;
             k1[j] = rstd[c] * ((float)sums[C + c] * inv);
         }
-        for (int64_t nodeA = nbeg + threadIdx.y; nodeA < nend; nodeA += 16) {
-            const bool hasB = nodeA + 8 < nend;
-            const int64_t nodeB = hasB ? nodeA + 8 : nodeA;        // loads of a missing node B alias node A (never stored)
+        for (int64_t nodeA = nbeg + threadIdx.y; nodeA < nend; nodeA += 2 * blockDim.y) {
+            const bool hasB = nodeA + blockDim.y < nend;
+            const int64_t nodeB = hasB ? nodeA + blockDim.y : nodeA;   // loads of a missing node B alias node A (never stored)
             float gv[2][4];
             int ss[2][4];
 #pragma unroll
@@ -631,8 +630,7 @@ __global__ void __launch_bounds__(256, 2) bn_relu_bwd_last_x2_kernel(const float
         for (int j = 0; j < 4; ++j) {
             if (c0 + j >= C) continue;
             float t = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x][j];
+            for (int i = 0; i < (int)blockDim.y; ++i) t += red[i][threadIdx.x][j];
             atomicAdd(colsum + c0 + j, (double)t);
         }
     }
@@ -640,12 +638,12 @@ __global__ void __launch_bounds__(256, 2) bn_relu_bwd_last_x2_kernel(const float
 
 __global__ void __launch_bounds__(256) edge_scatter_v4_kernel(const float *__restrict__ dz, int lddz, const int32_t *__restrict__ idx,
                                                               int k, int n_per_cloud, int64_t M, int H, float *__restrict__ dpq,
-                                                              int lddpq) {
-    const int c0 = (blockIdx.y * 32 + threadIdx.x) * 4;
+                                                              int lddpq, int npb) {
+    const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
     if (c0 >= H) return;
-    const int64_t nbeg = (int64_t)blockIdx.x * NV_NODES;
-    const int64_t nend = min(M, nbeg + NV_NODES);
-    for (int64_t node = nbeg + threadIdx.y; node < nend; node += 8) {
+    const int64_t nbeg = (int64_t)blockIdx.x * npb;
+    const int64_t nend = min(M, nbeg + npb);
+    for (int64_t node = nbeg + threadIdx.y; node < nend; node += blockDim.y) {
         const int64_t base = (node / n_per_cloud) * (int64_t)n_per_cloud;
         const int32_t *ip = idx + node * k;
         const float *zp = dz + node * k * (int64_t)lddz + c0;
@@ -670,6 +668,17 @@ __global__ void __launch_bounds__(256) edge_scatter_v4_kernel(const float *__res
 }
 
 static inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+// launch geometry of the quad kernels above for rows of `cols` columns
+static inline void quad_geometry(int cols, dim3 &block, unsigned &grid_y, int &npb) {
+    const int quads = (cols + 3) / 4;
+    if (quads <= 64) {
+        int ny = 256 / quads;
+        if (ny > 8) ny = 8;
+        block = dim3(quads, ny); grid_y = 1; npb = 4 * ny;
+    } else {
+        block = dim3(32, 8); grid_y = (quads + 31) / 32; npb = 32;
+    }
+}
 
 }  // namespace nt
 
@@ -741,13 +750,15 @@ extern "C" int nt_edge_activation(const float *pq, int ldpq, int qoff, const int
     if (rows == 0) return 0;
     dim3 block(32, 8);
     if (idx && (H & 3) == 0 && (ldpq & 3) == 0 && (qoff & 3) == 0 && (ldo & 3) == 0 && aligned16(pq) && aligned16(out) && rows % k == 0) {
-        dim3 grid(blocks_for(rows / k, NV_NODES), (H + 127) / 128);
+        unsigned gy; int npb;
+        quad_geometry(H, block, gy, npb);
+        dim3 grid(blocks_for(rows / k, npb), gy);
         if (k <= 5)
             edge_activation_x2_kernel<5><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pq, ldpq, qoff, idx, k, n_per_cloud,
-                                                                                                   rows / k, H, out, ldo, stats);
+                                                                                                   rows / k, H, out, ldo, stats, npb);
         else
             edge_activation_v4_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pq, ldpq, qoff, idx, k, n_per_cloud,
-                                                                                                rows / k, H, out, ldo, stats);
+                                                                                                rows / k, H, out, ldo, stats, npb);
     } else {
         dim3 grid(blocks_for(rows, EA_ROWS), (H + 127) / 128);
         edge_activation_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pq, ldpq, qoff, idx, k, n_per_cloud,
@@ -766,13 +777,15 @@ extern "C" int nt_bn_relu_bwd_last(const float *a, int lda, const float *g, int 
     dim3 block(32, 8);
     const int Cp = (C + 3) & ~3;      // the float4 kernel touches whole column quads: rows must be padded to a multiple of 4
     if ((lda & 3) == 0 && (lddz & 3) == 0 && lda >= Cp && lddz >= Cp && aligned16(a) && aligned16(dz)) {
-        dim3 grid(blocks_for(rows / k, NV_NODES), (C + 127) / 128);
+        unsigned gy; int npb;
+        quad_geometry(C, block, gy, npb);
+        dim3 grid(blocks_for(rows / k, npb), gy);
         if (k <= 5)
             bn_relu_bwd_last_x2_kernel<5><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-                a, lda, g, ldg, sel, k, s, mu, rstd, sums, count, rows / k, C, dz, lddz, colsum);
+                a, lda, g, ldg, sel, k, s, mu, rstd, sums, count, rows / k, C, dz, lddz, colsum, npb);
         else
             bn_relu_bwd_last_v4_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-                a, lda, g, ldg, sel, k, s, mu, rstd, sums, count, rows / k, C, dz, lddz, colsum);
+                a, lda, g, ldg, sel, k, s, mu, rstd, sums, count, rows / k, C, dz, lddz, colsum, npb);
     } else {
         dim3 grid(blocks_for(rows, BL_ROWS), (C + 127) / 128);
         bn_relu_bwd_last_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -798,9 +811,12 @@ extern "C" int nt_edge_scatter(const float *dz, int lddz, const int32_t *idx, in
                "nt_edge_scatter: bad arguments");
     if (M == 0) return 0;
     if ((H & 3) == 0 && (lddz & 3) == 0 && (lddpq & 3) == 0 && aligned16(dz) && aligned16(dpq)) {
-        dim3 grid(blocks_for(M, NV_NODES), (H + 127) / 128), block(32, 8);
+        dim3 block;
+        unsigned gy; int npb;
+        quad_geometry(H, block, gy, npb);
+        dim3 grid(blocks_for(M, npb), gy);
         edge_scatter_v4_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dz, lddz, idx, k, n_per_cloud, M, H,
-                                                                                         dpq, lddpq);
+                                                                                         dpq, lddpq, npb);
     } else {
         edge_scatter_kernel<<<blocks_for(M * H, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
             dz, lddz, idx, k, n_per_cloud, M, H, dpq, lddpq);
