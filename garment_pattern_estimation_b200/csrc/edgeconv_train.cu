@@ -71,9 +71,10 @@ bool make_plan(const nt_edgeconv_args *g, Plan &p) {
     o = 0;
     p.acc_doubles = (size_t)2 * g->H3 + g->H3 + (size_t)g->H3 * g->H2 + g->H2 + (size_t)g->H2 * g->H1 + g->H1;
     p.b_acc = seg(p.acc_doubles * 8);
-    p.b_dz3 = seg((size_t)p.R * p.ld3 * 4);
+    // dz3 is dead once dz2 exists, and dz1 is written after that: the two share one region (1.6 GB at C4: 2.56 M edge rows)
+    p.b_dz3 = seg((size_t)p.R * (p.ld3 > p.ld1 ? p.ld3 : p.ld1) * 4);
     p.b_dz2 = seg((size_t)p.R * p.ld2 * 4);
-    p.b_dz1 = seg((size_t)p.R * p.ld1 * 4);
+    p.b_dz1 = p.b_dz3;
     p.b_vec[0] = 0;
     for (int l = 1; l < 3; ++l) p.b_vec[l] = seg((size_t)2 * p.H[l - 1] * 4);          // k0 | k1 of the BN in front of Linear l
     p.b_dpq = seg((size_t)p.M * 2 * g->H1 * 4);
