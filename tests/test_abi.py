@@ -83,3 +83,41 @@ def test_empty_inputs_are_no_ops_and_new_entry_points_validate():
     assert b'unknown mode' in lib.nt_last_error()
     g.rows = 10
     assert lib.nt_gemm_nt_scatter_supported(ctypes.byref(g)) == 0                    # no scatter target requested
+
+
+def test_composite_edgeconv_entry_points_size_queries_and_validation():
+    """nt_edgeconv_train_fwd / _bwd: the size queries are pure host functions, and argument validation happens before
+    any CUDA call; the header's minimum set of section 8b is present by name."""
+    from garment_pattern_estimation_b200 import _lib
+    lib = _lib.load()
+    syms = _declared_symbols()
+    for must in ('nt_edgeconv_train_fwd', 'nt_edgeconv_train_bwd', 'nt_edgeconv_saved_bytes', 'nt_edgeconv_scratch_bytes',
+                 'nt_edgeconv_eval_fwd', 'nt_edgeconv_eval_supported'):
+        assert must in syms
+    assert lib.nt_sizeof(b'nt_edgeconv_args') == ctypes.sizeof(_lib.EdgeConvArgs)
+    g = _lib.EdgeConvArgs()
+    assert lib.nt_edgeconv_saved_bytes(ctypes.byref(g)) == -1                       # C = H = k = 0: bad shape
+    g.M, g.C, g.H1, g.H2, g.H3, g.k, g.n_per_cloud = 32 * 2048, 150, 200, 200, 150, 5, 2048
+    saved = lib.nt_edgeconv_saved_bytes(ctypes.byref(g))
+    fwd, bwd = lib.nt_edgeconv_scratch_bytes(ctypes.byref(g), 0), lib.nt_edgeconv_scratch_bytes(ctypes.byref(g), 1)
+    E = g.M * g.k
+    # saved = PQ + a1 + a2 + a3 (padded rows) + sel + vsel + small vectors; the backward keeps two edge-sized gradient buffers
+    assert saved % 256 == 0 and fwd % 256 == 0 and bwd % 256 == 0
+    assert 4 * E * (200 + 200 + 152) + 4 * g.M * 400 <= saved <= 4 * E * (200 + 200 + 152) + 4 * g.M * 400 + 5 * g.M * 150 + (1 << 21)
+    assert 4 * E * (200 + 200) <= bwd <= 4 * E * (200 + 200) + 4 * g.M * 400 + lib.nt_gemm_tn_workspace_bytes() + (8 << 20)
+    assert fwd < bwd
+    g2 = _lib.EdgeConvArgs()
+    ctypes.memmove(ctypes.byref(g2), ctypes.byref(g), ctypes.sizeof(g))
+    g2.M = 2 * g.M
+    assert lib.nt_edgeconv_saved_bytes(ctypes.byref(g2)) > saved
+    # nothing to do / missing buffers: status codes, never a crash
+    g0 = _lib.EdgeConvArgs()
+    ctypes.memmove(ctypes.byref(g0), ctypes.byref(g), ctypes.sizeof(g))
+    g0.M = 0
+    assert lib.nt_edgeconv_train_fwd(ctypes.byref(g0), None) == 0
+    assert lib.nt_edgeconv_train_bwd(ctypes.byref(g0), None) == 0
+    assert lib.nt_edgeconv_train_fwd(ctypes.byref(g), None) != 0
+    assert b'nt_edgeconv' in lib.nt_last_error()
+    g.k = 500
+    assert lib.nt_edgeconv_train_bwd(ctypes.byref(g), None) != 0
+    assert b'bad shape' in lib.nt_last_error()
