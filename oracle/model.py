@@ -11,8 +11,8 @@ Follows (reference file:line, relative to /root/reference):
   * ``panel_loop_loss``          nn/metrics/losses.py:19-51
   * ``main_losses``              nn/metrics/composed_loss.py:294-321 (the 4 components active in att.yaml:124)
 The module tree / parameter names reproduce the reference state_dict so the shipped checkpoints load
-with strict=True.  ``tests/test_oracle_vs_reference.py`` checks this file against the unmodified reference code
-executed through ``oracle.ref_stubs`` (bit-exact on CPU); the committed fixtures in tests/golden/ come from that run.
+with strict=True.  ``tests/test_oracle.py::test_oracle_equals_unmodified_reference_when_available`` checks this file against the
+unmodified reference code executed through ``oracle.ref_stubs`` (bit-exact on CPU); the committed fixtures in tests/golden/ come from that run.
 
 Differences from the reference that are deliberate and documented: ``init_state`` can be overridden by passing
 ``lstm_state=(h0, c0)`` (the reference's states are fresh random draws on every forward -- SURVEY.md F3 -- so parity
